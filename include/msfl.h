@@ -1,0 +1,218 @@
+/*
+ * msfl.h -- C ABI of the Blackwell-native LOAM scan-matching engine (libmsfl.so).
+ *
+ * This is the drop-in boundary for ONE hot path of kekeliu-whu/MSF_LOAM @ 96924b3
+ * (scanRegistration -> laserOdometry -> laserMapping).  Each entry point names the reference
+ * interface it replaces (paths relative to the reference tree).  Plain pointers and sizes only;
+ * no C++/torch types.  All functions return an int status and never throw:
+ *     MSFL_OK (0), MSFL_TOO_FEW (1: fewer than min_correspondences, odometry only --
+ *     odometry_scan_matcher.cc:262-267; the pose keeps the result of the completed outer
+ *     iterations), < 0 error (msfl_last_error() gives the text).
+ * There is no CPU fallback: every compute entry point fails with MSFL_ERR_CUDA when no sm_100
+ * device / kernel image is available.
+ *
+ * Conventions
+ *   pose      double[7] = [tx ty tz qx qy qz qw]   Rigid3d::ToVector7, rigid_transform.h:59-64
+ *   cloud     host AoS view (ptr, n, stride, field byte offsets) so a pcl::PointCloud<P> is passed
+ *             as (&cloud.points[0], cloud.size(), sizeof(P), offsetof(P,x), offsetof(P,intensity),
+ *             offsetof(P,ring) or MSFL_NO_FIELD).  Caller keeps ownership; nothing is retained
+ *             after return (laser_odometry.cc:90 shallow-copies scan_last_ = scan_curr).
+ *   threading one engine per matcher thread (MatchScan2Scan runs on the LiDAR callback thread,
+ *             MatchScan2Map on LaserMapping::Run, laser_mapping.cc:86); an engine owns one CUDA
+ *             stream and its device buffers and is not re-entrant.
+ */
+#ifndef MSFL_H
+#define MSFL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSFL_OK 0
+#define MSFL_TOO_FEW 1
+#define MSFL_ERR_ARG (-1)
+#define MSFL_ERR_CUDA (-2)
+#define MSFL_ERR_RING (-3)     /* ring >= 128 (kMaxScanNum, msf_loam_node.cc:79,136) or clouds not ring-sorted */
+#define MSFL_ERR_EMPTY (-4)    /* no valid points (CHECK_GT(_N, 0), msf_loam_node.cc:200) */
+#define MSFL_ERR_NOSUBMAP (-5)
+#define MSFL_ERR_GRID (-6)     /* submap bounding box too large for the dense cell index */
+
+#define MSFL_NO_FIELD ((size_t)-1)
+#define MSFL_MAX_OUTER 4
+#define MSFL_MAX_ATTEMPTS 16
+#define MSFL_MAX_RINGS 128
+
+/* Every constant of the hot path in one POD; msfl_default_params() fills the reference values. */
+typedef struct msfl_params {
+  /* feature extraction -- src/msf_loam_node.cc */
+  double min_range;            /* 0.3   ROS param minimum_range :434                  */
+  double scan_period;          /* 0.1   kScanPeriod :80                               */
+  double curvature_thresh;     /* 0.1   :275, :312                                    */
+  double neighbor_gap_sq;      /* 0.05  :293                                          */
+  int32_t n_sectors;           /* 6     :255                                          */
+  int32_t n_sharp;             /* 2     :277                                          */
+  int32_t n_less_sharp;        /* 20    :281                                          */
+  int32_t n_flat;              /* 4     :317                                          */
+  /* scan-to-scan -- odometry_scan_matcher.cc:15-18, :262 */
+  double dist_sq_thresh;       /* 25    kDistanceSqThreshold                          */
+  double nearby_scan;          /* 2.5   kNearByScan                                   */
+  int32_t min_correspondences; /* 10                                                  */
+  int32_t _pad0;
+  /* scan-to-map -- mapping_scan_matcher.cc:128, :147, :150, :216 */
+  double knn_max_sq;           /* 1.0   pointSearchSqDis[4] < 1.0                     */
+  double line_eig_ratio;       /* 3.0   eigenvalues[2] > 3 eigenvalues[1]             */
+  double line_half_len;        /* 0.1   point_a = 0.1 u + c                           */
+  double plane_tol;            /* 0.2                                                 */
+  /* solve -- call sites + Ceres defaults */
+  int32_t num_outer;           /* 2     kOptimalNum (<= MSFL_MAX_OUTER)               */
+  int32_t max_num_iterations;  /* 6     options.max_num_iterations (<= MSFL_MAX_ATTEMPTS) */
+  double huber_a;              /* 0.1   ceres::HuberLoss(0.1)                         */
+  double initial_radius;       /* 1e4   initial_trust_region_radius                   */
+  double max_radius;           /* 1e16  max_trust_region_radius                       */
+  double min_radius;           /* 1e-32 min_trust_region_radius                       */
+  double min_relative_decrease;/* 1e-3                                                */
+  double min_lm_diagonal;      /* 1e-6                                                */
+  double max_lm_diagonal;      /* 1e32                                                */
+  double function_tolerance;   /* 1e-6                                                */
+  double gradient_tolerance;   /* 1e-10                                               */
+  double parameter_tolerance;  /* 1e-8                                                */
+  int32_t max_consecutive_invalid_steps; /* 5                                         */
+  int32_t early_exit;          /* 1 = Ceres termination tests; 0 = fixed attempt count
+                                  (throughput schedule)                 */
+  /* engine */
+  int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan in the LM kernel:
+                                  0 = auto, else 1/2/4/8                              */
+  int32_t _pad1;
+} msfl_params;
+
+/* Host AoS cloud view (see "Conventions"). */
+typedef struct msfl_cloud {
+  const void *data;
+  size_t n;
+  size_t stride;
+  size_t off_xyz;        /* byte offset of float x; y, z follow                      */
+  size_t off_intensity;  /* byte offset of float intensity, or MSFL_NO_FIELD         */
+  size_t off_ring;       /* byte offset of uint16 ring, or MSFL_NO_FIELD             */
+} msfl_cloud;
+
+/* Ceres-style iteration log (summary.iterations / minimizer_progress_to_stdout). */
+typedef struct msfl_lm_iter {
+  double cost, cost_candidate, model_change, rho, radius;
+  int32_t valid, accepted;
+} msfl_lm_iter;
+
+typedef struct msfl_lm_log {
+  int32_t n_attempts;
+  int32_t termination; /* 0 max-iter, 1 parameter tol, 2 function tol, 3 gradient tol, 4 radius, 5 invalid */
+  double initial_cost, final_cost;
+  msfl_lm_iter it[MSFL_MAX_ATTEMPTS];
+} msfl_lm_log;
+
+typedef struct msfl_stats {
+  int32_t status;                    /* per-scan status (MSFL_OK / MSFL_TOO_FEW)     */
+  int32_t n_outer;                   /* outer iterations executed                    */
+  int32_t n_edge[MSFL_MAX_OUTER];    /* corner_num / corner_correspondence           */
+  int32_t n_plane[MSFL_MAX_OUTER];   /* surf_num / plane_correspondence              */
+  msfl_lm_log lm[MSFL_MAX_OUTER];
+} msfl_stats;
+
+/* Output of msfl_extract_features: caller-allocated arrays of capacity n_in. */
+typedef struct msfl_features {
+  float *full_xyzi;        /* [n_full][4] ring-major cloud_full_res, intensity := rel. time, extrinsic applied */
+  uint16_t *full_ring;     /* [n_full]                                               */
+  float *curvature;        /* [n_full] optional (NULL ok)                            */
+  int32_t *label;          /* [n_full] optional: 0 unknown 1 sharp 2 less-sharp 3 flat */
+  int32_t *idx_sharp;      /* indices into full_* in the reference's push order      */
+  int32_t *idx_less_sharp;
+  int32_t *idx_flat;
+  int32_t *idx_less_flat;
+  int32_t n_full, n_sharp, n_less_sharp, n_flat, n_less_flat;
+} msfl_features;
+
+typedef struct msfl_engine msfl_engine;
+
+void msfl_default_params(msfl_params *p);
+const char *msfl_last_error(void);
+const char *msfl_version(void);
+
+/* One engine per matcher object (replaces the members of OdometryScanMatcher /
+ * MappingScanMatcher, laser_odometry.cc:56, laser_mapping.cc:42).  `stream` (a cudaStream_t)
+ * may be NULL: the engine then creates its own non-blocking stream. */
+int msfl_create(const msfl_params *params, int device, msfl_engine **out);
+int msfl_create_on_stream(const msfl_params *params, int device, void *stream, msfl_engine **out);
+void msfl_destroy(msfl_engine *e);
+int msfl_sync(msfl_engine *e);
+void *msfl_stream(msfl_engine *e); /* cudaStream_t the engine launches on (for CUDA-event timing) */
+/* number of kernel launches issued by this engine since creation (evidence for gpu_launches) */
+uint64_t msfl_launch_count(const msfl_engine *e);
+
+/* ---- scan-to-map: MappingScanMatcher::MatchScan2Map, LiDAR-only branch
+ *      (mapping_scan_matcher.h:14-21, mapping_scan_matcher.cc:63-278) ------------------------- */
+
+/* cloud_map.cloud_corner_less_sharp / cloud_surf_less_flat (mapping_scan_matcher.cc:66-72: the
+ * two kd-tree builds).  H2D copy + cell-index build; the submap stays resident until replaced. */
+int msfl_set_submap(msfl_engine *e, const msfl_cloud *map_corner, const msfl_cloud *map_surf);
+/* Same, from device-resident packed float4 (x,y,z,*) arrays, e.g. after an NCCL broadcast. */
+int msfl_set_submap_device(msfl_engine *e, const float *d_corner_xyzi, size_t n_corner,
+                           const float *d_surf_xyzi, size_t n_surf);
+/* Device pointers of the resident packed submap arrays (for broadcasting from the owner rank). */
+int msfl_get_submap_device(msfl_engine *e, const float **d_corner_xyzi, size_t *n_corner,
+                           const float **d_surf_xyzi, size_t *n_surf);
+
+/* One scan vs the resident submap.  pose_tq: in = initial guess (*pose_estimate_map_scan2world),
+ * out = estimate.  stats may be NULL. */
+int msfl_scan2map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                  double pose_tq[7], msfl_stats *stats);
+/* B independent scans vs the resident submap (BASELINE.json configs 4-5).  poses_tq: B x 7
+ * in-out; stats: B entries or NULL.  Returns MSFL_OK or the first error. */
+int msfl_scan2map_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner,
+                        const msfl_cloud *scan_surf, double *poses_tq, msfl_stats *stats);
+/* Same with inputs already resident in HBM: packed float4 queries, per-scan offset tables
+ * (B+1 int32, device), poses (B x 7 double, device, in-out).  No host<->device traffic and no
+ * host synchronisation: returns after enqueueing on the engine stream. */
+int msfl_scan2map_batch_device(msfl_engine *e, int B,
+                               const float *d_corner_xyzi, const int32_t *d_corner_off, size_t n_corner_total,
+                               const float *d_surf_xyzi, const int32_t *d_surf_off, size_t n_surf_total,
+                               double *d_poses_tq, msfl_stats *d_stats /* device, B entries, or NULL */);
+/* Association only (a-6/a-7) at a given pose, for parity tests: knn_idx (n_corner+n_surf) x 5
+ * original submap indices (-1 where the d5^2 gate failed), corr (n_corner+n_surf) x 6 doubles
+ * [a_or_c(3), n(3)] (n = 0 where no factor was created).  Either output may be NULL. */
+int msfl_associate_map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                       const double pose_tq[7], int32_t *knn_idx, double *corr);
+
+/* ---- scan-to-scan: OdometryScanMatcher::MatchScan2Scan
+ *      (odometry_scan_matcher.h:10-12, odometry_scan_matcher.cc:43-285) ----------------------
+ * last_* must carry rings and be ring-sorted (Appendix B of SURVEY.md; the extraction emits
+ * ring by ring).  pose_tq in-out = *pose_estimate_curr2last. */
+int msfl_scan2scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp,
+                   const msfl_cloud *last_surf_less_flat, const msfl_cloud *curr_corner_sharp,
+                   const msfl_cloud *curr_surf_flat, double pose_tq[7], msfl_stats *stats);
+/* outer-iteration-0 association only (parity tests): assoc = n_sharp x 2 then n_flat x 3 ints */
+int msfl_associate_scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp,
+                        const msfl_cloud *last_surf_less_flat, const msfl_cloud *curr_corner_sharp,
+                        const msfl_cloud *curr_surf_flat, const double pose_tq[7], int32_t *assoc);
+
+/* ---- feature extraction: the block of RealHandleLaserCloudMessage between laser_cloud_in
+ *      (msf_loam_node.cc:166) and scan.* (msf_loam_node.cc:360-371) --------------------------
+ * raw needs xyz + ring (+ intensity, overwritten by relative time as the reference does).
+ * T_lidar2imu: extrinsic applied to all outputs (msf_loam_node.cc:367-371), NULL = identity. */
+int msfl_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T_lidar2imu[7],
+                          msfl_features *out);
+
+/* ---- caller-side pcl::VoxelGrid<PointXYZI> (laser_mapping.cc:264-270) --
+ * out_xyzi capacity in->n x 4 floats; *n_out receives the number of centroids. */
+int msfl_voxel_grid(msfl_engine *e, const msfl_cloud *in, float leaf, float *out_xyzi, size_t *n_out);
+
+/* ---- LM building block, exposed for parity tests (a-8 + reduction): cost, H (6x6 row-major),
+ *      g at pose over explicit correspondences: p n x 3 float, corr n x 6 double, first
+ *      n_edge rows are edge factors, the rest plane factors. ---------------------------------- */
+int msfl_accumulate(msfl_engine *e, const float *p_xyz, const double *corr, int n_edge, int n_plane,
+                    const double pose_tq[7], double *cost, double H[36], double g[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSFL_H */

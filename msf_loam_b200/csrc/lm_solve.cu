@@ -1,0 +1,374 @@
+// lm_solve.cu -- the Gauss-Newton / Levenberg-Marquardt solve on SE(3):
+//   LidarEdgeFactorSE3 / LidarPlaneFactorSE3 residual + analytic Jacobian (lidar_factor.cc:7-44),
+//   Huber(0.1) corrector, warp-shuffle + fixed-order block reduction of the 6x6 J^T J, J^T r and
+//   cost, and a Ceres-compatible trust-region loop (replacing ceres::Solve at
+//   odometry_scan_matcher.cc:270-280 and mapping_scan_matcher.cc:250-272) -- all inside ONE kernel
+//   per outer iteration, one thread-block cluster per scan, no host round trip between attempts.
+//
+// Every attempt is ONE sweep over the scan's correspondences: cost, H and g are evaluated together
+// at the candidate x+, so an accepted step needs no second pass (the (1+L) factor of the byte
+// formula in SURVEY.md 8d).  All factor math is fp64 (the reference's is); sums are combined in a
+// fixed order, so results are bit-reproducible run to run and independent of the batch size.
+#include <cooperative_groups.h>
+
+#include "msfl_internal.h"
+#include "msfl_math.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace msfl {
+
+constexpr int kLmThreads = 256;
+constexpr int kAcc = 28;  // 21 upper-tri H + 6 g + 1 cost
+
+struct LmShared {
+  double x[7], xc[7];
+  double H[21], g[6], cost;
+  double red[kLmThreads / 32][kAcc];
+  double cand[kAcc];
+  double S[6], diag[6];
+  double radius, nu, x_norm, model;
+  int reuse, n_invalid, iteration, done, step_successful, termination, n_edge, n_plane, too_few;
+  int cnt[kLmThreads / 32][2];
+};
+
+// One residual row: H += J J^T, g += J r.
+__device__ __forceinline__ void acc_row(double (&acc)[kAcc], const double J[6], double r) {
+  int k = 0;
+#pragma unroll
+  for (int u = 0; u < 6; ++u)
+#pragma unroll
+    for (int v = u; v < 6; ++v) acc[k++] += J[u] * J[v];
+#pragma unroll
+  for (int u = 0; u < 6; ++u) acc[21 + u] += J[u] * r;
+}
+
+// Huber loss + Ceres corrector (loss_function.cc HuberLoss::Evaluate; corrector.cc: rho'' <= 0 so
+// residual and Jacobian are both scaled by sqrt(rho')).  Returns the scale, adds 0.5 rho to cost.
+__device__ __forceinline__ double huber_scale(double s, double a, double &cost) {
+  const double b = a * a;
+  if (s > b) {
+    const double r = sqrt(s);
+    cost += 0.5 * (2.0 * a * r - b);
+    return sqrt(fmax(2.2250738585072014e-308, a / r));
+  }
+  cost += 0.5 * s;
+  return 1.0;
+}
+
+// Sweep this thread's share of the correspondences at `pose`: edge factors over the corner
+// queries, then plane factors over the surf queries.
+// p*: query points (raw, fp32 -- quirk Q4: factors use the untransformed point); corr*: 6 doubles
+// per query [a_or_c(3), n(3)], n = 0 where no factor exists.
+__device__ __forceinline__ void sweep(double (&acc)[kAcc], const float4 *__restrict__ pe, const double *__restrict__ corr_e,
+                                      uint32_t n_e, const float4 *__restrict__ pp, const double *__restrict__ corr_p,
+                                      uint32_t n_p, const double *pose, double huber_a, uint32_t tid, uint32_t nthreads,
+                                      int &cnt_edge, int &cnt_plane) {
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+  double R[9];
+  quat_to_R(pose + 3, R);
+  const double t0 = pose[0], t1 = pose[1], t2 = pose[2];
+  cnt_edge = 0;
+  cnt_plane = 0;
+#define MSFL_LOAD_CORR(CORR, P)                                                                    \
+  const double2 *cp = reinterpret_cast<const double2 *>((CORR) + (size_t)i * 6);                   \
+  const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];                                                \
+  const double a0 = c0.x, a1 = c0.y, a2 = c1.x, n0 = c1.y, n1 = c2.x, n2 = c2.y;                   \
+  if (n0 == 0.0 && n1 == 0.0 && n2 == 0.0) continue; /* no factor for this query */                \
+  const float4 pf = (P)[i];                                                                        \
+  const double p0 = pf.x, p1 = pf.y, p2 = pf.z;                                                    \
+  /* d = R p + t - a */                                                                            \
+  const double d0 = R[0] * p0 + R[1] * p1 + R[2] * p2 + t0 - a0;                                   \
+  const double d1 = R[3] * p0 + R[4] * p1 + R[5] * p2 + t1 - a1;                                   \
+  const double d2 = R[6] * p0 + R[7] * p1 + R[8] * p2 + t2 - a2;                                   \
+  /* M = R [p]x, columns m.0 m.1 m.2 */                                                            \
+  const double m00 = R[1] * p2 - R[2] * p1, m10 = R[4] * p2 - R[5] * p1, m20 = R[7] * p2 - R[8] * p1; \
+  const double m01 = R[2] * p0 - R[0] * p2, m11 = R[5] * p0 - R[3] * p2, m21 = R[8] * p0 - R[6] * p2; \
+  const double m02 = R[0] * p1 - R[1] * p0, m12 = R[3] * p1 - R[4] * p0, m22 = R[6] * p1 - R[7] * p0;
+
+  for (uint32_t i = tid; i < n_e; i += nthreads) {
+    MSFL_LOAD_CORR(corr_e, pe)
+    ++cnt_edge;
+    // r = n x d ; J = [ [n]x | -[n]x M ]   (lidar_factor.cc:12,18-19)
+    const double r0 = n1 * d2 - n2 * d1, r1 = n2 * d0 - n0 * d2, r2 = n0 * d1 - n1 * d0;
+    const double sc = huber_scale(r0 * r0 + r1 * r1 + r2 * r2, huber_a, acc[27]);
+    double J[6];
+    // row 0 of [n]x = (0, -n2, n1)
+    J[0] = 0.0; J[1] = -n2 * sc; J[2] = n1 * sc;
+    J[3] = -(-n2 * m10 + n1 * m20) * sc; J[4] = -(-n2 * m11 + n1 * m21) * sc; J[5] = -(-n2 * m12 + n1 * m22) * sc;
+    acc_row(acc, J, r0 * sc);
+    // row 1 = (n2, 0, -n0)
+    J[0] = n2 * sc; J[1] = 0.0; J[2] = -n0 * sc;
+    J[3] = -(n2 * m00 - n0 * m20) * sc; J[4] = -(n2 * m01 - n0 * m21) * sc; J[5] = -(n2 * m02 - n0 * m22) * sc;
+    acc_row(acc, J, r1 * sc);
+    // row 2 = (-n1, n0, 0)
+    J[0] = -n1 * sc; J[1] = n0 * sc; J[2] = 0.0;
+    J[3] = -(-n1 * m00 + n0 * m10) * sc; J[4] = -(-n1 * m01 + n0 * m11) * sc; J[5] = -(-n1 * m02 + n0 * m12) * sc;
+    acc_row(acc, J, r2 * sc);
+  }
+  for (uint32_t i = tid; i < n_p; i += nthreads) {
+    MSFL_LOAD_CORR(corr_p, pp)
+    ++cnt_plane;
+    // r = n . d ; J = [ n^T | -n^T M ]   (lidar_factor.cc:32,38-39)
+    const double r = n0 * d0 + n1 * d1 + n2 * d2;
+    const double sc = huber_scale(r * r, huber_a, acc[27]);
+    double J[6];
+    J[0] = n0 * sc; J[1] = n1 * sc; J[2] = n2 * sc;
+    J[3] = -(n0 * m00 + n1 * m10 + n2 * m20) * sc;
+    J[4] = -(n0 * m01 + n1 * m11 + n2 * m21) * sc;
+    J[5] = -(n0 * m02 + n1 * m12 + n2 * m22) * sc;
+    acc_row(acc, J, r * sc);
+  }
+#undef MSFL_LOAD_CORR
+}
+
+// Block reduction: warp shuffle tree, then warps combined in index order (deterministic).
+__device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) {
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    acc[k] = v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) sh.red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLmThreads / 32; ++w) v += sh.red[w][threadIdx.x];
+    sh.cand[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+__device__ inline double norm7(const double *x) {
+  double s = 0;
+  for (int i = 0; i < 7; ++i) s += x[i] * x[i];
+  return sqrt(s);
+}
+
+// trust_region_minimizer.cc EvaluateGradientAndJacobian: max-norm of x - Plus(x, -g)
+__device__ inline double gradient_max_norm(const double *x, const double *g) {
+  double ng[6], xp[7], m = 0;
+  for (int i = 0; i < 6; ++i) ng[i] = -g[i];
+  pose_plus(x, ng, xp);
+  for (int i = 0; i < 7; ++i) m = fmax(m, fabs(x[i] - xp[i]));
+  return m;
+}
+
+// Thread-0 control: top of the Ceres loop up to the candidate point.  Sets sh.done or sh.xc.
+__device__ void lm_prepare_step(LmShared &sh, const KParams &kp, msfl_lm_log *log) {
+  for (;;) {
+    // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (sh.iteration >= kp.max_it) { sh.done = 1; sh.termination = 0; return; }
+    if (kp.early_exit && sh.step_successful && gradient_max_norm(sh.x, sh.g) <= kp.gtol) { sh.done = 1; sh.termination = 3; return; }
+    if (sh.radius <= kp.min_radius) { sh.done = 1; sh.termination = 4; return; }
+    sh.iteration++;
+    msfl_lm_iter *L = log ? &log->it[sh.iteration - 1] : nullptr;
+    if (log) log->n_attempts = sh.iteration;
+    if (L) { L->cost = sh.cost; L->cost_candidate = sh.cost; L->model_change = 0; L->rho = 0; L->radius = sh.radius; L->valid = 0; L->accepted = 0; }
+    double Hs[36], gs[6], A[36], nb[6], y[6];
+    for (int u = 0; u < 6; ++u) {
+      gs[u] = sh.S[u] * sh.g[u];
+      for (int v = u; v < 6; ++v) {
+        const double h = sh.S[u] * sh.H[tri6(u, v)] * sh.S[v];
+        Hs[u * 6 + v] = h;
+        Hs[v * 6 + u] = h;
+      }
+    }
+    if (!sh.reuse)
+      for (int k = 0; k < 6; ++k) sh.diag[k] = fmin(fmax(Hs[k * 6 + k], kp.min_diag), kp.max_diag);
+    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
+    for (int k = 0; k < 6; ++k) { A[k * 6 + k] += sh.diag[k] / sh.radius; nb[k] = -gs[k]; }
+    const bool ok = chol_solve6(A, nb, y);
+    sh.reuse = 1;  // LevenbergMarquardtStrategy::ComputeStep
+    double model = 0;
+    if (ok) {
+      double yg = 0, yHy = 0;
+      for (int u = 0; u < 6; ++u) {
+        yg += y[u] * gs[u];
+        double t = 0;
+        for (int v = 0; v < 6; ++v) t += Hs[u * 6 + v] * y[v];
+        yHy += y[u] * t;
+      }
+      model = -(yg + 0.5 * yHy);
+    }
+    sh.step_successful = 0;
+    if (!ok || !(model > 0.0)) {  // HandleInvalidStep
+      if (L) L->model_change = model;
+      if (++sh.n_invalid >= kp.max_invalid) { sh.done = 1; sh.termination = 5; return; }
+      sh.radius *= 0.5;  // StepIsInvalid
+      sh.reuse = 0;
+      continue;
+    }
+    sh.n_invalid = 0;
+    sh.model = model;
+    double delta[6];
+    for (int k = 0; k < 6; ++k) delta[k] = y[k] * sh.S[k];
+    pose_plus(sh.x, delta, sh.xc);
+    if (L) { L->valid = 1; L->model_change = model; }
+    return;
+  }
+}
+
+// Thread-0 control after the candidate sweep: tolerance tests, step quality, accept / reject.
+__device__ void lm_finish_step(LmShared &sh, const KParams &kp, msfl_lm_log *log) {
+  msfl_lm_iter *L = log ? &log->it[sh.iteration - 1] : nullptr;
+  const double cost_c = sh.cand[27];
+  if (L) L->cost_candidate = cost_c;
+  if (kp.early_exit) {
+    double sn = 0;
+    for (int i = 0; i < 7; ++i) sn += (sh.x[i] - sh.xc[i]) * (sh.x[i] - sh.xc[i]);
+    sn = sqrt(sn);
+    if (sn <= kp.ptol * (sh.x_norm + kp.ptol)) { sh.done = 1; sh.termination = 1; return; }
+    if (fabs(sh.cost - cost_c) <= kp.ftol * sh.cost) { sh.done = 1; sh.termination = 2; return; }
+  }
+  const double rho = (sh.cost - cost_c) / sh.model;
+  if (L) L->rho = rho;
+  if (rho > kp.min_rel_decrease) {
+    for (int i = 0; i < 7; ++i) sh.x[i] = sh.xc[i];
+    sh.x_norm = norm7(sh.x);
+    for (int k = 0; k < 21; ++k) sh.H[k] = sh.cand[k];
+    for (int k = 0; k < 6; ++k) sh.g[k] = sh.cand[21 + k];
+    sh.cost = cost_c;
+    sh.step_successful = 1;
+    if (L) L->accepted = 1;
+    const double t = 2.0 * rho - 1.0;
+    sh.radius = fmin(kp.max_radius, sh.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+    sh.nu = 2.0;
+    sh.reuse = 0;
+  } else {
+    sh.radius = sh.radius / sh.nu;
+    sh.nu *= 2.0;
+    sh.reuse = 1;
+  }
+}
+
+__global__ void __launch_bounds__(kLmThreads)
+k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
+           const float4 *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
+           double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
+           int min_corr) {
+  __shared__ LmShared sh;
+  const int b = blockIdx.x;
+  const uint32_t eo = (uint32_t)e_off[b], n_e = (uint32_t)e_off[b + 1] - eo;
+  const uint32_t po = (uint32_t)p_off[b], n_p = (uint32_t)p_off[b + 1] - po;
+  const float4 *pe = qe + eo, *pp = qp + po;
+  const double *ce_ = corr + (size_t)eo * 6, *cp_ = corr + ((size_t)n_edge_total + po) * 6;
+  msfl_stats *st = stats ? stats + b : nullptr;
+  msfl_lm_log *log = st ? &st->lm[outer] : nullptr;
+  const uint32_t tid = threadIdx.x;
+
+  if (outer > 0 && status[b] != MSFL_OK) return;  // an earlier outer iteration bailed out (odometry :266)
+
+  if (tid < 7) sh.x[tid] = poses[(size_t)b * 7 + tid];
+  if (tid == 0) { sh.done = 0; sh.too_few = 0; }
+  __syncthreads();
+
+  double acc[kAcc];
+  int ce, cpl;
+  sweep(acc, pe, ce_, n_e, pp, cp_, n_p, sh.x, kp.huber_a, tid, kLmThreads, ce, cpl);
+  // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
+  for (int o = 16; o > 0; o >>= 1) {
+    ce += __shfl_down_sync(0xffffffffu, ce, o);
+    cpl += __shfl_down_sync(0xffffffffu, cpl, o);
+  }
+  if ((tid & 31) == 0) { sh.cnt[tid >> 5][0] = ce; sh.cnt[tid >> 5][1] = cpl; }
+  block_reduce(acc, sh);
+  if (tid == 0) {
+    int ne = 0, np = 0;
+    for (int w = 0; w < kLmThreads / 32; ++w) { ne += sh.cnt[w][0]; np += sh.cnt[w][1]; }
+    sh.n_edge = ne;
+    sh.n_plane = np;
+    if (st) {
+      st->n_edge[outer] = ne;
+      st->n_plane[outer] = np;
+      st->n_outer = outer + 1;
+      if (outer == 0) st->status = MSFL_OK;
+    }
+    if (outer == 0) status[b] = MSFL_OK;
+    if (log) { log->n_attempts = 0; log->termination = 0; log->initial_cost = sh.cand[27]; log->final_cost = sh.cand[27]; }
+    if (ne + np < min_corr) {  // odometry_scan_matcher.cc:262-267: return false, pose untouched
+      sh.done = 1;
+      sh.too_few = 1;
+      status[b] = MSFL_TOO_FEW;
+      if (st) st->status = MSFL_TOO_FEW;
+    } else if (ne + np == 0) {  // no residual blocks: nothing for the solver to do
+      sh.done = 1;
+      if (log) log->termination = 2;
+    } else {
+      for (int k = 0; k < 21; ++k) sh.H[k] = sh.cand[k];
+      for (int k = 0; k < 6; ++k) sh.g[k] = sh.cand[21 + k];
+      sh.cost = sh.cand[27];
+      // jacobi scaling, fixed at iteration 0 (trust_region_minimizer.cc)
+      for (int k = 0; k < 6; ++k) sh.S[k] = 1.0 / (1.0 + sqrt(sh.H[tri6(k, k)]));
+      sh.x_norm = norm7(sh.x);
+      sh.radius = kp.initial_radius;
+      sh.nu = 2.0;
+      sh.reuse = 0;
+      sh.n_invalid = 0;
+      sh.iteration = 0;
+      sh.step_successful = 1;
+      sh.termination = 0;
+      lm_prepare_step(sh, kp, log);
+    }
+  }
+  __syncthreads();
+  while (!sh.done) {
+    sweep(acc, pe, ce_, n_e, pp, cp_, n_p, sh.xc, kp.huber_a, tid, kLmThreads, ce, cpl);
+    block_reduce(acc, sh);
+    if (tid == 0) {
+      lm_finish_step(sh, kp, log);
+      if (!sh.done) lm_prepare_step(sh, kp, log);
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && log && !sh.too_few && sh.n_edge + sh.n_plane > 0) {
+    log->termination = sh.termination;
+    log->final_cost = sh.cost;
+  }
+  if (tid < 7 && !sh.too_few) poses[(size_t)b * 7 + tid] = sh.x[tid];
+}
+
+int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                    const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
+                    msfl_stats *d_stats, int outer, int min_corr) {
+  if (B <= 0) return MSFL_OK;
+  k_lm_solve<<<B, kLmThreads, 0, e->stream>>>(e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status,
+                                              d_stats, outer, min_corr);
+  e->launches += 1;
+  MSFL_CUDA_OK(cudaGetLastError());
+  return MSFL_OK;
+}
+
+// ---- test hook: plain accumulate at a pose (cost, H, g), one block ---------------------------
+__global__ void __launch_bounds__(kLmThreads)
+k_accumulate(KParams kp, const float4 *__restrict__ p, const double *__restrict__ corr, uint32_t n_edge, uint32_t n_total,
+             const double *__restrict__ pose, double *__restrict__ out28) {
+  __shared__ LmShared sh;
+  if (threadIdx.x < 7) sh.x[threadIdx.x] = pose[threadIdx.x];
+  __syncthreads();
+  double acc[kAcc];
+  int ce, cpl;
+  sweep(acc, p, corr, n_edge, p + n_edge, corr + (size_t)n_edge * 6, n_total - n_edge, sh.x, kp.huber_a, threadIdx.x,
+        kLmThreads, ce, cpl);
+  block_reduce(acc, sh);
+  if (threadIdx.x < kAcc) out28[threadIdx.x] = sh.cand[threadIdx.x];
+}
+
+int launch_accumulate(msfl_engine *e, const float4 *d_p, const double *d_corr, int n_edge, int n_plane,
+                      const double *d_pose, double *d_out28) {
+  k_accumulate<<<1, kLmThreads, 0, e->stream>>>(e->kp, d_p, d_corr, (uint32_t)n_edge, (uint32_t)(n_edge + n_plane), d_pose,
+                                                d_out28);
+  e->launches += 1;
+  MSFL_CUDA_OK(cudaGetLastError());
+  return MSFL_OK;
+}
+
+}  // namespace msfl

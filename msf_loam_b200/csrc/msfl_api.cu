@@ -1,0 +1,461 @@
+// msfl_api.cu -- the C ABI of libmsfl.so (include/msfl.h): engine lifetime, host<->device
+// marshalling of AoS cloud views, and the launch sequences of the scan-matching path.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "msfl_internal.h"
+
+namespace msfl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return MSFL_OK;
+  size_t want = bytes + bytes / 4 + 256;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  MSFL_CUDA_OK(cudaMalloc(&p, want));
+  cap = want;
+  return MSFL_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+int PinBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return MSFL_OK;
+  size_t want = bytes + bytes / 4 + 256;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  MSFL_CUDA_OK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+  cap = want;
+  return MSFL_OK;
+}
+void PinBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+// smallest float f with (double)d < T  <=>  d < f for every float d
+static float float_bound(double T) {
+  float f = (float)T;
+  if ((double)f < T) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+static void fill_kparams(msfl_engine *e) {
+  const msfl_params &p = e->params;
+  KParams &k = e->kp;
+  k.knn_max_sq_f = float_bound(p.knn_max_sq);
+  k.dist_sq_thresh_f = float_bound(p.dist_sq_thresh);
+  k.dist_sq_thresh = p.dist_sq_thresh;
+  k.nearby_scan = p.nearby_scan;
+  k.line_eig_ratio = p.line_eig_ratio;
+  k.line_half_len = p.line_half_len;
+  k.plane_tol = p.plane_tol;
+  k.max_it = p.max_num_iterations;
+  k.early_exit = p.early_exit;
+  k.max_invalid = p.max_consecutive_invalid_steps;
+  k.min_corr = p.min_correspondences;
+  k.huber_a = p.huber_a;
+  k.initial_radius = p.initial_radius;
+  k.max_radius = p.max_radius;
+  k.min_radius = p.min_radius;
+  k.min_rel_decrease = p.min_relative_decrease;
+  k.min_diag = p.min_lm_diagonal;
+  k.max_diag = p.max_lm_diagonal;
+  k.ftol = p.function_tolerance;
+  k.gtol = p.gradient_tolerance;
+  k.ptol = p.parameter_tolerance;
+}
+
+static int check_cloud(const msfl_cloud *c, bool need_ring, const char *what) {
+  if (!c) { set_error("%s: null cloud", what); return MSFL_ERR_ARG; }
+  if (c->n > 0 && !c->data) { set_error("%s: null data with n=%zu", what, c->n); return MSFL_ERR_ARG; }
+  if (c->n > 0 && (c->stride < 12 || c->off_xyz + 12 > c->stride)) { set_error("%s: bad stride/offset", what); return MSFL_ERR_ARG; }
+  if (need_ring && c->off_ring == MSFL_NO_FIELD) { set_error("%s: ring field required", what); return MSFL_ERR_ARG; }
+  if (c->n > 0x7fffffffull) { set_error("%s: too many points", what); return MSFL_ERR_ARG; }
+  return MSFL_OK;
+}
+
+// host AoS view -> packed float4 (x, y, z, intensity) [+ uint16 ring] in (pinned) host memory
+static void pack_cloud_host(const msfl_cloud *c, float *dst4, uint16_t *ring_dst) {
+  const size_t n = c->n;
+  const char *base = (const char *)c->data;
+  if (c->stride == 16 && c->off_xyz == 0 && (c->off_intensity == 12 || c->off_intensity == MSFL_NO_FIELD)) {
+    memcpy(dst4, base, n * 16);
+  } else {
+    const bool has_i = c->off_intensity != MSFL_NO_FIELD;
+    for (size_t i = 0; i < n; ++i) {
+      const char *pt = base + i * c->stride;
+      memcpy(dst4 + 4 * i, pt + c->off_xyz, 12);
+      float w = 0.f;
+      if (has_i) memcpy(&w, pt + c->off_intensity, 4);
+      dst4[4 * i + 3] = w;
+    }
+  }
+  if (ring_dst) {
+    if (c->off_ring == MSFL_NO_FIELD) memset(ring_dst, 0, n * 2);
+    else
+      for (size_t i = 0; i < n; ++i) memcpy(ring_dst + i, base + i * c->stride + c->off_ring, 2);
+  }
+}
+
+}  // namespace msfl
+
+using namespace msfl;
+
+extern "C" {
+
+const char *msfl_last_error(void) { return g_err; }
+const char *msfl_version(void) { return "msfl 0.1 (sm_100a)"; }
+
+void msfl_default_params(msfl_params *p) {
+  memset(p, 0, sizeof *p);
+  p->min_range = 0.3;
+  p->scan_period = 0.1;
+  p->curvature_thresh = 0.1;
+  p->neighbor_gap_sq = 0.05;
+  p->n_sectors = 6;
+  p->n_sharp = 2;
+  p->n_less_sharp = 20;
+  p->n_flat = 4;
+  p->dist_sq_thresh = 25.0;
+  p->nearby_scan = 2.5;
+  p->min_correspondences = 10;
+  p->knn_max_sq = 1.0;
+  p->line_eig_ratio = 3.0;
+  p->line_half_len = 0.1;
+  p->plane_tol = 0.2;
+  p->num_outer = 2;
+  p->max_num_iterations = 6;
+  p->huber_a = 0.1;
+  p->initial_radius = 1e4;
+  p->max_radius = 1e16;
+  p->min_radius = 1e-32;
+  p->min_relative_decrease = 1e-3;
+  p->min_lm_diagonal = 1e-6;
+  p->max_lm_diagonal = 1e32;
+  p->function_tolerance = 1e-6;
+  p->gradient_tolerance = 1e-10;
+  p->parameter_tolerance = 1e-8;
+  p->max_consecutive_invalid_steps = 5;
+  p->early_exit = 1;
+  p->lm_cluster = 0;
+}
+
+int msfl_create_on_stream(const msfl_params *params, int device, void *stream, msfl_engine **out) {
+  if (!out) { set_error("msfl_create: null out"); return MSFL_ERR_ARG; }
+  *out = nullptr;
+  msfl_params p;
+  if (params) p = *params;
+  else msfl_default_params(&p);
+  if (p.num_outer < 1 || p.num_outer > MSFL_MAX_OUTER || p.max_num_iterations < 0 ||
+      p.max_num_iterations > MSFL_MAX_ATTEMPTS || p.n_sectors < 1 || p.n_sectors > 64 || !(p.knn_max_sq > 0) ||
+      !(p.dist_sq_thresh > 0)) {
+    set_error("msfl_create: parameter out of range");
+    return MSFL_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) {
+    set_error("msfl_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+    return MSFL_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("msfl_create: device %d out of range", device); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MSFL_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("msfl_create: device %d is sm_%d%d; libmsfl carries sm_100a code only", device, prop.major, prop.minor);
+    return MSFL_ERR_CUDA;
+  }
+  msfl_engine *e = new msfl_engine();
+  e->params = p;
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  fill_kparams(e);
+  if (stream) {
+    e->stream = (cudaStream_t)stream;
+    e->own_stream = false;
+  } else {
+    cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+      set_error("cudaStreamCreate failed: %s", cudaGetErrorString(se));
+      delete e;
+      return MSFL_ERR_CUDA;
+    }
+    e->own_stream = true;
+  }
+  *out = e;
+  return MSFL_OK;
+}
+
+int msfl_create(const msfl_params *params, int device, msfl_engine **out) {
+  return msfl_create_on_stream(params, device, nullptr, out);
+}
+
+void msfl_destroy(msfl_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  submap_release(e->map_corner);
+  submap_release(e->map_surf);
+  DevBuf *dbs[] = {&e->d_queries, &e->d_corr, &e->d_poses, &e->d_status, &e->d_stats, &e->d_knn, &e->d_off, &e->d_misc,
+                   &e->d_last_corner, &e->d_last_surf, &e->d_last_corner_ring, &e->d_last_surf_ring, &e->d_ring_tab,
+                   &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,
+                   &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
+                   &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc};
+  for (DevBuf *b : dbs) b->release();
+  PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc};
+  for (PinBuf *b : pbs) b->release();
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int msfl_sync(msfl_engine *e) {
+  if (!e) return MSFL_ERR_ARG;
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return MSFL_OK;
+}
+
+void *msfl_stream(msfl_engine *e) { return e ? (void *)e->stream : nullptr; }
+uint64_t msfl_launch_count(const msfl_engine *e) { return e ? e->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// submap
+// ------------------------------------------------------------------------------------------------
+static float cell_edge(const msfl_engine *e) {
+  const double r = sqrt(e->params.knn_max_sq);
+  if (r == 1.0) return 1.0f;  // floor(x * 1.0f) is exact: the 27-cell search is exact w.r.t. the gate
+  return (float)(r * 1.0001);
+}
+
+int msfl_set_submap_device(msfl_engine *e, const float *d_corner, size_t n_corner, const float *d_surf, size_t n_surf) {
+  if (!e || !d_corner || !d_surf) { set_error("msfl_set_submap_device: null argument"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  e->has_submap = false;
+  int rc;
+  if ((rc = submap_build(e, e->map_corner, (const float4 *)d_corner, n_corner, cell_edge(e)))) return rc;
+  if ((rc = submap_build(e, e->map_surf, (const float4 *)d_surf, n_surf, cell_edge(e)))) return rc;
+  e->has_submap = true;
+  return MSFL_OK;
+}
+
+int msfl_set_submap(msfl_engine *e, const msfl_cloud *map_corner, const msfl_cloud *map_surf) {
+  if (!e) { set_error("msfl_set_submap: null engine"); return MSFL_ERR_ARG; }
+  int rc;
+  if ((rc = check_cloud(map_corner, false, "map_corner"))) return rc;
+  if ((rc = check_cloud(map_surf, false, "map_surf"))) return rc;
+  if (map_corner->n == 0 || map_surf->n == 0) { set_error("msfl_set_submap: empty submap class"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  const size_t nc = map_corner->n, ns = map_surf->n;
+  if ((rc = e->h_stage.reserve((nc + ns) * 16))) return rc;
+  float *h = e->h_stage.as<float>();
+  pack_cloud_host(map_corner, h, nullptr);
+  pack_cloud_host(map_surf, h + 4 * nc, nullptr);
+  if ((rc = e->map_corner.orig.reserve(nc * 16))) return rc;
+  if ((rc = e->map_surf.orig.reserve(ns * 16))) return rc;
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->map_corner.orig.p, h, nc * 16, cudaMemcpyHostToDevice, e->stream));
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->map_surf.orig.p, h + 4 * nc, ns * 16, cudaMemcpyHostToDevice, e->stream));
+  return msfl_set_submap_device(e, e->map_corner.orig.as<float>(), nc, e->map_surf.orig.as<float>(), ns);
+}
+
+int msfl_get_submap_device(msfl_engine *e, const float **d_corner, size_t *n_corner, const float **d_surf, size_t *n_surf) {
+  if (!e || !e->has_submap) { set_error("msfl_get_submap_device: no submap"); return MSFL_ERR_NOSUBMAP; }
+  if (d_corner) *d_corner = e->map_corner.orig.as<float>();
+  if (n_corner) *n_corner = e->map_corner.n;
+  if (d_surf) *d_surf = e->map_surf.orig.as<float>();
+  if (n_surf) *n_surf = e->map_surf.n;
+  return MSFL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan-to-map
+// ------------------------------------------------------------------------------------------------
+static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t nct,
+                            const float4 *d_qs, const int32_t *d_s_off, uint32_t nst, double *d_poses,
+                            msfl_stats *d_stats) {
+  int rc;
+  if ((rc = e->d_corr.reserve(((size_t)nct + nst + 1) * 6 * sizeof(double)))) return rc;
+  if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
+  for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
+    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr)))
+      return rc;
+    if ((rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
+                              e->d_status.as<int32_t>(), d_stats, outer, /*min_corr=*/0)))
+      return rc;
+  }
+  return MSFL_OK;
+}
+
+int msfl_scan2map_batch_device(msfl_engine *e, int B, const float *d_corner, const int32_t *d_corner_off,
+                               size_t n_corner_total, const float *d_surf, const int32_t *d_surf_off,
+                               size_t n_surf_total, double *d_poses, msfl_stats *d_stats) {
+  if (!e || B <= 0 || !d_corner_off || !d_surf_off || !d_poses) { set_error("msfl_scan2map_batch_device: bad argument"); return MSFL_ERR_ARG; }
+  if (!e->has_submap) { set_error("msfl_scan2map: no submap set"); return MSFL_ERR_NOSUBMAP; }
+  if (n_corner_total + n_surf_total > 0x7fffffffull) { set_error("batch too large"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  return scan2map_enqueue(e, B, (const float4 *)d_corner, d_corner_off, (uint32_t)n_corner_total, (const float4 *)d_surf,
+                          d_surf_off, (uint32_t)n_surf_total, d_poses, d_stats);
+}
+
+// uploads B (corner, surf) cloud pairs into the engine's batch buffers; fills totals
+static int upload_batch(msfl_engine *e, int B, const msfl_cloud *corner, const msfl_cloud *surf, const double *poses,
+                        uint32_t *nct_out, uint32_t *nst_out) {
+  int rc;
+  size_t nct = 0, nst = 0;
+  for (int b = 0; b < B; ++b) {
+    if ((rc = check_cloud(&corner[b], false, "scan_corner"))) return rc;
+    if ((rc = check_cloud(&surf[b], false, "scan_surf"))) return rc;
+    nct += corner[b].n;
+    nst += surf[b].n;
+  }
+  if (nct + nst > 0x7fffffffull) { set_error("batch too large"); return MSFL_ERR_ARG; }
+  const size_t off_bytes = (size_t)2 * (B + 1) * 4;
+  const size_t pose_bytes = (size_t)B * 7 * 8;
+  // staging layout: [queries (nct+nst) float4 | offsets 2(B+1) int32 | poses B*7 double]
+  const size_t q_bytes = (nct + nst) * 16;
+  const size_t q_pad = (q_bytes + 15) & ~(size_t)15;
+  const size_t off_pad = (off_bytes + 15) & ~(size_t)15;
+  if ((rc = e->h_stage.reserve(q_pad + off_pad + pose_bytes))) return rc;
+  if ((rc = e->d_queries.reserve(q_pad + off_pad + pose_bytes))) return rc;
+  char *h = e->h_stage.as<char>();
+  float *hq = (float *)h;
+  int32_t *hoff = (int32_t *)(h + q_pad);
+  double *hpose = (double *)(h + q_pad + off_pad);
+  size_t ci = 0, si = 0;
+  for (int b = 0; b < B; ++b) {
+    hoff[b] = (int32_t)ci;
+    hoff[B + 1 + b] = (int32_t)si;
+    pack_cloud_host(&corner[b], hq + 4 * ci, nullptr);
+    pack_cloud_host(&surf[b], hq + 4 * (nct + si), nullptr);
+    ci += corner[b].n;
+    si += surf[b].n;
+  }
+  hoff[B] = (int32_t)ci;
+  hoff[2 * B + 1] = (int32_t)si;
+  memcpy(hpose, poses, pose_bytes);
+  // one H2D copy for the whole batch
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->d_queries.p, h, q_pad + off_pad + pose_bytes, cudaMemcpyHostToDevice, e->stream));
+  *nct_out = (uint32_t)nct;
+  *nst_out = (uint32_t)nst;
+  return MSFL_OK;
+}
+
+int msfl_scan2map_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                        double *poses_tq, msfl_stats *stats) {
+  if (!e || B <= 0 || !scan_corner || !scan_surf || !poses_tq) { set_error("msfl_scan2map_batch: bad argument"); return MSFL_ERR_ARG; }
+  if (!e->has_submap) { set_error("msfl_scan2map: no submap set"); return MSFL_ERR_NOSUBMAP; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  int rc;
+  uint32_t nct = 0, nst = 0;
+  if ((rc = upload_batch(e, B, scan_corner, scan_surf, poses_tq, &nct, &nst))) return rc;
+  const size_t q_pad = (((size_t)nct + nst) * 16 + 15) & ~(size_t)15;
+  const size_t off_pad = ((size_t)2 * (B + 1) * 4 + 15) & ~(size_t)15;
+  char *d = e->d_queries.as<char>();
+  const float4 *d_qc = (const float4 *)d;
+  const float4 *d_qs = d_qc + nct;
+  const int32_t *d_c_off = (const int32_t *)(d + q_pad);
+  const int32_t *d_s_off = d_c_off + (B + 1);
+  double *d_poses = (double *)(d + q_pad + off_pad);
+  msfl_stats *d_stats = nullptr;
+  if (stats) {
+    if ((rc = e->d_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    if ((rc = e->h_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    d_stats = e->d_stats.as<msfl_stats>();
+    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, (size_t)B * sizeof(msfl_stats), e->stream));
+  }
+  if ((rc = scan2map_enqueue(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, d_stats))) return rc;
+  if ((rc = e->h_poses.reserve((size_t)B * 7 * 8))) return rc;
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->h_poses.p, d_poses, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (stats)
+    MSFL_CUDA_OK(cudaMemcpyAsync(e->h_stats.p, d_stats, (size_t)B * sizeof(msfl_stats), cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  memcpy(poses_tq, e->h_poses.p, (size_t)B * 7 * 8);
+  if (stats) memcpy(stats, e->h_stats.p, (size_t)B * sizeof(msfl_stats));
+  return MSFL_OK;
+}
+
+int msfl_scan2map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf, double pose_tq[7],
+                  msfl_stats *stats) {
+  return msfl_scan2map_batch(e, 1, scan_corner, scan_surf, pose_tq, stats);
+}
+
+int msfl_associate_map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                       const double pose_tq[7], int32_t *knn_idx, double *corr) {
+  if (!e || !scan_corner || !scan_surf || !pose_tq) { set_error("msfl_associate_map: bad argument"); return MSFL_ERR_ARG; }
+  if (!e->has_submap) { set_error("msfl_associate_map: no submap set"); return MSFL_ERR_NOSUBMAP; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  int rc;
+  uint32_t nct = 0, nst = 0;
+  if ((rc = upload_batch(e, 1, scan_corner, scan_surf, pose_tq, &nct, &nst))) return rc;
+  const size_t total = (size_t)nct + nst;
+  if (total == 0) return MSFL_OK;
+  const size_t q_pad = (total * 16 + 15) & ~(size_t)15;
+  const size_t off_pad = ((size_t)2 * 2 * 4 + 15) & ~(size_t)15;
+  char *d = e->d_queries.as<char>();
+  const float4 *d_qc = (const float4 *)d;
+  const float4 *d_qs = d_qc + nct;
+  const int32_t *d_c_off = (const int32_t *)(d + q_pad);
+  const int32_t *d_s_off = d_c_off + 2;
+  double *d_poses = (double *)(d + q_pad + off_pad);
+  if ((rc = e->d_corr.reserve((total + 1) * 6 * 8))) return rc;
+  if ((rc = e->d_knn.reserve(total * 5 * 4))) return rc;
+  if ((rc = launch_associate_map(e, 1, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(),
+                                 e->d_knn.as<int32_t>())))
+    return rc;
+  if (knn_idx) MSFL_CUDA_OK(cudaMemcpyAsync(knn_idx, e->d_knn.p, total * 5 * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (corr) MSFL_CUDA_OK(cudaMemcpyAsync(corr, e->d_corr.p, total * 6 * 8, cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return MSFL_OK;
+}
+
+int msfl_accumulate(msfl_engine *e, const float *p_xyz, const double *corr, int n_edge, int n_plane,
+                    const double pose_tq[7], double *cost, double H[36], double g[6]) {
+  if (!e || !p_xyz || !corr || !pose_tq || n_edge < 0 || n_plane < 0) { set_error("msfl_accumulate: bad argument"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  const size_t n = (size_t)n_edge + n_plane;
+  int rc;
+  if ((rc = e->h_stage.reserve(n * 16 + 64))) return rc;
+  if ((rc = e->d_queries.reserve(n * 16 + 64))) return rc;
+  if ((rc = e->d_corr.reserve((n + 1) * 48))) return rc;
+  if ((rc = e->d_misc.reserve(64 * 8))) return rc;
+  float *h = e->h_stage.as<float>();
+  for (size_t i = 0; i < n; ++i) {
+    h[4 * i] = p_xyz[3 * i]; h[4 * i + 1] = p_xyz[3 * i + 1]; h[4 * i + 2] = p_xyz[3 * i + 2]; h[4 * i + 3] = 0.f;
+  }
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->d_queries.p, h, n * 16, cudaMemcpyHostToDevice, e->stream));
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->d_corr.p, corr, n * 48, cudaMemcpyHostToDevice, e->stream));
+  double *d_pose = e->d_misc.as<double>();
+  MSFL_CUDA_OK(cudaMemcpyAsync(d_pose, pose_tq, 56, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = launch_accumulate(e, e->d_queries.as<float4>(), e->d_corr.as<double>(), n_edge, n_plane, d_pose, d_pose + 8)))
+    return rc;
+  double out[28];
+  MSFL_CUDA_OK(cudaMemcpyAsync(out, d_pose + 8, sizeof out, cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  if (cost) *cost = out[27];
+  if (g) for (int i = 0; i < 6; ++i) g[i] = out[21 + i];
+  if (H) {
+    int k = 0;
+    for (int u = 0; u < 6; ++u)
+      for (int v = u; v < 6; ++v) { H[u * 6 + v] = out[k]; H[v * 6 + u] = out[k]; ++k; }
+  }
+  return MSFL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// msfl_internal.h -- engine state shared by the translation units of libmsfl.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/msfl.h"
+
+namespace msfl {
+
+void set_error(const char *fmt, ...);
+
+#define MSFL_CUDA_OK(expr)                                                                       \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      msfl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MSFL_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+// grow-only device / pinned-host buffers
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Dense cell index over one submap class.  Cells are `edge` metres wide; the grid covers the
+// occupied cell range padded by 2 cells on every side, so any query whose cell lies in
+// [1, n-2] on every axis has its whole 3x3x3 neighbourhood in range and any other query has no
+// occupied neighbour.  Points are sorted by linear cell id ((z*ny + y)*nx + x), so the three
+// x-adjacent cells of a neighbourhood row are one contiguous range.
+struct GridView {
+  const float4 *pts_sorted;   // xyz + original index (int bits in w)
+  const float4 *pts_orig;     // original order (xyz, *), for gathering the k neighbours
+  const uint32_t *cell_start; // ncell + 1
+  int nx, ny, nz;
+  int ox, oy, oz;             // cell coordinate (floor(x * inv_edge)) of grid cell (0,0,0)
+  float inv_edge;
+  uint32_t n;
+};
+
+struct Submap {
+  DevBuf orig, sorted, cell_start, keys, keys_alt, vals, vals_alt, cub_tmp, bounds;
+  GridView view{};
+  size_t n = 0;
+};
+
+// packed constants handed to the kernels
+struct KParams {
+  float knn_max_sq_f;     // smallest float >= knn_max_sq (so that (double)d2 < T  <=>  d2 < T_f)
+  float dist_sq_thresh_f;
+  double dist_sq_thresh;
+  double nearby_scan;
+  double line_eig_ratio, line_half_len, plane_tol;
+  int max_it, early_exit, max_invalid, min_corr;
+  double huber_a, initial_radius, max_radius, min_radius, min_rel_decrease;
+  double min_diag, max_diag, ftol, gtol, ptol;
+};
+
+}  // namespace msfl
+
+struct msfl_engine {
+  msfl_params params;
+  msfl::KParams kp;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  msfl::Submap map_corner, map_surf;
+  bool has_submap = false;
+
+  // batch scratch
+  msfl::DevBuf d_queries, d_corr, d_poses, d_status, d_stats, d_knn, d_off, d_misc;
+  msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
+
+  // odometry scratch
+  msfl::DevBuf d_last_corner, d_last_surf, d_last_corner_ring, d_last_surf_ring, d_ring_tab, d_assoc;
+
+  // feature extraction scratch
+  msfl::DevBuf f_raw, f_keys, f_keys_alt, f_vals, f_vals_alt, f_tmp, f_full, f_ring, f_curv, f_label,
+      f_idx, f_cnt, f_angle, f_misc;
+  // voxel grid scratch
+  msfl::DevBuf v_in, v_keys, v_keys_alt, v_vals, v_vals_alt, v_tmp, v_out, v_misc;
+};
+
+namespace msfl {
+
+// ---- submap_index.cu
+int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge);
+void submap_release(Submap &m);
+
+// ---- associate_map.cu
+// batch layout: queries = [all corner | all surf] as two packed float4 arrays with per-scan
+// offset tables (B+1 int32, device); corr = (n_corner_total + n_surf_total) x 6 doubles in the
+// same flat order.
+int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
+                         const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
+                         double *d_corr, int32_t *d_knn);
+
+// ---- lm_solve.cu
+// outer: outer-iteration index (stats slot); min_corr: 0 for mapping, params.min_correspondences for odometry
+int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                    const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
+                    msfl_stats *d_stats, int outer, int min_corr);
+int launch_accumulate(msfl_engine *e, const float4 *d_p, const double *d_corr, int n_edge, int n_plane,
+                      const double *d_pose, double *d_out28);
+
+// ---- scan2scan.cu
+int launch_associate_scan(msfl_engine *e, const float4 *d_last_corner, const uint16_t *d_last_corner_ring, uint32_t n_lc,
+                          const float4 *d_last_surf, const uint16_t *d_last_surf_ring, uint32_t n_ls,
+                          const uint32_t *d_ring_start_corner, const uint32_t *d_ring_start_surf,
+                          const float4 *d_queries, uint32_t n_sharp, uint32_t n_flat, const double *d_pose,
+                          double *d_corr, int32_t *d_assoc);
+
+// ---- features.cu
+int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7], msfl_features *out);
+
+// ---- voxel_grid.cu
+int run_voxel_grid(msfl_engine *e, const float4 *d_in, size_t n, float leaf, float4 *d_out, size_t *n_out);
+
+// ---- repack (msfl_api.cu)
+int upload_cloud_packed(msfl_engine *e, const msfl_cloud *c, float4 *d_dst, uint16_t *d_ring_dst);
+
+}  // namespace msfl

@@ -1,0 +1,140 @@
+"""Parity of the CUDA scan-to-map path (through the C ABI) against the CPU oracle.
+
+Tolerances: kNN indices bit-exact (integer/fp32 compare-select work); line/plane fit constants
+1e-9 absolute (fp64, different FMA contraction); pose <= 1e-4 m / 1e-4 rad (north_star) -- in
+practice ~1e-10; LM trace (attempts, accept/reject pattern) identical, costs 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from msf_loam_b200 import Engine, MappingScanMatcher, TimestampedPointCloud, default_params, to_pcl
+from msf_loam_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-4
+POSE_TOL_RAD = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng(vlp16_case):
+    e = Engine()
+    e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+    yield e
+    e.close()
+
+
+def _oracle_corr_full(P, case, q, pose):
+    """oracle association expanded to one row per query (zeros where no factor)."""
+    corr, ne, npl, kidx = O.associate_map(P, case["map_corner"], case["map_surf"], q["corner"], q["surf"], pose)
+    return corr, ne, npl, kidx
+
+
+def test_knn_indices_bit_exact(eng, vlp16_case):
+    P = O.default_params()
+    for q in vlp16_case["queries"]:
+        knn, _ = eng.associate_map(q["corner"], q["surf"], q["init"])
+        _, _, _, kidx = _oracle_corr_full(P, vlp16_case, q, q["init"])
+        assert knn.shape == kidx.shape
+        assert np.array_equal(knn, kidx)
+        assert (knn[:, 0] >= 0).sum() > 1000  # the case is not degenerate
+
+
+def test_fit_constants_match(eng, vlp16_case):
+    P = O.default_params()
+    q = vlp16_case["queries"][0]
+    _, corr_gpu = eng.associate_map(q["corner"], q["surf"], q["init"])
+    corr, ne, npl, _ = _oracle_corr_full(P, vlp16_case, q, q["init"])
+    has = np.any(corr_gpu[:, 3:] != 0, axis=1)
+    nc = q["corner"].shape[0]
+    assert has[:nc].sum() == ne and has[nc:].sum() == npl
+    got = corr_gpu[has]
+    assert np.abs(got[:, :3] - corr[:, 4:7]).max() < 1e-9
+    dn = np.minimum(np.abs(got[:, 3:] - corr[:, 7:10]).max(axis=1), np.abs(got[:, 3:] + corr[:, 7:10]).max(axis=1))
+    assert dn.max() < 1e-9
+
+
+def test_accumulate_matches_oracle(eng, vlp16_case):
+    P = O.default_params()
+    q = vlp16_case["queries"][1]
+    corr, ne, npl, _ = _oracle_corr_full(P, vlp16_case, q, q["init"])
+    cost, H, g = O.accumulate(P, corr, q["init"])
+    cost_g, H_g, g_g = eng.accumulate(corr[:, 1:4], corr[:, 4:10], ne, npl, q["init"])
+    assert abs(cost_g - cost) <= 1e-12 * abs(cost)
+    assert np.abs(H_g - H).max() <= 1e-11 * np.abs(H).max()
+    assert np.abs(g_g - g).max() <= 1e-11 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("schedule", ["reference", "fixed10"])
+def test_pose_parity(vlp16_case, schedule):
+    over = {} if schedule == "reference" else {"early_exit": 0, "max_num_iterations": 5}
+    P = O.default_params(**over)
+    e = Engine(default_params(**over))
+    e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+    for q in vlp16_case["queries"]:
+        x_ref, logs, counts = O.scan2map(P, vlp16_case["map_corner"], vlp16_case["map_surf"], q["corner"], q["surf"], q["init"])
+        rc, x, st = e.scan2map(q["corner"], q["surf"], q["init"])
+        assert rc == 0
+        dt, dr = S.pose_error(x, x_ref)
+        assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
+        assert dt < 1e-8 and dr < 1e-8  # what the fp64 path actually achieves
+        assert st["n_edge"] == list(counts[:, 0]) and st["n_plane"] == list(counts[:, 1])
+        for lg, lr in zip(st["lm"], logs):
+            assert lg["n_attempts"] == lr["n_attempts"] and lg["termination"] == lr["termination"]
+            assert [i["accepted"] for i in lg["iters"]] == [i["accepted"] for i in lr["iters"]]
+            assert abs(lg["final_cost"] - lr["final_cost"]) <= 1e-9 * lr["final_cost"]
+        # and the estimate is a sane localisation (synthetic noise 1 cm)
+        dt_gt, dr_gt = S.pose_error(x, q["gt"])
+        assert dt_gt < 0.03 and dr_gt < 0.005
+    e.close()
+
+
+def test_batch_equals_singles_bitwise(eng, vlp16_case):
+    qs = vlp16_case["queries"]
+    singles = [eng.scan2map(q["corner"], q["surf"], q["init"])[1] for q in qs]
+    # ragged batch incl. an empty scan and a repeated one
+    empty = np.zeros((0, 4), np.float32)
+    corners = [qs[0]["corner"], empty, qs[1]["corner"], qs[2]["corner"], qs[0]["corner"]]
+    surfs = [qs[0]["surf"], empty, qs[1]["surf"], qs[2]["surf"], qs[0]["surf"]]
+    inits = [qs[0]["init"], qs[1]["init"], qs[1]["init"], qs[2]["init"], qs[0]["init"]]
+    rc, xs, st = eng.scan2map_batch(corners, surfs, inits, want_stats=True)
+    assert rc == 0
+    assert np.array_equal(xs[0], singles[0]) and np.array_equal(xs[2], singles[1])
+    assert np.array_equal(xs[3], singles[2]) and np.array_equal(xs[4], singles[0])
+    assert np.array_equal(xs[1], np.asarray(inits[1]))  # empty scan: pose untouched
+    assert st[1]["n_edge"] == [0, 0] and st[1]["n_plane"] == [0, 0]
+
+
+def test_no_correspondence_leaves_pose_untouched(eng, vlp16_case):
+    q = vlp16_case["queries"][0]
+    far = np.array([500.0, 500.0, 50.0, 0, 0, 0, 1.0])
+    rc, x, st = eng.scan2map(q["corner"], q["surf"], far)
+    assert rc == 0 and np.array_equal(x, far)
+    assert st["n_edge"] == [0, 0] and st["n_plane"] == [0, 0]
+    x_ref, _, _ = O.scan2map(O.default_params(), vlp16_case["map_corner"], vlp16_case["map_surf"], q["corner"], q["surf"], far)
+    assert np.array_equal(x_ref, far)
+
+
+def test_pcl_point_layout_and_matcher_interface(vlp16_case):
+    """Same call shape as the reference: MatchScan2Map(cloud_map, scan_curr, false, ..., &pose) with
+    32-byte pcl::PointXYZI clouds (stride/offset marshalling)."""
+    q = vlp16_case["queries"][0]
+    m = MappingScanMatcher()
+    cloud_map = TimestampedPointCloud(cloud_corner_less_sharp=to_pcl(vlp16_case["map_corner"]),
+                                      cloud_surf_less_flat=to_pcl(vlp16_case["map_surf"]))
+    scan = TimestampedPointCloud(cloud_corner_less_sharp=to_pcl(q["corner"]), cloud_surf_less_flat=to_pcl(q["surf"]))
+    ok, pose = m.MatchScan2Map(cloud_map, scan, False, q["init"])
+    assert ok is True
+    x_ref, _, _ = O.scan2map(O.default_params(), vlp16_case["map_corner"], vlp16_case["map_surf"], q["corner"], q["surf"], q["init"])
+    dt, dr = S.pose_error(pose, x_ref)
+    assert dt < 1e-8 and dr < 1e-8
+    m.engine.close()
+
+
+def test_requires_submap():
+    from msf_loam_b200 import MsflError
+    e = Engine()
+    with pytest.raises(MsflError):
+        e.scan2map(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32), S.pose_identity())
+    e.close()
