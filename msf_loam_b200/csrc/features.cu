@@ -1,0 +1,409 @@
+// features.cu -- scan registration: the block of RealHandleLaserCloudMessage
+// between laser_cloud_in (msf_loam_node.cc:166) and scan.* (msf_loam_node.cc:360-371).
+//   a-1  invalid-point removal (:86-111), stable ring split + relative time from azimuth (:128-156)
+//   a-2  11-tap curvature, fp32 sum in source order, squares in fp64 (:213-240)
+//   a-3  per ring, 6 sectors in order: sort by curvature, greedy pick of 2 sharp / 20 less-sharp /
+//        4 flat with +-5 neighbour suppression, everything FLAT/UNKNOWN -> less-flat (:251-351)
+//   a-4  extrinsic applied to every output cloud (:367-371)
+// The greedy pick is sequential inside a ring (flags leak across sector borders), so the pick
+// kernel runs one CTA per ring: the sector sort is a block-wide bitonic sort in shared memory,
+// lane 0 does the order-dependent sweeps, warp 0 compacts the less-flat list.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <limits.h>
+
+#include "msfl_internal.h"
+#include "msfl_math.cuh"
+
+namespace msfl {
+
+constexpr int kMaxSectorPts = 4096;
+constexpr int kPickThreads = 256;
+constexpr double kTwoPi = 2 * 3.14159265358979323846;
+
+struct FeatMeta {
+  int first_valid, bad_ring, n_valid, sector_overflow;
+  uint32_t ring_start[MSFL_MAX_RINGS + 1];
+  int first_dec[MSFL_MAX_RINGS];
+  int cnt[4][MSFL_MAX_RINGS];  // per ring: sharp, less_sharp, flat, less_flat
+  int tot[4];
+};
+
+__global__ void k_feat_init(FeatMeta *m) {
+  const int t = threadIdx.x;
+  if (t == 0) { m->first_valid = INT_MAX; m->bad_ring = 0; m->n_valid = 0; m->sector_overflow = 0; }
+  if (t < MSFL_MAX_RINGS) {
+    m->first_dec[t] = INT_MAX;
+    for (int k = 0; k < 4; ++k) m->cnt[k][t] = 0;
+  }
+  if (t < 4) m->tot[t] = 0;
+}
+
+// RemoveInvalidPointsFromCloud (:96-103): float norm vs double min_range, non-finite dropped.
+__global__ void k_feat_keys(const float4 *__restrict__ raw, const uint16_t *__restrict__ ring, uint32_t n, double min_range,
+                            uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, FeatMeta *m) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = raw[i];
+  const float nr = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)), __fmul_rn(p.z, p.z)));
+  const bool valid = !((double)nr < min_range || !isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z));
+  uint32_t key = 255u;
+  if (valid) {
+    const uint32_t r = ring[i];
+    if (r >= MSFL_MAX_RINGS) atomicOr(&m->bad_ring, 1);  // CHECK_LT(point.ring, ...) :136
+    else key = r;
+    atomicMin(&m->first_valid, (int)i);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+__global__ void k_feat_ring_start(const uint32_t *__restrict__ keys_sorted, uint32_t n, FeatMeta *m) {
+  const uint32_t r = threadIdx.x;
+  if (r > MSFL_MAX_RINGS) return;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (keys_sorted[mid] < r) lo = mid + 1;
+    else hi = mid;
+  }
+  m->ring_start[r] = lo;
+  if (r == MSFL_MAX_RINGS) m->n_valid = (int)lo;
+}
+
+// ComputeRelaTimeForEachPoint (:131-151), first half: the raw relative angle of every point.
+__global__ void k_feat_angles(const float4 *__restrict__ raw, const uint32_t *__restrict__ vals, const FeatMeta *__restrict__ m,
+                              double *__restrict__ rel) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (uint32_t)m->n_valid) return;
+  const float4 f = raw[m->first_valid];
+  const double start_ori = -atan2((double)f.y, (double)f.x);  // :131
+  const float4 p = raw[vals[j]];
+  const double ori = -atan2((double)p.y, (double)p.x);        // :139
+  rel[j] = fmod(__dadd_rn(__dsub_rn(ori, start_ori), kTwoPi), kTwoPi);  // :142
+}
+
+// "if (relative_angle < last_relative_angles[ring]) += 2 pi" (:145-149): once a point of a ring is
+// bumped every later point of that ring is bumped too, so the recurrence collapses to "j >= first
+// position whose raw angle is below its predecessor's".
+__global__ void k_feat_first_dec(const uint32_t *__restrict__ keys_sorted, const double *__restrict__ rel, FeatMeta *m) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0 || j >= (uint32_t)m->n_valid) return;
+  const uint32_t r = keys_sorted[j];
+  if (keys_sorted[j - 1] == r && rel[j] < rel[j - 1]) atomicMin(&m->first_dec[r], (int)j);
+}
+
+__global__ void k_feat_full(const float4 *__restrict__ raw, const uint32_t *__restrict__ keys_sorted,
+                            const uint32_t *__restrict__ vals, const double *__restrict__ rel, const FeatMeta *__restrict__ m,
+                            double scan_period, float4 *__restrict__ full, uint16_t *__restrict__ ring_out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (uint32_t)m->n_valid) return;
+  const uint32_t r = keys_sorted[j];
+  double a = rel[j];
+  if ((int)j >= m->first_dec[r]) a = __dadd_rn(a, kTwoPi);
+  const double t = __dmul_rn(__ddiv_rn(a, kTwoPi), scan_period);  // :151
+  const float4 p = raw[vals[j]];
+  full[j] = make_float4(p.x, p.y, p.z, (float)t);  // intensity := time (:152-153)
+  ring_out[j] = (uint16_t)r;
+}
+
+// a-2 curvature (:213-240)
+__global__ void k_feat_curv(const float4 *__restrict__ full, const FeatMeta *__restrict__ m, float *__restrict__ curv,
+                            int32_t *__restrict__ label, uint8_t *__restrict__ picked) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = m->n_valid;
+  if (i >= N) return;
+  label[i] = 0;
+  picked[i] = 0;
+  float c = 0.f;
+  if (i >= 5 && i < N - 5) {
+    float4 q[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) q[k] = full[i - 5 + k];
+    double d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#define AX(k) (a == 0 ? q[k].x : (a == 1 ? q[k].y : q[k].z))
+      float s = __fadd_rn(AX(0), AX(1));
+      s = __fadd_rn(s, AX(2));
+      s = __fadd_rn(s, AX(3));
+      s = __fadd_rn(s, AX(4));
+      s = __fsub_rn(s, __fmul_rn(10.0f, AX(5)));
+      s = __fadd_rn(s, AX(6));
+      s = __fadd_rn(s, AX(7));
+      s = __fadd_rn(s, AX(8));
+      s = __fadd_rn(s, AX(9));
+      s = __fadd_rn(s, AX(10));
+#undef AX
+      d[a] = (double)s;
+    }
+    c = (float)__dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));  // :236
+  }
+  curv[i] = c;
+}
+
+__device__ __forceinline__ float gap_sq(const float4 a, const float4 b) {  // Vector3f squaredNorm (:291-293)
+  const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// a-3: one CTA per ring.
+__global__ void __launch_bounds__(kPickThreads)
+k_feat_pick(const float4 *__restrict__ full, const float *__restrict__ curv, int32_t *__restrict__ label,
+            uint8_t *__restrict__ picked, FeatMeta *m, double curv_thr, double gap_thr, int n_sectors, int n_sharp,
+            int n_less, int n_flat, int32_t *__restrict__ slot_sharp, int32_t *__restrict__ slot_less,
+            int32_t *__restrict__ slot_flat, int32_t *__restrict__ lessflat_tmp) {
+  __shared__ unsigned long long keys[kMaxSectorPts];
+  __shared__ int s_lf;
+  const int r = blockIdx.x;
+  const int rs = (int)m->ring_start[r], re = (int)m->ring_start[r + 1];
+  const int start = rs + 5, end = re - 6;  // :192-194
+  if (end - start < 6) return;             // :252
+  const int tid = threadIdx.x;
+  int ns = 0, nl = 0, nf = 0;
+  if (tid == 0) s_lf = 0;
+  int32_t *my_sharp = slot_sharp + (size_t)r * n_sectors * n_sharp;
+  int32_t *my_less = slot_less + (size_t)r * n_sectors * n_less;
+  int32_t *my_flat = slot_flat + (size_t)r * n_sectors * n_flat;
+  int32_t *my_lf = lessflat_tmp + rs;
+  for (int j = 0; j < n_sectors; ++j) {
+    const int sp = start + (end - start) * j / n_sectors;           // :256-259
+    const int ep = start + (end - start) * (j + 1) / n_sectors - 1;
+    const int cnt = ep - sp + 1;
+    if (cnt <= 0) continue;
+    if (cnt > kMaxSectorPts) {
+      if (tid == 0) atomicOr(&m->sector_overflow, 1);
+      return;
+    }
+    int P = 1;
+    while (P < cnt) P <<= 1;
+    for (int k = tid; k < P; k += kPickThreads)
+      keys[k] = (k < cnt) ? (((unsigned long long)__float_as_uint(curv[sp + k]) << 32) | (unsigned)(sp + k)) : ~0ull;
+    __syncthreads();
+    // std::sort by curvature (:263) -> bitonic sort on (curvature bits, index): curvature >= 0 so
+    // the uint order of the bits is the float order; ties resolved by index (deterministic).
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (P >> 1); t += kPickThreads) {
+          const int lo = (t / stride) * (stride << 1) + (t % stride);
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const unsigned long long a = keys[lo], b = keys[hi];
+          if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      int largest = 0;
+      for (int k = cnt - 1; k >= 0; --k) {  // :272-305
+        const int ind = (int)(unsigned)(keys[k] & 0xffffffffull);
+        if (!picked[ind] && (double)curv[ind] > curv_thr) {
+          ++largest;
+          if (largest <= n_sharp) {
+            label[ind] = 1;
+            my_sharp[ns++] = ind;
+            my_less[nl++] = ind;
+          } else if (largest <= n_less) {
+            label[ind] = 2;
+            my_less[nl++] = ind;
+          } else {
+            break;
+          }
+          picked[ind] = 1;
+          for (int l = 1; l <= 5; ++l) {
+            if ((double)gap_sq(full[ind + l], full[ind + l - 1]) > gap_thr) break;
+            picked[ind + l] = 1;
+            label[ind + l] = 2;
+          }
+          for (int l = -1; l >= -5; --l) {
+            if ((double)gap_sq(full[ind + l], full[ind + l + 1]) > gap_thr) break;
+            picked[ind + l] = 1;
+            label[ind + l] = 2;
+          }
+        }
+      }
+      int smallest = 0;
+      for (int k = 0; k < cnt; ++k) {  // :309-336
+        const int ind = (int)(unsigned)(keys[k] & 0xffffffffull);
+        if (!picked[ind] && (double)curv[ind] < curv_thr) {
+          label[ind] = 3;
+          my_flat[nf++] = ind;
+          if (++smallest >= n_flat) break;
+          picked[ind] = 1;
+          for (int l = 1; l <= 5; ++l) {
+            if ((double)gap_sq(full[ind + l], full[ind + l - 1]) > gap_thr) break;
+            picked[ind + l] = 1;
+          }
+          for (int l = -1; l >= -5; --l) {
+            if ((double)gap_sq(full[ind + l], full[ind + l + 1]) > gap_thr) break;
+            picked[ind + l] = 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {  // :339-344, order-preserving compaction by warp 0
+      int base = s_lf;
+      for (int k0 = sp; k0 <= ep; k0 += 32) {
+        const int k = k0 + tid;
+        const bool take = (k <= ep) && (label[k] == 3 || label[k] == 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (take) my_lf[base + __popc(bal & ((1u << tid) - 1u))] = k;
+        base += __popc(bal);
+      }
+      if (tid == 0) s_lf = base;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    m->cnt[0][r] = ns;
+    m->cnt[1][r] = nl;
+    m->cnt[2][r] = nf;
+    m->cnt[3][r] = s_lf;
+  }
+}
+
+// ring-major concatenation of the per-ring lists (the push_back order of :279-283, :314, :350)
+__global__ void k_feat_compact(FeatMeta *m, int n_sectors, int n_sharp, int n_less, int n_flat,
+                               const int32_t *__restrict__ slot_sharp, const int32_t *__restrict__ slot_less,
+                               const int32_t *__restrict__ slot_flat, const int32_t *__restrict__ lessflat_tmp,
+                               int32_t *__restrict__ out_sharp, int32_t *__restrict__ out_less,
+                               int32_t *__restrict__ out_flat, int32_t *__restrict__ out_lf) {
+  __shared__ int off[4][MSFL_MAX_RINGS + 1];
+  if (threadIdx.x < 4) {
+    int s = 0;
+    for (int r = 0; r < MSFL_MAX_RINGS; ++r) { off[threadIdx.x][r] = s; s += m->cnt[threadIdx.x][r]; }
+    off[threadIdx.x][MSFL_MAX_RINGS] = s;
+    m->tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+  for (int r = 0; r < MSFL_MAX_RINGS; ++r) {
+    for (int k = threadIdx.x; k < m->cnt[0][r]; k += blockDim.x) out_sharp[off[0][r] + k] = slot_sharp[(size_t)r * n_sectors * n_sharp + k];
+    for (int k = threadIdx.x; k < m->cnt[1][r]; k += blockDim.x) out_less[off[1][r] + k] = slot_less[(size_t)r * n_sectors * n_less + k];
+    for (int k = threadIdx.x; k < m->cnt[2][r]; k += blockDim.x) out_flat[off[2][r] + k] = slot_flat[(size_t)r * n_sectors * n_flat + k];
+    for (int k = threadIdx.x; k < m->cnt[3][r]; k += blockDim.x) out_lf[off[3][r] + k] = lessflat_tmp[m->ring_start[r] + k];
+  }
+}
+
+// a-4 TransformPointCloudInPlace (:367-371; rigid_transform.h:140-145)
+struct Pose7 { double v[7]; };
+__global__ void k_feat_extrinsic(const float4 *__restrict__ in, const FeatMeta *__restrict__ m, Pose7 T, float4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m->n_valid) return;
+  const float4 p = in[i];
+  const float3 x = transform_point_f(T.v, p.x, p.y, p.z);
+  out[i] = make_float4(x.x, x.y, x.z, p.w);
+}
+
+int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7], msfl_features *out) {
+  cudaStream_t st = e->stream;
+  const size_t n = raw->n;
+  const uint32_t N = (uint32_t)n;
+  const msfl_params &P = e->params;
+  int rc;
+  // host pack + upload
+  if ((rc = e->h_stage.reserve(n * 16 + n * 2 + 64))) return rc;
+  float *h4 = e->h_stage.as<float>();
+  uint16_t *hr = (uint16_t *)(e->h_stage.as<char>() + n * 16);
+  {
+    const char *base = (const char *)raw->data;
+    const bool has_i = raw->off_intensity != MSFL_NO_FIELD;
+    for (size_t i = 0; i < n; ++i) {
+      const char *pt = base + i * raw->stride;
+      memcpy(h4 + 4 * i, pt + raw->off_xyz, 12);
+      float w = 0.f;
+      if (has_i) memcpy(&w, pt + raw->off_intensity, 4);
+      h4[4 * i + 3] = w;
+      memcpy(hr + i, pt + raw->off_ring, 2);
+    }
+  }
+  const int S = P.n_sectors;
+  const size_t slots = (size_t)MSFL_MAX_RINGS * S * (P.n_sharp + P.n_less_sharp + P.n_flat);
+  if ((rc = e->f_raw.reserve(n * 16 + n * 2 + 64))) return rc;
+  if ((rc = e->f_keys.reserve(n * 4))) return rc;
+  if ((rc = e->f_keys_alt.reserve(n * 4))) return rc;
+  if ((rc = e->f_vals.reserve(n * 4))) return rc;
+  if ((rc = e->f_vals_alt.reserve(n * 4))) return rc;
+  if ((rc = e->f_angle.reserve(n * 8))) return rc;
+  if ((rc = e->f_full.reserve(2 * n * 16))) return rc;  // pre- and post-extrinsic
+  if ((rc = e->f_ring.reserve(n * 2 + 64))) return rc;
+  if ((rc = e->f_curv.reserve(n * 4))) return rc;
+  if ((rc = e->f_label.reserve(n * 4 + n))) return rc;  // labels + picked flags
+  if ((rc = e->f_idx.reserve((5 * n + slots) * 4))) return rc;
+  if ((rc = e->f_cnt.reserve(sizeof(FeatMeta)))) return rc;
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_raw.p, e->h_stage.p, n * 16 + n * 2, cudaMemcpyHostToDevice, st));
+  const float4 *d_raw = e->f_raw.as<float4>();
+  const uint16_t *d_ring_in = (const uint16_t *)(e->f_raw.as<char>() + n * 16);
+  FeatMeta *meta = e->f_cnt.as<FeatMeta>();
+  uint32_t *keys = e->f_keys.as<uint32_t>(), *vals = e->f_vals.as<uint32_t>();
+  const int tb = 256;
+  const unsigned gb = (N + tb - 1) / tb;
+  k_feat_init<<<1, 128, 0, st>>>(meta);
+  k_feat_keys<<<gb, tb, 0, st>>>(d_raw, d_ring_in, N, P.min_range, keys, vals, meta);
+  cub::DoubleBuffer<uint32_t> dk(keys, e->f_keys_alt.as<uint32_t>()), dv(vals, e->f_vals_alt.as<uint32_t>());
+  size_t tmp = 0;
+  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)N, 0, 8, st));
+  if ((rc = e->f_tmp.reserve(tmp))) return rc;
+  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->f_tmp.p, tmp, dk, dv, (int)N, 0, 8, st));
+  const uint32_t *ks = dk.Current(), *vs = dv.Current();
+  k_feat_ring_start<<<1, 160, 0, st>>>(ks, N, meta);
+  double *rel = e->f_angle.as<double>();
+  float4 *full_pre = e->f_full.as<float4>(), *full_post = full_pre + n;
+  uint16_t *d_ring = e->f_ring.as<uint16_t>();
+  float *curv = e->f_curv.as<float>();
+  int32_t *label = e->f_label.as<int32_t>();
+  uint8_t *picked = (uint8_t *)(label + n);
+  int32_t *o_sharp = e->f_idx.as<int32_t>(), *o_less = o_sharp + n, *o_flat = o_less + n, *o_lf = o_flat + n,
+          *lf_tmp = o_lf + n, *slot_sharp = lf_tmp + n, *slot_less = slot_sharp + (size_t)MSFL_MAX_RINGS * S * P.n_sharp,
+          *slot_flat = slot_less + (size_t)MSFL_MAX_RINGS * S * P.n_less_sharp;
+  k_feat_angles<<<gb, tb, 0, st>>>(d_raw, vs, meta, rel);
+  k_feat_first_dec<<<gb, tb, 0, st>>>(ks, rel, meta);
+  k_feat_full<<<gb, tb, 0, st>>>(d_raw, ks, vs, rel, meta, P.scan_period, full_pre, d_ring);
+  k_feat_curv<<<gb, tb, 0, st>>>(full_pre, meta, curv, label, picked);
+  k_feat_pick<<<MSFL_MAX_RINGS, kPickThreads, 0, st>>>(full_pre, curv, label, picked, meta, P.curvature_thresh,
+                                                       P.neighbor_gap_sq, S, P.n_sharp, P.n_less_sharp, P.n_flat,
+                                                       slot_sharp, slot_less, slot_flat, lf_tmp);
+  k_feat_compact<<<1, 256, 0, st>>>(meta, S, P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat,
+                                    lf_tmp, o_sharp, o_less, o_flat, o_lf);
+  Pose7 T7;
+  for (int i = 0; i < 7; ++i) T7.v[i] = T ? T[i] : (i == 6 ? 1.0 : 0.0);
+  k_feat_extrinsic<<<gb, tb, 0, st>>>(full_pre, meta, T7, full_post);
+  e->launches += 10 + 3;
+  MSFL_CUDA_OK(cudaGetLastError());
+  FeatMeta hm;
+  MSFL_CUDA_OK(cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  if (hm.bad_ring) { set_error("extract_features: ring >= %d (kMaxScanNum)", MSFL_MAX_RINGS); return MSFL_ERR_RING; }
+  if (hm.n_valid <= 0) { set_error("extract_features: no valid points"); return MSFL_ERR_EMPTY; }
+  if (hm.sector_overflow) { set_error("extract_features: a ring sector holds more than %d points", kMaxSectorPts); return MSFL_ERR_ARG; }
+  const size_t nv = (size_t)hm.n_valid;
+  out->n_full = hm.n_valid;
+  out->n_sharp = hm.tot[0];
+  out->n_less_sharp = hm.tot[1];
+  out->n_flat = hm.tot[2];
+  out->n_less_flat = hm.tot[3];
+  if (out->full_xyzi) MSFL_CUDA_OK(cudaMemcpyAsync(out->full_xyzi, full_post, nv * 16, cudaMemcpyDeviceToHost, st));
+  if (out->full_ring) MSFL_CUDA_OK(cudaMemcpyAsync(out->full_ring, d_ring, nv * 2, cudaMemcpyDeviceToHost, st));
+  if (out->curvature) MSFL_CUDA_OK(cudaMemcpyAsync(out->curvature, curv, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (out->label) MSFL_CUDA_OK(cudaMemcpyAsync(out->label, label, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_sharp) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_sharp, o_sharp, (size_t)hm.tot[0] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_less_sharp) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_less_sharp, o_less, (size_t)hm.tot[1] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_flat) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_flat, o_flat, (size_t)hm.tot[2] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_less_flat) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_less_flat, o_lf, (size_t)hm.tot[3] * 4, cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  return MSFL_OK;
+}
+
+}  // namespace msfl
+
+using namespace msfl;
+
+extern "C" int msfl_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T_lidar2imu[7], msfl_features *out) {
+  if (!e || !raw || !out) { set_error("msfl_extract_features: bad argument"); return MSFL_ERR_ARG; }
+  out->n_full = out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
+  if (raw->n == 0 || !raw->data) { set_error("extract_features: empty cloud"); return MSFL_ERR_EMPTY; }
+  if (raw->off_ring == MSFL_NO_FIELD || raw->stride < 12 || raw->n > 0x3fffffffull) { set_error("extract_features: cloud needs xyz + ring"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  return run_extract_features(e, raw, T_lidar2imu, out);
+}

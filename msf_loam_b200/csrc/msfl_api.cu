@@ -215,6 +215,8 @@ void msfl_destroy(msfl_engine *e) {
   cudaStreamSynchronize(e->stream);
   submap_release(e->map_corner);
   submap_release(e->map_surf);
+  submap_release(e->last_corner_grid);
+  submap_release(e->last_surf_grid);
   DevBuf *dbs[] = {&e->d_queries, &e->d_corr, &e->d_poses, &e->d_status, &e->d_stats, &e->d_knn, &e->d_off, &e->d_misc,
                    &e->d_last_corner, &e->d_last_surf, &e->d_last_corner_ring, &e->d_last_surf_ring, &e->d_ring_tab,
                    &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,

@@ -81,6 +81,7 @@ struct msfl_engine {
   int sm_count = 148;
 
   msfl::Submap map_corner, map_surf;
+  msfl::Submap last_corner_grid, last_surf_grid;  // scan-to-scan: cell index over the last scan's features
   bool has_submap = false;
 
   // batch scratch

@@ -1,0 +1,180 @@
+"""Parity of the CUDA feature extraction / VoxelGrid / scan-to-scan path against the CPU oracle.
+
+Bit-exact: ring-major order, rings, curvature (fp32), labels, the four index lists, voxel-grid
+centroids, odometry associations.  Relative time (stored in `intensity`): the double-precision
+atan2 of glibc and of CUDA's libm may differ in the last bit, which can flip the final float
+rounding -> compared to 1 float ulp (~4e-9 s).  Poses: <= 1e-4 m / 1e-4 rad (north_star).
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from msf_loam_b200 import (Engine, OdometryScanMatcher, ScanRegistration, TimestampedPointCloud,
+                           MsflError, to_pcl)
+from msf_loam_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine()
+    yield e
+    e.close()
+
+
+def _check_features(f, g, check_time=True):
+    assert f["full"].shape == g["full"].shape
+    assert np.array_equal(f["ring"], g["ring"])
+    assert np.array_equal(f["full"][:, :3], g["full"][:, :3])
+    if check_time:
+        assert np.abs(f["full"][:, 3] - g["full"][:, 3]).max() <= 8e-9
+    assert np.array_equal(f["curvature"], g["curvature"])
+    assert np.array_equal(f["label"], g["label"])
+    for k in ("idx_sharp", "idx_less_sharp", "idx_flat", "idx_less_flat"):
+        assert np.array_equal(f[k], g[k]), k
+
+
+@pytest.mark.parametrize("sensor,scene", [("vlp16", "room40"), ("hdl64", "room80")])
+def test_extract_features_bit_exact(eng, sensor, scene):
+    P = O.default_params()
+    sc = S.make_scene(scene)
+    traj = S.trajectory(3)
+    T = np.array([0.1, -0.2, 0.3, 0.0, 0.0, np.sin(0.05), np.cos(0.05)])
+    for k in range(2):
+        xyzi, ring = S.raycast_scan(sc, sensor, traj[k], seed=40 + k)
+        f = O.extract_features(P, xyzi, ring, T)
+        g = eng.extract_features(xyzi, ring, T)
+        assert len(f["idx_sharp"]) > 50 and len(f["idx_flat"]) > 100
+        _check_features(f, g)
+
+
+def test_extract_ring_major_input_invalid_points_and_ragged_rings(eng):
+    """ring-major input, NaN / too-close points removed, rings with < 12 points skipped."""
+    P = O.default_params()
+    sc = S.make_scene()
+    xyzi, ring = S.raycast_scan(sc, "vlp16", S.trajectory(1)[0], seed=7)
+    order = np.argsort(ring, kind="stable")
+    xyzi, ring = xyzi[order].copy(), ring[order].copy()
+    rng = np.random.default_rng(3)
+    bad = rng.choice(len(xyzi), 300, replace=False)
+    xyzi[bad[:100], 0] = np.nan
+    xyzi[bad[100:200], :3] *= 1e-3          # inside min_range
+    xyzi[bad[200:], 2] = np.inf
+    keep = ~((ring == 4) & (np.arange(len(ring)) % 200 != 0))  # ring 4 keeps ~9 points -> skipped (:252)
+    xyzi, ring = xyzi[keep], ring[keep]
+    f = O.extract_features(P, xyzi, ring, None)
+    g = eng.extract_features(xyzi, ring, None)
+    fin = np.isfinite(xyzi[:, :3]).all(axis=1)
+    with np.errstate(invalid="ignore"):
+        close = np.sqrt((xyzi[:, :3].astype(np.float32) ** 2).sum(axis=1)) < 0.3
+    assert f["full"].shape[0] == int((fin & ~close).sum()) < len(xyzi) - 200
+    _check_features(f, g)
+    assert not np.any(f["ring"][f["idx_flat"]] == 4)
+
+
+def test_extract_errors(eng):
+    xyzi = np.ones((50, 4), np.float32)
+    with pytest.raises(MsflError):  # ring >= 128 (CHECK_LT, msf_loam_node.cc:136)
+        eng.extract_features(xyzi, np.full(50, 200, np.uint16))
+    with pytest.raises(MsflError):  # no valid point (CHECK_GT(_N, 0), :200)
+        eng.extract_features(np.zeros((50, 4), np.float32), np.zeros(50, np.uint16))
+
+
+def test_voxel_grid_bit_exact(eng):
+    P = O.default_params()
+    sc = S.make_scene()
+    xyzi, ring = S.raycast_scan(sc, "vlp16", S.trajectory(1)[0], seed=9)
+    f = O.extract_features(P, xyzi, ring, None)
+    for cloud, leaf in ((f["full"][f["idx_less_flat"]], 0.4), (f["full"][f["idx_less_sharp"]], 0.2),
+                        (f["full"], 0.4), (f["full"][:1], 0.2)):
+        a = O.voxel_grid(cloud, leaf)
+        b = eng.voxel_grid(cloud, leaf)
+        assert a.shape == b.shape and np.array_equal(a, b)
+        assert np.array_equal(a, S.voxel_grid_np(cloud, leaf))
+    assert eng.voxel_grid(np.zeros((0, 4), np.float32), 0.4).shape == (0, 4)
+
+
+def _scan_pair(seed0=100):
+    P = O.default_params()
+    sc = S.make_scene()
+    traj = S.trajectory(3)
+    out = []
+    for k in range(2):
+        xyzi, ring = S.raycast_scan(sc, "vlp16", traj[k], seed=seed0 + k)
+        out.append(O.extract_features(P, xyzi, ring, None))
+    gt = S.pose_mul(S.pose_inv(traj[0]), traj[1])
+    return P, out[0], out[1], gt
+
+
+def test_scan2scan_association_bit_exact(eng):
+    P, f0, f1, gt = _scan_pair()
+    lc, lcr = f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]]
+    ls, lsr = f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]]
+    cs, cf = f1["full"][f1["idx_sharp"]], f1["full"][f1["idx_flat"]]
+    for init in (S.pose_identity(), gt):
+        rc, x, logs, counts, assoc = O.scan2scan(P, lc, lcr, ls, lsr, cs, cf, init)
+        got = eng.associate_scan(to_pcl(lc, lcr), to_pcl(ls, lsr), cs, cf, init)
+        assert np.array_equal(got, assoc)
+        assert (assoc >= 0).sum() > 800
+
+
+def test_scan2scan_pose_parity_config1(eng):
+    """BASELINE config 1: single VLP-16 scan pair, scan-to-scan odometry."""
+    P, f0, f1, gt = _scan_pair()
+    lc, lcr = f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]]
+    ls, lsr = f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]]
+    cs, cf = f1["full"][f1["idx_sharp"]], f1["full"][f1["idx_flat"]]
+    rc_ref, x_ref, logs, counts, _ = O.scan2scan(P, lc, lcr, ls, lsr, cs, cf, S.pose_identity())
+    rc, x, st = eng.scan2scan(to_pcl(lc, lcr), to_pcl(ls, lsr), cs, cf, S.pose_identity())
+    assert rc == rc_ref == 0
+    dt, dr = S.pose_error(x, x_ref)
+    assert dt <= 1e-4 and dr <= 1e-4
+    assert dt < 1e-8 and dr < 1e-8
+    assert st["n_edge"] == list(counts[:, 0]) and st["n_plane"] == list(counts[:, 1])
+    for lg, lr in zip(st["lm"], logs):
+        assert lg["n_attempts"] == lr["n_attempts"] and lg["termination"] == lr["termination"]
+    dt_gt, dr_gt = S.pose_error(x, gt)
+    assert dt_gt < 0.05 and dr_gt < 0.01
+
+
+def test_scan2scan_too_few_correspondences(eng):
+    """< 10 correspondences -> false, pose untouched (odometry_scan_matcher.cc:262-267)."""
+    P, f0, f1, gt = _scan_pair()
+    lc, lcr = f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]]
+    ls, lsr = f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]]
+    cs, cf = f1["full"][f1["idx_sharp"]][:3], f1["full"][f1["idx_flat"]][:4]
+    init = np.array([0.01, 0.02, 0.0, 0, 0, 0, 1.0])
+    rc_ref, x_ref, _, counts, _ = O.scan2scan(P, lc, lcr, ls, lsr, cs, cf, init)
+    rc, x, st = eng.scan2scan(to_pcl(lc, lcr), to_pcl(ls, lsr), cs, cf, init)
+    assert rc_ref == 1 and rc == 1
+    assert np.array_equal(x, init) and np.array_equal(x_ref, init)
+    assert st["status"] == 1 and st["n_edge"][0] == counts[0, 0] and st["n_plane"][0] == counts[0, 1]
+    m = OdometryScanMatcher(eng)
+    ok, pose = m.MatchScan2Scan(
+        TimestampedPointCloud(cloud_corner_less_sharp=lc, ring_corner_less_sharp=lcr,
+                              cloud_surf_less_flat=ls, ring_surf_less_flat=lsr),
+        TimestampedPointCloud(cloud_corner_sharp=cs, cloud_surf_flat=cf), init)
+    assert ok is False and np.array_equal(pose, init)
+
+
+def test_scan2scan_rejects_unsorted_rings(eng):
+    P, f0, f1, gt = _scan_pair()
+    lc, lcr = f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]].copy()
+    lcr[10], lcr[400] = lcr[400], lcr[10]
+    ls, lsr = f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]]
+    with pytest.raises(MsflError):
+        eng.scan2scan(to_pcl(lc, lcr), to_pcl(ls, lsr), f1["full"][f1["idx_sharp"]], f1["full"][f1["idx_flat"]],
+                      S.pose_identity())
+
+
+def test_registration_to_mapping_pipeline(eng):
+    """extract -> scan-to-scan through the reference-shaped host classes."""
+    sc = S.make_scene()
+    traj = S.trajectory(3)
+    reg = ScanRegistration(eng)
+    scans = [reg.extract(*S.raycast_scan(sc, "vlp16", traj[k], seed=60 + k)) for k in range(2)]
+    ok, pose = OdometryScanMatcher(eng).MatchScan2Scan(scans[0], scans[1], S.pose_identity())
+    gt = S.pose_mul(S.pose_inv(traj[0]), traj[1])
+    dt, dr = S.pose_error(pose, gt)
+    assert ok and dt < 0.05 and dr < 0.01
