@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the LOAM scan-to-map hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+One "step" = one pass of MatchScan2Map over a batch of independent synthetic scans against one
+shared submap (BASELINE config 2 shape at N=1: VLP-16 scan vs 5-scan corner/surf submap, 2 outer
+iterations x 5 LM attempts; config 4 at N>1: scans sharded over GPUs, submap broadcast with NCCL).
+Inputs are produced by the product path itself (ray-cast -> CUDA feature extraction -> CUDA
+VoxelGrid); the CPU oracle is only executed for `cpu_baseline`, the pose check, and `--impl reference`.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from msf_loam_b200 import synth as S  # noqa: E402
+
+WORKLOADS = {
+    # name: (sensor, scene, description)
+    "vlp16": ("vlp16", "room40", "VLP-16 scan-to-map: 29k-pt scan vs 5-scan corner/surf submap, 10 LM iters"),
+    "hdl64": ("hdl64", "room80", "HDL-64E-shape scan (~130k pts) scan-to-map vs 5-scan submap, 10 LM iters"),
+    "os1-128": ("os1-128", "room80", "OS1-128-shape scan (~260k pts) scan-to-map vs 5-scan submap, 10 LM iters"),
+}
+N_MAP_SCANS = 5
+SIGMA = 0.01
+K_OUTER, L_ATTEMPTS = 2, 5  # "10 LM iters" = 2 outer x 5 attempts, fixed count
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vlp16", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=2048, help="scans per GPU per step")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct query scans (replicated to fill the batch)")
+    ap.add_argument("--cpu-sample", type=int, default=384, help="scans timed on the CPU oracle for cpu_baseline")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# workload generation
+# ------------------------------------------------------------------------------------------------
+def raw_scans(workload, n_distinct):
+    sensor, scene_kind, _ = WORKLOADS[workload]
+    scene = S.make_scene(scene_kind)
+    traj = S.trajectory(N_MAP_SCANS + n_distinct)
+    scans = [S.raycast_scan(scene, sensor, traj[k], seed=100 + k, sigma=SIGMA) for k in range(len(traj))]
+    return traj, scans
+
+
+def build_case_gpu(eng, workload, n_distinct):
+    """submap + query features through the product path (CUDA extraction + CUDA VoxelGrid)."""
+    traj, scans = raw_scans(workload, n_distinct)
+    mc, ms, queries, n_pts = [], [], [], []
+    for k, (xyzi, ring) in enumerate(scans):
+        f = eng.extract_features(xyzi, ring, None)
+        n_pts.append(f["full"].shape[0])
+        corner, surf = f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]]
+        if k < N_MAP_SCANS:
+            mc.append(S.transform_cloud(traj[k], corner))
+            ms.append(S.transform_cloud(traj[k], surf))
+        else:
+            queries.append((eng.voxel_grid(corner, 0.2), eng.voxel_grid(surf, 0.4), traj[k]))
+    map_corner = eng.voxel_grid(np.concatenate(mc), 0.2)
+    map_surf = eng.voxel_grid(np.concatenate(ms), 0.4)
+    return map_corner, map_surf, queries, int(np.mean(n_pts))
+
+
+def build_case_cpu(workload, n_distinct):
+    """same case through the oracle (the reference arm must not touch our kernels)."""
+    import oracle as O
+    P = O.default_params()
+    traj, scans = raw_scans(workload, n_distinct)
+    mc, ms, queries, n_pts = [], [], [], []
+    for k, (xyzi, ring) in enumerate(scans):
+        f = O.extract_features(P, xyzi, ring, None)
+        n_pts.append(f["full"].shape[0])
+        corner, surf = f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]]
+        if k < N_MAP_SCANS:
+            mc.append(S.transform_cloud(traj[k], corner))
+            ms.append(S.transform_cloud(traj[k], surf))
+        else:
+            queries.append((O.voxel_grid(corner, 0.2), O.voxel_grid(surf, 0.4), traj[k]))
+    return O.voxel_grid(np.concatenate(mc), 0.2), O.voxel_grid(np.concatenate(ms), 0.4), queries, int(np.mean(n_pts))
+
+
+def assemble_batch(queries, B, seed):
+    """B scans: distinct scan (i mod D) with its own seeded initial-guess perturbation (0.10 m, 1 deg)."""
+    rng = np.random.default_rng(seed)
+    D = len(queries)
+    corners = [queries[i % D][0] for i in range(B)]
+    surfs = [queries[i % D][1] for i in range(B)]
+    inits = np.stack([S.perturb_pose(queries[i % D][2], rng) for i in range(B)])
+    c_off = np.concatenate([[0], np.cumsum([c.shape[0] for c in corners])]).astype(np.int32)
+    s_off = np.concatenate([[0], np.cumsum([c.shape[0] for c in surfs])]).astype(np.int32)
+    return np.concatenate(corners), c_off, np.concatenate(surfs), s_off, inits
+
+
+def algorithmic_bytes(N, M, K=K_OUTER, L=L_ATTEMPTS):
+    """bytes = K [16 M + 48 N + 48 (1+L) N]; also the per-launch split."""
+    assoc = 16 * M + 48 * N            # queries + submap once + correspondences written
+    solve = 48 * (1 + L) * N           # one fused residual/Jacobian/cost sweep per evaluation point
+    return K * (assoc + solve), assoc, solve
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v == "Active":
+                    reasons.add(nme)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # "under load" = samples in the upper half of the observed power range
+            pw = np.array(power)
+            load = pw >= (pw.min() + 0.5 * (pw.max() - pw.min())) if pw.max() > pw.min() else np.ones_like(pw, bool)
+            out.update(sm_mhz=float(np.median(np.array(sm)[load])), sm_max_mhz=float(max(smax)),
+                       reasons=sorted(reasons), samples=len(sm), power_w_max=float(pw.max()))
+        return out
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload, batch):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(f"{workload}:{batch}")
+        return (float(e["bytes_per_launch"]), e.get("kernel")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from msf_loam_b200 import Engine, default_params
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    over = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        eng = Engine(default_params(**over), device=local_rank, stream=stream.cuda_stream)
+        # ---- inputs (product path) -------------------------------------------------------------
+        map_corner, map_surf, queries, n_full = build_case_gpu(eng, args.workload, args.distinct)
+        qc, c_off, qs, s_off, inits = assemble_batch(queries, B, seed=1000 + rank)
+        Mc, Ms = map_corner.shape[0], map_surf.shape[0]
+        n_q = int(c_off[-1] + s_off[-1])
+        # submap: owned by rank 0, broadcast over NCCL (config 4), indexed on every rank
+        t_mc = torch.from_numpy(map_corner).to(dev) if rank == 0 else torch.empty((Mc, 4), dtype=torch.float32, device=dev)
+        t_ms = torch.from_numpy(map_surf).to(dev) if rank == 0 else torch.empty((Ms, 4), dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(t_mc, 0)
+            dist.broadcast(t_ms, 0)
+        stream.synchronize()
+        eng.set_submap_device(t_mc.data_ptr(), Mc, t_ms.data_ptr(), Ms)
+        # device-resident batch
+        d_qc, d_qs = torch.from_numpy(qc).to(dev), torch.from_numpy(qs).to(dev)
+        d_co, d_so = torch.from_numpy(c_off).to(dev), torch.from_numpy(s_off).to(dev)
+        d_p0 = torch.from_numpy(inits).to(dev)
+        d_p = d_p0.clone()
+
+        def step_device():
+            if world > 1:  # the shared submap travels once per batch (config 4)
+                dist.broadcast(t_mc, 0)
+                dist.broadcast(t_ms, 0)
+            d_p.copy_(d_p0)
+            eng.scan2map_batch_device(B, d_qc.data_ptr(), d_co.data_ptr(), int(c_off[-1]), d_qs.data_ptr(),
+                                      d_so.data_ptr(), int(s_off[-1]), d_p.data_ptr())
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        barrier()
+        eng.get_profile()
+        eng.set_profiling(True)
+        sampler = ClockSampler(local_rank) if True else None
+        launches0 = eng.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = eng.launch_count - launches0
+        stage_ms, stage_cnt = eng.get_profile()
+        eng.set_profiling(False)
+        poses_dev = d_p.cpu().numpy()
+
+        # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -----------
+        h_qc = torch.from_numpy(qc).pin_memory()
+        h_qs = torch.from_numpy(qs).pin_memory()
+        hc, hs = h_qc.numpy(), h_qs.numpy()
+        prepared = eng.prepare_batch([hc[c_off[i]:c_off[i + 1]] for i in range(B)],
+                                     [hs[s_off[i]:s_off[i + 1]] for i in range(B)])
+        h_p = inits.copy()
+        for _ in range(2):
+            h_p[:] = inits
+            eng.scan2map_prepared(prepared, h_p)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            h_p[:] = inits
+            eng.scan2map_prepared(prepared, h_p)  # synchronous: returns with poses on the host
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop()
+    assert np.array_equal(h_p, poses_dev), "host-buffer and device-resident paths disagree"
+
+    # max over ranks
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        M = Mc + Ms
+        total_bytes, assoc_bytes, solve_bytes = algorithmic_bytes(n_q, M)
+        # dominant kernel = the stage with the larger share of the step
+        names = {0: "k_associate_map (kNN + line/plane fit)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
+                 2: "query transform + cell sort"}
+        per_launch_ms = {s: stage_ms[s] / stage_cnt[s] for s in range(len(stage_ms)) if stage_cnt[s]}
+        dom = max(per_launch_ms, key=lambda s: stage_ms[s])
+        dom_bytes = assoc_bytes if dom in (0, 2) else solve_bytes
+        achieved = dom_bytes / (per_launch_ms[dom] * 1e-3) / 1e9
+        traffic, traffic_kernel = ncu_traffic(args.workload, B)
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak,
+                    "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                    "avg_launch_ms": round(per_launch_ms[dom], 4),
+                    "stage_share": {names[s]: round(stage_ms[s] / sum(stage_ms), 3) for s in per_launch_ms},
+                    "whole_step_GBps": round(total_bytes / (ms_per_step * 1e-3) / 1e9, 2),
+                    "note": "latency/issue-bound path: the submap and correspondences live in L2, see DESIGN.md"}
+        cpu = None
+        pose_err = None
+        if not args.no_cpu and world >= 1:
+            cpu, pose_err = cpu_baseline(map_corner, map_surf, qc, c_off, qs, s_off, inits, poses_dev,
+                                         min(args.cpu_sample, B), over)
+        out = {
+            "metric": "scans/sec scan-to-map", "value": round(value, 1), "unit": "scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][2], "sensor": args.workload,
+                       "scans_per_gpu_per_step": B, "distinct_scans": len(queries),
+                       "points_per_scan": n_full, "queries_per_scan": round(n_q / B, 1),
+                       "submap_points": {"corner": Mc, "surf": Ms}, "outer_iterations": K_OUTER,
+                       "lm_attempts_per_outer": L_ATTEMPTS, "early_exit": False,
+                       "range_noise_sigma_m": SIGMA, "parallelism": f"scan-sharded x{world}" + (
+                           ", NCCL submap broadcast per step" if world > 1 else ""),
+                       "l2": "per-step inputs + correspondences (%.0f MB) exceed the 126 MB L2" % (
+                           (n_q * 16 + n_q * 48) / 1e6)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "scans/s",
+                    "h2d_bytes_per_step": int(n_q * 16 + (2 * (B + 1)) * 4 + B * 56),
+                    "d2h_bytes_per_step": int(B * 56)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "pose_err_vs_oracle": pose_err,
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
+        }
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_baseline(map_corner, map_surf, qc, c_off, qs, s_off, inits, poses_gpu, n_sample, over):
+    """Oracle (kind "port"), one thread, on a bounded sample of the same batch; also the pose check."""
+    import oracle as O
+    P = O.default_params(**{k: v for k, v in over.items()})
+    n = n_sample
+    co, so = c_off[: n + 1], s_off[: n + 1]
+    t0 = time.perf_counter()
+    poses = O.scan2map_batch(P, map_corner, map_surf, qc[: co[-1]], co, qs[: so[-1]], so, inits[:n], n_threads=1)
+    dt = time.perf_counter() - t0
+    errs = [S.pose_error(poses_gpu[i], poses[i]) for i in range(n)]
+    pose_err = {"max_trans_m": float(max(e[0] for e in errs)), "max_rot_rad": float(max(e[1] for e in errs)),
+                "scans_checked": n, "tolerance": "1e-4 m / 1e-4 rad"}
+    cpu = {"value": round(n / dt, 2), "unit": "scans/s", "cores": 1, "kind": "port",
+           "sample": f"first {n} scans of the batch, {dt:.1f} s, single thread, kd-trees built once for the batch",
+           "host_cpus": os.cpu_count()}
+    return cpu, pose_err
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference path on all host threads
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return None
+    import oracle as O
+    threads = os.cpu_count() or 1
+    over = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
+    P = O.default_params(**over)
+    map_corner, map_surf, queries, n_full = build_case_cpu(args.workload, min(args.distinct, 16))
+    n = max(threads * 2, 8)  # bounded sample per step
+    qc, c_off, qs, s_off, inits = assemble_batch(queries, n, seed=1000)
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.scan2map_batch(P, map_corner, map_surf, qc, c_off, qs, s_off, inits, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.scan2map_batch(P, map_corner, map_surf, qc, c_off, qs, s_off, inits, n_threads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    return {
+        "impl": "reference", "metric": "scans/sec scan-to-map", "value": round(value, 2), "unit": "scans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][2], "sensor": args.workload,
+                   "scans_per_step": n, "points_per_scan": n_full, "queries_per_scan": round(int(c_off[-1] + s_off[-1]) / n, 1),
+                   "submap_points": {"corner": int(map_corner.shape[0]), "surf": int(map_surf.shape[0])},
+                   "outer_iterations": K_OUTER, "lm_attempts_per_outer": L_ATTEMPTS, "early_exit": False},
+        "cpu_baseline": {"value": round(value, 2), "unit": "scans/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} scans per step x {args.steps} steps, pthreads over independent scans; "
+                                   "CPU restatement of the reference PCL+Ceres path (libraries not installable offline)"},
+        "e2e": {"value": round(value, 2), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    args = parse_args()
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,14 @@ void *msfl_stream(msfl_engine *e); /* cudaStream_t the engine launches on (for C
 /* number of kernel launches issued by this engine since creation (evidence for gpu_launches) */
 uint64_t msfl_launch_count(const msfl_engine *e);
 
+/* Per-stage device timing (the reference's LOG_STEP_TIME lines, tic_toc.h:29-30, as CUDA events on
+ * the engine stream).  Stages: 0 "Data association" (mapping_scan_matcher.cc:248), 1 "Solver time"
+ * (:264), 2 query transform + cell sort (part of data association).  msfl_get_profile synchronises,
+ * returns the summed milliseconds and launch counts since the last call and resets them. */
+#define MSFL_N_STAGES 4
+int msfl_set_profiling(msfl_engine *e, int on);
+int msfl_get_profile(msfl_engine *e, double ms[MSFL_N_STAGES], int32_t count[MSFL_N_STAGES]);
+
 /* ---- scan-to-map: MappingScanMatcher::MatchScan2Map, LiDAR-only branch
  *      (mapping_scan_matcher.h:14-21, mapping_scan_matcher.cc:63-278) ------------------------- */
 

@@ -115,11 +115,57 @@ static void pack_cloud_host(const msfl_cloud *c, float *dst4, uint16_t *ring_dst
   }
 }
 
+static cudaEvent_t take_event(msfl_engine *e) {
+  if (!e->event_pool.empty()) {
+    cudaEvent_t ev = e->event_pool.back();
+    e->event_pool.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev = nullptr;
+  cudaEventCreate(&ev);
+  return ev;
+}
+
+void stage_begin(msfl_engine *e, int stage) {
+  if (!e->profiling) return;
+  msfl_engine::StageEv s{take_event(e), take_event(e), stage};
+  cudaEventRecord(s.a, e->stream);
+  e->stage_events.push_back(s);
+}
+
+void stage_end(msfl_engine *e) {
+  if (!e->profiling || e->stage_events.empty()) return;
+  cudaEventRecord(e->stage_events.back().b, e->stream);
+}
+
 }  // namespace msfl
 
 using namespace msfl;
 
 extern "C" {
+
+int msfl_set_profiling(msfl_engine *e, int on) {
+  if (!e) return MSFL_ERR_ARG;
+  e->profiling = on != 0;
+  return MSFL_OK;
+}
+
+int msfl_get_profile(msfl_engine *e, double ms[MSFL_N_STAGES], int32_t count[MSFL_N_STAGES]) {
+  if (!e || !ms || !count) return MSFL_ERR_ARG;
+  for (int i = 0; i < MSFL_N_STAGES; ++i) { ms[i] = 0; count[i] = 0; }
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  for (auto &s : e->stage_events) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.stage >= 0 && s.stage < MSFL_N_STAGES) {
+      ms[s.stage] += t;
+      count[s.stage] += 1;
+    }
+    e->event_pool.push_back(s.a);
+    e->event_pool.push_back(s.b);
+  }
+  e->stage_events.clear();
+  return MSFL_OK;
+}
 
 const char *msfl_last_error(void) { return g_err; }
 const char *msfl_version(void) { return "msfl 0.1 (sm_100a)"; }
@@ -225,6 +271,8 @@ void msfl_destroy(msfl_engine *e) {
   for (DevBuf *b : dbs) b->release();
   PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc};
   for (PinBuf *b : pbs) b->release();
+  for (auto &s : e->stage_events) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (auto ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -296,11 +344,15 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   if ((rc = e->d_corr.reserve(((size_t)nct + nst + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
-    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr)))
-      return rc;
-    if ((rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
-                              e->d_status.as<int32_t>(), d_stats, outer, /*min_corr=*/0)))
-      return rc;
+    stage_begin(e, 0);
+    rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr);
+    stage_end(e);
+    if (rc) return rc;
+    stage_begin(e, 1);
+    rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
+                         e->d_status.as<int32_t>(), d_stats, outer, /*min_corr=*/0);
+    stage_end(e);
+    if (rc) return rc;
   }
   return MSFL_OK;
 }
@@ -340,20 +392,40 @@ static int upload_batch(msfl_engine *e, int B, const msfl_cloud *corner, const m
   float *hq = (float *)h;
   int32_t *hoff = (int32_t *)(h + q_pad);
   double *hpose = (double *)(h + q_pad + off_pad);
+  // Fast path: every cloud is packed float4 and the clouds of a class are back to back in one host
+  // allocation (e.g. one pinned buffer) -> DMA straight from the caller's memory, no host repack.
+  bool contiguous = true;
+  for (int b = 0; b < B && contiguous; ++b) {
+    const msfl_cloud *cl[2] = {&corner[b], &surf[b]};
+    const msfl_cloud *nx[2] = {b + 1 < B ? &corner[b + 1] : nullptr, b + 1 < B ? &surf[b + 1] : nullptr};
+    for (int c = 0; c < 2; ++c) {
+      if (cl[c]->stride != 16 || cl[c]->off_xyz != 0) contiguous = false;
+      if (nx[c] && (const char *)nx[c]->data != (const char *)cl[c]->data + cl[c]->n * 16) contiguous = false;
+    }
+  }
   size_t ci = 0, si = 0;
   for (int b = 0; b < B; ++b) {
     hoff[b] = (int32_t)ci;
     hoff[B + 1 + b] = (int32_t)si;
-    pack_cloud_host(&corner[b], hq + 4 * ci, nullptr);
-    pack_cloud_host(&surf[b], hq + 4 * (nct + si), nullptr);
+    if (!contiguous) {
+      pack_cloud_host(&corner[b], hq + 4 * ci, nullptr);
+      pack_cloud_host(&surf[b], hq + 4 * (nct + si), nullptr);
+    }
     ci += corner[b].n;
     si += surf[b].n;
   }
   hoff[B] = (int32_t)ci;
   hoff[2 * B + 1] = (int32_t)si;
   memcpy(hpose, poses, pose_bytes);
-  // one H2D copy for the whole batch
-  MSFL_CUDA_OK(cudaMemcpyAsync(e->d_queries.p, h, q_pad + off_pad + pose_bytes, cudaMemcpyHostToDevice, e->stream));
+  if (contiguous) {
+    char *d = e->d_queries.as<char>();
+    if (nct) MSFL_CUDA_OK(cudaMemcpyAsync(d, corner[0].data, nct * 16, cudaMemcpyHostToDevice, e->stream));
+    if (nst) MSFL_CUDA_OK(cudaMemcpyAsync(d + nct * 16, surf[0].data, nst * 16, cudaMemcpyHostToDevice, e->stream));
+    MSFL_CUDA_OK(cudaMemcpyAsync(d + q_pad, h + q_pad, off_pad + pose_bytes, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    // one H2D copy for the whole batch
+    MSFL_CUDA_OK(cudaMemcpyAsync(e->d_queries.p, h, q_pad + off_pad + pose_bytes, cudaMemcpyHostToDevice, e->stream));
+  }
   *nct_out = (uint32_t)nct;
   *nst_out = (uint32_t)nst;
   return MSFL_OK;

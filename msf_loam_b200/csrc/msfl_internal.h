@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/msfl.h"
 
@@ -80,6 +81,12 @@ struct msfl_engine {
   uint64_t launches = 0;
   int sm_count = 148;
 
+  // per-stage CUDA-event timing (msfl_set_profiling)
+  bool profiling = false;
+  struct StageEv { cudaEvent_t a, b; int stage; };
+  std::vector<StageEv> stage_events;
+  std::vector<cudaEvent_t> event_pool;
+
   msfl::Submap map_corner, map_surf;
   msfl::Submap last_corner_grid, last_surf_grid;  // scan-to-scan: cell index over the last scan's features
   bool has_submap = false;
@@ -99,6 +106,10 @@ struct msfl_engine {
 };
 
 namespace msfl {
+
+// stage timing helpers (msfl_api.cu): no-ops unless profiling is on
+void stage_begin(msfl_engine *e, int stage);
+void stage_end(msfl_engine *e);
 
 // ---- submap_index.cu
 int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge);

@@ -117,6 +117,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.msfl_launch_count(self.h))
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.msfl_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def get_profile(self):
+        """(ms[stage], count[stage]) since the last call; stages: 0 association, 1 solver, 2 sort."""
+        ms = (C.c_double * _lib.N_STAGES)()
+        cnt = (C.c_int32 * _lib.N_STAGES)()
+        self._check(self.lib.msfl_get_profile(self.h, ms, cnt))
+        return list(ms), list(cnt)
+
     # ---------------------------------------------------------------- submap
     def set_submap(self, map_corner, map_surf):
         vc, vs = _View(map_corner), _View(map_surf)
@@ -153,6 +163,21 @@ class Engine:
         rc = self._check(self.lib.msfl_scan2map_batch(self.h, C.c_int(B), carr, sarr,
                                                       x.ctypes.data_as(C.POINTER(C.c_double)), st))
         return rc, x, ([s.as_dict() for s in st] if st is not None else None)
+
+    def prepare_batch(self, scan_corners, scan_surfs):
+        """Builds the msfl_cloud tables once so a timed loop only pays the C call."""
+        B = len(scan_corners)
+        vcs = [_View(a) for a in scan_corners]
+        vss = [_View(a) for a in scan_surfs]
+        return {"B": B, "views": (vcs, vss), "carr": (Cloud * B)(*[v.cloud for v in vcs]),
+                "sarr": (Cloud * B)(*[v.cloud for v in vss])}
+
+    def scan2map_prepared(self, batch, poses_inout: np.ndarray):
+        """msfl_scan2map_batch on a prepared batch; poses_inout (B,7) float64 is updated in place."""
+        assert poses_inout.dtype == np.float64 and poses_inout.flags.c_contiguous
+        return self._check(self.lib.msfl_scan2map_batch(
+            self.h, C.c_int(batch["B"]), batch["carr"], batch["sarr"],
+            poses_inout.ctypes.data_as(C.POINTER(C.c_double)), None))
 
     def scan2map_batch_device(self, B, d_corner, d_corner_off, n_corner_total, d_surf, d_surf_off,
                               n_surf_total, d_poses, d_stats=0):
