@@ -223,11 +223,12 @@ def run_ours(args):
         Mc, Ms = map_corner.shape[0], map_surf.shape[0]
         n_q = int(c_off[-1] + s_off[-1])
         # submap: owned by rank 0, broadcast over NCCL (config 4), indexed on every rank
-        t_mc = torch.from_numpy(map_corner).to(dev) if rank == 0 else torch.empty((Mc, 4), dtype=torch.float32, device=dev)
-        t_ms = torch.from_numpy(map_surf).to(dev) if rank == 0 else torch.empty((Ms, 4), dtype=torch.float32, device=dev)
         if world > 1:
-            dist.broadcast(t_mc, 0)
-            dist.broadcast(t_ms, 0)
+            from msf_loam_b200 import sharding
+            t_mc, t_ms = sharding.broadcast_submap(map_corner if rank == 0 else None, map_surf if rank == 0 else None,
+                                                   src=0, device=dev)
+        else:
+            t_mc, t_ms = torch.from_numpy(map_corner).to(dev), torch.from_numpy(map_surf).to(dev)
         stream.synchronize()
         eng.set_submap_device(t_mc.data_ptr(), Mc, t_ms.data_ptr(), Ms)
         # device-resident batch
@@ -249,12 +250,12 @@ def run_ours(args):
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
+        sampler = ClockSampler(local_rank)
         for _ in range(max(args.warmup, 3)):
             step_device()
         barrier()
         eng.get_profile()
         eng.set_profiling(True)
-        sampler = ClockSampler(local_rank) if True else None
         launches0 = eng.launch_count
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
