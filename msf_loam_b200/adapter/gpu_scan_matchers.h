@@ -1,0 +1,105 @@
+// gpu_scan_matchers.h -- reference-side adapters: drop-in subclasses of MSF_LOAM's matchers that
+// forward to libmsfl.so through the C ABI (include/msfl.h).  These files are meant to be compiled
+// INSIDE the reference tree (they include its headers, PCL and Eigen); they are not built in this
+// repository because PCL/Eigen/Ceres are not available here.  See INTEGRATION.md.
+//
+//   OdometryScanMatcher::MatchScan2Scan   odometry_scan_matcher.h:10-12   -> msfl_scan2scan
+//   MappingScanMatcher::MatchScan2Map     mapping_scan_matcher.h:14-21    -> msfl_set_submap + msfl_scan2map
+#pragma once
+
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+
+#include "msfl.h"
+#include "slam/local/scan_matching/mapping_scan_matcher.h"
+#include "slam/local/scan_matching/odometry_scan_matcher.h"
+
+namespace msfl_adapter {
+
+template <typename PointT>
+inline msfl_cloud View(const pcl::PointCloud<PointT> &c, bool with_ring);
+
+template <>
+inline msfl_cloud View<PointType>(const pcl::PointCloud<PointType> &c, bool) {  // pcl::PointXYZI
+  return msfl_cloud{c.empty() ? nullptr : &c.points[0], c.size(), sizeof(PointType), offsetof(PointType, x),
+                    offsetof(PointType, intensity), MSFL_NO_FIELD};
+}
+template <>
+inline msfl_cloud View<PointTypeOriginal>(const pcl::PointCloud<PointTypeOriginal> &c, bool with_ring) {  // PointXYZIRT
+  return msfl_cloud{c.empty() ? nullptr : &c.points[0], c.size(), sizeof(PointTypeOriginal),
+                    offsetof(PointTypeOriginal, x), offsetof(PointTypeOriginal, intensity),
+                    with_ring ? offsetof(PointTypeOriginal, ring) : MSFL_NO_FIELD};
+}
+
+inline void ToArray(const Rigid3d &T, double out[7]) {  // Rigid3d::ToVector7 order (rigid_transform.h:59-64)
+  out[0] = T.translation().x(); out[1] = T.translation().y(); out[2] = T.translation().z();
+  out[3] = T.rotation().x(); out[4] = T.rotation().y(); out[5] = T.rotation().z(); out[6] = T.rotation().w();
+}
+inline Rigid3d FromArray(const double in[7]) {
+  return Rigid3d(Eigen::Vector3d(in[0], in[1], in[2]), Eigen::Quaterniond(in[6], in[3], in[4], in[5]));
+}
+
+class Engine {
+ public:
+  explicit Engine(int device = 0) {
+    msfl_params p;
+    msfl_default_params(&p);
+    if (msfl_create(&p, device, &e_) != MSFL_OK) throw std::runtime_error(std::string("msfl_create: ") + msfl_last_error());
+  }
+  ~Engine() { msfl_destroy(e_); }
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+  msfl_engine *get() const { return e_; }
+
+ private:
+  msfl_engine *e_ = nullptr;
+};
+
+}  // namespace msfl_adapter
+
+// Replaces `scan_matcher_(std::make_unique<OdometryScanMatcher>())` at laser_odometry.cc:56.
+class GpuOdometryScanMatcher : public OdometryScanMatcher {
+ public:
+  bool MatchScan2Scan(const TimestampedPointCloud<PointTypeOriginal> &scan_last,
+                      const TimestampedPointCloud<PointTypeOriginal> &scan_curr,
+                      Rigid3d *pose_estimate_curr2last) override {
+    using msfl_adapter::View;
+    const msfl_cloud lc = View(*scan_last.cloud_corner_less_sharp, true), ls = View(*scan_last.cloud_surf_less_flat, true);
+    const msfl_cloud cs = View(*scan_curr.cloud_corner_sharp, false), cf = View(*scan_curr.cloud_surf_flat, false);
+    double pose[7];
+    msfl_adapter::ToArray(*pose_estimate_curr2last, pose);
+    const int rc = msfl_scan2scan(engine_.get(), &lc, &ls, &cs, &cf, pose, nullptr);
+    CHECK_GE(rc, 0) << msfl_last_error();             // fatal errors abort, like the reference's glog CHECKs
+    *pose_estimate_curr2last = msfl_adapter::FromArray(pose);
+    return rc == MSFL_OK;                              // false <=> fewer than 10 correspondences (:262-267)
+  }
+
+ private:
+  msfl_adapter::Engine engine_;
+};
+
+// Replaces `scan_matcher_(std::make_unique<MappingScanMatcher>())` at laser_mapping.cc:42.
+class GpuMappingScanMatcher : public MappingScanMatcher {
+ public:
+  bool MatchScan2Map(const TimestampedPointCloud<PointType> &cloud_map, const TimestampedPointCloud<PointType> &scan_curr,
+                     const bool is_initialized, const std::shared_ptr<IntegrationBase> &preintegration,
+                     const Vector3d &gravity_vector, const RobotState &prev_state, Rigid3d *pose_estimate_map_scan2world,
+                     Vector3d *velocity) override {
+    if (is_initialized)  // IMU-deskew factor variants are not on the GPU path yet
+      return MappingScanMatcher::MatchScan2Map(cloud_map, scan_curr, is_initialized, preintegration, gravity_vector,
+                                               prev_state, pose_estimate_map_scan2world, velocity);
+    using msfl_adapter::View;
+    const msfl_cloud mc = View(*cloud_map.cloud_corner_less_sharp, false), ms = View(*cloud_map.cloud_surf_less_flat, false);
+    const msfl_cloud sc = View(*scan_curr.cloud_corner_less_sharp, false), ss = View(*scan_curr.cloud_surf_less_flat, false);
+    CHECK_EQ(msfl_set_submap(engine_.get(), &mc, &ms), MSFL_OK) << msfl_last_error();  // the two kd-tree builds (:66-72)
+    double pose[7];
+    msfl_adapter::ToArray(*pose_estimate_map_scan2world, pose);
+    CHECK_EQ(msfl_scan2map(engine_.get(), &sc, &ss, pose, nullptr), MSFL_OK) << msfl_last_error();
+    *pose_estimate_map_scan2world = msfl_adapter::FromArray(pose);
+    return true;  // :277
+  }
+
+ private:
+  msfl_adapter::Engine engine_;
+};
