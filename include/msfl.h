@@ -85,7 +85,8 @@ typedef struct msfl_params {
   /* engine */
   int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan in the LM kernel:
                                   0 = auto, else 1/2/4/8                              */
-  int32_t _pad1;
+  int32_t assoc_sorted;        /* scan-to-map association order: 0 = auto (sort the batch's queries
+                                  by submap cell when it holds >= 65536 queries), 1 = never, 2 = always */
 } msfl_params;
 
 /* Host AoS cloud view (see "Conventions"). */

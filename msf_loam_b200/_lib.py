@@ -50,7 +50,7 @@ class Params(C.Structure):
         ("max_lm_diagonal", C.c_double), ("function_tolerance", C.c_double),
         ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
         ("max_consecutive_invalid_steps", C.c_int32), ("early_exit", C.c_int32),
-        ("lm_cluster", C.c_int32), ("_pad1", C.c_int32),
+        ("lm_cluster", C.c_int32), ("assoc_sorted", C.c_int32),
     ]
 
 

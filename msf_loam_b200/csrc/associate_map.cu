@@ -7,6 +7,8 @@
 // covering every query of the batch (scan id by binary search in the offset table).  kNN distances are fp32 ((dx*dx)+dy*dy)+dz*dz without FMA
 // contraction (FLANN L2_Simple<float>), candidates are ordered by (d2, original index), the fit
 // is fp64.  Output per query: 6 doubles [a_or_c(3), n(3)]; n = 0 marks "no factor".
+#include <cub/device/device_radix_sort.cuh>
+
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
 
@@ -45,26 +47,51 @@ __device__ __forceinline__ void top5_insert(Top5 &t, float d, int id) {
 
 // 5-NN of q among the 27 cells around it, restricted to d2 < thresh.  Returns true when five
 // such neighbours exist (<=> pointSearchSqDis[4] < thresh for the exact 5-NN).
+//
+// Rows (dy, dz) are visited nearest-first and a row -- or its left / right cell -- is skipped when
+// even the closest possible point in it cannot enter the current top-5.  The bounds are exact in
+// fp32: with 1 m cells the cell boundaries are integers, float subtraction / squaring / addition
+// are monotone, and the bound is accumulated in the same order as the distance itself
+// ((bx^2 + by^2) + bz^2), so  bound > worst  implies  d > worst  for every point of that cell.
 __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy, float qz, float thresh, Top5 &t) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     t.d[s] = thresh;
     t.i[s] = -1;
   }
-  const int cx = (int)floorf(qx * g.inv_edge) - g.ox;
-  const int cy = (int)floorf(qy * g.inv_edge) - g.oy;
-  const int cz = (int)floorf(qz * g.inv_edge) - g.oz;
+  const float fxq = floorf(qx * g.inv_edge), fyq = floorf(qy * g.inv_edge), fzq = floorf(qz * g.inv_edge);
+  const int cx = (int)fxq - g.ox, cy = (int)fyq - g.oy, cz = (int)fzq - g.oz;
   if (cx < 1 || cy < 1 || cz < 1 || cx > g.nx - 2 || cy > g.ny - 2 || cz > g.nz - 2) return false;
-  for (int dz = -1; dz <= 1; ++dz) {
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int row = ((cz + dz) * g.ny + (cy + dy)) * g.nx + cx;
-      const uint32_t s = __ldg(g.cell_start + row - 1), e = __ldg(g.cell_start + row + 2);
-      for (uint32_t j = s; j < e; ++j) {
-        const float4 m = __ldg(g.pts_sorted + j);
-        const float dx = __fsub_rn(qx, m.x), dy2 = __fsub_rn(qy, m.y), dz2 = __fsub_rn(qz, m.z);
-        float d = __fmul_rn(dx, dx);
-        d = __fadd_rn(d, __fmul_rn(dy2, dy2));
-        d = __fadd_rn(d, __fmul_rn(dz2, dz2));
+  const bool exact_cells = (g.inv_edge == 1.0f);
+  // distance from q to the lower / upper faces of its own cell (>= 0); 0 disables pruning
+  const float lox = exact_cells ? __fsub_rn(qx, fxq) : 0.f, hix = exact_cells ? __fsub_rn(fxq + 1.0f, qx) : 0.f;
+  const float loy = exact_cells ? __fsub_rn(qy, fyq) : 0.f, hiy = exact_cells ? __fsub_rn(fyq + 1.0f, qy) : 0.f;
+  const float loz = exact_cells ? __fsub_rn(qz, fzq) : 0.f, hiz = exact_cells ? __fsub_rn(fzq + 1.0f, qz) : 0.f;
+  const float bx2[2] = {__fmul_rn(lox, lox), __fmul_rn(hix, hix)};  // left cell, right cell
+  // nearest-first row order: centre, 4 face neighbours, 4 diagonal neighbours
+  constexpr int kDy[9] = {0, -1, 1, 0, 0, -1, -1, 1, 1};
+  constexpr int kDz[9] = {0, 0, 0, -1, 1, -1, 1, -1, 1};
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int dy = kDy[r], dz = kDz[r];
+    const float by = dy == 0 ? 0.f : (dy < 0 ? loy : hiy), bz = dz == 0 ? 0.f : (dz < 0 ? loz : hiz);
+    const float by2 = __fmul_rn(by, by), bz2 = __fmul_rn(bz, bz);
+    const float row_lb = __fadd_rn(by2, bz2);  // (0 + by^2) + bz^2
+    if (row_lb > t.d[4] || row_lb >= thresh) continue;
+    const int row = ((cz + dz) * g.ny + (cy + dy)) * g.nx + cx;
+    const uint32_t s0 = __ldg(g.cell_start + row - 1), s1 = __ldg(g.cell_start + row),
+                   s2 = __ldg(g.cell_start + row + 1), s3 = __ldg(g.cell_start + row + 2);
+    const float lbl = __fadd_rn(__fadd_rn(bx2[0], by2), bz2), lbr = __fadd_rn(__fadd_rn(bx2[1], by2), bz2);
+    const uint32_t js = (lbl > t.d[4] || lbl >= thresh) ? s1 : s0;
+    const uint32_t je = (lbr > t.d[4] || lbr >= thresh) ? s2 : s3;
+#pragma unroll 4
+    for (uint32_t j = js; j < je; ++j) {
+      const float4 m = __ldg(g.pts_sorted + j);
+      const float dx = __fsub_rn(qx, m.x), dy2 = __fsub_rn(qy, m.y), dz2 = __fsub_rn(qz, m.z);
+      float d = __fmul_rn(dx, dx);
+      d = __fadd_rn(d, __fmul_rn(dy2, dy2));
+      d = __fadd_rn(d, __fmul_rn(dz2, dz2));
+      if (d <= t.d[4]) {  // cheap filter; exact (d2, index) order inside
         const int id = __float_as_int(m.w);
         if (cand_less(d, id, t.d[4], t.i[4])) top5_insert(t, d, id);
       }
@@ -91,12 +118,22 @@ __device__ __forceinline__ int find_scan(const int32_t *__restrict__ off, int B,
   return lo;
 }
 
-// Flat 1-D grid over all queries of the batch: [all corner queries | all surf queries].
-__global__ void __launch_bounds__(128)
-k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
-                const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
-                const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
-                double *__restrict__ corr, int32_t *__restrict__ knn_out) {
+// cell id of x in grid g, or -1 when x has no occupied neighbour cell
+__device__ __forceinline__ int cell_of(const GridView &g, float x, float y, float z) {
+  const int cx = (int)floorf(x * g.inv_edge) - g.ox, cy = (int)floorf(y * g.inv_edge) - g.oy,
+            cz = (int)floorf(z * g.inv_edge) - g.oz;
+  if (cx < 1 || cy < 1 || cz < 1 || cx > g.nx - 2 || cy > g.ny - 2 || cz > g.nz - 2) return -1;
+  return (cz * g.ny + cy) * g.nx + cx;
+}
+
+// Pass 1 of the sorted path: transform every query by its scan's pose (mapping_scan_matcher.cc:123 /
+// :193) and emit a sort key = cell id of the transformed point (corner grid first, then surf grid; one
+// sentinel cell per class for queries with no occupied neighbourhood).
+__global__ void __launch_bounds__(256)
+k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc, const int32_t *__restrict__ c_off,
+                 uint32_t n_corner_total, const float4 *__restrict__ qs, const int32_t *__restrict__ s_off,
+                 uint32_t n_surf_total, const double *__restrict__ poses, float4 *__restrict__ xq,
+                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_corner_total + n_surf_total) return;
   const bool is_corner = k < n_corner_total;
@@ -105,9 +142,47 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
   double pose[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) pose[i] = __ldg(poses + (size_t)scan * 7 + i);
-  const size_t q = k;
   const float4 p = __ldg((is_corner ? qc : qs) + kk);
-  const float3 x = transform_point_f(pose, p.x, p.y, p.z);  // mapping_scan_matcher.cc:123 / :193
+  const float3 x = transform_point_f(pose, p.x, p.y, p.z);
+  const uint32_t ncell_c = (uint32_t)(gc.nx * gc.ny * gc.nz), ncell_s = (uint32_t)(gs.nx * gs.ny * gs.nz);
+  const int c = cell_of(is_corner ? gc : gs, x.x, x.y, x.z);
+  uint32_t key;
+  if (is_corner) key = c < 0 ? ncell_c : (uint32_t)c;
+  else key = ncell_c + 1u + (c < 0 ? ncell_s : (uint32_t)c);
+  xq[k] = make_float4(x.x, x.y, x.z, 0.f);
+  keys[k] = key;
+  vals[k] = k;
+}
+
+// Association kernel.  SORTED = false: thread k handles flat query k and transforms it itself.
+// SORTED = true: thread s handles query perm[s] (queries ordered by the cell of their transformed
+// point, so the lanes of a warp walk the same candidate ranges: uniform trip counts and broadcast
+// loads) and reads the transformed point stored by k_transform_keys.
+template <bool SORTED>
+__global__ void __launch_bounds__(128)
+k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
+                const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
+                const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
+                const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, double *__restrict__ corr,
+                int32_t *__restrict__ knn_out) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_corner_total + n_surf_total) return;
+  const uint32_t k = SORTED ? __ldg(perm + slot) : slot;
+  const bool is_corner = k < n_corner_total;
+  float3 x;
+  if (SORTED) {
+    const float4 xs = __ldg(xq + k);
+    x = make_float3(xs.x, xs.y, xs.z);
+  } else {
+    const uint32_t kk = is_corner ? k : k - n_corner_total;
+    const int scan = find_scan(is_corner ? c_off : s_off, B, kk);
+    double pose[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pose[i] = __ldg(poses + (size_t)scan * 7 + i);
+    const float4 p = __ldg((is_corner ? qc : qs) + kk);
+    x = transform_point_f(pose, p.x, p.y, p.z);  // mapping_scan_matcher.cc:123 / :193
+  }
+  const size_t q = k;
   const GridView &g = is_corner ? gc : gs;
   Top5 t;
   const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);  // :125-128 / :195-198
@@ -175,10 +250,46 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   const uint32_t total = n_corner_total + n_surf_total;
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
-  k_associate_map<<<(total + tb - 1) / tb, tb, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, B, d_qc, d_c_off,
-                                                              n_corner_total, d_qs, d_s_off, n_surf_total, d_poses,
-                                                              d_corr, d_knn);
-  e->launches += 1;
+  const GridView &gc = e->map_corner.view, &gs = e->map_surf.view;
+  const int mode = e->params.assoc_sorted;  // 0 auto, 1 never, 2 always
+  const bool sorted = mode == 2 || (mode == 0 && total >= 65536u);
+  if (!sorted) {
+    stage_begin(e, 0);
+    k_associate_map<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
+                                                                       d_s_off, n_surf_total, d_poses, nullptr, nullptr,
+                                                                       d_corr, d_knn);
+    stage_end(e);
+    e->launches += 1;
+    MSFL_CUDA_OK(cudaGetLastError());
+    return MSFL_OK;
+  }
+  // sorted path: transform + cell keys -> radix sort -> association in cell order
+  int rc;
+  if ((rc = e->a_xq.reserve((size_t)total * 16))) return rc;
+  if ((rc = e->a_keys.reserve((size_t)total * 4))) return rc;
+  if ((rc = e->a_keys_alt.reserve((size_t)total * 4))) return rc;
+  if ((rc = e->a_vals.reserve((size_t)total * 4))) return rc;
+  if ((rc = e->a_vals_alt.reserve((size_t)total * 4))) return rc;
+  const long long ncell = (long long)gc.nx * gc.ny * gc.nz + (long long)gs.nx * gs.ny * gs.nz + 2;
+  int end_bit = 1;
+  while ((1ll << end_bit) < ncell) ++end_bit;
+  cub::DoubleBuffer<uint32_t> dk(e->a_keys.as<uint32_t>(), e->a_keys_alt.as<uint32_t>()),
+      dv(e->a_vals.as<uint32_t>(), e->a_vals_alt.as<uint32_t>());
+  size_t tmp = 0;
+  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
+  if ((rc = e->a_tmp.reserve(tmp))) return rc;
+  stage_begin(e, 2);
+  k_transform_keys<<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                              n_surf_total, d_poses, e->a_xq.as<float4>(), dk.Current(),
+                                                              dv.Current());
+  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
+  stage_end(e);
+  stage_begin(e, 0);
+  k_associate_map<true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
+                                                                    d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(),
+                                                                    dv.Current(), d_corr, d_knn);
+  stage_end(e);
+  e->launches += 2 + 3;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }

@@ -147,6 +147,136 @@ __device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) 
   __syncthreads();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk, 1-D) staging of correspondence tiles.  The per-scan arrays are contiguous, so
+// a tile of kTile entries is two bulk copies (points: 16 B/entry, constants: 48 B/entry) that land
+// in shared memory and complete on an mbarrier; a 3-stage ring keeps two tiles in flight while one
+// is consumed, which takes the L2/HBM latency off the fp64 critical path.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile = kLmThreads;  // one entry per thread per tile
+constexpr int kStages = 3;
+constexpr int kStageBytes = kTile * 16 + kTile * 48;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct TileSrc {
+  const float4 *pe, *pp;
+  const double *ce, *cp;
+  uint32_t n_e, n_p, tiles_e, tiles;
+};
+
+// issue the two bulk copies of tile t into stage buffer `buf`
+__device__ __forceinline__ void issue_tile(const TileSrc &ts, uint32_t t, unsigned char *buf, uint64_t *bar) {
+  const bool edge = t < ts.tiles_e;
+  const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
+  const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
+  const float4 *p = (edge ? ts.pe : ts.pp) + base;
+  const double *c = (edge ? ts.ce : ts.cp) + (size_t)base * 6;
+  mbar_expect_tx(bar, cnt * 64u);
+  tma_load_1d(buf, p, cnt * 16u, bar);
+  tma_load_1d(buf + kTile * 16, c, cnt * 48u, bar);
+}
+
+// One fused sweep over the scan's correspondences at `pose`, tiles streamed through the smem ring.
+// `tile_ctr` counts tiles consumed since kernel start (stage = ctr % kStages, parity = (ctr / kStages) & 1).
+__device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &ts, unsigned char *ring, uint64_t *bars,
+                                            uint32_t &tile_ctr, const double *pose, double huber_a, int &cnt_edge,
+                                            int &cnt_plane) {
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+  double R[9];
+  quat_to_R(pose + 3, R);
+  const double t0 = pose[0], t1 = pose[1], t2 = pose[2];
+  cnt_edge = 0;
+  cnt_plane = 0;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    for (uint32_t t = 0; t < min((uint32_t)(kStages - 1), ts.tiles); ++t) {
+      const uint32_t g = tile_ctr + t;
+      issue_tile(ts, t, ring + (g % kStages) * kStageBytes, bars + (g % kStages));
+    }
+  }
+  for (uint32_t t = 0; t < ts.tiles; ++t) {
+    const uint32_t g = tile_ctr + t, stage = g % kStages;
+    if (tid == 0 && t + kStages - 1 < ts.tiles) {
+      const uint32_t gn = g + kStages - 1;
+      issue_tile(ts, t + kStages - 1, ring + (gn % kStages) * kStageBytes, bars + (gn % kStages));
+    }
+    mbar_wait(bars + stage, (g / kStages) & 1u);
+    const bool edge = t < ts.tiles_e;
+    const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
+    const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
+    if (tid < cnt) {
+      const unsigned char *buf = ring + stage * kStageBytes;
+      const float4 pf = reinterpret_cast<const float4 *>(buf)[tid];
+      const double2 *cp = reinterpret_cast<const double2 *>(buf + kTile * 16 + tid * 48);
+      const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];
+      const double a0 = c0.x, a1 = c0.y, a2 = c1.x, n0 = c1.y, n1 = c2.x, n2 = c2.y;
+      if (!(n0 == 0.0 && n1 == 0.0 && n2 == 0.0)) {
+        const double p0 = pf.x, p1 = pf.y, p2 = pf.z;
+        const double d0 = R[0] * p0 + R[1] * p1 + R[2] * p2 + t0 - a0;
+        const double d1 = R[3] * p0 + R[4] * p1 + R[5] * p2 + t1 - a1;
+        const double d2 = R[6] * p0 + R[7] * p1 + R[8] * p2 + t2 - a2;
+        const double m00 = R[1] * p2 - R[2] * p1, m10 = R[4] * p2 - R[5] * p1, m20 = R[7] * p2 - R[8] * p1;
+        const double m01 = R[2] * p0 - R[0] * p2, m11 = R[5] * p0 - R[3] * p2, m21 = R[8] * p0 - R[6] * p2;
+        const double m02 = R[0] * p1 - R[1] * p0, m12 = R[3] * p1 - R[4] * p0, m22 = R[6] * p1 - R[7] * p0;
+        if (edge) {
+          ++cnt_edge;
+          const double r0 = n1 * d2 - n2 * d1, r1 = n2 * d0 - n0 * d2, r2 = n0 * d1 - n1 * d0;
+          const double sc = huber_scale(r0 * r0 + r1 * r1 + r2 * r2, huber_a, acc[27]);
+          double J[6];
+          J[0] = 0.0; J[1] = -n2 * sc; J[2] = n1 * sc;
+          J[3] = -(-n2 * m10 + n1 * m20) * sc; J[4] = -(-n2 * m11 + n1 * m21) * sc; J[5] = -(-n2 * m12 + n1 * m22) * sc;
+          acc_row(acc, J, r0 * sc);
+          J[0] = n2 * sc; J[1] = 0.0; J[2] = -n0 * sc;
+          J[3] = -(n2 * m00 - n0 * m20) * sc; J[4] = -(n2 * m01 - n0 * m21) * sc; J[5] = -(n2 * m02 - n0 * m22) * sc;
+          acc_row(acc, J, r1 * sc);
+          J[0] = -n1 * sc; J[1] = n0 * sc; J[2] = 0.0;
+          J[3] = -(-n1 * m00 + n0 * m10) * sc; J[4] = -(-n1 * m01 + n0 * m11) * sc; J[5] = -(-n1 * m02 + n0 * m12) * sc;
+          acc_row(acc, J, r2 * sc);
+        } else {
+          ++cnt_plane;
+          const double r = n0 * d0 + n1 * d1 + n2 * d2;
+          const double sc = huber_scale(r * r, huber_a, acc[27]);
+          double J[6];
+          J[0] = n0 * sc; J[1] = n1 * sc; J[2] = n2 * sc;
+          J[3] = -(n0 * m00 + n1 * m10 + n2 * m20) * sc;
+          J[4] = -(n0 * m01 + n1 * m11 + n2 * m21) * sc;
+          J[5] = -(n0 * m02 + n1 * m12 + n2 * m22) * sc;
+          acc_row(acc, J, r * sc);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with this stage before it is refilled
+  }
+  tile_ctr += ts.tiles;
+}
+
 __device__ inline double norm7(const double *x) {
   double s = 0;
   for (int i = 0; i < 7; ++i) s += x[i] * x[i];
@@ -250,12 +380,14 @@ __device__ void lm_finish_step(LmShared &sh, const KParams &kp, msfl_lm_log *log
   }
 }
 
-__global__ void __launch_bounds__(kLmThreads)
+__global__ void __launch_bounds__(kLmThreads, 2)
 k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const float4 *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
            int min_corr) {
   __shared__ LmShared sh;
+  __shared__ __align__(8) uint64_t bars[kStages];
+  extern __shared__ __align__(128) unsigned char ring[];
   const int b = blockIdx.x;
   const uint32_t eo = (uint32_t)e_off[b], n_e = (uint32_t)e_off[b + 1] - eo;
   const uint32_t po = (uint32_t)p_off[b], n_p = (uint32_t)p_off[b + 1] - po;
@@ -268,12 +400,23 @@ k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict_
   if (outer > 0 && status[b] != MSFL_OK) return;  // an earlier outer iteration bailed out (odometry :266)
 
   if (tid < 7) sh.x[tid] = poses[(size_t)b * 7 + tid];
-  if (tid == 0) { sh.done = 0; sh.too_few = 0; }
+  if (tid == 0) {
+    sh.done = 0;
+    sh.too_few = 0;
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  TileSrc ts;
+  ts.pe = pe; ts.pp = pp; ts.ce = ce_; ts.cp = cp_;
+  ts.n_e = n_e; ts.n_p = n_p;
+  ts.tiles_e = (n_e + kTile - 1) / kTile;
+  ts.tiles = ts.tiles_e + (n_p + kTile - 1) / kTile;
+  uint32_t tile_ctr = 0;
 
   double acc[kAcc];
   int ce, cpl;
-  sweep(acc, pe, ce_, n_e, pp, cp_, n_p, sh.x, kp.huber_a, tid, kLmThreads, ce, cpl);
+  sweep_tiled(acc, ts, ring, bars, tile_ctr, sh.x, kp.huber_a, ce, cpl);
   // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
   for (int o = 16; o > 0; o >>= 1) {
     ce += __shfl_down_sync(0xffffffffu, ce, o);
@@ -321,7 +464,7 @@ k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict_
   }
   __syncthreads();
   while (!sh.done) {
-    sweep(acc, pe, ce_, n_e, pp, cp_, n_p, sh.xc, kp.huber_a, tid, kLmThreads, ce, cpl);
+    sweep_tiled(acc, ts, ring, bars, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
     block_reduce(acc, sh);
     if (tid == 0) {
       lm_finish_step(sh, kp, log);
@@ -340,7 +483,12 @@ int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_
                     const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
                     msfl_stats *d_stats, int outer, int min_corr) {
   if (B <= 0) return MSFL_OK;
-  k_lm_solve<<<B, kLmThreads, 0, e->stream>>>(e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status,
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kStageBytes));
+    attr_set = true;
+  }
+  k_lm_solve<<<B, kLmThreads, kStages * kStageBytes, e->stream>>>(e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status,
                                               d_stats, outer, min_corr);
   e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());

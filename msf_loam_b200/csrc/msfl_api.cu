@@ -202,6 +202,7 @@ void msfl_default_params(msfl_params *p) {
   p->max_consecutive_invalid_steps = 5;
   p->early_exit = 1;
   p->lm_cluster = 0;
+  p->assoc_sorted = 0;
 }
 
 int msfl_create_on_stream(const msfl_params *params, int device, void *stream, msfl_engine **out) {
@@ -267,7 +268,8 @@ void msfl_destroy(msfl_engine *e) {
                    &e->d_last_corner, &e->d_last_surf, &e->d_last_corner_ring, &e->d_last_surf_ring, &e->d_ring_tab,
                    &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,
                    &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
-                   &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc};
+                   &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc,
+                   &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp};
   for (DevBuf *b : dbs) b->release();
   PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc};
   for (PinBuf *b : pbs) b->release();
@@ -344,10 +346,8 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   if ((rc = e->d_corr.reserve(((size_t)nct + nst + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
-    stage_begin(e, 0);
-    rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr);
-    stage_end(e);
-    if (rc) return rc;
+    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr)))
+      return rc;
     stage_begin(e, 1);
     rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
                          e->d_status.as<int32_t>(), d_stats, outer, /*min_corr=*/0);

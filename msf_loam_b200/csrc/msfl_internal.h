@@ -94,6 +94,8 @@ struct msfl_engine {
   // batch scratch
   msfl::DevBuf d_queries, d_corr, d_poses, d_status, d_stats, d_knn, d_off, d_misc;
   msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
+  // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
+  msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp;
 
   // odometry scratch
   msfl::DevBuf d_last_corner, d_last_surf, d_last_corner_ring, d_last_surf_ring, d_ring_tab, d_assoc;

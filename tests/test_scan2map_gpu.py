@@ -106,6 +106,27 @@ def test_batch_equals_singles_bitwise(eng, vlp16_case):
     assert st[1]["n_edge"] == [0, 0] and st[1]["n_plane"] == [0, 0]
 
 
+def test_sorted_association_path_is_bitwise_identical(vlp16_case):
+    """assoc_sorted = 2 (queries ordered by submap cell, used for large batches) vs 1 (flat order)."""
+    P = O.default_params()
+    qs = vlp16_case["queries"]
+    res = {}
+    for mode in (1, 2):
+        e = Engine(default_params(assoc_sorted=mode))
+        e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+        knn, corr = e.associate_map(qs[0]["corner"], qs[0]["surf"], qs[0]["init"])
+        far = np.array([500.0, 500.0, 50.0, 0, 0, 0, 1.0])
+        rc, xs, st = e.scan2map_batch([q["corner"] for q in qs] + [qs[0]["corner"]],
+                                      [q["surf"] for q in qs] + [qs[0]["surf"]],
+                                      [q["init"] for q in qs] + [far], want_stats=True)
+        res[mode] = (knn, corr, xs, [s["n_edge"] + s["n_plane"] for s in st])
+        e.close()
+    assert np.array_equal(res[1][0], res[2][0]) and np.array_equal(res[1][1], res[2][1])
+    assert np.array_equal(res[1][2], res[2][2]) and res[1][3] == res[2][3]
+    _, _, _, kidx = _oracle_corr_full(P, vlp16_case, qs[0], qs[0]["init"])
+    assert np.array_equal(res[2][0], kidx)
+
+
 def test_no_correspondence_leaves_pose_untouched(eng, vlp16_case):
     q = vlp16_case["queries"][0]
     far = np.array([500.0, 500.0, 50.0, 0, 0, 0, 1.0])
