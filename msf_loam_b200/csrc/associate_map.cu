@@ -68,12 +68,15 @@ __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy,
   const float loy = exact_cells ? __fsub_rn(qy, fyq) : 0.f, hiy = exact_cells ? __fsub_rn(fyq + 1.0f, qy) : 0.f;
   const float loz = exact_cells ? __fsub_rn(qz, fzq) : 0.f, hiz = exact_cells ? __fsub_rn(fzq + 1.0f, qz) : 0.f;
   const float bx2[2] = {__fmul_rn(lox, lox), __fmul_rn(hix, hix)};  // left cell, right cell
-  // nearest-first row order: centre, 4 face neighbours, 4 diagonal neighbours
-  constexpr int kDy[9] = {0, -1, 1, 0, 0, -1, -1, 1, 1};
-  constexpr int kDz[9] = {0, 0, 0, -1, 1, -1, 1, -1, 1};
-#pragma unroll
+  // nearest-first row order: centre, 4 face neighbours, 4 diagonal neighbours; (dy+1, dz+1) packed
+  // 2 bits each so the row loop stays rolled (the unrolled form thrashed the instruction cache)
+  //            r:   0      1      2      3      4      5      6      7      8
+  //      (dy,dz): (0,0) (-1,0) (1,0) (0,-1) (0,1) (-1,-1) (-1,1) (1,-1) (1,1)
+  constexpr uint32_t kDyPacked = 1u | (0u << 2) | (2u << 4) | (1u << 6) | (1u << 8) | (0u << 10) | (0u << 12) | (2u << 14) | (2u << 16);
+  constexpr uint32_t kDzPacked = 1u | (1u << 2) | (1u << 4) | (0u << 6) | (2u << 8) | (0u << 10) | (2u << 12) | (0u << 14) | (2u << 16);
+#pragma unroll 1
   for (int r = 0; r < 9; ++r) {
-    const int dy = kDy[r], dz = kDz[r];
+    const int dy = (int)((kDyPacked >> (2 * r)) & 3u) - 1, dz = (int)((kDzPacked >> (2 * r)) & 3u) - 1;
     const float by = dy == 0 ? 0.f : (dy < 0 ? loy : hiy), bz = dz == 0 ? 0.f : (dz < 0 ? loz : hiz);
     const float by2 = __fmul_rn(by, by), bz2 = __fmul_rn(bz, bz);
     const float row_lb = __fadd_rn(by2, bz2);  // (0 + by^2) + bz^2
@@ -84,7 +87,7 @@ __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy,
     const float lbl = __fadd_rn(__fadd_rn(bx2[0], by2), bz2), lbr = __fadd_rn(__fadd_rn(bx2[1], by2), bz2);
     const uint32_t js = (lbl > t.d[4] || lbl >= thresh) ? s1 : s0;
     const uint32_t je = (lbr > t.d[4] || lbr >= thresh) ? s2 : s3;
-#pragma unroll 4
+#pragma unroll 2
     for (uint32_t j = js; j < je; ++j) {
       const float4 m = __ldg(g.pts_sorted + j);
       const float dx = __fsub_rn(qx, m.x), dy2 = __fsub_rn(qy, m.y), dz2 = __fsub_rn(qz, m.z);
@@ -149,6 +152,15 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
   uint32_t key;
   if (is_corner) key = c < 0 ? ncell_c : (uint32_t)c;
   else key = ncell_c + 1u + (c < 0 ? ncell_s : (uint32_t)c);
+  // refine the order inside a cell by a 4x4x4 sub-cell index so the lanes of a warp are spatial
+  // neighbours (<= 0.25 m apart): their row / cell pruning decisions in knn5_grid then agree
+  {
+    const GridView &g = is_corner ? gc : gs;
+    const float ux = x.x * g.inv_edge, uy = x.y * g.inv_edge, uz = x.z * g.inv_edge;
+    const int sx = min(3, max(0, (int)((ux - floorf(ux)) * 4.0f))), sy = min(3, max(0, (int)((uy - floorf(uy)) * 4.0f))),
+              sz = min(3, max(0, (int)((uz - floorf(uz)) * 4.0f)));
+    key = (key << 6) | (uint32_t)((sz * 4 + sy) * 4 + sx);
+  }
   xq[k] = make_float4(x.x, x.y, x.z, 0.f);
   keys[k] = key;
   vals[k] = k;
@@ -273,6 +285,8 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   const long long ncell = (long long)gc.nx * gc.ny * gc.nz + (long long)gs.nx * gs.ny * gs.nz + 2;
   int end_bit = 1;
   while ((1ll << end_bit) < ncell) ++end_bit;
+  end_bit += 6;  // 4x4x4 sub-cell index in the low bits
+  if (end_bit > 32) { set_error("submap grid too large for the sorted association path"); return MSFL_ERR_GRID; }
   cub::DoubleBuffer<uint32_t> dk(e->a_keys.as<uint32_t>(), e->a_keys_alt.as<uint32_t>()),
       dv(e->a_vals.as<uint32_t>(), e->a_vals_alt.as<uint32_t>());
   size_t tmp = 0;

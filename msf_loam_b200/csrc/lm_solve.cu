@@ -48,9 +48,10 @@ __device__ __forceinline__ void acc_row(double (&acc)[kAcc], const double J[6], 
 __device__ __forceinline__ double huber_scale(double s, double a, double &cost) {
   const double b = a * a;
   if (s > b) {
-    const double r = sqrt(s);
-    cost += 0.5 * (2.0 * a * r - b);
-    return sqrt(fmax(2.2250738585072014e-308, a / r));
+    // rho = 2 a sqrt(s) - a^2, rho' = a / sqrt(s); one rsqrt feeds both (sqrt(s) = s * rsqrt(s))
+    const double rs = rsqrt(s);
+    cost += 0.5 * (2.0 * a * (s * rs) - b);
+    return sqrt(fmax(2.2250738585072014e-308, a * rs));
   }
   cost += 0.5 * s;
   return 1.0;
@@ -154,7 +155,8 @@ __device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) 
 // in shared memory and complete on an mbarrier; a 3-stage ring keeps two tiles in flight while one
 // is consumed, which takes the L2/HBM latency off the fp64 critical path.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTile = kLmThreads;  // one entry per thread per tile
+constexpr int kPerThread = 2;              // entries per thread per tile
+constexpr int kTile = kLmThreads * kPerThread;
 constexpr int kStages = 3;
 constexpr int kStageBytes = kTile * 16 + kTile * 48;
 
@@ -231,10 +233,11 @@ __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &
     const bool edge = t < ts.tiles_e;
     const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
     const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
-    if (tid < cnt) {
+#pragma unroll 1
+    for (uint32_t ent = tid; ent < cnt; ent += kLmThreads) {
       const unsigned char *buf = ring + stage * kStageBytes;
-      const float4 pf = reinterpret_cast<const float4 *>(buf)[tid];
-      const double2 *cp = reinterpret_cast<const double2 *>(buf + kTile * 16 + tid * 48);
+      const float4 pf = reinterpret_cast<const float4 *>(buf)[ent];
+      const double2 *cp = reinterpret_cast<const double2 *>(buf + kTile * 16 + ent * 48);
       const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];
       const double a0 = c0.x, a1 = c0.y, a2 = c1.x, n0 = c1.y, n1 = c2.x, n2 = c2.y;
       if (!(n0 == 0.0 && n1 == 0.0 && n2 == 0.0)) {

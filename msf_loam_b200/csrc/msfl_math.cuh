@@ -200,34 +200,54 @@ __device__ inline void lstsq_5x3(double A[5][3], double b[5], double x[3]) {
 // 6x6 SPD solve by Cholesky (the LM normal equations).  Returns false when not positive
 // definite / non-finite (Ceres LINEAR_SOLVER_FAILURE -> invalid step).
 __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6], double y[6]) {
+  // every loop has compile-time bounds and is fully unrolled, so L, z live in registers
   double L[36];
+#pragma unroll
   for (int i = 0; i < 36; ++i) L[i] = 0;
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
-    if (!(d > 0) || !isfinite(d)) return false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < j) d -= L[j * 6 + k] * L[j * 6 + k];
+    if (!(d > 0) || !isfinite(d)) ok = false;
     d = sqrt(d);
     L[j * 6 + j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      double s = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-      L[i * 6 + j] = s / d;
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double s = A[i * 6 + j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < j) s -= L[i * 6 + k] * L[j * 6 + k];
+        L[i * 6 + j] = s * inv;
+      }
     }
   }
+  if (!ok) return false;
   double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * z[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < i) s -= L[i * 6 + k] * z[k];
     z[i] = s / L[i * 6 + i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k > i) s -= L[k * 6 + i] * y[k];
     y[i] = s / L[i * 6 + i];
   }
+#pragma unroll
   for (int i = 0; i < 6; ++i)
-    if (!isfinite(y[i])) return false;
-  return true;
+    if (!isfinite(y[i])) ok = false;
+  return ok;
 }
 
 // index of the (u,v) entry, u <= v, in the packed upper triangle of a 6x6 (row-major)

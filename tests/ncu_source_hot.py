@@ -25,7 +25,8 @@ for r in rows:
     if hdr and r and r[0].isdigit():
         key = (cur_file, int(r[0]), r[1].strip()[:90])
         a = agg.setdefault(key, [0, 0, 0])
-        a[0] += int(r[i_s] or 0); a[1] += int(r[i_i] or 0); a[2] += int(r[i_t] or 0)
+        f=lambda v: int(v) if v.strip().lstrip('-').isdigit() else 0
+        a[0] += f(r[i_s]); a[1] += f(r[i_i]); a[2] += f(r[i_t])
 tot_s = sum(a[0] for a in agg.values()) or 1
 tot_i = sum(a[1] for a in agg.values()) or 1
 print(f"total samples {tot_s}, warp instructions {tot_i}")
