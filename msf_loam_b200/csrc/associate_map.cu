@@ -169,8 +169,10 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
 // Association kernel.  SORTED = false: thread k handles flat query k and transforms it itself.
 // SORTED = true: thread s handles query perm[s] (queries ordered by the cell of their transformed
 // point, so the lanes of a warp walk the same candidate ranges: uniform trip counts and broadcast
-// loads) and reads the transformed point stored by k_transform_keys.
-template <bool SORTED>
+// loads).  STORED_X: read the transformed point stored by k_transform_keys (the permutation was
+// built for the current poses); otherwise transform here (the permutation of an earlier outer
+// iteration is reused -- it is only a locality hint, the result does not depend on it).
+template <bool SORTED, bool STORED_X>
 __global__ void __launch_bounds__(128)
 k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
                 const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
@@ -182,7 +184,7 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
   const uint32_t k = SORTED ? __ldg(perm + slot) : slot;
   const bool is_corner = k < n_corner_total;
   float3 x;
-  if (SORTED) {
+  if (STORED_X) {
     const float4 xs = __ldg(xq + k);
     x = make_float3(xs.x, xs.y, xs.z);
   } else {
@@ -258,7 +260,7 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
 
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn) {
+                         double *d_corr, int32_t *d_knn, bool reuse_order) {
   const uint32_t total = n_corner_total + n_surf_total;
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
@@ -267,7 +269,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   const bool sorted = mode == 2 || (mode == 0 && total >= 65536u);
   if (!sorted) {
     stage_begin(e, 0);
-    k_associate_map<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
+    k_associate_map<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
                                                                        d_s_off, n_surf_total, d_poses, nullptr, nullptr,
                                                                        d_corr, d_knn);
     stage_end(e);
@@ -277,6 +279,18 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   }
   // sorted path: transform + cell keys -> radix sort -> association in cell order
   int rc;
+  if (reuse_order && e->a_perm_valid == total && e->a_perm != nullptr) {
+    // later outer iteration: poses moved by centimetres, the previous cell order is still a good
+    // locality hint -> skip the transform/sort pass, transform inside the association kernel
+    stage_begin(e, 0);
+    k_associate_map<true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total,
+                                                                             d_qs, d_s_off, n_surf_total, d_poses, nullptr,
+                                                                             e->a_perm, d_corr, d_knn);
+    stage_end(e);
+    e->launches += 1;
+    MSFL_CUDA_OK(cudaGetLastError());
+    return MSFL_OK;
+  }
   if ((rc = e->a_xq.reserve((size_t)total * 16))) return rc;
   if ((rc = e->a_keys.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_keys_alt.reserve((size_t)total * 4))) return rc;
@@ -298,10 +312,12 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
                                                               dv.Current());
   MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
   stage_end(e);
+  e->a_perm = dv.Current();
+  e->a_perm_valid = total;
   stage_begin(e, 0);
-  k_associate_map<true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
-                                                                    d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(),
-                                                                    dv.Current(), d_corr, d_knn);
+  k_associate_map<true, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
+                                                                          d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(),
+                                                                          e->a_perm, d_corr, d_knn);
   stage_end(e);
   e->launches += 2 + 3;
   MSFL_CUDA_OK(cudaGetLastError());

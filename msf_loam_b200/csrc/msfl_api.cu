@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "msfl_internal.h"
@@ -275,6 +276,8 @@ void msfl_destroy(msfl_engine *e) {
   for (PinBuf *b : pbs) b->release();
   for (auto &s : e->stage_events) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
+  for (auto ev : e->chunk_events) cudaEventDestroy(ev);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->own_stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -345,8 +348,11 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   int rc;
   if ((rc = e->d_corr.reserve(((size_t)nct + nst + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
+  e->a_perm_valid = 0;  // a new batch: the cell order of the previous one does not apply
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
-    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr)))
+    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr,
+                                   /*reuse_order=*/false)))  // measured: re-sorting per outer iteration is faster
+                                                              // (the first solve moves points by up to ~0.3 m)
       return rc;
     stage_begin(e, 1);
     rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
@@ -431,12 +437,141 @@ static int upload_batch(msfl_engine *e, int B, const msfl_cloud *corner, const m
   return MSFL_OK;
 }
 
+// Large host batches: split the scans into chunks and overlap the H2D copy of chunk c+1 (copy
+// stream) with the kernels of chunk c (engine stream).  Scans are independent, so the poses are
+// bit-identical to the single-shot path.
+static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *corner, const msfl_cloud *surf,
+                                    double *poses_tq, msfl_stats *stats, int n_chunks) {
+  int rc;
+  size_t nct = 0, nst = 0;
+  bool contiguous = true;
+  for (int b = 0; b < B; ++b) {
+    if ((rc = check_cloud(&corner[b], false, "scan_corner"))) return rc;
+    if ((rc = check_cloud(&surf[b], false, "scan_surf"))) return rc;
+    const msfl_cloud *cl[2] = {&corner[b], &surf[b]};
+    const msfl_cloud *nx[2] = {b + 1 < B ? &corner[b + 1] : nullptr, b + 1 < B ? &surf[b + 1] : nullptr};
+    for (int c = 0; c < 2; ++c) {
+      if (cl[c]->stride != 16 || cl[c]->off_xyz != 0) contiguous = false;
+      if (nx[c] && (const char *)nx[c]->data != (const char *)cl[c]->data + cl[c]->n * 16) contiguous = false;
+    }
+    nct += corner[b].n;
+    nst += surf[b].n;
+  }
+  if (nct + nst > 0x7fffffffull) { set_error("batch too large"); return MSFL_ERR_ARG; }
+  if (!e->copy_stream) MSFL_CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  while ((int)e->chunk_events.size() < n_chunks) {
+    cudaEvent_t ev;
+    MSFL_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->chunk_events.push_back(ev);
+  }
+  const size_t q_bytes = (nct + nst) * 16, q_pad = (q_bytes + 15) & ~(size_t)15;
+  const size_t off_bytes = (size_t)2 * (B + n_chunks) * 4, off_pad = (off_bytes + 15) & ~(size_t)15;
+  const size_t pose_bytes = (size_t)B * 7 * 8;
+  if ((rc = e->h_stage.reserve(q_pad + off_pad + pose_bytes))) return rc;
+  if ((rc = e->d_queries.reserve(q_pad + off_pad + pose_bytes))) return rc;
+  char *h = e->h_stage.as<char>(), *d = e->d_queries.as<char>();
+  float *hq = (float *)h;
+  int32_t *hoff = (int32_t *)(h + q_pad);
+  double *hpose = (double *)(h + q_pad + off_pad);
+  // chunk tables: per chunk two rebased offset tables (Bc+1 each), stored back to back
+  struct Chunk { int b0, b1; size_t ci0, ci1, si0, si1; size_t off_pos; };
+  std::vector<Chunk> ch(n_chunks);
+  {
+    size_t ci = 0, si = 0, pos = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      Chunk &k = ch[c];
+      // geometric chunk sizes (1, 2, 4, ... , rest): the copy of chunk c+1 (PCIe is ~2x faster than the
+      // kernels consume scans) hides behind the kernels of chunk c, and only the small first copy is exposed
+      const long long denom = 1ll << n_chunks;
+      k.b0 = c == 0 ? 0 : (int)((long long)B * ((1ll << c) - 1) / denom);
+      k.b1 = c == n_chunks - 1 ? B : (int)((long long)B * ((1ll << (c + 1)) - 1) / denom);
+      k.ci0 = ci; k.si0 = si; k.off_pos = pos;
+      const int Bc = k.b1 - k.b0;
+      int32_t *co = hoff + pos, *so = co + (Bc + 1);
+      for (int b = k.b0; b < k.b1; ++b) {
+        co[b - k.b0] = (int32_t)(ci - k.ci0);
+        so[b - k.b0] = (int32_t)(si - k.si0);
+        ci += corner[b].n;
+        si += surf[b].n;
+      }
+      co[Bc] = (int32_t)(ci - k.ci0);
+      so[Bc] = (int32_t)(si - k.si0);
+      k.ci1 = ci; k.si1 = si;
+      pos += 2 * (size_t)(Bc + 1);
+    }
+  }
+  memcpy(hpose, poses_tq, pose_bytes);
+  // scratch sized once for the largest chunk so no buffer is re-allocated while kernels run
+  size_t max_total = 0;
+  for (auto &k : ch) max_total = std::max(max_total, (k.ci1 - k.ci0) + (k.si1 - k.si0));
+  if ((rc = e->d_corr.reserve((max_total + 1) * 6 * sizeof(double)))) return rc;
+  if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
+  if ((rc = e->a_xq.reserve(max_total * 16))) return rc;
+  if ((rc = e->a_keys.reserve(max_total * 4))) return rc;
+  if ((rc = e->a_keys_alt.reserve(max_total * 4))) return rc;
+  if ((rc = e->a_vals.reserve(max_total * 4))) return rc;
+  if ((rc = e->a_vals_alt.reserve(max_total * 4))) return rc;
+  if ((rc = e->a_tmp.reserve(max_total * 8 + (1 << 20)))) return rc;
+  msfl_stats *d_stats = nullptr;
+  if (stats) {
+    if ((rc = e->d_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    if ((rc = e->h_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    d_stats = e->d_stats.as<msfl_stats>();
+    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, (size_t)B * sizeof(msfl_stats), e->stream));
+  }
+  if ((rc = e->h_poses.reserve(pose_bytes))) return rc;
+  cudaStream_t cs = e->copy_stream;
+  MSFL_CUDA_OK(cudaMemcpyAsync(d + q_pad, h + q_pad, off_pad + pose_bytes, cudaMemcpyHostToDevice, cs));
+  float4 *d_qc = (float4 *)d, *d_qs = d_qc + nct;
+  const int32_t *d_off = (const int32_t *)(d + q_pad);
+  double *d_poses = (double *)(d + q_pad + off_pad);
+  for (int c = 0; c < n_chunks; ++c) {
+    const Chunk &k = ch[c];
+    const size_t ncc = k.ci1 - k.ci0, nsc = k.si1 - k.si0;
+    if (contiguous) {
+      if (ncc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qc + k.ci0, (const char *)corner[0].data + k.ci0 * 16, ncc * 16, cudaMemcpyHostToDevice, cs));
+      if (nsc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qs + k.si0, (const char *)surf[0].data + k.si0 * 16, nsc * 16, cudaMemcpyHostToDevice, cs));
+    } else {
+      size_t ci = k.ci0, si = k.si0;
+      for (int b = k.b0; b < k.b1; ++b) {
+        pack_cloud_host(&corner[b], hq + 4 * ci, nullptr);
+        pack_cloud_host(&surf[b], hq + 4 * (nct + si), nullptr);
+        ci += corner[b].n;
+        si += surf[b].n;
+      }
+      if (ncc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qc + k.ci0, hq + 4 * k.ci0, ncc * 16, cudaMemcpyHostToDevice, cs));
+      if (nsc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qs + k.si0, hq + 4 * (nct + k.si0), nsc * 16, cudaMemcpyHostToDevice, cs));
+    }
+    MSFL_CUDA_OK(cudaEventRecord(e->chunk_events[c], cs));
+    MSFL_CUDA_OK(cudaStreamWaitEvent(e->stream, e->chunk_events[c], 0));
+    const int Bc = k.b1 - k.b0;
+    const int32_t *co = d_off + k.off_pos, *so = co + (Bc + 1);
+    if ((rc = scan2map_enqueue(e, Bc, d_qc + k.ci0, co, (uint32_t)ncc, d_qs + k.si0, so, (uint32_t)nsc, d_poses + (size_t)k.b0 * 7,
+                               d_stats ? d_stats + k.b0 : nullptr)))
+      return rc;
+  }
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->h_poses.p, d_poses, pose_bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (stats)
+    MSFL_CUDA_OK(cudaMemcpyAsync(e->h_stats.p, d_stats, (size_t)B * sizeof(msfl_stats), cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  memcpy(poses_tq, e->h_poses.p, pose_bytes);
+  if (stats) memcpy(stats, e->h_stats.p, (size_t)B * sizeof(msfl_stats));
+  return MSFL_OK;
+}
+
 int msfl_scan2map_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
                         double *poses_tq, msfl_stats *stats) {
   if (!e || B <= 0 || !scan_corner || !scan_surf || !poses_tq) { set_error("msfl_scan2map_batch: bad argument"); return MSFL_ERR_ARG; }
   if (!e->has_submap) { set_error("msfl_scan2map: no submap set"); return MSFL_ERR_NOSUBMAP; }
   MSFL_CUDA_OK(cudaSetDevice(e->device));
   int rc;
+  {
+    // pipeline H2D against compute when the batch is big enough to split into efficient chunks
+    size_t total = 0;
+    for (int b = 0; b < B; ++b) total += scan_corner[b].n + scan_surf[b].n;
+    const int n_chunks = (B >= 256 && total >= 2000000) ? 4 : ((B >= 64 && total >= 500000) ? 2 : 1);
+    if (n_chunks >= 2) return scan2map_batch_pipelined(e, B, scan_corner, scan_surf, poses_tq, stats, n_chunks);
+  }
   uint32_t nct = 0, nst = 0;
   if ((rc = upload_batch(e, B, scan_corner, scan_surf, poses_tq, &nct, &nst))) return rc;
   const size_t q_pad = (((size_t)nct + nst) * 16 + 15) & ~(size_t)15;

@@ -78,6 +78,8 @@ struct msfl_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;         // H2D of chunk c+1 overlaps the kernels of chunk c
+  std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
   int sm_count = 148;
 
@@ -96,6 +98,8 @@ struct msfl_engine {
   msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
   // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp;
+  const uint32_t *a_perm = nullptr;  // cell-order permutation of the current batch (valid for a_perm_valid queries)
+  uint32_t a_perm_valid = 0;
 
   // odometry scratch
   msfl::DevBuf d_last_corner, d_last_surf, d_last_corner_ring, d_last_surf_ring, d_ring_tab, d_assoc;
@@ -123,7 +127,7 @@ void submap_release(Submap &m);
 // same flat order.
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn);
+                         double *d_corr, int32_t *d_knn, bool reuse_order = false);
 
 // ---- lm_solve.cu
 // outer: outer-iteration index (stats slot); min_corr: 0 for mapping, params.min_correspondences for odometry

@@ -127,6 +127,30 @@ def test_sorted_association_path_is_bitwise_identical(vlp16_case):
     assert np.array_equal(res[2][0], kidx)
 
 
+def test_large_host_batch_pipelined_path_bitwise(eng, vlp16_case):
+    """B = 512 host batch (> 2M queries) takes the chunked H2D/compute pipeline; every replica must
+    equal the single-scan result bit for bit, for packed-contiguous and for PCL-layout inputs."""
+    qs = vlp16_case["queries"]
+    singles = [eng.scan2map(q["corner"], q["surf"], q["init"])[1] for q in qs]
+    B = 512
+    inits = np.stack([qs[i % 3]["init"] for i in range(B)])
+    # (a) one contiguous pinned-style buffer per class
+    cat_c = np.concatenate([qs[i % 3]["corner"] for i in range(B)])
+    cat_s = np.concatenate([qs[i % 3]["surf"] for i in range(B)])
+    co = np.concatenate([[0], np.cumsum([qs[i % 3]["corner"].shape[0] for i in range(B)])])
+    so = np.concatenate([[0], np.cumsum([qs[i % 3]["surf"].shape[0] for i in range(B)])])
+    rc, xs, _ = eng.scan2map_batch([cat_c[co[i]:co[i + 1]] for i in range(B)], [cat_s[so[i]:so[i + 1]] for i in range(B)], inits)
+    assert rc == 0
+    for i in range(B):
+        assert np.array_equal(xs[i], singles[i % 3])
+    # (b) separate 32-byte PCL-layout clouds (host repack per chunk)
+    pc = [to_pcl(q["corner"]) for q in qs]
+    ps = [to_pcl(q["surf"]) for q in qs]
+    rc, xs2, st = eng.scan2map_batch([pc[i % 3] for i in range(B)], [ps[i % 3] for i in range(B)], inits, want_stats=True)
+    assert rc == 0 and np.array_equal(xs2, xs)
+    assert st[B - 1]["n_plane"] == st[(B - 1) % 3]["n_plane"] and st[B - 1]["lm"][1]["n_attempts"] > 0
+
+
 def test_no_correspondence_leaves_pose_untouched(eng, vlp16_case):
     q = vlp16_case["queries"][0]
     far = np.array([500.0, 500.0, 50.0, 0, 0, 0, 1.0])
