@@ -192,6 +192,27 @@ int msfl_scan2map_batch_device(msfl_engine *e, int B,
 int msfl_associate_map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
                        const double pose_tq[7], int32_t *knn_idx, double *corr);
 
+/* ---- scan-to-map, IMU-initialised branch: the LiDAR part of
+ *      MappingScanMatcher::MatchScan2Map with is_initialized == true
+ *      (mapping_scan_matcher.cc:107-246 with LidarEdgeFactorDeskewSE3 / LidarPlaneFactorDeskewSE3,
+ *      lidar_factor.cc:46-100, and GetDeltaQP, scan_undistortion.cc:22-42).  Each point carries its
+ *      relative time in `intensity`; the preintegration buffers give (delta_q, delta_p) at that time.
+ *      The speed-bias block is constant in the reference's problem (:94) so only the pose is
+ *      optimised and *velocity is returned unchanged.  The IMU-only predict (:35-60) stays with the
+ *      caller: pose_tq comes in as pose_j after it. ------------------------------------------------ */
+typedef struct msfl_deskew {
+  const double *sum_dt;   /* [n]    IntegrationBase::sum_dt_buf_                */
+  const double *delta_q;  /* [n][4] delta_q_buf_ coefficients x y z w           */
+  const double *delta_p;  /* [n][3] delta_p_buf_                                */
+  int32_t n;
+  int32_t _pad;
+  double velocity[3];     /* bias_j.head<3>()                                   */
+  double gravity[3];      /* gravity_vector                                     */
+} msfl_deskew;
+/* MSFL_ERR_ARG when a point time lies outside [sum_dt[0], sum_dt[n-1]] (the reference CHECK-fails). */
+int msfl_scan2map_deskew(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                         const msfl_deskew *deskew, double pose_tq[7], msfl_stats *stats);
+
 /* ---- scan-to-scan: OdometryScanMatcher::MatchScan2Scan
  *      (odometry_scan_matcher.h:10-12, odometry_scan_matcher.cc:43-285) ----------------------
  * last_* must carry rings and be ring-sorted (Appendix B of SURVEY.md; the extraction emits

@@ -24,7 +24,7 @@ EXPORTS = [
     "msfl_destroy", "msfl_sync", "msfl_stream", "msfl_launch_count", "msfl_set_profiling",
     "msfl_get_profile", "msfl_set_submap",
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
-    "msfl_scan2map_batch_device", "msfl_associate_map", "msfl_scan2scan", "msfl_associate_scan",
+    "msfl_scan2map_batch_device", "msfl_scan2map_deskew", "msfl_associate_map", "msfl_scan2scan", "msfl_associate_scan",
     "msfl_extract_features", "msfl_voxel_grid", "msfl_accumulate",
 ]
 
@@ -87,6 +87,12 @@ class Stats(C.Structure):
             "n_edge": list(self.n_edge)[: self.n_outer], "n_plane": list(self.n_plane)[: self.n_outer],
             "lm": [self.lm[i].as_dict() for i in range(self.n_outer)],
         }
+
+
+class Deskew(C.Structure):
+    _fields_ = [("sum_dt", C.POINTER(C.c_double)), ("delta_q", C.POINTER(C.c_double)),
+                ("delta_p", C.POINTER(C.c_double)), ("n", C.c_int32), ("_pad", C.c_int32),
+                ("velocity", C.c_double * 3), ("gravity", C.c_double * 3)]
 
 
 class Features(C.Structure):

@@ -10,6 +10,7 @@
 #include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "msfl.h"
 #include "slam/local/scan_matching/mapping_scan_matcher.h"
@@ -86,10 +87,32 @@ class GpuMappingScanMatcher : public MappingScanMatcher {
                      const bool is_initialized, const std::shared_ptr<IntegrationBase> &preintegration,
                      const Vector3d &gravity_vector, const RobotState &prev_state, Rigid3d *pose_estimate_map_scan2world,
                      Vector3d *velocity) override {
-    if (is_initialized)  // IMU-deskew factor variants are not on the GPU path yet
-      return MappingScanMatcher::MatchScan2Map(cloud_map, scan_curr, is_initialized, preintegration, gravity_vector,
-                                               prev_state, pose_estimate_map_scan2world, velocity);
     using msfl_adapter::View;
+    if (is_initialized) {
+      // IMU side-car stays on the host: the IMU-only Ceres predict (mapping_scan_matcher.cc:28-60) must be
+      // factored into a protected base-class method `PredictWithImu` (a pure move of those lines); it sets
+      // *pose_estimate_map_scan2world = pose_j and *velocity = bias_j.head<3>().
+      this->PredictWithImu(prev_state, pose_estimate_map_scan2world, velocity);
+      const msfl_cloud mc = View(*cloud_map.cloud_corner_less_sharp, false), ms = View(*cloud_map.cloud_surf_less_flat, false);
+      const msfl_cloud sc = View(*scan_curr.cloud_corner_less_sharp, false), ss = View(*scan_curr.cloud_surf_less_flat, false);
+      CHECK_EQ(msfl_set_submap(engine_.get(), &mc, &ms), MSFL_OK) << msfl_last_error();
+      // IntegrationBase buffers -> msfl_deskew (GetDeltaQP inputs, scan_undistortion.cc:22-42)
+      const auto &pi = *preintegration;
+      std::vector<double> dq(4 * pi.delta_q_buf_.size()), dp(3 * pi.delta_p_buf_.size());
+      for (size_t i = 0; i < pi.delta_q_buf_.size(); ++i) {
+        const auto &q = pi.delta_q_buf_[i];
+        dq[4 * i] = q.x(); dq[4 * i + 1] = q.y(); dq[4 * i + 2] = q.z(); dq[4 * i + 3] = q.w();
+        for (int k = 0; k < 3; ++k) dp[3 * i + k] = pi.delta_p_buf_[i][k];
+      }
+      msfl_deskew dk{pi.sum_dt_buf_.data(), dq.data(), dp.data(), (int32_t)pi.sum_dt_buf_.size(), 0,
+                     {(*velocity)[0], (*velocity)[1], (*velocity)[2]},
+                     {gravity_vector[0], gravity_vector[1], gravity_vector[2]}};
+      double pose[7];
+      msfl_adapter::ToArray(*pose_estimate_map_scan2world, pose);
+      CHECK_EQ(msfl_scan2map_deskew(engine_.get(), &sc, &ss, &dk, pose, nullptr), MSFL_OK) << msfl_last_error();
+      *pose_estimate_map_scan2world = msfl_adapter::FromArray(pose);
+      return true;  // the speed-bias block is constant in the reference's problem (:94): *velocity is unchanged
+    }
     const msfl_cloud mc = View(*cloud_map.cloud_corner_less_sharp, false), ms = View(*cloud_map.cloud_surf_less_flat, false);
     const msfl_cloud sc = View(*scan_curr.cloud_corner_less_sharp, false), ss = View(*scan_curr.cloud_surf_less_flat, false);
     CHECK_EQ(msfl_set_submap(engine_.get(), &mc, &ms), MSFL_OK) << msfl_last_error();  // the two kd-tree builds (:66-72)

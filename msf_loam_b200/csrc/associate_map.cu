@@ -166,24 +166,106 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
   vals[k] = k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// IMU-deskew branch (mapping_scan_matcher.cc:112-121, :182-191 with
+// is_initialized == true).  Per query: (dq, dp) = GetDeltaQP(preintegration, dt)
+// (scan_undistortion.cc:22-42: upper_bound + Eigen slerp + lerp), dt = intensity; the kNN query is
+//   TransformPoint(pose * Rigid3d{q^-1 (V dt - g dt^2 / 2) + dp, dq}, p)
+// and the factor sees p' = dq p + dp (fp64) and the constant offset o = V dt - g dt^2 / 2
+// (lidar_factor.cc:53,81), which is folded into the line point / plane centre (C' = C - o).
+// ---------------------------------------------------------------------------------------------
+struct DeskewTable {
+  const double *sum_dt, *delta_q, *delta_p;  // device arrays: [n], [n][4] xyzw, [n][3]
+  int n;
+  double V[3], G[3];
+};
+
+// per query: dq(4) dp(3) dt(1) -> dsk[8]; p' -> pprime (double4).  flag |= 1 when dt is out of range.
+__global__ void k_deskew_prepare(DeskewTable tb, const float4 *__restrict__ q, uint32_t n, double *__restrict__ dsk,
+                                 double *__restrict__ pprime, int *__restrict__ flag) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float4 p = q[k];
+  const double dt = (double)p.w;  // auto dt = pointOri.intensity  (:114)
+  if (tb.n < 2 || !(dt <= tb.sum_dt[tb.n - 1] && dt >= tb.sum_dt[0])) {  // CHECK scan_undistortion.cc:26
+    atomicOr(flag, 1);
+    return;
+  }
+  int lo = 0, hi = tb.n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (dt < tb.sum_dt[mid]) hi = mid; else lo = mid + 1;
+  }
+  int idx = lo - 1;
+  if (idx > tb.n - 2) idx = tb.n - 2;
+  const double s = __ddiv_rn(__dsub_rn(dt, tb.sum_dt[idx]), __dsub_rn(tb.sum_dt[idx + 1], tb.sum_dt[idx]));
+  const double *qa = tb.delta_q + 4 * idx, *qb = qa + 4;
+  const double d = qa[0] * qb[0] + qa[1] * qb[1] + qa[2] * qb[2] + qa[3] * qb[3];
+  double s0, s1;
+  if (fabs(d) >= 1.0 - 2.220446049250313e-16) {
+    s0 = 1.0 - s; s1 = s;
+  } else {
+    const double th = acos(fabs(d)), sn = sin(th);
+    s0 = sin((1.0 - s) * th) / sn;
+    s1 = sin(s * th) / sn;
+  }
+  if (d < 0) s1 = -s1;
+  double dq[4], dp[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dq[i] = __dadd_rn(__dmul_rn(s0, qa[i]), __dmul_rn(s1, qb[i]));
+  const double *pa = tb.delta_p + 3 * idx, *pb = pa + 3;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dp[i] = __dadd_rn(__dmul_rn(1 - s, pa[i]), __dmul_rn(s, pb[i]));
+  double *o = dsk + (size_t)k * 8;
+  o[0] = dq[0]; o[1] = dq[1]; o[2] = dq[2]; o[3] = dq[3]; o[4] = dp[0]; o[5] = dp[1]; o[6] = dp[2]; o[7] = dt;
+  double r0, r1, r2;
+  quat_rotate_exact(dq, (double)p.x, (double)p.y, (double)p.z, r0, r1, r2);
+  double *pp = pprime + (size_t)k * 4;
+  pp[0] = __dadd_rn(r0, dp[0]); pp[1] = __dadd_rn(r1, dp[1]); pp[2] = __dadd_rn(r2, dp[2]); pp[3] = 0.0;
+}
+
+// the total transform of the deskew branch applied to p, rounded to fp32 like TransformPoint
+__device__ __forceinline__ float3 deskew_transform(const double pose[7], const DeskewTable &tb, const double *dsk8, float px,
+                                                   float py, float pz, double o[3]) {
+  const double dt = dsk8[7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = __dsub_rn(__dmul_rn(tb.V[i], dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, tb.G[i]), dt), dt));
+  const double qc[4] = {-pose[3], -pose[4], -pose[5], pose[6]};
+  double t0, t1, t2, u0, u1, u2;
+  quat_rotate_exact(qc, o[0], o[1], o[2], t0, t1, t2);
+  t0 = __dadd_rn(t0, dsk8[4]); t1 = __dadd_rn(t1, dsk8[5]); t2 = __dadd_rn(t2, dsk8[6]);
+  quat_rotate_exact(pose + 3, t0, t1, t2, u0, u1, u2);
+  const double *a = pose + 3, *b = dsk8;  // (q * dq).normalized(), Eigen product order
+  double qt[4];
+  qt[3] = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(a[3], b[3]), __dmul_rn(a[0], b[0])), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+  qt[0] = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(a[3], b[0]), __dmul_rn(a[0], b[3])), __dmul_rn(a[1], b[2])), __dmul_rn(a[2], b[1]));
+  qt[1] = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(a[3], b[1]), __dmul_rn(a[1], b[3])), __dmul_rn(a[2], b[0])), __dmul_rn(a[0], b[2]));
+  qt[2] = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(a[3], b[2]), __dmul_rn(a[2], b[3])), __dmul_rn(a[0], b[1])), __dmul_rn(a[1], b[0]));
+  const double nq = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(qt[0], qt[0]), __dmul_rn(qt[1], qt[1])), __dmul_rn(qt[2], qt[2])), __dmul_rn(qt[3], qt[3])));
+  double T[7] = {__dadd_rn(u0, pose[0]), __dadd_rn(u1, pose[1]), __dadd_rn(u2, pose[2]),
+                 __ddiv_rn(qt[0], nq), __ddiv_rn(qt[1], nq), __ddiv_rn(qt[2], nq), __ddiv_rn(qt[3], nq)};
+  return transform_point_f(T, px, py, pz);
+}
+
 // Association kernel.  SORTED = false: thread k handles flat query k and transforms it itself.
 // SORTED = true: thread s handles query perm[s] (queries ordered by the cell of their transformed
 // point, so the lanes of a warp walk the same candidate ranges: uniform trip counts and broadcast
 // loads).  STORED_X: read the transformed point stored by k_transform_keys (the permutation was
 // built for the current poses); otherwise transform here (the permutation of an earlier outer
 // iteration is reused -- it is only a locality hint, the result does not depend on it).
-template <bool SORTED, bool STORED_X>
+template <bool SORTED, bool STORED_X, bool DESKEW>
 __global__ void __launch_bounds__(128)
 k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
                 const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
                 const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
                 const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, double *__restrict__ corr,
-                int32_t *__restrict__ knn_out) {
+                int32_t *__restrict__ knn_out, DeskewTable tb, const double *__restrict__ dsk) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_corner_total + n_surf_total) return;
   const uint32_t k = SORTED ? __ldg(perm + slot) : slot;
   const bool is_corner = k < n_corner_total;
   float3 x;
+  double dsk_o[3] = {0, 0, 0};  // deskew branch: per-point offset V dt - g dt^2 / 2
   if (STORED_X) {
     const float4 xs = __ldg(xq + k);
     x = make_float3(xs.x, xs.y, xs.z);
@@ -194,7 +276,8 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
 #pragma unroll
     for (int i = 0; i < 7; ++i) pose[i] = __ldg(poses + (size_t)scan * 7 + i);
     const float4 p = __ldg((is_corner ? qc : qs) + kk);
-    x = transform_point_f(pose, p.x, p.y, p.z);  // mapping_scan_matcher.cc:123 / :193
+    if (DESKEW) x = deskew_transform(pose, tb, dsk + (size_t)k * 8, p.x, p.y, p.z, dsk_o);  // :120 / :190
+    else x = transform_point_f(pose, p.x, p.y, p.z);  // mapping_scan_matcher.cc:123 / :193
   }
   const size_t q = k;
   const GridView &g = is_corner ? gc : gs;
@@ -255,6 +338,9 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
       }
     }
   }
+  if (DESKEW && (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0)) {  // fold the constant offset: C' = C - o
+    a[0] -= dsk_o[0]; a[1] -= dsk_o[1]; a[2] -= dsk_o[2];
+  }
   store_corr(corr, q, a, n);
 }
 
@@ -269,9 +355,9 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   const bool sorted = mode == 2 || (mode == 0 && total >= 65536u);
   if (!sorted) {
     stage_begin(e, 0);
-    k_associate_map<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
-                                                                       d_s_off, n_surf_total, d_poses, nullptr, nullptr,
-                                                                       d_corr, d_knn);
+    k_associate_map<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, nullptr, d_corr, d_knn,
+        DeskewTable{}, nullptr);
     stage_end(e);
     e->launches += 1;
     MSFL_CUDA_OK(cudaGetLastError());
@@ -283,9 +369,9 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     // later outer iteration: poses moved by centimetres, the previous cell order is still a good
     // locality hint -> skip the transform/sort pass, transform inside the association kernel
     stage_begin(e, 0);
-    k_associate_map<true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total,
-                                                                             d_qs, d_s_off, n_surf_total, d_poses, nullptr,
-                                                                             e->a_perm, d_corr, d_knn);
+    k_associate_map<true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, e->a_perm, d_corr, d_knn,
+        DeskewTable{}, nullptr);
     stage_end(e);
     e->launches += 1;
     MSFL_CUDA_OK(cudaGetLastError());
@@ -315,11 +401,39 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   e->a_perm = dv.Current();
   e->a_perm_valid = total;
   stage_begin(e, 0);
-  k_associate_map<true, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs,
-                                                                          d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(),
-                                                                          e->a_perm, d_corr, d_knn);
+  k_associate_map<true, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+      gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm,
+      d_corr, d_knn, DeskewTable{}, nullptr);
   stage_end(e);
   e->launches += 2 + 3;
+  MSFL_CUDA_OK(cudaGetLastError());
+  return MSFL_OK;
+}
+
+// ---- deskew branch launchers (single scan) ------------------------------------------------------
+int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
+                          const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,
+                          double *d_pprime, int *d_flag) {
+  DeskewTable tb{d_sum_dt, d_dq, d_dp, n_tab, {V[0], V[1], V[2]}, {G[0], G[1], G[2]}};
+  k_deskew_prepare<<<(n + 127) / 128, 128, 0, e->stream>>>(tb, d_q, n, d_dsk, d_pprime, d_flag);
+  e->launches += 1;
+  MSFL_CUDA_OK(cudaGetLastError());
+  return MSFL_OK;
+}
+
+int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_t *d_c_off, uint32_t nc, const float4 *d_qs,
+                                const int32_t *d_s_off, uint32_t ns, const double *d_pose, const double *d_sum_dt,
+                                const double *d_dq, const double *d_dp, int n_tab, const double V[3], const double G[3],
+                                const double *d_dsk, double *d_corr, int32_t *d_knn) {
+  const uint32_t total = nc + ns;
+  if (total == 0) return MSFL_OK;
+  DeskewTable tb{d_sum_dt, d_dq, d_dp, n_tab, {V[0], V[1], V[2]}, {G[0], G[1], G[2]}};
+  stage_begin(e, 0);
+  k_associate_map<false, false, true><<<(total + 127) / 128, 128, 0, e->stream>>>(
+      e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_corr,
+      d_knn, tb, d_dsk);
+  stage_end(e);
+  e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }

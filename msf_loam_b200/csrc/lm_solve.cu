@@ -158,7 +158,7 @@ __device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) 
 constexpr int kPerThread = 2;              // entries per thread per tile
 constexpr int kTile = kLmThreads * kPerThread;
 constexpr int kStages = 3;
-constexpr int kStageBytes = kTile * 16 + kTile * 48;
+template <int PB> constexpr int stage_bytes() { return kTile * PB + kTile * 48; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -187,25 +187,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 struct TileSrc {
-  const float4 *pe, *pp;
+  const unsigned char *pe, *pp;  // point arrays (PB bytes per entry)
   const double *ce, *cp;
   uint32_t n_e, n_p, tiles_e, tiles;
 };
 
 // issue the two bulk copies of tile t into stage buffer `buf`
+template <int PB>
 __device__ __forceinline__ void issue_tile(const TileSrc &ts, uint32_t t, unsigned char *buf, uint64_t *bar) {
   const bool edge = t < ts.tiles_e;
   const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
   const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
-  const float4 *p = (edge ? ts.pe : ts.pp) + base;
+  const unsigned char *p = (edge ? ts.pe : ts.pp) + (size_t)base * PB;
   const double *c = (edge ? ts.ce : ts.cp) + (size_t)base * 6;
-  mbar_expect_tx(bar, cnt * 64u);
-  tma_load_1d(buf, p, cnt * 16u, bar);
-  tma_load_1d(buf + kTile * 16, c, cnt * 48u, bar);
+  mbar_expect_tx(bar, cnt * (uint32_t)(PB + 48));
+  tma_load_1d(buf, p, cnt * (uint32_t)PB, bar);
+  tma_load_1d(buf + kTile * PB, c, cnt * 48u, bar);
 }
 
 // One fused sweep over the scan's correspondences at `pose`, tiles streamed through the smem ring.
 // `tile_ctr` counts tiles consumed since kernel start (stage = ctr % kStages, parity = (ctr / kStages) & 1).
+template <int PB>
 __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &ts, unsigned char *ring, uint64_t *bars,
                                             uint32_t &tile_ctr, const double *pose, double huber_a, int &cnt_edge,
                                             int &cnt_plane) {
@@ -220,14 +222,14 @@ __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &
   if (tid == 0) {
     for (uint32_t t = 0; t < min((uint32_t)(kStages - 1), ts.tiles); ++t) {
       const uint32_t g = tile_ctr + t;
-      issue_tile(ts, t, ring + (g % kStages) * kStageBytes, bars + (g % kStages));
+      issue_tile<PB>(ts, t, ring + (g % kStages) * stage_bytes<PB>(), bars + (g % kStages));
     }
   }
   for (uint32_t t = 0; t < ts.tiles; ++t) {
     const uint32_t g = tile_ctr + t, stage = g % kStages;
     if (tid == 0 && t + kStages - 1 < ts.tiles) {
       const uint32_t gn = g + kStages - 1;
-      issue_tile(ts, t + kStages - 1, ring + (gn % kStages) * kStageBytes, bars + (gn % kStages));
+      issue_tile<PB>(ts, t + kStages - 1, ring + (gn % kStages) * stage_bytes<PB>(), bars + (gn % kStages));
     }
     mbar_wait(bars + stage, (g / kStages) & 1u);
     const bool edge = t < ts.tiles_e;
@@ -235,13 +237,19 @@ __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &
     const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
 #pragma unroll 1
     for (uint32_t ent = tid; ent < cnt; ent += kLmThreads) {
-      const unsigned char *buf = ring + stage * kStageBytes;
-      const float4 pf = reinterpret_cast<const float4 *>(buf)[ent];
-      const double2 *cp = reinterpret_cast<const double2 *>(buf + kTile * 16 + ent * 48);
+      const unsigned char *buf = ring + stage * stage_bytes<PB>();
+      double p0, p1, p2;
+      if (PB == 16) {
+        const float4 pf = reinterpret_cast<const float4 *>(buf)[ent];
+        p0 = pf.x; p1 = pf.y; p2 = pf.z;
+      } else {
+        const double2 pa = reinterpret_cast<const double2 *>(buf)[2 * ent], pb = reinterpret_cast<const double2 *>(buf)[2 * ent + 1];
+        p0 = pa.x; p1 = pa.y; p2 = pb.x;
+      }
+      const double2 *cp = reinterpret_cast<const double2 *>(buf + kTile * PB + ent * 48);
       const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];
       const double a0 = c0.x, a1 = c0.y, a2 = c1.x, n0 = c1.y, n1 = c2.x, n2 = c2.y;
       if (!(n0 == 0.0 && n1 == 0.0 && n2 == 0.0)) {
-        const double p0 = pf.x, p1 = pf.y, p2 = pf.z;
         const double d0 = R[0] * p0 + R[1] * p1 + R[2] * p2 + t0 - a0;
         const double d1 = R[3] * p0 + R[4] * p1 + R[5] * p2 + t1 - a1;
         const double d2 = R[6] * p0 + R[7] * p1 + R[8] * p2 + t2 - a2;
@@ -383,9 +391,10 @@ __device__ void lm_finish_step(LmShared &sh, const KParams &kp, msfl_lm_log *log
   }
 }
 
+template <int PB>
 __global__ void __launch_bounds__(kLmThreads, 2)
-k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
-           const float4 *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
+k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
+           const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
            int min_corr) {
   __shared__ LmShared sh;
@@ -394,7 +403,7 @@ k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict_
   const int b = blockIdx.x;
   const uint32_t eo = (uint32_t)e_off[b], n_e = (uint32_t)e_off[b + 1] - eo;
   const uint32_t po = (uint32_t)p_off[b], n_p = (uint32_t)p_off[b + 1] - po;
-  const float4 *pe = qe + eo, *pp = qp + po;
+  const unsigned char *pe = (const unsigned char *)qe + (size_t)eo * PB, *pp = (const unsigned char *)qp + (size_t)po * PB;
   const double *ce_ = corr + (size_t)eo * 6, *cp_ = corr + ((size_t)n_edge_total + po) * 6;
   msfl_stats *st = stats ? stats + b : nullptr;
   msfl_lm_log *log = st ? &st->lm[outer] : nullptr;
@@ -419,7 +428,7 @@ k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict_
 
   double acc[kAcc];
   int ce, cpl;
-  sweep_tiled(acc, ts, ring, bars, tile_ctr, sh.x, kp.huber_a, ce, cpl);
+  sweep_tiled<PB>(acc, ts, ring, bars, tile_ctr, sh.x, kp.huber_a, ce, cpl);
   // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
   for (int o = 16; o > 0; o >>= 1) {
     ce += __shfl_down_sync(0xffffffffu, ce, o);
@@ -467,7 +476,7 @@ k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict_
   }
   __syncthreads();
   while (!sh.done) {
-    sweep_tiled(acc, ts, ring, bars, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
+    sweep_tiled<PB>(acc, ts, ring, bars, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
     block_reduce(acc, sh);
     if (tid == 0) {
       lm_finish_step(sh, kp, log);
@@ -482,20 +491,38 @@ k_lm_solve(KParams kp, const float4 *__restrict__ qe, const int32_t *__restrict_
   if (tid < 7 && !sh.too_few) poses[(size_t)b * 7 + tid] = sh.x[tid];
 }
 
+template <int PB>
+static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                             const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
+                             int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
+  static bool attr_set = false;
+  constexpr int smem = kStages * stage_bytes<PB>();
+  if (!attr_set) {
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_lm_solve<PB><<<B, kLmThreads, smem, e->stream>>>(e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
+                                                     d_status, d_stats, outer, min_corr);
+  e->launches += 1;
+  MSFL_CUDA_OK(cudaGetLastError());
+  return MSFL_OK;
+}
+
 int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                     const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
                     msfl_stats *d_stats, int outer, int min_corr) {
   if (B <= 0) return MSFL_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kStageBytes));
-    attr_set = true;
-  }
-  k_lm_solve<<<B, kLmThreads, kStages * kStageBytes, e->stream>>>(e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status,
-                                              d_stats, outer, min_corr);
-  e->launches += 1;
-  MSFL_CUDA_OK(cudaGetLastError());
-  return MSFL_OK;
+  return launch_lm_solve_t<16>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                               min_corr);
+}
+
+// deskewed points: double4 (p' = dq p + dp in fp64, lidar_factor.cc:53), 32 B per entry
+int launch_lm_solve_pd(msfl_engine *e, int B, const double *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                       const double *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
+                       msfl_stats *d_stats, int outer, int min_corr) {
+  if (B <= 0) return MSFL_OK;
+  return launch_lm_solve_t<32>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                               min_corr);
 }
 
 // ---- test hook: plain accumulate at a pose (cost, H, g), one block ---------------------------

@@ -270,7 +270,8 @@ void msfl_destroy(msfl_engine *e) {
                    &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,
                    &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
                    &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc,
-                   &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp};
+                   &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp,
+                   &e->k_table, &e->k_dsk, &e->k_pprime};
   for (DevBuf *b : dbs) b->release();
   PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc};
   for (PinBuf *b : pbs) b->release();
@@ -603,6 +604,75 @@ int msfl_scan2map_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner, co
 int msfl_scan2map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf, double pose_tq[7],
                   msfl_stats *stats) {
   return msfl_scan2map_batch(e, 1, scan_corner, scan_surf, pose_tq, stats);
+}
+
+int msfl_scan2map_deskew(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                         const msfl_deskew *dk, double pose_tq[7], msfl_stats *stats) {
+  if (!e || !scan_corner || !scan_surf || !dk || !pose_tq) { set_error("msfl_scan2map_deskew: bad argument"); return MSFL_ERR_ARG; }
+  if (!e->has_submap) { set_error("msfl_scan2map_deskew: no submap set"); return MSFL_ERR_NOSUBMAP; }
+  if (dk->n < 2 || !dk->sum_dt || !dk->delta_q || !dk->delta_p) { set_error("msfl_scan2map_deskew: preintegration table needs >= 2 samples"); return MSFL_ERR_ARG; }
+  if (scan_corner->off_intensity == MSFL_NO_FIELD || scan_surf->off_intensity == MSFL_NO_FIELD) { set_error("msfl_scan2map_deskew: clouds need the intensity (relative time) field"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  int rc;
+  uint32_t nc = 0, ns = 0;
+  if ((rc = upload_batch(e, 1, scan_corner, scan_surf, pose_tq, &nc, &ns))) return rc;
+  const size_t total = (size_t)nc + ns;
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (total == 0) return MSFL_OK;
+  const size_t q_pad = (total * 16 + 15) & ~(size_t)15, off_pad = ((size_t)2 * 2 * 4 + 15) & ~(size_t)15;
+  char *d = e->d_queries.as<char>();
+  const float4 *d_qc = (const float4 *)d, *d_qs = d_qc + nc;
+  const int32_t *d_c_off = (const int32_t *)(d + q_pad), *d_s_off = d_c_off + 2;
+  double *d_pose = (double *)(d + q_pad + off_pad);
+  // preintegration table -> device: [sum_dt n | delta_q 4n | delta_p 3n | flag]
+  const size_t n = (size_t)dk->n;
+  if ((rc = e->k_table.reserve(n * 8 * 8 + 64))) return rc;
+  if ((rc = e->h_misc.reserve(n * 8 * 8 + 64))) return rc;
+  double *ht = e->h_misc.as<double>();
+  memcpy(ht, dk->sum_dt, n * 8);
+  memcpy(ht + n, dk->delta_q, n * 32);
+  memcpy(ht + 5 * n, dk->delta_p, n * 24);
+  memset(ht + 8 * n, 0, 8);
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->k_table.p, ht, n * 64 + 8, cudaMemcpyHostToDevice, st));
+  const double *t_dt = e->k_table.as<double>(), *t_dq = t_dt + n, *t_dp = t_dt + 5 * n;
+  int *d_flag = (int *)(e->k_table.as<double>() + 8 * n);
+  if ((rc = e->k_dsk.reserve(total * 64))) return rc;
+  if ((rc = e->k_pprime.reserve(total * 32))) return rc;
+  if ((rc = e->d_corr.reserve((total + 1) * 48))) return rc;
+  if ((rc = e->d_status.reserve(16))) return rc;
+  msfl_stats *d_stats = nullptr;
+  if (stats) {
+    if ((rc = e->d_stats.reserve(sizeof(msfl_stats)))) return rc;
+    d_stats = e->d_stats.as<msfl_stats>();
+    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(msfl_stats), st));
+  }
+  if ((rc = launch_deskew_prepare(e, t_dt, t_dq, t_dp, dk->n, dk->velocity, dk->gravity, d_qc, (uint32_t)total,
+                                  e->k_dsk.as<double>(), e->k_pprime.as<double>(), d_flag)))
+    return rc;
+  const double *pp_c = e->k_pprime.as<double>(), *pp_s = pp_c + (size_t)nc * 4;
+  for (int outer = 0; outer < e->params.num_outer; ++outer) {
+    if ((rc = launch_associate_map_deskew(e, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, t_dt, t_dq, t_dp, dk->n, dk->velocity,
+                                          dk->gravity, e->k_dsk.as<double>(), e->d_corr.as<double>(), nullptr)))
+      return rc;
+    stage_begin(e, 1);
+    rc = launch_lm_solve_pd(e, 1, pp_c, d_c_off, nc, pp_s, d_s_off, e->d_corr.as<double>(), d_pose, e->d_status.as<int32_t>(),
+                            d_stats, outer, 0);
+    stage_end(e);
+    if (rc) return rc;
+  }
+  int h_flag = 0;
+  MSFL_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+  double h_pose[7];
+  MSFL_CUDA_OK(cudaMemcpyAsync(h_pose, d_pose, 56, cudaMemcpyDeviceToHost, st));
+  if (stats) MSFL_CUDA_OK(cudaMemcpyAsync(stats, d_stats, sizeof(msfl_stats), cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  if (h_flag) {
+    set_error("msfl_scan2map_deskew: a point time lies outside the preintegration window [%g, %g]", dk->sum_dt[0], dk->sum_dt[n - 1]);
+    return MSFL_ERR_ARG;
+  }
+  memcpy(pose_tq, h_pose, 56);
+  return MSFL_OK;
 }
 
 int msfl_associate_map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,

@@ -98,6 +98,7 @@ struct msfl_engine {
   msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
   // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp;
+  msfl::DevBuf k_table, k_dsk, k_pprime;  // deskew branch: preintegration table, per-query (dq, dp, dt), p'
   const uint32_t *a_perm = nullptr;  // cell-order permutation of the current batch (valid for a_perm_valid queries)
   uint32_t a_perm_valid = 0;
 
@@ -129,11 +130,22 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
                          double *d_corr, int32_t *d_knn, bool reuse_order = false);
 
+int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
+                          const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,
+                          double *d_pprime, int *d_flag);
+int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_t *d_c_off, uint32_t nc, const float4 *d_qs,
+                                const int32_t *d_s_off, uint32_t ns, const double *d_pose, const double *d_sum_dt,
+                                const double *d_dq, const double *d_dp, int n_tab, const double V[3], const double G[3],
+                                const double *d_dsk, double *d_corr, int32_t *d_knn);
+
 // ---- lm_solve.cu
 // outer: outer-iteration index (stats slot); min_corr: 0 for mapping, params.min_correspondences for odometry
 int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                     const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
                     msfl_stats *d_stats, int outer, int min_corr);
+int launch_lm_solve_pd(msfl_engine *e, int B, const double *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                       const double *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
+                       msfl_stats *d_stats, int outer, int min_corr);
 int launch_accumulate(msfl_engine *e, const float4 *d_p, const double *d_corr, int n_edge, int n_plane,
                       const double *d_pose, double *d_out28);
 

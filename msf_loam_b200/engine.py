@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Cloud, Features, MsflError, Params, Stats, NO_FIELD, MSFL_OK, MSFL_TOO_FEW
+from ._lib import Cloud, Deskew, Features, MsflError, Params, Stats, NO_FIELD, MSFL_OK, MSFL_TOO_FEW
 
 # memory layouts of the reference's point types (common.h:44-62; pcl::PointXYZI)
 POINT_XYZI = np.dtype({"names": ["x", "y", "z", "intensity"], "formats": ["f4"] * 4,
@@ -164,6 +164,23 @@ class Engine:
                                                       x.ctypes.data_as(C.POINTER(C.c_double)), st))
         return rc, x, ([s.as_dict() for s in st] if st is not None else None)
 
+    def scan2map_deskew(self, scan_corner, scan_surf, sum_dt, delta_q, delta_p, velocity, gravity, pose,
+                        want_stats=True):
+        """IMU-initialised branch: preintegration buffers (sum_dt [n], delta_q [n,4] xyzw, delta_p [n,3])."""
+        vc, vs = _View(scan_corner), _View(scan_surf)
+        t = np.ascontiguousarray(sum_dt, dtype=np.float64)
+        q = np.ascontiguousarray(delta_q, dtype=np.float64).reshape(-1, 4)
+        p = np.ascontiguousarray(delta_p, dtype=np.float64).reshape(-1, 3)
+        dk = Deskew(t.ctypes.data_as(C.POINTER(C.c_double)), q.ctypes.data_as(C.POINTER(C.c_double)),
+                    p.ctypes.data_as(C.POINTER(C.c_double)), t.shape[0], 0,
+                    (C.c_double * 3)(*velocity), (C.c_double * 3)(*gravity))
+        x = _pose(pose)
+        st = Stats() if want_stats else None
+        rc = self._check(self.lib.msfl_scan2map_deskew(self.h, C.byref(vc.cloud), C.byref(vs.cloud), C.byref(dk),
+                                                       x.ctypes.data_as(C.POINTER(C.c_double)),
+                                                       C.byref(st) if st is not None else None))
+        return rc, x, (st.as_dict() if st is not None else None)
+
     def prepare_batch(self, scan_corners, scan_surfs):
         """Builds the msfl_cloud tables once so a timed loop only pays the C call."""
         B = len(scan_corners)
@@ -293,11 +310,19 @@ class MappingScanMatcher:
         self.last_stats = None
 
     def MatchScan2Map(self, cloud_map: TimestampedPointCloud, scan_curr: TimestampedPointCloud,
-                      is_initialized: bool, pose_estimate_map_scan2world):
-        """Returns (True, pose) like the reference (the bool is always true, :277)."""
-        if is_initialized:
-            raise NotImplementedError("IMU-deskew branch (SURVEY.md 8f row 3) is not built yet")
+                      is_initialized: bool, pose_estimate_map_scan2world, preintegration=None,
+                      gravity_vector=None, velocity=None):
+        """Returns (True, pose) like the reference (the bool is always true, :277).  With
+        is_initialized the deskew factors are used; `preintegration` = (sum_dt, delta_q, delta_p) buffers
+        and the pose must already include the caller's IMU-only predict (:35-60)."""
         self.engine.set_submap(cloud_map.cloud_corner_less_sharp, cloud_map.cloud_surf_less_flat)
+        if is_initialized:
+            sum_dt, dq, dp = preintegration
+            _, pose, st = self.engine.scan2map_deskew(scan_curr.cloud_corner_less_sharp, scan_curr.cloud_surf_less_flat,
+                                                      sum_dt, dq, dp, velocity, gravity_vector,
+                                                      pose_estimate_map_scan2world)
+            self.last_stats = st
+            return True, pose
         _, pose, st = self.engine.scan2map(scan_curr.cloud_corner_less_sharp, scan_curr.cloud_surf_less_flat,
                                            pose_estimate_map_scan2world)
         self.last_stats = st

@@ -220,6 +220,33 @@ def scan2map(params, map_corner, map_surf, scan_corner, scan_surf, pose):
     return x, [l.as_dict() for l in logs], counts.reshape(-1, 2)
 
 
+class Deskew(C.Structure):
+    _fields_ = [("sum_dt", C.POINTER(C.c_double)), ("delta_q", C.POINTER(C.c_double)),
+                ("delta_p", C.POINTER(C.c_double)), ("n", C.c_int), ("velocity", C.c_double * 3),
+                ("gravity", C.c_double * 3)]
+
+
+def scan2map_deskew(params, map_corner, map_surf, scan_corner, scan_surf, sum_dt, delta_q, delta_p, velocity,
+                    gravity, pose):
+    """IMU-initialised branch of MatchScan2Map (LiDAR part).  Returns (rc, pose, logs, counts, knn_idx)."""
+    mc, ms, sc, ss = (_f32(a, 4) for a in (map_corner, map_surf, scan_corner, scan_surf))
+    t = np.ascontiguousarray(sum_dt, dtype=np.float64)
+    q = np.ascontiguousarray(delta_q, dtype=np.float64).reshape(-1, 4)
+    p = np.ascontiguousarray(delta_p, dtype=np.float64).reshape(-1, 3)
+    dk = Deskew(_ptr(t, C.c_double), _ptr(q, C.c_double), _ptr(p, C.c_double), t.shape[0],
+                (C.c_double * 3)(*velocity), (C.c_double * 3)(*gravity))
+    x = _pose(pose)
+    logs = (LmLog * params.num_outer)()
+    counts = np.zeros(2 * params.num_outer, np.int32)
+    kidx = np.full((sc.shape[0] + ss.shape[0], 5), -1, np.int32)
+    rc = lib().msflo_scan2map_deskew(C.byref(params), _ptr(mc, C.c_float), C.c_int(mc.shape[0]),
+                                     _ptr(ms, C.c_float), C.c_int(ms.shape[0]), _ptr(sc, C.c_float),
+                                     C.c_int(sc.shape[0]), _ptr(ss, C.c_float), C.c_int(ss.shape[0]),
+                                     C.byref(dk), _ptr(x, C.c_double), logs, _ptr(counts, C.c_int),
+                                     _ptr(kidx, C.c_int))
+    return rc, x, [l.as_dict() for l in logs], counts.reshape(-1, 2), kidx
+
+
 def scan2map_batch(params, map_corner, map_surf, scan_corner, corner_off, scan_surf, surf_off, poses,
                    n_threads=1):
     mc, ms, sc, ss = (_f32(a, 4) for a in (map_corner, map_surf, scan_corner, scan_surf))

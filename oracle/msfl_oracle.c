@@ -304,7 +304,26 @@ static double gradient_max_norm(const double x[7], const double g[6]) {
  *   loop guard (FinalizeIterationAndCheckIfMinimizerCanContinue): iteration >= max_num_iterations,
  *             gradient max-norm <= gtol (after successful steps / iteration 0), radius <= min_radius.
  */
+typedef void (*lm_eval_fn)(const msflo_params *P, const void *ctx, const double pose[7], double *cost, double H[36],
+                           double g[6]);
+
+typedef struct { const double *corr; int n; } plain_ctx;
+static void eval_plain(const msflo_params *P, const void *vctx, const double pose[7], double *cost, double H[36],
+                       double g[6]) {
+  const plain_ctx *c = (const plain_ctx *)vctx;
+  msflo_accumulate(P, c->corr, c->n, pose, cost, H, g);
+}
+
+static int lm_solve_generic(const msflo_params *P, lm_eval_fn eval, const void *ctx, int n_corr, double pose[7],
+                            msflo_lm_log *log);
+
 int msflo_lm_solve(const msflo_params *P, const double *corr, int n_corr, double pose[7], msflo_lm_log *log) {
+  plain_ctx c = {corr, n_corr};
+  return lm_solve_generic(P, eval_plain, &c, n_corr, pose, log);
+}
+
+static int lm_solve_generic(const msflo_params *P, lm_eval_fn eval, const void *ctx, int n_corr, double pose[7],
+                            msflo_lm_log *log) {
   double x[7], H[36], g[6], S[6], diag[6] = {0, 0, 0, 0, 0, 0};
   double cost, radius = P->initial_radius, nu = 2.0;
   int reuse = 0, n_invalid = 0, termination = 0;
@@ -316,7 +335,7 @@ int msflo_lm_solve(const msflo_params *P, const double *corr, int n_corr, double
     if (log) log->termination = 2;
     return 0;
   }
-  msflo_accumulate(P, corr, n_corr, x, &cost, H, g);
+  eval(P, ctx, x, &cost, H, g);
   for (int k = 0; k < 6; k++) S[k] = 1.0 / (1.0 + sqrt(H[k * 6 + k]));
   double x_norm = norm7(x);
   if (log) log->initial_cost = cost;
@@ -367,7 +386,7 @@ int msflo_lm_solve(const msflo_params *P, const double *corr, int n_corr, double
     double delta[6], xc[7], cost_c;
     for (int k = 0; k < 6; k++) delta[k] = y[k] * S[k];
     msflo_pose_plus(x, delta, xc);
-    msflo_accumulate(P, corr, n_corr, xc, &cost_c, 0, 0);
+    eval(P, ctx, xc, &cost_c, 0, 0);
     if (L) { L->valid = 1; L->model_change = model; L->cost_candidate = cost_c; }
     if (P->early_exit) {
       double sn = 0;
@@ -381,7 +400,7 @@ int msflo_lm_solve(const msflo_params *P, const double *corr, int n_corr, double
     if (rho > P->min_relative_decrease) {
       memcpy(x, xc, sizeof x);
       x_norm = norm7(x);
-      msflo_accumulate(P, corr, n_corr, x, &cost, H, g);
+      eval(P, ctx, x, &cost, H, g);
       step_successful = 1;
       if (L) L->accepted = 1;
       const double t = 2.0 * rho - 1.0;
@@ -836,6 +855,236 @@ int msflo_scan2map_batch(const msflo_params *P,
   msflo_kdtree_free(tc);
   msflo_kdtree_free(ts);
   return 0;
+}
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* 8f row 3: IMU-deskew branch (mapping_scan_matcher.cc:107-246, is_initialized == true)       */
+/* ------------------------------------------------------------------------------------------ */
+static void quat_mul(const double a[4], const double b[4], double o[4]) { /* Eigen product, x y z w */
+  o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+
+/* GetDeltaQP (scan_undistortion.cc:22-42): upper_bound, slerp (Eigen semantics), lerp */
+int msflo_get_delta_qp(const msflo_deskew *dk, double dt, double dq[4], double dp[3]) {
+  const int n = dk->n;
+  if (n < 2 || !(dt <= dk->sum_dt[n - 1] && dt >= dk->sum_dt[0])) return -1; /* CHECK :26 */
+  int lo = 0, hi = n; /* first index with dt < sum_dt[idx] */
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    if (dt < dk->sum_dt[mid]) hi = mid; else lo = mid + 1;
+  }
+  int idx = lo - 1;
+  if (idx > n - 2) idx = n - 2; /* dt == back(): the reference reads one past the end; clamp */
+  const double s = (dt - dk->sum_dt[idx]) / (dk->sum_dt[idx + 1] - dk->sum_dt[idx]);
+  const double *qa = dk->delta_q + 4 * idx, *qb = qa + 4;
+  const double d = qa[0] * qb[0] + qa[1] * qb[1] + qa[2] * qb[2] + qa[3] * qb[3];
+  const double absd = fabs(d);
+  double s0, s1;
+  if (absd >= 1.0 - DBL_EPSILON) {
+    s0 = 1.0 - s; s1 = s;
+  } else {
+    const double th = acos(absd), sn = sin(th);
+    s0 = sin((1.0 - s) * th) / sn;
+    s1 = sin(s * th) / sn;
+  }
+  if (d < 0) s1 = -s1;
+  for (int k = 0; k < 4; k++) dq[k] = s0 * qa[k] + s1 * qb[k];
+  const double *pa = dk->delta_p + 3 * idx, *pb = pa + 3;
+  for (int k = 0; k < 3; k++) dp[k] = (1 - s) * pa[k] + s * pb[k];
+  return 0;
+}
+
+/* LidarEdgeFactorDeskewSE3::Evaluate (lidar_factor.cc:46-72), pose block only */
+void msflo_edge_factor_deskew(const double pose[7], const double V[3], const double p[3], const double C[3],
+                              const double N[3], const double dp[3], const double dq[4], double dt, const double G[3],
+                              double r[3], double J[21]) {
+  double pp[3], x[3], d[3];
+  quat_rotate(dq, p, pp);
+  for (int k = 0; k < 3; k++) pp[k] += dp[k];
+  quat_rotate(pose + 3, pp, x);
+  for (int k = 0; k < 3; k++) d[k] = x[k] + V[k] * dt - 0.5 * G[k] * dt * dt + pose[k] - C[k];
+  r[0] = N[1] * d[2] - N[2] * d[1];
+  r[1] = N[2] * d[0] - N[0] * d[2];
+  r[2] = N[0] * d[1] - N[1] * d[0];
+  if (J) {
+    double R[9], Sp[9], Sn[9], RSp[9], M[9];
+    quat_to_R(pose + 3, R);
+    skew(pp, Sp);
+    skew(N, Sn);
+    mat3_mul(R, Sp, RSp);
+    mat3_mul(Sn, RSp, M);
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) { J[i * 7 + j] = Sn[i * 3 + j]; J[i * 7 + 3 + j] = -M[i * 3 + j]; }
+      J[i * 7 + 6] = 0;
+    }
+  }
+}
+
+/* LidarPlaneFactorDeskewSE3::Evaluate (lidar_factor.cc:74-100), pose block only */
+void msflo_plane_factor_deskew(const double pose[7], const double V[3], const double p[3], const double C[3],
+                               const double N[3], const double dp[3], const double dq[4], double dt, const double G[3],
+                               double r[1], double J[7]) {
+  double pp[3], x[3], d[3];
+  quat_rotate(dq, p, pp);
+  for (int k = 0; k < 3; k++) pp[k] += dp[k];
+  quat_rotate(pose + 3, pp, x);
+  for (int k = 0; k < 3; k++) d[k] = x[k] + V[k] * dt - 0.5 * G[k] * dt * dt + pose[k] - C[k];
+  r[0] = N[0] * d[0] + N[1] * d[1] + N[2] * d[2];
+  if (J) {
+    double R[9], Sp[9], RSp[9];
+    quat_to_R(pose + 3, R);
+    skew(pp, Sp);
+    mat3_mul(R, Sp, RSp);
+    for (int j = 0; j < 3; j++) {
+      J[j] = N[j];
+      J[3 + j] = -(N[0] * RSp[0 * 3 + j] + N[1] * RSp[1 * 3 + j] + N[2] * RSp[2 * 3 + j]);
+    }
+    J[6] = 0;
+  }
+}
+
+/* deskew correspondence row: [type, p(3), C(3), N(3), dp(3), dq(4), dt] = 18 doubles */
+#define DSK_STRIDE 18
+typedef struct { const double *corr; int n; const msflo_deskew *dk; } deskew_ctx;
+
+static void eval_deskew(const msflo_params *P, const void *vctx, const double pose[7], double *cost_out, double H[36],
+                        double g[6]) {
+  const deskew_ctx *c = (const deskew_ctx *)vctx;
+  const double a = P->huber_a, b = a * a;
+  double cost = 0;
+  if (H) memset(H, 0, 36 * sizeof(double));
+  if (g) memset(g, 0, 6 * sizeof(double));
+  for (int i = 0; i < c->n; i++) {
+    const double *e = c->corr + (size_t)i * DSK_STRIDE;
+    double r[3], J[21];
+    int nres;
+    if ((int)e[0] == 0) {
+      msflo_edge_factor_deskew(pose, c->dk->velocity, e + 1, e + 4, e + 7, e + 10, e + 13, e[17], c->dk->gravity, r, (H || g) ? J : 0);
+      nres = 3;
+    } else {
+      msflo_plane_factor_deskew(pose, c->dk->velocity, e + 1, e + 4, e + 7, e + 10, e + 13, e[17], c->dk->gravity, r, (H || g) ? J : 0);
+      nres = 1;
+    }
+    double s = 0;
+    for (int k = 0; k < nres; k++) s += r[k] * r[k];
+    double rho0, rho1;
+    if (s > b) { const double rr = sqrt(s); rho0 = 2.0 * a * rr - b; rho1 = fmax(DBL_MIN, a / rr); }
+    else { rho0 = s; rho1 = 1.0; }
+    cost += 0.5 * rho0;
+    if (H || g) {
+      const double sc = sqrt(rho1);
+      for (int k = 0; k < nres; k++) {
+        const double rk = r[k] * sc;
+        double Jk[6];
+        for (int j = 0; j < 6; j++) Jk[j] = J[k * 7 + j] * sc;
+        if (g) for (int j = 0; j < 6; j++) g[j] += Jk[j] * rk;
+        if (H) for (int u = 0; u < 6; u++) for (int v = 0; v < 6; v++) H[u * 6 + v] += Jk[u] * Jk[v];
+      }
+    }
+  }
+  *cost_out = cost;
+}
+
+/* pointSel = TransformPoint(pose * Rigid3d{q^-1 (V dt - g dt^2/2) + dp, dq}, pointOri)  (:120, :190) */
+static void deskew_transform(const double pose[7], const msflo_deskew *dk, const double dq[4], const double dp[3],
+                             double dt, const float in[3], float out[3]) {
+  double o[3], qc[4] = {-pose[3], -pose[4], -pose[5], pose[6]}, tr[3], tt[3], qt[4], T[7];
+  for (int k = 0; k < 3; k++) o[k] = dk->velocity[k] * dt - 0.5 * dk->gravity[k] * dt * dt;
+  quat_rotate(qc, o, tr);
+  for (int k = 0; k < 3; k++) tr[k] += dp[k];
+  quat_rotate(pose + 3, tr, tt); /* Rigid3 operator* (rigid_transform.h:105-111) */
+  quat_mul(pose + 3, dq, qt);
+  const double nq = sqrt(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+  for (int k = 0; k < 3; k++) T[k] = tt[k] + pose[k];
+  for (int k = 0; k < 4; k++) T[3 + k] = qt[k] / nq;
+  msflo_transform_point_f(T, in, out);
+}
+
+int msflo_scan2map_deskew(const msflo_params *P,
+                          const float *map_corner, int n_map_corner, const float *map_surf, int n_map_surf,
+                          const float *scan_corner, int n_scan_corner, const float *scan_surf, int n_scan_surf,
+                          const msflo_deskew *dk, double pose[7], msflo_lm_log *logs, int *counts, int *knn_idx_out) {
+  msflo_kdtree *tc = msflo_kdtree_build(map_corner, n_map_corner);
+  msflo_kdtree *ts = msflo_kdtree_build(map_surf, n_map_surf);
+  const int nq = n_scan_corner + n_scan_surf;
+  double *corr = (double *)malloc(sizeof(double) * DSK_STRIDE * ((size_t)nq + 1));
+  int rc = 0;
+  for (int it = 0; it < P->num_outer && rc == 0; it++) {
+    int ne = 0, np = 0, nc = 0;
+    for (int i = 0; i < nq; i++) {
+      const int is_corner = i < n_scan_corner;
+      const float *po = is_corner ? scan_corner + 4 * (size_t)i : scan_surf + 4 * (size_t)(i - n_scan_corner);
+      const double dt = (double)po[3]; /* auto dt = pointOri.intensity (float) :114 */
+      double dq[4], dp[3];
+      if (msflo_get_delta_qp(dk, dt, dq, dp)) { rc = -1; break; }
+      float sel[3];
+      deskew_transform(pose, dk, dq, dp, dt, po, sel);
+      int idx[5];
+      float d2[5];
+      const float *map = is_corner ? map_corner : map_surf;
+      int found = msflo_kdtree_knn(is_corner ? tc : ts, sel, 5, idx, d2);
+      int gate = (found == 5) && ((double)d2[4] < P->knn_max_sq);
+      if (knn_idx_out && it == 0)
+        for (int j = 0; j < 5; j++) knn_idx_out[(size_t)i * 5 + j] = gate ? idx[j] : -1;
+      if (!gate) continue;
+      double m[5][3], c[3] = {0, 0, 0};
+      for (int j = 0; j < 5; j++)
+        for (int d = 0; d < 3; d++) { m[j][d] = (double)map[4 * (size_t)idx[j] + d]; c[d] += m[j][d]; }
+      for (int d = 0; d < 3; d++) c[d] /= 5.0;
+      double a[3], n[3];
+      int ok = 0;
+      if (is_corner) {
+        double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ev[3], V[9];
+        for (int j = 0; j < 5; j++) {
+          double e[3] = {m[j][0] - c[0], m[j][1] - c[1], m[j][2] - c[2]};
+          for (int u = 0; u < 3; u++) for (int v = 0; v < 3; v++) cov[u * 3 + v] += e[u] * e[v];
+        }
+        msflo_sym_eig3(cov, ev, V);
+        if (ev[2] > P->line_eig_ratio * ev[1]) {
+          double b[3];
+          for (int d = 0; d < 3; d++) {
+            a[d] = P->line_half_len * V[d * 3 + 2] + c[d];
+            b[d] = -P->line_half_len * V[d * 3 + 2] + c[d];
+            n[d] = a[d] - b[d];
+          }
+          double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+          if (nn > 0) for (int d = 0; d < 3; d++) n[d] /= nn;
+          ok = 1;
+        }
+      } else {
+        double A[15], bb[5] = {-1, -1, -1, -1, -1};
+        for (int j = 0; j < 5; j++) for (int d = 0; d < 3; d++) A[j * 3 + d] = m[j][d];
+        msflo_lstsq_5x3(A, bb, n);
+        double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        for (int d = 0; d < 3; d++) { n[d] /= nn; a[d] = c[d]; }
+        ok = 1;
+        for (int j = 0; j < 5; j++) {
+          double dd = n[0] * (m[j][0] - c[0]) + n[1] * (m[j][1] - c[1]) + n[2] * (m[j][2] - c[2]);
+          if (!(fabs(dd) <= P->plane_tol)) { ok = 0; break; }
+        }
+      }
+      if (!ok) continue;
+      double *o = corr + (size_t)nc * DSK_STRIDE;
+      o[0] = is_corner ? 0 : 1;
+      for (int d = 0; d < 3; d++) { o[1 + d] = (double)po[d]; o[4 + d] = a[d]; o[7 + d] = n[d]; o[10 + d] = dp[d]; }
+      for (int d = 0; d < 4; d++) o[13 + d] = dq[d];
+      o[17] = dt;
+      nc++;
+      if (is_corner) ne++; else np++;
+    }
+    if (rc) break;
+    if (counts) { counts[2 * it] = ne; counts[2 * it + 1] = np; }
+    deskew_ctx ctx = {corr, nc, dk};
+    lm_solve_generic(P, eval_deskew, &ctx, nc, pose, logs ? &logs[it] : 0);
+  }
+  free(corr);
+  msflo_kdtree_free(tc);
+  msflo_kdtree_free(ts);
+  return rc;
 }
 
 /* ------------------------------------------------------------------------------------------ */

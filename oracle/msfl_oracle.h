@@ -152,6 +152,33 @@ int msflo_scan2map_batch(const msflo_params *P,
                          const float *scan_surf, const int *surf_off,
                          double *poses /* B x 7 */, int n_threads);
 
+/* ---- 8f row 3: IMU-deskew branch of MatchScan2Map (is_initialized == true), LiDAR part only
+ *      (mapping_scan_matcher.cc:107-246 with the Deskew factors, lidar_factor.cc:46-100;
+ *      GetDeltaQP scan_undistortion.cc:22-42).  The IMU-only predict (:35-60) is the IMU side-car
+ *      and stays with the caller: `pose` comes in as pose_j after that predict.  The speed-bias
+ *      block is constant in the reference's problem (:94), so only the pose is optimised. ---- */
+typedef struct msflo_deskew {
+  const double *sum_dt;   /* [n] preintegration->sum_dt_buf_            */
+  const double *delta_q;  /* [n][4] delta_q_buf_, x y z w               */
+  const double *delta_p;  /* [n][3] delta_p_buf_                        */
+  int n;
+  double velocity[3];     /* Vi = bias_j.head<3>()                      */
+  double gravity[3];      /* gravity_vector                             */
+} msflo_deskew;
+/* returns 0, or -1 when dt is outside [sum_dt.front(), sum_dt.back()] (the reference CHECK-fails) */
+int msflo_get_delta_qp(const msflo_deskew *dk, double dt, double dq[4], double dp[3]);
+void msflo_edge_factor_deskew(const double pose[7], const double V[3], const double p[3], const double C[3],
+                              const double N[3], const double dp[3], const double dq[4], double dt, const double G[3],
+                              double r[3], double J[21]);
+void msflo_plane_factor_deskew(const double pose[7], const double V[3], const double p[3], const double C[3],
+                               const double N[3], const double dp[3], const double dq[4], double dt, const double G[3],
+                               double r[1], double J[7]);
+int msflo_scan2map_deskew(const msflo_params *P,
+                          const float *map_corner, int n_map_corner, const float *map_surf, int n_map_surf,
+                          const float *scan_corner, int n_scan_corner, const float *scan_surf, int n_scan_surf,
+                          const msflo_deskew *dk, double pose[7], msflo_lm_log *logs, int *counts,
+                          int *knn_idx_out /* optional, outer 0 */);
+
 /* ---- a-5 full MatchScan2Scan (odometry_scan_matcher.cc:43-285) ----
  * returns 0 ok, 1 too few correspondences */
 int msflo_scan2scan(const msflo_params *P,
