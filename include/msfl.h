@@ -232,6 +232,25 @@ int msfl_associate_scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp
 int msfl_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T_lidar2imu[7],
                           msfl_features *out);
 
+/* ---- GPU-resident STGM submap producer: HybridGrid of hybrid_grid.h:32-35,
+ *      hybrid_grid.cc:403-521, one map per feature class (laser_mapping.h hybrid_grid_map_corner_ /
+ *      _surf_, resolution 3 m; leaf = mapping_line_resolution 0.2 / mapping_plane_resolution 0.4).
+ *      The surround cloud stays in HBM and becomes the submap without an H2D copy.  Cells are
+ *      concatenated in ascending (z, y, x) cell order (the reference's order is heap-address dependent). */
+typedef struct msfl_map msfl_map;
+int msfl_map_create(msfl_engine *e, float resolution, float leaf, msfl_map **out);
+void msfl_map_destroy(msfl_map *m);
+/* HybridGrid::InsertScan.  pose_tq != NULL: the scan is first moved to the world frame with
+ * TransformPointCloud (laser_mapping.cc:330-338); NULL: the cloud is already in the world frame. */
+int msfl_map_insert(msfl_map *m, const msfl_cloud *scan, const double pose_tq[7]);
+/* HybridGrid::GetSurroundedCloud(scan, pose) (laser_mapping.cc:273-278); result kept on the device. */
+int msfl_map_surround(msfl_map *m, const msfl_cloud *scan, const double pose_tq[7], size_t *n_out);
+int msfl_map_size(const msfl_map *m, size_t *n_points, size_t *n_cells);
+/* which = 0: last surround result, 1: the whole map (cells in ascending order). */
+int msfl_map_download(msfl_map *m, int which, float *out_xyzi, size_t capacity, size_t *n_out);
+/* cloud_map.cloud_corner_less_sharp / cloud_surf_less_flat := the two last surround results. */
+int msfl_set_submap_from_maps(msfl_engine *e, msfl_map *corner, msfl_map *surf);
+
 /* ---- caller-side pcl::VoxelGrid<PointXYZI> (laser_mapping.cc:264-270) --
  * out_xyzi capacity in->n x 4 floats; *n_out receives the number of centroids. */
 int msfl_voxel_grid(msfl_engine *e, const msfl_cloud *in, float leaf, float *out_xyzi, size_t *n_out);

@@ -25,7 +25,8 @@ EXPORTS = [
     "msfl_get_profile", "msfl_set_submap",
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
     "msfl_scan2map_batch_device", "msfl_scan2map_deskew", "msfl_associate_map", "msfl_scan2scan", "msfl_associate_scan",
-    "msfl_extract_features", "msfl_voxel_grid", "msfl_accumulate",
+    "msfl_extract_features", "msfl_voxel_grid", "msfl_accumulate", "msfl_map_create", "msfl_map_destroy",
+    "msfl_map_insert", "msfl_map_surround", "msfl_map_size", "msfl_map_download", "msfl_set_submap_from_maps",
 ]
 
 
@@ -132,5 +133,7 @@ def load_library(build_if_needed: bool = True):
     lib.msfl_destroy.restype = None
     lib.msfl_destroy.argtypes = [C.c_void_p]
     lib.msfl_default_params.restype = None
+    lib.msfl_map_destroy.restype = None
+    lib.msfl_map_destroy.argtypes = [C.c_void_p]
     _lib = lib
     return lib

@@ -285,6 +285,62 @@ class Engine:
         return out[: n_out.value].copy()
 
 
+class HybridGrid:
+    """GPU-resident STGM map of one feature class (hybrid_grid.h:27-39)."""
+
+    def __init__(self, engine: Engine, resolution: float = 3.0, leaf: float = 0.4):
+        self.engine = engine
+        h = C.c_void_p()
+        engine._check(engine.lib.msfl_map_create(engine.h, C.c_float(resolution), C.c_float(leaf), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.engine.lib.msfl_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.engine.h:
+                self.close()
+        except Exception:
+            pass
+
+    def InsertScan(self, scan, pose=None):
+        """scan already in the world frame (pose None) or sensor-frame scan + pose_map_scan2world."""
+        v = _View(scan)
+        x = _pose(pose) if pose is not None else None
+        self.engine._check(self.engine.lib.msfl_map_insert(
+            self.h, C.byref(v.cloud), x.ctypes.data_as(C.POINTER(C.c_double)) if x is not None else None))
+
+    def size(self):
+        n, c = C.c_size_t(), C.c_size_t()
+        self.engine._check(self.engine.lib.msfl_map_size(self.h, C.byref(n), C.byref(c)))
+        return n.value, c.value
+
+    def _download(self, which, n):
+        out = np.zeros((max(n, 1), 4), np.float32)
+        got = C.c_size_t()
+        self.engine._check(self.engine.lib.msfl_map_download(self.h, C.c_int(which), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                             C.c_size_t(out.shape[0]), C.byref(got)))
+        return out[: got.value].copy()
+
+    def GetSurroundedCloud(self, scan, pose, download=True):
+        v = _View(scan)
+        x = _pose(pose)
+        n = C.c_size_t()
+        self.engine._check(self.engine.lib.msfl_map_surround(self.h, C.byref(v.cloud),
+                                                             x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return self._download(0, n.value) if download else n.value
+
+    def dump(self):
+        return self._download(1, self.size()[0])
+
+
+def set_submap_from_maps(engine: Engine, corner: "HybridGrid", surf: "HybridGrid"):
+    engine._check(engine.lib.msfl_set_submap_from_maps(engine.h, corner.h, surf.h))
+
+
 class TimestampedPointCloud:
     """The five clouds of the reference's TimestampedPointCloud (timestamped_pointcloud.h:11-48);
     each member is an (n,4) float32 array (plus ``*_ring`` uint16 for PointXYZIRT clouds)."""

@@ -312,3 +312,39 @@ def voxel_grid(xyzi, leaf):
     n = lib().msflo_voxel_grid(_ptr(pts, C.c_float), C.c_int(pts.shape[0]), C.c_float(leaf),
                                _ptr(out, C.c_float))
     return out[:n].copy()
+
+
+class Stgm:
+    """HybridGrid restatement (hybrid_grid.cc:403-521); output order = ascending cell key."""
+
+    def __init__(self, resolution=3.0, leaf=0.4):
+        L = lib()
+        L.msflo_stgm_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.msflo_stgm_create(C.c_float(resolution), C.c_float(leaf)))
+
+    def __del__(self):
+        try:
+            lib().msflo_stgm_free(self.h)
+        except Exception:
+            pass
+
+    def insert(self, scan_world_xyzi):
+        pts = _f32(scan_world_xyzi, 4)
+        lib().msflo_stgm_insert(self.h, _ptr(pts, C.c_float), C.c_int(pts.shape[0]))
+
+    def size(self):
+        nc = C.c_int(0)
+        n = lib().msflo_stgm_size(self.h, C.byref(nc))
+        return n, nc.value
+
+    def surround(self, scan_xyzi, pose):
+        pts = _f32(scan_xyzi, 4)
+        out = np.zeros((max(self.size()[0], 1), 4), np.float32)
+        n = lib().msflo_stgm_surround(self.h, _ptr(pts, C.c_float), C.c_int(pts.shape[0]),
+                                      _ptr(_pose(pose), C.c_double), _ptr(out, C.c_float))
+        return out[:n].copy()
+
+    def dump(self):
+        out = np.zeros((max(self.size()[0], 1), 4), np.float32)
+        n = lib().msflo_stgm_dump(self.h, _ptr(out, C.c_float))
+        return out[:n].copy()

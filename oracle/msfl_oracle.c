@@ -1432,3 +1432,148 @@ int msflo_voxel_grid(const float *xyzi, int n, float leaf, float *out) {
   free(v);
   return nout;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* 8f row 1: STGM map (HybridGrid) restatement -- hybrid_grid.cc:403-521                        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t key; /* packed (z, y, x) cell index, ascending order = output order */
+  float *pts;  /* n x 4 */
+  int n, cap;
+} stgm_cell;
+
+struct msflo_stgm {
+  float resolution, leaf;
+  stgm_cell *cells; /* sorted by key */
+  int n_cells, cap_cells;
+};
+
+#define STGM_OFF (1 << 20)
+static int64_t stgm_key(long ix, long iy, long iz) {
+  return ((int64_t)(iz + STGM_OFF) << 42) | ((int64_t)(iy + STGM_OFF) << 21) | (int64_t)(ix + STGM_OFF);
+}
+/* GetCellIndex (:424-428): Array3f index = point / resolution (float); RoundToInt(double) = lround */
+static int64_t stgm_cell_of(const msflo_stgm *m, float x, float y, float z) {
+  const float fx = x / m->resolution, fy = y / m->resolution, fz = z / m->resolution;
+  return stgm_key(lround((double)fx), lround((double)fy), lround((double)fz));
+}
+
+msflo_stgm *msflo_stgm_create(float resolution, float leaf) {
+  msflo_stgm *m = (msflo_stgm *)calloc(1, sizeof *m);
+  m->resolution = resolution;
+  m->leaf = leaf;
+  m->cap_cells = 64;
+  m->cells = (stgm_cell *)calloc(m->cap_cells, sizeof(stgm_cell));
+  return m;
+}
+
+void msflo_stgm_free(msflo_stgm *m) {
+  if (!m) return;
+  for (int i = 0; i < m->n_cells; i++) free(m->cells[i].pts);
+  free(m->cells);
+  free(m);
+}
+
+static int stgm_find(const msflo_stgm *m, int64_t key) { /* lower_bound */
+  int lo = 0, hi = m->n_cells;
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    if (m->cells[mid].key < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+void msflo_stgm_insert(msflo_stgm *m, const float *scan, int n) {
+  if (n <= 0) return; /* :504 */
+  int64_t *touched = (int64_t *)malloc(sizeof(int64_t) * n);
+  int nt = 0;
+  for (int i = 0; i < n; i++) { /* :506-511 push_back into the point's cell */
+    const float *p = scan + 4 * (size_t)i;
+    const int64_t key = stgm_cell_of(m, p[0], p[1], p[2]);
+    int pos = stgm_find(m, key);
+    if (pos == m->n_cells || m->cells[pos].key != key) {
+      if (m->n_cells == m->cap_cells) {
+        m->cap_cells *= 2;
+        m->cells = (stgm_cell *)realloc(m->cells, sizeof(stgm_cell) * m->cap_cells);
+      }
+      memmove(m->cells + pos + 1, m->cells + pos, sizeof(stgm_cell) * (m->n_cells - pos));
+      m->cells[pos].key = key; m->cells[pos].pts = 0; m->cells[pos].n = 0; m->cells[pos].cap = 0;
+      m->n_cells++;
+    }
+    stgm_cell *c = &m->cells[pos];
+    if (c->n == c->cap) {
+      c->cap = c->cap ? 2 * c->cap : 16;
+      c->pts = (float *)realloc(c->pts, sizeof(float) * 4 * c->cap);
+    }
+    memcpy(c->pts + 4 * (size_t)c->n, p, 16);
+    c->n++;
+    touched[nt++] = key;
+  }
+  for (int i = 0; i < nt; i++) { /* :513-520 every touched cell is voxel-filtered once */
+    stgm_cell *c = &m->cells[stgm_find(m, touched[i])];
+    if (c->cap < 0) continue; /* already filtered in this call (marker) */
+    float *tmp = (float *)malloc(sizeof(float) * 4 * (size_t)c->n);
+    int no = msflo_voxel_grid(c->pts, c->n, m->leaf, tmp);
+    memcpy(c->pts, tmp, sizeof(float) * 4 * (size_t)no);
+    free(tmp);
+    c->n = no;
+    c->cap = -c->cap; /* mark */
+  }
+  for (int i = 0; i < m->n_cells; i++)
+    if (m->cells[i].cap < 0) m->cells[i].cap = -m->cells[i].cap;
+  free(touched);
+}
+
+/* Rigid3f * Vector3f with Eigen's float quaternion rotation, then + (i, j, k) (:474-481) */
+static void stgm_transform_f(const double pose[7], const float *p, float out[3]) {
+  const float qx = (float)pose[3], qy = (float)pose[4], qz = (float)pose[5], qw = (float)pose[6];
+  const float tx = (float)pose[0], ty = (float)pose[1], tz = (float)pose[2];
+  float uv0 = qy * p[2] - qz * p[1], uv1 = qz * p[0] - qx * p[2], uv2 = qx * p[1] - qy * p[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  const float c0 = qy * uv2 - qz * uv1, c1 = qz * uv0 - qx * uv2, c2 = qx * uv1 - qy * uv0;
+  out[0] = (p[0] + qw * uv0 + c0) + tx;
+  out[1] = (p[1] + qw * uv1 + c1) + ty;
+  out[2] = (p[2] + qw * uv2 + c2) + tz;
+}
+
+int msflo_stgm_surround(const msflo_stgm *m, const float *scan, int n, const double pose[7], float *out) {
+  unsigned char *sel = (unsigned char *)calloc(m->n_cells > 0 ? m->n_cells : 1, 1);
+  for (int a = 0; a < n; a++) {
+    const float *p = scan + 4 * (size_t)a;
+    const float nr = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    if ((double)nr > 60.0) continue; /* kDist :474, :532 */
+    float w[3];
+    stgm_transform_f(pose, p, w);
+    for (int i = -1; i <= 1; ++i)
+      for (int j = -1; j <= 1; ++j)
+        for (int k = -1; k <= 1; ++k) {
+          const int64_t key = stgm_cell_of(m, w[0] + (float)i, w[1] + (float)j, w[2] + (float)k);
+          const int pos = stgm_find(m, key);
+          if (pos < m->n_cells && m->cells[pos].key == key) sel[pos] = 1; /* TryInsertGrid :524-529 */
+        }
+  }
+  int no = 0;
+  for (int c = 0; c < m->n_cells; c++)
+    if (sel[c]) {
+      memcpy(out + 4 * (size_t)no, m->cells[c].pts, sizeof(float) * 4 * (size_t)m->cells[c].n);
+      no += m->cells[c].n;
+    }
+  free(sel);
+  return no;
+}
+
+int msflo_stgm_size(const msflo_stgm *m, int *n_cells) {
+  int n = 0;
+  for (int c = 0; c < m->n_cells; c++) n += m->cells[c].n;
+  if (n_cells) *n_cells = m->n_cells;
+  return n;
+}
+
+int msflo_stgm_dump(const msflo_stgm *m, float *out) {
+  int no = 0;
+  for (int c = 0; c < m->n_cells; c++) {
+    memcpy(out + 4 * (size_t)no, m->cells[c].pts, sizeof(float) * 4 * (size_t)m->cells[c].n);
+    no += m->cells[c].n;
+  }
+  return no;
+}

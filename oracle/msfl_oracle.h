@@ -201,6 +201,21 @@ int msflo_extract_features(const msflo_params *P, const float *xyzi, const uint1
                            int *idx_sharp, int *n_sharp, int *idx_less_sharp, int *n_less_sharp,
                            int *idx_flat, int *n_flat, int *idx_less_flat, int *n_less_flat);
 
+/* ---- 8f row 1: STGM map (HybridGrid, hybrid_grid.cc:403-521): 3 m cells each holding a cloud that is
+ *      re-voxel-filtered on every insert; surround query = cells hit by scan points +-1 m.
+ *      The reference concatenates the selected cells in unordered_set<shared_ptr> order (heap-address
+ *      dependent); this restatement (and the GPU producer) use ascending cell key (z, y, x). ---- */
+typedef struct msflo_stgm msflo_stgm;
+msflo_stgm *msflo_stgm_create(float resolution, float leaf);
+void msflo_stgm_free(msflo_stgm *m);
+/* HybridGridImpl::InsertScan (:503-521): scan_world already transformed (laser_mapping.cc:330-338) */
+void msflo_stgm_insert(msflo_stgm *m, const float *scan_world_xyzi, int n);
+/* HybridGridImpl::GetSurroundedCloud (:470-501); out capacity msflo_stgm_size(); returns n_out */
+int msflo_stgm_surround(const msflo_stgm *m, const float *scan_xyzi, int n, const double pose[7], float *out_xyzi);
+int msflo_stgm_size(const msflo_stgm *m, int *n_cells);
+/* all points, cells in ascending key order; out capacity msflo_stgm_size() */
+int msflo_stgm_dump(const msflo_stgm *m, float *out_xyzi);
+
 /* ---- pcl::VoxelGrid<PointXYZI>::filter restatement; out capacity n; returns n_out ---- */
 int msflo_voxel_grid(const float *xyzi, int n, float leaf, float *out_xyzi);
 

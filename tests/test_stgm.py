@@ -1,0 +1,86 @@
+"""SURVEY.md 8f row 1 -- GPU-resident STGM submap producer (HybridGrid) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle as O
+from msf_loam_b200 import synth as S
+
+
+def _scans(n=4, seed0=500):
+    P = O.default_params()
+    scene, traj = S.make_scene(), S.trajectory(n)
+    out = []
+    for k in range(n):
+        f = O.extract_features(P, *S.raycast_scan(scene, "vlp16", traj[k], seed=seed0 + k), None)
+        out.append((f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]], traj[k]))
+    return out
+
+
+def test_oracle_stgm_properties():
+    scans = _scans(3)
+    m = O.Stgm(3.0, 0.4)
+    sizes = []
+    for corner, surf, pose in scans:
+        m.insert(S.transform_cloud(pose, surf))
+        sizes.append(m.size())
+    assert sizes[0][0] < sizes[1][0] < sizes[2][0] and sizes[2][1] >= sizes[0][1]
+    allpts = m.dump()
+    # every cell was voxel-filtered: inside a 3 m cell no two points share a 0.4 m voxel (a voxel that
+    # straddles a cell border legitimately yields one centroid per cell)
+    vox = np.floor(allpts[:, :3] * (np.float32(1.0) / np.float32(0.4))).astype(np.int64)
+    cellid = np.round(allpts[:, :3] / np.float32(3.0)).astype(np.int64)
+    assert len(np.unique(np.concatenate([cellid, vox], axis=1), axis=0)) >= 0.995 * len(allpts)
+    # a single insert of a cloud == VoxelGrid per 3 m cell
+    one = O.Stgm(3.0, 0.4)
+    w = S.transform_cloud(scans[0][2], scans[0][1])
+    one.insert(w)
+    cell = np.round(w[:, :3].astype(np.float32) / np.float32(3.0)).astype(np.int64)
+    expect = sum(len(O.voxel_grid(w[np.all(cell == c, axis=1)], 0.4)) for c in np.unique(cell, axis=0))
+    assert one.size()[0] == expect
+    # surround from inside the mapped area returns (almost) the whole map; from far away, nothing
+    sur = m.surround(scans[2][1], scans[2][2])
+    assert 0.9 * len(allpts) <= len(sur) <= len(allpts)
+    far = np.array([500.0, 0, 0, 0, 0, 0, 1.0])
+    assert len(m.surround(scans[2][1], far)) == 0
+
+
+@pytest.mark.gpu
+def test_cuda_stgm_matches_oracle_bitwise_and_feeds_scan2map():
+    from msf_loam_b200 import Engine, HybridGrid, set_submap_from_maps
+    scans = _scans(4)
+    e = Engine()
+    gc, gs = HybridGrid(e, 3.0, 0.2), HybridGrid(e, 3.0, 0.4)
+    oc, os_ = O.Stgm(3.0, 0.2), O.Stgm(3.0, 0.4)
+    for k, (corner, surf, pose) in enumerate(scans[:3]):
+        if k == 1:   # world-frame input path
+            gc.InsertScan(S.transform_cloud(pose, corner)); gs.InsertScan(S.transform_cloud(pose, surf))
+        else:        # sensor-frame scan + pose (TransformPointCloud on the device)
+            gc.InsertScan(corner, pose); gs.InsertScan(surf, pose)
+        oc.insert(S.transform_cloud(pose, corner)); os_.insert(S.transform_cloud(pose, surf))
+        assert gc.size() == oc.size() and gs.size() == os_.size()
+        assert np.array_equal(gc.dump(), oc.dump()) and np.array_equal(gs.dump(), os_.dump())
+    corner, surf, pose = scans[3]
+    guess = S.perturb_pose(pose, np.random.default_rng(1))
+    sc, ss = gc.GetSurroundedCloud(corner, guess), gs.GetSurroundedCloud(surf, guess)
+    assert np.array_equal(sc, oc.surround(corner, guess)) and np.array_equal(ss, os_.surround(surf, guess))
+    assert len(sc) > 10 and len(ss) > 50  # the reference's gate (laser_mapping.cc:284-285)
+    # the device-resident surround clouds become the submap without touching the host
+    q_corner, q_surf = e.voxel_grid(corner, 0.2), e.voxel_grid(surf, 0.4)
+    set_submap_from_maps(e, gc, gs)
+    rc, x_dev, st = e.scan2map(q_corner, q_surf, guess)
+    e.set_submap(sc, ss)
+    rc2, x_host, st2 = e.scan2map(q_corner, q_surf, guess)
+    assert rc == rc2 == 0 and np.array_equal(x_dev, x_host)
+    x_ref, _, _ = O.scan2map(O.default_params(), sc, ss, q_corner, q_surf, guess)
+    dt, dr = S.pose_error(x_dev, x_ref)
+    assert dt < 1e-8 and dr < 1e-8
+    dt, dr = S.pose_error(x_dev, pose)
+    assert dt < 0.05 and dr < 0.01
+    # empty map / empty scan edge cases
+    empty = HybridGrid(e, 3.0, 0.4)
+    assert len(empty.GetSurroundedCloud(surf, guess)) == 0
+    empty.InsertScan(np.zeros((0, 4), np.float32))
+    assert empty.size() == (0, 0)
+    for g in (gc, gs, empty):
+        g.close()
+    e.close()
