@@ -251,6 +251,21 @@ int msfl_map_download(msfl_map *m, int which, float *out_xyzi, size_t capacity, 
 /* cloud_map.cloud_corner_less_sharp / cloud_surf_less_flat := the two last surround results. */
 int msfl_set_submap_from_maps(msfl_engine *e, msfl_map *corner, msfl_map *surf);
 
+/* ---- wire format: view a sensor_msgs/PointCloud2 data buffer as an msfl_cloud
+ *      (what pcl::fromROSMsg does at msf_loam_node.cc:166-167 with the field list of common.h:53-62).
+ *      x, y, z must be FLOAT32 (datatype 7), intensity FLOAT32 (optional), ring UINT16 (datatype 4,
+ *      optional); little-endian, rows dense (row_step == width * point_step).  No copy is made: the
+ *      unpack to float4 happens on the GPU inside msfl_extract_features. -------------------------- */
+typedef struct msfl_pc2_field {
+  const char *name;
+  uint32_t offset;
+  uint8_t datatype;
+  uint32_t count;
+} msfl_pc2_field;
+int msfl_cloud_from_pointcloud2(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step,
+                                uint32_t row_step, int is_bigendian, const msfl_pc2_field *fields, int n_fields,
+                                msfl_cloud *out);
+
 /* ---- caller-side pcl::VoxelGrid<PointXYZI> (laser_mapping.cc:264-270) --
  * out_xyzi capacity in->n x 4 floats; *n_out receives the number of centroids. */
 int msfl_voxel_grid(msfl_engine *e, const msfl_cloud *in, float leaf, float *out_xyzi, size_t *n_out);

@@ -26,7 +26,7 @@ EXPORTS = [
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
     "msfl_scan2map_batch_device", "msfl_scan2map_deskew", "msfl_associate_map", "msfl_scan2scan", "msfl_associate_scan",
     "msfl_extract_features", "msfl_voxel_grid", "msfl_accumulate", "msfl_map_create", "msfl_map_destroy",
-    "msfl_map_insert", "msfl_map_surround", "msfl_map_size", "msfl_map_download", "msfl_set_submap_from_maps",
+    "msfl_cloud_from_pointcloud2", "msfl_map_insert", "msfl_map_surround", "msfl_map_size", "msfl_map_download", "msfl_set_submap_from_maps",
 ]
 
 
@@ -94,6 +94,10 @@ class Deskew(C.Structure):
     _fields_ = [("sum_dt", C.POINTER(C.c_double)), ("delta_q", C.POINTER(C.c_double)),
                 ("delta_p", C.POINTER(C.c_double)), ("n", C.c_int32), ("_pad", C.c_int32),
                 ("velocity", C.c_double * 3), ("gravity", C.c_double * 3)]
+
+
+class Pc2Field(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
 
 
 class Features(C.Structure):

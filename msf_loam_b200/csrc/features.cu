@@ -39,6 +39,33 @@ __global__ void k_feat_init(FeatMeta *m) {
   if (t < 4) m->tot[t] = 0;
 }
 
+// Wire format -> packed arrays on the GPU: the raw AoS bytes of a
+// pcl::PointCloud<PointXYZIRT> / sensor_msgs::PointCloud2 data buffer (fields x, y, z, intensity, ring at
+// arbitrary, possibly unaligned byte offsets; pcl::fromROSMsg at msf_loam_node.cc:166-167, field list
+// common.h:53-62) are copied to the device as they are and unpacked here, so the host never loops over points.
+__device__ __forceinline__ float load_f32_unaligned(const unsigned char *p) {
+  const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+  return __uint_as_float(v);
+}
+
+__global__ void k_unpack_aos(const unsigned char *__restrict__ raw, uint32_t n, uint32_t stride, uint32_t off_xyz,
+                             uint32_t off_i, uint32_t off_ring, int has_i, float4 *__restrict__ pts,
+                             uint16_t *__restrict__ ring) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char *p = raw + (size_t)i * stride;
+  float4 o;
+  if (((stride | off_xyz) & 3u) == 0) {  // aligned fast path (PCL structs are 16-byte aligned)
+    const float *f = reinterpret_cast<const float *>(p + off_xyz);
+    o.x = f[0]; o.y = f[1]; o.z = f[2];
+  } else {
+    o.x = load_f32_unaligned(p + off_xyz); o.y = load_f32_unaligned(p + off_xyz + 4); o.z = load_f32_unaligned(p + off_xyz + 8);
+  }
+  o.w = has_i ? load_f32_unaligned(p + off_i) : 0.f;
+  pts[i] = o;
+  ring[i] = (uint16_t)((uint32_t)p[off_ring] | ((uint32_t)p[off_ring + 1] << 8));
+}
+
 // RemoveInvalidPointsFromCloud (:96-103): float norm vs double min_range, non-finite dropped.
 __global__ void k_feat_keys(const float4 *__restrict__ raw, const uint16_t *__restrict__ ring, uint32_t n, double min_range,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, FeatMeta *m) {
@@ -302,25 +329,12 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
   const uint32_t N = (uint32_t)n;
   const msfl_params &P = e->params;
   int rc;
-  // host pack + upload
-  if ((rc = e->h_stage.reserve(n * 16 + n * 2 + 64))) return rc;
-  float *h4 = e->h_stage.as<float>();
-  uint16_t *hr = (uint16_t *)(e->h_stage.as<char>() + n * 16);
-  {
-    const char *base = (const char *)raw->data;
-    const bool has_i = raw->off_intensity != MSFL_NO_FIELD;
-    for (size_t i = 0; i < n; ++i) {
-      const char *pt = base + i * raw->stride;
-      memcpy(h4 + 4 * i, pt + raw->off_xyz, 12);
-      float w = 0.f;
-      if (has_i) memcpy(&w, pt + raw->off_intensity, 4);
-      h4[4 * i + 3] = w;
-      memcpy(hr + i, pt + raw->off_ring, 2);
-    }
-  }
+  // raw AoS bytes -> device, unpacked there (no per-point host loop)
+  const size_t raw_bytes = n * raw->stride;
   const int S = P.n_sectors;
   const size_t slots = (size_t)MSFL_MAX_RINGS * S * (P.n_sharp + P.n_less_sharp + P.n_flat);
   if ((rc = e->f_raw.reserve(n * 16 + n * 2 + 64))) return rc;
+  if ((rc = e->f_misc.reserve(raw_bytes + 64))) return rc;
   if ((rc = e->f_keys.reserve(n * 4))) return rc;
   if ((rc = e->f_keys_alt.reserve(n * 4))) return rc;
   if ((rc = e->f_vals.reserve(n * 4))) return rc;
@@ -332,9 +346,13 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
   if ((rc = e->f_label.reserve(n * 4 + n))) return rc;  // labels + picked flags
   if ((rc = e->f_idx.reserve((5 * n + slots) * 4))) return rc;
   if ((rc = e->f_cnt.reserve(sizeof(FeatMeta)))) return rc;
-  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_raw.p, e->h_stage.p, n * 16 + n * 2, cudaMemcpyHostToDevice, st));
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_misc.p, raw->data, raw_bytes, cudaMemcpyHostToDevice, st));
   const float4 *d_raw = e->f_raw.as<float4>();
   const uint16_t *d_ring_in = (const uint16_t *)(e->f_raw.as<char>() + n * 16);
+  k_unpack_aos<<<(N + 255) / 256, 256, 0, st>>>(e->f_misc.as<unsigned char>(), N, (uint32_t)raw->stride, (uint32_t)raw->off_xyz,
+                                               raw->off_intensity == MSFL_NO_FIELD ? 0u : (uint32_t)raw->off_intensity,
+                                               (uint32_t)raw->off_ring, raw->off_intensity != MSFL_NO_FIELD,
+                                               e->f_raw.as<float4>(), (uint16_t *)(e->f_raw.as<char>() + n * 16));
   FeatMeta *meta = e->f_cnt.as<FeatMeta>();
   uint32_t *keys = e->f_keys.as<uint32_t>(), *vals = e->f_vals.as<uint32_t>();
   const int tb = 256;
@@ -369,7 +387,7 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
   Pose7 T7;
   for (int i = 0; i < 7; ++i) T7.v[i] = T ? T[i] : (i == 6 ? 1.0 : 0.0);
   k_feat_extrinsic<<<gb, tb, 0, st>>>(full_pre, meta, T7, full_post);
-  e->launches += 10 + 3;
+  e->launches += 11 + 3;
   MSFL_CUDA_OK(cudaGetLastError());
   FeatMeta hm;
   MSFL_CUDA_OK(cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, st));
@@ -403,7 +421,12 @@ extern "C" int msfl_extract_features(msfl_engine *e, const msfl_cloud *raw, cons
   if (!e || !raw || !out) { set_error("msfl_extract_features: bad argument"); return MSFL_ERR_ARG; }
   out->n_full = out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
   if (raw->n == 0 || !raw->data) { set_error("extract_features: empty cloud"); return MSFL_ERR_EMPTY; }
-  if (raw->off_ring == MSFL_NO_FIELD || raw->stride < 12 || raw->n > 0x3fffffffull) { set_error("extract_features: cloud needs xyz + ring"); return MSFL_ERR_ARG; }
+  if (raw->off_ring == MSFL_NO_FIELD || raw->stride < 14 || raw->n > 0x3fffffffull || raw->off_xyz + 12 > raw->stride ||
+      raw->off_ring + 2 > raw->stride || (raw->off_intensity != MSFL_NO_FIELD && raw->off_intensity + 4 > raw->stride) ||
+      raw->n * raw->stride > 0x7fffffffull) {
+    set_error("extract_features: cloud needs xyz + ring inside the point stride");
+    return MSFL_ERR_ARG;
+  }
   MSFL_CUDA_OK(cudaSetDevice(e->device));
   return run_extract_features(e, raw, T_lidar2imu, out);
 }

@@ -704,6 +704,37 @@ int msfl_associate_map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl
   return MSFL_OK;
 }
 
+int msfl_cloud_from_pointcloud2(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step,
+                                uint32_t row_step, int is_bigendian, const msfl_pc2_field *fields, int n_fields,
+                                msfl_cloud *out) {
+  if (!out || !fields || n_fields <= 0 || (!data && (size_t)width * height > 0)) { set_error("pointcloud2: bad argument"); return MSFL_ERR_ARG; }
+  if (is_bigendian) { set_error("pointcloud2: big-endian data is not supported"); return MSFL_ERR_ARG; }
+  if (row_step != width * point_step) { set_error("pointcloud2: padded rows (row_step != width * point_step)"); return MSFL_ERR_ARG; }
+  size_t ox = MSFL_NO_FIELD, oy = MSFL_NO_FIELD, oz = MSFL_NO_FIELD, oi = MSFL_NO_FIELD, orr = MSFL_NO_FIELD;
+  for (int i = 0; i < n_fields; ++i) {
+    const msfl_pc2_field &f = fields[i];
+    if (!f.name) continue;
+    const bool f32 = f.datatype == 7, u16 = f.datatype == 4;
+    if (!strcmp(f.name, "x") && f32) ox = f.offset;
+    else if (!strcmp(f.name, "y") && f32) oy = f.offset;
+    else if (!strcmp(f.name, "z") && f32) oz = f.offset;
+    else if (!strcmp(f.name, "intensity") && f32) oi = f.offset;
+    else if (!strcmp(f.name, "ring") && u16) orr = f.offset;
+  }
+  if (ox == MSFL_NO_FIELD || oy != ox + 4 || oz != ox + 8) { set_error("pointcloud2: needs consecutive FLOAT32 x, y, z fields"); return MSFL_ERR_ARG; }
+  if (ox + 12 > point_step || (oi != MSFL_NO_FIELD && oi + 4 > point_step) || (orr != MSFL_NO_FIELD && orr + 2 > point_step)) {
+    set_error("pointcloud2: field outside point_step");
+    return MSFL_ERR_ARG;
+  }
+  out->data = data;
+  out->n = (size_t)width * height;
+  out->stride = point_step;
+  out->off_xyz = ox;
+  out->off_intensity = oi;
+  out->off_ring = orr;
+  return MSFL_OK;
+}
+
 int msfl_accumulate(msfl_engine *e, const float *p_xyz, const double *corr, int n_edge, int n_plane,
                     const double pose_tq[7], double *cost, double H[36], double g[6]) {
   if (!e || !p_xyz || !corr || !pose_tq || n_edge < 0 || n_plane < 0) { set_error("msfl_accumulate: bad argument"); return MSFL_ERR_ARG; }
