@@ -305,11 +305,11 @@ def run_ours(args):
         M = Mc + Ms
         total_bytes, assoc_bytes, solve_bytes = algorithmic_bytes(n_q, M)
         # dominant kernel = the stage with the larger share of the step
-        names = {0: "k_associate_map (kNN + line/plane fit)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
-                 2: "query transform + cell sort"}
+        names = {0: "k_knn5 (5-NN search over the submap cell index)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
+                 2: "k_transform_keys + cell radix sort", 3: "k_fit (fp64 line/plane fit)"}
         per_launch_ms = {s: stage_ms[s] / stage_cnt[s] for s in range(len(stage_ms)) if stage_cnt[s]}
         dom = max(per_launch_ms, key=lambda s: stage_ms[s])
-        dom_bytes = assoc_bytes if dom in (0, 2) else solve_bytes
+        dom_bytes = assoc_bytes if dom in (0, 2, 3) else solve_bytes  # the association pass of SURVEY 8d
         achieved = dom_bytes / (per_launch_ms[dom] * 1e-3) / 1e9
         traffic, traffic_kernel = ncu_traffic(args.workload, B)
         roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak,

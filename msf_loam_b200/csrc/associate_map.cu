@@ -247,19 +247,19 @@ __device__ __forceinline__ float3 deskew_transform(const double pose[7], const D
   return transform_point_f(T, px, py, pz);
 }
 
-// Association kernel.  SORTED = false: thread k handles flat query k and transforms it itself.
+// Search kernel.  SORTED = false: thread k handles flat query k and transforms it itself.
 // SORTED = true: thread s handles query perm[s] (queries ordered by the cell of their transformed
 // point, so the lanes of a warp walk the same candidate ranges: uniform trip counts and broadcast
 // loads).  STORED_X: read the transformed point stored by k_transform_keys (the permutation was
 // built for the current poses); otherwise transform here (the permutation of an earlier outer
 // iteration is reused -- it is only a locality hint, the result does not depend on it).
 template <bool SORTED, bool STORED_X, bool DESKEW>
-__global__ void __launch_bounds__(128)
-k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
-                const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
-                const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
-                const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, double *__restrict__ corr,
-                int32_t *__restrict__ knn_out, DeskewTable tb, const double *__restrict__ dsk) {
+__global__ void __launch_bounds__(128, 10)
+k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
+       const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
+       const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
+       const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, DeskewTable tb,
+       const double *__restrict__ dsk) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_corner_total + n_surf_total) return;
   const uint32_t k = SORTED ? __ldg(perm + slot) : slot;
@@ -279,20 +279,36 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
     if (DESKEW) x = deskew_transform(pose, tb, dsk + (size_t)k * 8, p.x, p.y, p.z, dsk_o);  // :120 / :190
     else x = transform_point_f(pose, p.x, p.y, p.z);  // mapping_scan_matcher.cc:123 / :193
   }
-  const size_t q = k;
   const GridView &g = is_corner ? gc : gs;
   Top5 t;
   const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);  // :125-128 / :195-198
-  if (knn_out) {
+  // 5 neighbour indices per query (-1 when the d5^2 gate fails), consumed by k_fit
+  int32_t *o = knn_out + (size_t)k * 5;
 #pragma unroll
-    for (int s = 0; s < 5; ++s) knn_out[q * 5 + s] = gate ? t.i[s] : -1;
-  }
+  for (int s = 0; s < 5; ++s) o[s] = gate ? t.i[s] : -1;
+}
+
+// Line / plane fit of every gated query (fp64): thread k reads its five neighbours and writes the factor
+// constants [a_or_c(3), n(3)]; n = 0 marks "no factor".  Kept apart from the search kernel so that the
+// search runs at 40 registers / 75 % occupancy (it is L2-latency bound) while the register-hungry
+// Jacobi / Householder code does not throttle it.
+template <bool DESKEW>
+__global__ void __launch_bounds__(128)
+k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
+      double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_total) return;
+  const bool is_corner = k < n_corner_total;
+  const GridView &g = is_corner ? gc : gs;
+  int idx[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)k * 5 + s);
   double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
-  if (gate) {
+  if (idx[4] >= 0) {
     double m[5][3];
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
-      const float4 mp = __ldg(g.pts_orig + t.i[s]);
+      const float4 mp = __ldg(g.pts_orig + idx[s]);
       m[s][0] = (double)mp.x; m[s][1] = (double)mp.y; m[s][2] = (double)mp.z;
     }
     double c[3];
@@ -338,10 +354,12 @@ k_associate_map(GridView gc, GridView gs, KParams kp, int B, const float4 *__res
       }
     }
   }
-  if (DESKEW && (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0)) {  // fold the constant offset: C' = C - o
-    a[0] -= dsk_o[0]; a[1] -= dsk_o[1]; a[2] -= dsk_o[2];
+  if (DESKEW && (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0)) {  // fold the constant offset: C' = C - o, o = V dt - g dt^2 / 2
+    const double dt = dsk[(size_t)k * 8 + 7];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) a[d] -= __dsub_rn(__dmul_rn(tb.V[d], dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, tb.G[d]), dt), dt));
   }
-  store_corr(corr, q, a, n);
+  store_corr(corr, k, a, n);
 }
 
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
@@ -351,15 +369,21 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
   const GridView &gc = e->map_corner.view, &gs = e->map_surf.view;
+  if (!d_knn) {  // neighbour indices travel from the search kernel to the fit kernel through this scratch
+    int rck;
+    if ((rck = e->d_knn.reserve((size_t)total * 5 * 4))) return rck;
+    d_knn = e->d_knn.as<int32_t>();
+  }
   const int mode = e->params.assoc_sorted;  // 0 auto, 1 never, 2 always
   const bool sorted = mode == 2 || (mode == 0 && total >= 65536u);
   if (!sorted) {
     stage_begin(e, 0);
-    k_associate_map<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, nullptr, d_corr, d_knn,
+    k_knn5<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, nullptr, d_knn,
         DeskewTable{}, nullptr);
+    k_fit<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
     stage_end(e);
-    e->launches += 1;
+    e->launches += 2;
     MSFL_CUDA_OK(cudaGetLastError());
     return MSFL_OK;
   }
@@ -369,11 +393,12 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     // later outer iteration: poses moved by centimetres, the previous cell order is still a good
     // locality hint -> skip the transform/sort pass, transform inside the association kernel
     stage_begin(e, 0);
-    k_associate_map<true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, e->a_perm, d_corr, d_knn,
+    k_knn5<true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, e->a_perm, d_knn,
         DeskewTable{}, nullptr);
+    k_fit<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
     stage_end(e);
-    e->launches += 1;
+    e->launches += 2;
     MSFL_CUDA_OK(cudaGetLastError());
     return MSFL_OK;
   }
@@ -401,11 +426,14 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   e->a_perm = dv.Current();
   e->a_perm_valid = total;
   stage_begin(e, 0);
-  k_associate_map<true, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-      gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm,
-      d_corr, d_knn, DeskewTable{}, nullptr);
+  k_knn5<true, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+      gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
+      DeskewTable{}, nullptr);
   stage_end(e);
-  e->launches += 2 + 3;
+  stage_begin(e, 3);
+  k_fit<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+  stage_end(e);
+  e->launches += 3 + 3;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }
@@ -427,13 +455,19 @@ int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_
                                 const double *d_dsk, double *d_corr, int32_t *d_knn) {
   const uint32_t total = nc + ns;
   if (total == 0) return MSFL_OK;
+  if (!d_knn) {
+    int rck;
+    if ((rck = e->d_knn.reserve((size_t)total * 5 * 4))) return rck;
+    d_knn = e->d_knn.as<int32_t>();
+  }
   DeskewTable tb{d_sum_dt, d_dq, d_dp, n_tab, {V[0], V[1], V[2]}, {G[0], G[1], G[2]}};
   stage_begin(e, 0);
-  k_associate_map<false, false, true><<<(total + 127) / 128, 128, 0, e->stream>>>(
-      e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_corr,
-      d_knn, tb, d_dsk);
+  k_knn5<false, false, true><<<(total + 127) / 128, 128, 0, e->stream>>>(
+      e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_knn, tb,
+      d_dsk);
+  k_fit<true><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk);
   stage_end(e);
-  e->launches += 1;
+  e->launches += 2;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }

@@ -507,6 +507,7 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
   for (auto &k : ch) max_total = std::max(max_total, (k.ci1 - k.ci0) + (k.si1 - k.si0));
   if ((rc = e->d_corr.reserve((max_total + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
+  if ((rc = e->d_knn.reserve(max_total * 20))) return rc;
   if ((rc = e->a_xq.reserve(max_total * 16))) return rc;
   if ((rc = e->a_keys.reserve(max_total * 4))) return rc;
   if ((rc = e->a_keys_alt.reserve(max_total * 4))) return rc;

@@ -139,62 +139,78 @@ __device__ inline void sym_eig3_top(double a00, double a01, double a02, double a
 
 // ---------------------------------------------------------------------------------------------
 // 5x3 least squares A x = b by column-pivoted Householder QR (stands in for
-// matA0.colPivHouseholderQr().solve(matB0), mapping_scan_matcher.cc:210).
+// matA0.colPivHouseholderQr().solve(matB0), mapping_scan_matcher.cc:210).  Every index is a
+// compile-time constant (the pivot is applied as a conditional column swap), so A, b and the
+// reflector stay in registers -- the dynamically indexed version lived in local memory.
 // ---------------------------------------------------------------------------------------------
-__device__ inline void lstsq_5x3(double A[5][3], double b[5], double x[3]) {
+template <int K>
+__device__ __forceinline__ void qr_step(double (&A)[5][3], double (&b)[5], int (&perm)[3], double (&Rdiag)[3], int &rank,
+                                        double &maxpiv) {
+  if (rank < 3) return;  // an earlier column was (numerically) zero: Eigen stops there too
+  // pivot: first remaining column with the largest norm over rows K..4
+  double cn[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = K; j < 3; ++j)
+#pragma unroll
+    for (int i = K; i < 5; ++i) cn[j] += A[i][j] * A[i][j];
+  int best = K;
+  double bn = cn[K];
+#pragma unroll
+  for (int j = K + 1; j < 3; ++j)
+    if (cn[j] > bn) { bn = cn[j]; best = j; }
+#pragma unroll
+  for (int j = K + 1; j < 3; ++j) {
+    if (best == j) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { const double t = A[i][K]; A[i][K] = A[i][j]; A[i][j] = t; }
+      const int t = perm[K]; perm[K] = perm[j]; perm[j] = t;
+    }
+  }
+  const double nrm = sqrt(bn);
+  if (K == 0) maxpiv = nrm;
+  if (!(nrm > maxpiv * 1e-14) || nrm == 0.0) { rank = K; return; }
+  const double alpha = (A[K][K] > 0) ? -nrm : nrm;
+  double v[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) v[i] = i >= K ? A[i][K] : 0.0;
+  v[K] -= alpha;
+  double vv = 0;
+#pragma unroll
+  for (int i = K; i < 5; ++i) vv += v[i] * v[i];
+  if (vv > 0) {
+#pragma unroll
+    for (int j = K; j < 3; ++j) {
+      double s = 0;
+#pragma unroll
+      for (int i = K; i < 5; ++i) s += v[i] * A[i][j];
+      s = 2.0 * s / vv;
+#pragma unroll
+      for (int i = K; i < 5; ++i) A[i][j] -= s * v[i];
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = K; i < 5; ++i) s += v[i] * b[i];
+    s = 2.0 * s / vv;
+#pragma unroll
+    for (int i = K; i < 5; ++i) b[i] -= s * v[i];
+  }
+  Rdiag[K] = A[K][K];
+}
+
+__device__ __forceinline__ void lstsq_5x3(double (&A)[5][3], double (&b)[5], double (&x)[3]) {
   int perm[3] = {0, 1, 2};
   double Rdiag[3] = {0, 0, 0};
   int rank = 3;
   double maxpiv = 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (k >= rank) break;
-    int best = k;
-    double bn = -1;
-    for (int j = k; j < 3; ++j) {
-      double s = 0;
-      for (int i = k; i < 5; ++i) s += A[i][j] * A[i][j];
-      if (s > bn) { bn = s; best = j; }
-    }
-    if (best != k) {
-      for (int i = 0; i < 5; ++i) { const double t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; }
-      const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
-    }
-    const double nrm = sqrt(bn);
-    if (k == 0) maxpiv = nrm;
-    if (!(nrm > maxpiv * 1e-14) || nrm == 0.0) { rank = k; break; }
-    const double alpha = (A[k][k] > 0) ? -nrm : nrm;
-    double v[5] = {0, 0, 0, 0, 0};
-    for (int i = k; i < 5; ++i) v[i] = A[i][k];
-    v[k] -= alpha;
-    double vv = 0;
-    for (int i = k; i < 5; ++i) vv += v[i] * v[i];
-    if (vv > 0) {
-      for (int j = k; j < 3; ++j) {
-        double s = 0;
-        for (int i = k; i < 5; ++i) s += v[i] * A[i][j];
-        s = 2.0 * s / vv;
-        for (int i = k; i < 5; ++i) A[i][j] -= s * v[i];
-      }
-      double s = 0;
-      for (int i = k; i < 5; ++i) s += v[i] * b[i];
-      s = 2.0 * s / vv;
-      for (int i = k; i < 5; ++i) b[i] -= s * v[i];
-    }
-    Rdiag[k] = A[k][k];
-  }
+  qr_step<0>(A, b, perm, Rdiag, rank, maxpiv);
+  qr_step<1>(A, b, perm, Rdiag, rank, maxpiv);
+  qr_step<2>(A, b, perm, Rdiag, rank, maxpiv);
   double y[3] = {0, 0, 0};
-  for (int i = 2; i >= 0; --i) {
-    if (i >= rank) continue;
-    double s = b[i];
-    for (int j = i + 1; j < rank; ++j) s -= A[i][j] * y[j];
-    y[i] = s / Rdiag[i];
-  }
-  x[0] = x[1] = x[2] = 0;
-  for (int i = 0; i < 3; ++i) {
-    const int pi = perm[i];
-    if (pi == 0) x[0] = y[i]; else if (pi == 1) x[1] = y[i]; else x[2] = y[i];
-  }
+  if (rank > 2) y[2] = b[2] / Rdiag[2];
+  if (rank > 1) y[1] = (b[1] - (rank > 2 ? A[1][2] * y[2] : 0.0)) / Rdiag[1];
+  if (rank > 0) y[0] = ((b[0] - (rank > 1 ? A[0][1] * y[1] : 0.0)) - (rank > 2 ? A[0][2] * y[2] : 0.0)) / Rdiag[0];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = perm[0] == c ? y[0] : (perm[1] == c ? y[1] : y[2]);
 }
 
 // 6x6 SPD solve by Cholesky (the LM normal equations).  Returns false when not positive
