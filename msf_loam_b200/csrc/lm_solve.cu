@@ -18,7 +18,7 @@ namespace cg = cooperative_groups;
 
 namespace msfl {
 
-constexpr int kLmThreads = 256;
+constexpr int kLmThreads = 128;
 constexpr int kAcc = 28;  // 21 upper-tri H + 6 g + 1 cost
 
 struct LmShared {
@@ -392,7 +392,7 @@ __device__ void lm_finish_step(LmShared &sh, const KParams &kp, msfl_lm_log *log
 }
 
 template <int PB>
-__global__ void __launch_bounds__(kLmThreads, 2)
+__global__ void __launch_bounds__(kLmThreads, 4)
 k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
