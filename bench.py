@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=32, help="distinct query scans (replicated to fill the batch)")
     ap.add_argument("--cpu-sample", type=int, default=384, help="scans timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    ap.add_argument("--map-scans", type=int, default=N_MAP_SCANS, help="scans merged into the submap (config 5: 50)")
     return ap.parse_args()
 
 
@@ -60,23 +61,24 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # workload generation
 # ------------------------------------------------------------------------------------------------
-def raw_scans(workload, n_distinct):
+def raw_scans(workload, n_distinct, n_map=N_MAP_SCANS):
     sensor, scene_kind, _ = WORKLOADS[workload]
     scene = S.make_scene(scene_kind)
-    traj = S.trajectory(N_MAP_SCANS + n_distinct)
+    # long maps: shorter steps so the trajectory stays inside the room
+    traj = S.trajectory(n_map + n_distinct, step=0.5 if n_map <= 8 else 0.25, yaw_deg=1.0 if n_map <= 8 else 0.5)
     scans = [S.raycast_scan(scene, sensor, traj[k], seed=100 + k, sigma=SIGMA) for k in range(len(traj))]
     return traj, scans
 
 
-def build_case_gpu(eng, workload, n_distinct):
+def build_case_gpu(eng, workload, n_distinct, n_map=N_MAP_SCANS):
     """submap + query features through the product path (CUDA extraction + CUDA VoxelGrid)."""
-    traj, scans = raw_scans(workload, n_distinct)
+    traj, scans = raw_scans(workload, n_distinct, n_map)
     mc, ms, queries, n_pts = [], [], [], []
     for k, (xyzi, ring) in enumerate(scans):
         f = eng.extract_features(xyzi, ring, None)
         n_pts.append(f["full"].shape[0])
         corner, surf = f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]]
-        if k < N_MAP_SCANS:
+        if k < n_map:
             mc.append(S.transform_cloud(traj[k], corner))
             ms.append(S.transform_cloud(traj[k], surf))
         else:
@@ -86,17 +88,17 @@ def build_case_gpu(eng, workload, n_distinct):
     return map_corner, map_surf, queries, int(np.mean(n_pts))
 
 
-def build_case_cpu(workload, n_distinct):
+def build_case_cpu(workload, n_distinct, n_map=N_MAP_SCANS):
     """same case through the oracle (the reference arm must not touch our kernels)."""
     import oracle as O
     P = O.default_params()
-    traj, scans = raw_scans(workload, n_distinct)
+    traj, scans = raw_scans(workload, n_distinct, n_map)
     mc, ms, queries, n_pts = [], [], [], []
     for k, (xyzi, ring) in enumerate(scans):
         f = O.extract_features(P, xyzi, ring, None)
         n_pts.append(f["full"].shape[0])
         corner, surf = f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]]
-        if k < N_MAP_SCANS:
+        if k < n_map:
             mc.append(S.transform_cloud(traj[k], corner))
             ms.append(S.transform_cloud(traj[k], surf))
         else:
@@ -218,7 +220,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         eng = Engine(default_params(**over), device=local_rank, stream=stream.cuda_stream)
         # ---- inputs (product path) -------------------------------------------------------------
-        map_corner, map_surf, queries, n_full = build_case_gpu(eng, args.workload, args.distinct)
+        map_corner, map_surf, queries, n_full = build_case_gpu(eng, args.workload, args.distinct, args.map_scans)
         qc, c_off, qs, s_off, inits = assemble_batch(queries, B, seed=1000 + rank)
         Mc, Ms = map_corner.shape[0], map_surf.shape[0]
         n_q = int(c_off[-1] + s_off[-1])
@@ -332,7 +334,7 @@ def run_ours(args):
             "config": {"workload": WORKLOADS[args.workload][2], "sensor": args.workload,
                        "scans_per_gpu_per_step": B, "distinct_scans": len(queries),
                        "points_per_scan": n_full, "queries_per_scan": round(n_q / B, 1),
-                       "submap_points": {"corner": Mc, "surf": Ms}, "outer_iterations": K_OUTER,
+                       "submap_points": {"corner": Mc, "surf": Ms}, "submap_scans": args.map_scans, "outer_iterations": K_OUTER,
                        "lm_attempts_per_outer": L_ATTEMPTS, "early_exit": False,
                        "range_noise_sigma_m": SIGMA, "parallelism": f"scan-sharded x{world}" + (
                            ", NCCL submap broadcast per step" if world > 1 else ""),
@@ -384,7 +386,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     over = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
     P = O.default_params(**over)
-    map_corner, map_surf, queries, n_full = build_case_cpu(args.workload, min(args.distinct, 16))
+    map_corner, map_surf, queries, n_full = build_case_cpu(args.workload, min(args.distinct, 16), args.map_scans)
     n = max(threads * 2, 8)  # bounded sample per step
     qc, c_off, qs, s_off, inits = assemble_batch(queries, n, seed=1000)
     for _ in range(max(1, min(args.warmup, 2))):
