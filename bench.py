@@ -320,7 +320,7 @@ def run_ours(args):
                     "avg_launch_ms": round(per_launch_ms[dom], 4),
                     "stage_share": {names[s]: round(stage_ms[s] / sum(stage_ms), 3) for s in per_launch_ms},
                     "whole_step_GBps": round(total_bytes / (ms_per_step * 1e-3) / 1e9, 2),
-                    "note": "latency/issue-bound path: the submap and correspondences live in L2, see DESIGN.md"}
+                    "note": "achieved = SURVEY 8d algorithmic bytes of that pass / CUDA-event time; see DESIGN.md section 4"}
         cpu = None
         pose_err = None
         if not args.no_cpu and world >= 1:
