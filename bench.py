@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--workload", default="vlp16", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=2048, help="scans per GPU per step")
     ap.add_argument("--distinct", type=int, default=32, help="distinct query scans (replicated to fill the batch)")
-    ap.add_argument("--cpu-sample", type=int, default=384, help="scans timed on the CPU oracle for cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=1536, help="scans timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--map-scans", type=int, default=N_MAP_SCANS, help="scans merged into the submap (config 5: 50)")
     return ap.parse_args()

@@ -157,7 +157,8 @@ __device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) 
 // ---------------------------------------------------------------------------------------------
 constexpr int kPerThread = 2;              // entries per thread per tile
 constexpr int kTile = kLmThreads * kPerThread;
-constexpr int kStages = 3;
+constexpr int kStages = 3;      // ring depth of the streaming (throughput) configuration
+constexpr int kMaxStages = 13;  // resident configuration (clustered launches): up to 13 x 16 KB tiles stay in smem
 template <int PB> constexpr int stage_bytes() { return kTile * PB + kTile * 48; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -206,11 +207,16 @@ __device__ __forceinline__ void issue_tile(const TileSrc &ts, uint32_t t, unsign
 }
 
 // One fused sweep over the scan's correspondences at `pose`, tiles streamed through the smem ring.
-// `tile_ctr` counts tiles consumed since kernel start (stage = ctr % kStages, parity = (ctr / kStages) & 1).
+// `tile_ctr` counts tiles consumed since kernel start (stage = ctr % n_stages, parity = (ctr / n_stages) & 1).
+// When all of the CTA's tiles fit in the ring (tiles <= n_stages, the clustered / small-scan case) they are
+// loaded once by the first sweep and every later sweep reads them from shared memory without any copy or
+// barrier: tile t lives in stage t.
 template <int PB>
 __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &ts, unsigned char *ring, uint64_t *bars,
-                                            uint32_t &tile_ctr, const double *pose, double huber_a, int &cnt_edge,
-                                            int &cnt_plane) {
+                                            uint32_t n_stages, uint32_t &tile_ctr, const double *pose, double huber_a,
+                                            int &cnt_edge, int &cnt_plane) {
+  const bool resident = ts.tiles <= n_stages;
+  const bool first_sweep = tile_ctr == 0;
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
   double R[9];
@@ -220,18 +226,27 @@ __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &
   cnt_plane = 0;
   const uint32_t tid = threadIdx.x;
   if (tid == 0) {
-    for (uint32_t t = 0; t < min((uint32_t)(kStages - 1), ts.tiles); ++t) {
-      const uint32_t g = tile_ctr + t;
-      issue_tile<PB>(ts, t, ring + (g % kStages) * stage_bytes<PB>(), bars + (g % kStages));
+    if (resident) {
+      if (first_sweep)
+        for (uint32_t t = 0; t < ts.tiles; ++t) issue_tile<PB>(ts, t, ring + t * stage_bytes<PB>(), bars + t);
+    } else {
+      for (uint32_t t = 0; t < min(n_stages - 1, ts.tiles); ++t) {
+        const uint32_t g = tile_ctr + t;
+        issue_tile<PB>(ts, t, ring + (g % n_stages) * stage_bytes<PB>(), bars + (g % n_stages));
+      }
     }
   }
   for (uint32_t t = 0; t < ts.tiles; ++t) {
-    const uint32_t g = tile_ctr + t, stage = g % kStages;
-    if (tid == 0 && t + kStages - 1 < ts.tiles) {
-      const uint32_t gn = g + kStages - 1;
-      issue_tile<PB>(ts, t + kStages - 1, ring + (gn % kStages) * stage_bytes<PB>(), bars + (gn % kStages));
+    const uint32_t g = tile_ctr + t, stage = resident ? t : g % n_stages;
+    if (!resident) {
+      if (tid == 0 && t + n_stages - 1 < ts.tiles) {
+        const uint32_t gn = g + n_stages - 1;
+        issue_tile<PB>(ts, t + n_stages - 1, ring + (gn % n_stages) * stage_bytes<PB>(), bars + (gn % n_stages));
+      }
+      mbar_wait(bars + stage, (g / n_stages) & 1u);
+    } else if (first_sweep) {
+      mbar_wait(bars + stage, 0u);
     }
-    mbar_wait(bars + stage, (g / kStages) & 1u);
     const bool edge = t < ts.tiles_e;
     const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
     const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
@@ -283,7 +298,7 @@ __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &
         }
       }
     }
-    __syncthreads();  // every thread is done with this stage before it is refilled
+    if (!resident) __syncthreads();  // every thread is done with this stage before it is refilled
   }
   tile_ctr += ts.tiles;
 }
@@ -391,21 +406,66 @@ __device__ void lm_finish_step(LmShared &sh, const KParams &kp, msfl_lm_log *log
   }
 }
 
+// ---- cluster-level combine over distributed shared memory (G CTAs per scan) ---------------------
+// rank 0 adds the other CTAs' block sums in rank order (deterministic), then owns the LM step.
+__device__ __forceinline__ void cluster_reduce(cg::cluster_group &cluster, LmShared &sh, uint32_t G, uint32_t rank,
+                                               bool with_counts) {
+  cluster.sync();  // every CTA's sh.cand (and counts) are written
+  if (rank == 0) {
+    if (threadIdx.x < kAcc) {
+      double v = sh.cand[threadIdx.x];
+      for (uint32_t r = 1; r < G; ++r) v += *cluster.map_shared_rank(&sh.cand[threadIdx.x], r);
+      sh.cand[threadIdx.x] = v;
+    } else if (with_counts && threadIdx.x == 32) {
+      int ne = sh.n_edge, np = sh.n_plane;
+      for (uint32_t r = 1; r < G; ++r) {
+        ne += *cluster.map_shared_rank(&sh.n_edge, r);
+        np += *cluster.map_shared_rank(&sh.n_plane, r);
+      }
+      sh.n_edge = ne;
+      sh.n_plane = np;
+    }
+    __syncthreads();
+  }
+}
+
+// rank 0 publishes the candidate pose / done flag; the other CTAs copy them into their own smem
+__device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, LmShared &sh, uint32_t rank) {
+  cluster.sync();  // rank 0's xc / done are final
+  if (rank != 0) {
+    if (threadIdx.x < 7) sh.xc[threadIdx.x] = *cluster.map_shared_rank(&sh.xc[threadIdx.x], 0);
+    if (threadIdx.x == 7) sh.done = *cluster.map_shared_rank(&sh.done, 0);
+    if (threadIdx.x == 8) sh.too_few = *cluster.map_shared_rank(&sh.too_few, 0);
+  }
+  __syncthreads();
+}
+
 template <int PB>
 __global__ void __launch_bounds__(kLmThreads, 4)
 k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
-           int min_corr) {
+           int min_corr, uint32_t n_stages) {
   __shared__ LmShared sh;
-  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ __align__(8) uint64_t bars[kMaxStages];
   extern __shared__ __align__(128) unsigned char ring[];
-  const int b = blockIdx.x;
-  const uint32_t eo = (uint32_t)e_off[b], n_e = (uint32_t)e_off[b + 1] - eo;
-  const uint32_t po = (uint32_t)p_off[b], n_p = (uint32_t)p_off[b + 1] - po;
+  // One thread-block cluster per scan: G CTAs (G = 1, 2, 4 or 8) each sweep 1/G of the scan's
+  // correspondences; partial sums meet in the rank-0 CTA through distributed shared memory.
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t G = cluster.num_blocks(), rank = cluster.block_rank();
+  const int b = blockIdx.x / G;
+  uint32_t eo = (uint32_t)e_off[b], n_e = (uint32_t)e_off[b + 1] - eo;
+  uint32_t po = (uint32_t)p_off[b], n_p = (uint32_t)p_off[b + 1] - po;
+  if (G > 1) {  // this CTA's contiguous share of each class
+    const uint32_t ce_chunk = (n_e + G - 1) / G, cp_chunk = (n_p + G - 1) / G;
+    const uint32_t e0 = min(n_e, rank * ce_chunk), e1 = min(n_e, e0 + ce_chunk);
+    const uint32_t p0 = min(n_p, rank * cp_chunk), p1 = min(n_p, p0 + cp_chunk);
+    eo += e0; n_e = e1 - e0;
+    po += p0; n_p = p1 - p0;
+  }
   const unsigned char *pe = (const unsigned char *)qe + (size_t)eo * PB, *pp = (const unsigned char *)qp + (size_t)po * PB;
   const double *ce_ = corr + (size_t)eo * 6, *cp_ = corr + ((size_t)n_edge_total + po) * 6;
-  msfl_stats *st = stats ? stats + b : nullptr;
+  msfl_stats *st = (stats && rank == 0) ? stats + b : nullptr;
   msfl_lm_log *log = st ? &st->lm[outer] : nullptr;
   const uint32_t tid = threadIdx.x;
 
@@ -415,7 +475,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   if (tid == 0) {
     sh.done = 0;
     sh.too_few = 0;
-    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < kMaxStages; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -428,7 +488,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
 
   double acc[kAcc];
   int ce, cpl;
-  sweep_tiled<PB>(acc, ts, ring, bars, tile_ctr, sh.x, kp.huber_a, ce, cpl);
+  sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.x, kp.huber_a, ce, cpl);
   // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
   for (int o = 16; o > 0; o >>= 1) {
     ce += __shfl_down_sync(0xffffffffu, ce, o);
@@ -441,6 +501,10 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
     for (int w = 0; w < kLmThreads / 32; ++w) { ne += sh.cnt[w][0]; np += sh.cnt[w][1]; }
     sh.n_edge = ne;
     sh.n_plane = np;
+  }
+  if (G > 1) cluster_reduce(cluster, sh, G, rank, /*with_counts=*/true);
+  if (tid == 0 && rank == 0) {
+    const int ne = sh.n_edge, np = sh.n_plane;
     if (st) {
       st->n_edge[outer] = ne;
       st->n_plane[outer] = np;
@@ -474,35 +538,61 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
       lm_prepare_step(sh, kp, log);
     }
   }
-  __syncthreads();
+  if (G > 1) cluster_broadcast(cluster, sh, rank);
+  else __syncthreads();
   while (!sh.done) {
-    sweep_tiled<PB>(acc, ts, ring, bars, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
+    sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
     block_reduce(acc, sh);
-    if (tid == 0) {
+    if (G > 1) cluster_reduce(cluster, sh, G, rank, false);
+    if (tid == 0 && rank == 0) {
       lm_finish_step(sh, kp, log);
       if (!sh.done) lm_prepare_step(sh, kp, log);
     }
-    __syncthreads();
+    if (G > 1) cluster_broadcast(cluster, sh, rank);
+    else __syncthreads();
   }
-  if (tid == 0 && log && !sh.too_few && sh.n_edge + sh.n_plane > 0) {
-    log->termination = sh.termination;
-    log->final_cost = sh.cost;
+  if (rank == 0) {
+    if (tid == 0 && log && !sh.too_few && sh.n_edge + sh.n_plane > 0) {
+      log->termination = sh.termination;
+      log->final_cost = sh.cost;
+    }
+    if (tid < 7 && !sh.too_few) poses[(size_t)b * 7 + tid] = sh.x[tid];
   }
-  if (tid < 7 && !sh.too_few) poses[(size_t)b * 7 + tid] = sh.x[tid];
+  if (G > 1) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
 template <int PB>
 static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                              const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
                              int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
-  static bool attr_set = false;
-  constexpr int smem = kStages * stage_bytes<PB>();
+  bool &attr_set = e->lm_attr_set[PB == 16 ? 0 : 1];  // per engine: function attributes are per device
   if (!attr_set) {
-    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (kMaxStages * stage_bytes<PB>() <= 227 * 1024 ? kMaxStages : 227 * 1024 / stage_bytes<PB>()) *
+                                          stage_bytes<PB>()));
     attr_set = true;
   }
-  k_lm_solve<PB><<<B, kLmThreads, smem, e->stream>>>(e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
-                                                     d_status, d_stats, outer, min_corr);
+  int G = e->params.lm_cluster;
+  if (G != 2 && G != 4 && G != 8) G = 1;  // 0 / 1: one CTA per scan (results are then independent of the batch shape)
+  // streaming ring (3 stages, 4 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
+  // occupancy is irrelevant) a deep ring so that a CTA's tiles stay resident in smem across the sweeps
+  const int max_stages = kMaxStages * stage_bytes<PB>() <= 227 * 1024 ? kMaxStages : (227 * 1024) / stage_bytes<PB>();
+  const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)kStages;
+  const int smem = (int)n_stages * stage_bytes<PB>();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)B * G);
+  cfg.blockDim = dim3(kLmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
+                                  d_status, d_stats, outer, min_corr, n_stages));
   e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;

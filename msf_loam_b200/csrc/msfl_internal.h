@@ -81,6 +81,7 @@ struct msfl_engine {
   cudaStream_t copy_stream = nullptr;         // H2D of chunk c+1 overlaps the kernels of chunk c
   std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
+  bool lm_attr_set[2] = {false, false};
   int sm_count = 148;
 
   // per-stage CUDA-event timing (msfl_set_profiling)

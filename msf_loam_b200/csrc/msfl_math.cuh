@@ -58,13 +58,13 @@ __host__ __device__ inline void pose_plus(const double x[7], const double d[6], 
   const double vx = d[3], vy = d[4], vz = d[5];
   const double theta = sqrt(vx * vx + vy * vy + vz * vz);
   const double half_theta = 0.5 * theta;
-  double imag;
-  const double real = cos(half_theta);
+  double imag, real, sh;
+  sincos(half_theta, &sh, &real);
   if (theta < 1e-6) {
     const double t2 = theta * theta, t4 = t2 * t2;
     imag = 0.5 - (1 / 48.) * t2 + (1 / 3840.) * t4;
   } else {
-    imag = sin(half_theta) / theta;
+    imag = sh / theta;
   }
   const double bx = imag * vx, by = imag * vy, bz = imag * vz, bw = real;
   const double ax = x[3], ay = x[4], az = x[5], aw = x[6];
@@ -76,7 +76,7 @@ __host__ __device__ inline void pose_plus(const double x[7], const double d[6], 
   out[0] = x[0] + d[0];
   out[1] = x[1] + d[1];
   out[2] = x[2] + d[2];
-  if (n > 0) { qx /= n; qy /= n; qz /= n; w /= n; }
+  if (n > 0) { const double rn = 1.0 / n; qx *= rn; qy *= rn; qz *= rn; w *= rn; }
   out[3] = qx; out[4] = qy; out[5] = qz; out[6] = w;
 }
 
@@ -216,8 +216,10 @@ __device__ __forceinline__ void lstsq_5x3(double (&A)[5][3], double (&b)[5], dou
 // 6x6 SPD solve by Cholesky (the LM normal equations).  Returns false when not positive
 // definite / non-finite (Ceres LINEAR_SOLVER_FAILURE -> invalid step).
 __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6], double y[6]) {
-  // every loop has compile-time bounds and is fully unrolled, so L, z live in registers
-  double L[36];
+  // every loop has compile-time bounds and is fully unrolled, so L, z live in registers; one reciprocal
+  // square root per pivot replaces the sqrt + 4 divisions per column of the textbook form (this runs on
+  // a single thread between two sweeps, so its latency is exposed)
+  double L[36], inv[6];
 #pragma unroll
   for (int i = 0; i < 36; ++i) L[i] = 0;
   bool ok = true;
@@ -228,9 +230,12 @@ __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6
     for (int k = 0; k < 6; ++k)
       if (k < j) d -= L[j * 6 + k] * L[j * 6 + k];
     if (!(d > 0) || !isfinite(d)) ok = false;
-    d = sqrt(d);
-    L[j * 6 + j] = d;
-    const double inv = 1.0 / d;
+#ifdef __CUDA_ARCH__
+    inv[j] = rsqrt(d);
+#else
+    inv[j] = 1.0 / sqrt(d);
+#endif
+    L[j * 6 + j] = d * inv[j];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       if (i > j) {
@@ -238,7 +243,7 @@ __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6
 #pragma unroll
         for (int k = 0; k < 6; ++k)
           if (k < j) s -= L[i * 6 + k] * L[j * 6 + k];
-        L[i * 6 + j] = s * inv;
+        L[i * 6 + j] = s * inv[j];
       }
     }
   }
@@ -250,7 +255,7 @@ __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6
 #pragma unroll
     for (int k = 0; k < 6; ++k)
       if (k < i) s -= L[i * 6 + k] * z[k];
-    z[i] = s / L[i * 6 + i];
+    z[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
@@ -258,7 +263,7 @@ __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6
 #pragma unroll
     for (int k = 0; k < 6; ++k)
       if (k > i) s -= L[k * 6 + i] * y[k];
-    y[i] = s / L[i * 6 + i];
+    y[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)

@@ -151,6 +151,31 @@ def test_large_host_batch_pipelined_path_bitwise(eng, vlp16_case):
     assert st[B - 1]["n_plane"] == st[(B - 1) % 3]["n_plane"] and st[B - 1]["lm"][1]["n_attempts"] > 0
 
 
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_cluster_lm_matches_oracle(vlp16_case, G):
+    """lm_cluster = G: one thread-block cluster of G CTAs per scan, partial sums combined over DSMEM.
+    The summation grouping differs from G = 1, so parity is to rounding (1e-8), not bitwise."""
+    P = O.default_params()
+    e = Engine(default_params(lm_cluster=G))
+    e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+    qs = vlp16_case["queries"]
+    for q in qs:
+        x_ref, logs, counts = O.scan2map(P, vlp16_case["map_corner"], vlp16_case["map_surf"], q["corner"], q["surf"], q["init"])
+        rc, x, st = e.scan2map(q["corner"], q["surf"], q["init"])
+        dt, dr = S.pose_error(x, x_ref)
+        assert rc == 0 and dt < 1e-8 and dr < 1e-8
+        assert st["n_edge"] == list(counts[:, 0]) and st["n_plane"] == list(counts[:, 1])
+        assert [l["n_attempts"] for l in st["lm"]] == [l["n_attempts"] for l in logs]
+    # ragged batch with an empty scan and a no-correspondence scan through the clustered kernel
+    empty = np.zeros((0, 4), np.float32)
+    far = np.array([500.0, 500.0, 50.0, 0, 0, 0, 1.0])
+    rc, xs, st = e.scan2map_batch([qs[0]["corner"], empty, qs[1]["corner"]], [qs[0]["surf"], empty, qs[1]["surf"]],
+                                  [qs[0]["init"], qs[1]["init"], far], want_stats=True)
+    assert rc == 0 and np.array_equal(xs[1], qs[1]["init"]) and np.array_equal(xs[2], far)
+    assert S.pose_error(xs[0], qs[0]["gt"])[0] < 0.03
+    e.close()
+
+
 def test_no_correspondence_leaves_pose_untouched(eng, vlp16_case):
     q = vlp16_case["queries"][0]
     far = np.array([500.0, 500.0, 50.0, 0, 0, 0, 1.0])
