@@ -340,8 +340,8 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
 #pragma unroll
       for (int s = 0; s < 5; ++s) { A[s][0] = m[s][0]; A[s][1] = m[s][1]; A[s][2] = m[s][2]; }
       lstsq_5x3(A, bb, nrm);  // :210
-      const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
-      nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn;  // :211
+      const double inv_nn = 1.0 / sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+      nrm[0] *= inv_nn; nrm[1] *= inv_nn; nrm[2] *= inv_nn;  // norm.normalize() :211
       bool valid = true;
 #pragma unroll
       for (int s = 0; s < 5; ++s) {  // :214-220

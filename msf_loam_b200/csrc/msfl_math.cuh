@@ -178,19 +178,20 @@ __device__ __forceinline__ void qr_step(double (&A)[5][3], double (&b)[5], int (
 #pragma unroll
   for (int i = K; i < 5; ++i) vv += v[i] * v[i];
   if (vv > 0) {
+    const double two_over_vv = 2.0 / vv;  // one division per reflector
 #pragma unroll
     for (int j = K; j < 3; ++j) {
       double s = 0;
 #pragma unroll
       for (int i = K; i < 5; ++i) s += v[i] * A[i][j];
-      s = 2.0 * s / vv;
+      s = s * two_over_vv;
 #pragma unroll
       for (int i = K; i < 5; ++i) A[i][j] -= s * v[i];
     }
     double s = 0;
 #pragma unroll
     for (int i = K; i < 5; ++i) s += v[i] * b[i];
-    s = 2.0 * s / vv;
+    s = s * two_over_vv;
 #pragma unroll
     for (int i = K; i < 5; ++i) b[i] -= s * v[i];
   }
