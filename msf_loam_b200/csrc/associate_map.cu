@@ -292,7 +292,9 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
 // constants [a_or_c(3), n(3)]; n = 0 marks "no factor".  Kept apart from the search kernel so that the
 // search runs at 40 registers / 75 % occupancy (it is L2-latency bound) while the register-hungry
 // Jacobi / Householder code does not throttle it.
-template <bool DESKEW>
+// COMPACT: plane entries are written as 32 B {n, n.c} at corr + 48 n_corner_total + 32 i (the batch path: the LM
+// kernel only ever needs the plane's offset along its normal); otherwise 48 B {c, n} like the edge entries.
+template <bool DESKEW, bool COMPACT>
 __global__ void __launch_bounds__(128)
 k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
       double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk) {
@@ -359,12 +361,19 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
 #pragma unroll
     for (int d = 0; d < 3; ++d) a[d] -= __dsub_rn(__dmul_rn(tb.V[d], dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, tb.G[d]), dt), dt));
   }
-  store_corr(corr, k, a, n);
+  if (COMPACT && !is_corner) {
+    double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(corr + (size_t)n_corner_total * 6) +
+                                             (size_t)(k - n_corner_total) * 32);
+    o[0] = make_double2(n[0], n[1]);
+    o[1] = make_double2(n[2], n[0] * a[0] + n[1] * a[1] + n[2] * a[2]);
+  } else {
+    store_corr(corr, k, a, n);
+  }
 }
 
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool reuse_order) {
+                         double *d_corr, int32_t *d_knn, bool reuse_order, bool compact) {
   const uint32_t total = n_corner_total + n_surf_total;
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
@@ -381,7 +390,8 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     k_knn5<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
         gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, nullptr, d_knn,
         DeskewTable{}, nullptr);
-    k_fit<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+    if (compact) k_fit<false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+    else k_fit<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
     stage_end(e);
     e->launches += 2;
     MSFL_CUDA_OK(cudaGetLastError());
@@ -396,7 +406,8 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     k_knn5<true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
         gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, e->a_perm, d_knn,
         DeskewTable{}, nullptr);
-    k_fit<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+    if (compact) k_fit<false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+    else k_fit<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
     stage_end(e);
     e->launches += 2;
     MSFL_CUDA_OK(cudaGetLastError());
@@ -431,7 +442,8 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
       DeskewTable{}, nullptr);
   stage_end(e);
   stage_begin(e, 3);
-  k_fit<false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+  if (compact) k_fit<false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+  else k_fit<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
   stage_end(e);
   e->launches += 3 + 3;
   MSFL_CUDA_OK(cudaGetLastError());
@@ -465,7 +477,7 @@ int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_
   k_knn5<false, false, true><<<(total + 127) / 128, 128, 0, e->stream>>>(
       e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_knn, tb,
       d_dsk);
-  k_fit<true><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk);
+  k_fit<true, false><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk);
   stage_end(e);
   e->launches += 2;
   MSFL_CUDA_OK(cudaGetLastError());

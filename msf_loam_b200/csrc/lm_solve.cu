@@ -57,6 +57,54 @@ __device__ __forceinline__ double huber_scale(double s, double a, double &cost) 
   return 1.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The two factors (same residuals / Jacobians as lidar_factor.cc:7-44, regrouped so that R [p]x is
+// never formed).  With w = R^T n:
+//   plane:  r = n.(R p + t - c) = w.p + (n.t - n.c)            J = [ n^T | (p x w)^T ]
+//   edge :  r = n x (R p + t - a)                               J = [ [n]x | (w.p) R - (R p) w^T ]
+// ( -[n]x R [p]x = -R [w]x [p]x = -R (p w^T - (w.p) I) ).  Residual and Jacobian rows are scaled by
+// the Huber corrector before they enter H = J^T J, g = J^T r.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void eval_edge(double (&acc)[kAcc], const double (&R)[9], double t0, double t1, double t2, double p0,
+                                          double p1, double p2, double a0, double a1, double a2, double n0, double n1,
+                                          double n2, double huber_a) {
+  const double q0 = R[0] * p0 + R[1] * p1 + R[2] * p2, q1 = R[3] * p0 + R[4] * p1 + R[5] * p2,
+               q2 = R[6] * p0 + R[7] * p1 + R[8] * p2;  // R p
+  const double d0 = q0 + (t0 - a0), d1 = q1 + (t1 - a1), d2 = q2 + (t2 - a2);
+  const double w0 = R[0] * n0 + R[3] * n1 + R[6] * n2, w1 = R[1] * n0 + R[4] * n1 + R[7] * n2,
+               w2 = R[2] * n0 + R[5] * n1 + R[8] * n2;  // R^T n
+  const double r0 = n1 * d2 - n2 * d1, r1 = n2 * d0 - n0 * d2, r2 = n0 * d1 - n1 * d0;  // n x d  (lidar_factor.cc:12)
+  const double sc = huber_scale(r0 * r0 + r1 * r1 + r2 * r2, huber_a, acc[27]);
+  // J_theta = (w.p) R - (R p) w^T, scaled by sc
+  const double s = (w0 * p0 + w1 * p1 + w2 * p2) * sc;
+  const double u0 = q0 * sc, u1 = q1 * sc, u2 = q2 * sc;
+  const double m0 = n0 * sc, m1 = n1 * sc, m2 = n2 * sc;
+  double J[6];
+  // rows of J = [ [n]x | J_theta ] follow r0, r1, r2  (lidar_factor.cc:18-19)
+  J[0] = 0.0; J[1] = -m2; J[2] = m1;
+  J[3] = s * R[0] - u0 * w0; J[4] = s * R[1] - u0 * w1; J[5] = s * R[2] - u0 * w2;
+  acc_row(acc, J, r0 * sc);
+  J[0] = m2; J[1] = 0.0; J[2] = -m0;
+  J[3] = s * R[3] - u1 * w0; J[4] = s * R[4] - u1 * w1; J[5] = s * R[5] - u1 * w2;
+  acc_row(acc, J, r1 * sc);
+  J[0] = -m1; J[1] = m0; J[2] = 0.0;
+  J[3] = s * R[6] - u2 * w0; J[4] = s * R[7] - u2 * w1; J[5] = s * R[8] - u2 * w2;
+  acc_row(acc, J, r2 * sc);
+}
+
+// nc = n . c (the plane offset along its normal)
+__device__ __forceinline__ void eval_plane(double (&acc)[kAcc], const double (&R)[9], double t0, double t1, double t2, double p0,
+                                           double p1, double p2, double n0, double n1, double n2, double nc, double huber_a) {
+  const double w0 = R[0] * n0 + R[3] * n1 + R[6] * n2, w1 = R[1] * n0 + R[4] * n1 + R[7] * n2,
+               w2 = R[2] * n0 + R[5] * n1 + R[8] * n2;  // R^T n
+  const double r = (w0 * p0 + w1 * p1 + w2 * p2) + ((n0 * t0 + n1 * t1 + n2 * t2) - nc);  // lidar_factor.cc:32
+  const double sc = huber_scale(r * r, huber_a, acc[27]);
+  double J[6];
+  J[0] = n0 * sc; J[1] = n1 * sc; J[2] = n2 * sc;  // lidar_factor.cc:38-39
+  J[3] = (p1 * w2 - p2 * w1) * sc; J[4] = (p2 * w0 - p0 * w2) * sc; J[5] = (p0 * w1 - p1 * w0) * sc;
+  acc_row(acc, J, r * sc);
+}
+
 // Sweep this thread's share of the correspondences at `pose`: edge factors over the corner
 // queries, then plane factors over the surf queries.
 // p*: query points (raw, fp32 -- quirk Q4: factors use the untransformed point); corr*: 6 doubles
@@ -72,56 +120,22 @@ __device__ __forceinline__ void sweep(double (&acc)[kAcc], const float4 *__restr
   const double t0 = pose[0], t1 = pose[1], t2 = pose[2];
   cnt_edge = 0;
   cnt_plane = 0;
-#define MSFL_LOAD_CORR(CORR, P)                                                                    \
-  const double2 *cp = reinterpret_cast<const double2 *>((CORR) + (size_t)i * 6);                   \
-  const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];                                                \
-  const double a0 = c0.x, a1 = c0.y, a2 = c1.x, n0 = c1.y, n1 = c2.x, n2 = c2.y;                   \
-  if (n0 == 0.0 && n1 == 0.0 && n2 == 0.0) continue; /* no factor for this query */                \
-  const float4 pf = (P)[i];                                                                        \
-  const double p0 = pf.x, p1 = pf.y, p2 = pf.z;                                                    \
-  /* d = R p + t - a */                                                                            \
-  const double d0 = R[0] * p0 + R[1] * p1 + R[2] * p2 + t0 - a0;                                   \
-  const double d1 = R[3] * p0 + R[4] * p1 + R[5] * p2 + t1 - a1;                                   \
-  const double d2 = R[6] * p0 + R[7] * p1 + R[8] * p2 + t2 - a2;                                   \
-  /* M = R [p]x, columns m.0 m.1 m.2 */                                                            \
-  const double m00 = R[1] * p2 - R[2] * p1, m10 = R[4] * p2 - R[5] * p1, m20 = R[7] * p2 - R[8] * p1; \
-  const double m01 = R[2] * p0 - R[0] * p2, m11 = R[5] * p0 - R[3] * p2, m21 = R[8] * p0 - R[6] * p2; \
-  const double m02 = R[0] * p1 - R[1] * p0, m12 = R[3] * p1 - R[4] * p0, m22 = R[6] * p1 - R[7] * p0;
-
   for (uint32_t i = tid; i < n_e; i += nthreads) {
-    MSFL_LOAD_CORR(corr_e, pe)
+    const double2 *cp = reinterpret_cast<const double2 *>(corr_e + (size_t)i * 6);
+    const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];
+    if (c1.y == 0.0 && c2.x == 0.0 && c2.y == 0.0) continue;  // no factor for this query
+    const float4 pf = pe[i];
     ++cnt_edge;
-    // r = n x d ; J = [ [n]x | -[n]x M ]   (lidar_factor.cc:12,18-19)
-    const double r0 = n1 * d2 - n2 * d1, r1 = n2 * d0 - n0 * d2, r2 = n0 * d1 - n1 * d0;
-    const double sc = huber_scale(r0 * r0 + r1 * r1 + r2 * r2, huber_a, acc[27]);
-    double J[6];
-    // row 0 of [n]x = (0, -n2, n1)
-    J[0] = 0.0; J[1] = -n2 * sc; J[2] = n1 * sc;
-    J[3] = -(-n2 * m10 + n1 * m20) * sc; J[4] = -(-n2 * m11 + n1 * m21) * sc; J[5] = -(-n2 * m12 + n1 * m22) * sc;
-    acc_row(acc, J, r0 * sc);
-    // row 1 = (n2, 0, -n0)
-    J[0] = n2 * sc; J[1] = 0.0; J[2] = -n0 * sc;
-    J[3] = -(n2 * m00 - n0 * m20) * sc; J[4] = -(n2 * m01 - n0 * m21) * sc; J[5] = -(n2 * m02 - n0 * m22) * sc;
-    acc_row(acc, J, r1 * sc);
-    // row 2 = (-n1, n0, 0)
-    J[0] = -n1 * sc; J[1] = n0 * sc; J[2] = 0.0;
-    J[3] = -(-n1 * m00 + n0 * m10) * sc; J[4] = -(-n1 * m01 + n0 * m11) * sc; J[5] = -(-n1 * m02 + n0 * m12) * sc;
-    acc_row(acc, J, r2 * sc);
+    eval_edge(acc, R, t0, t1, t2, pf.x, pf.y, pf.z, c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, huber_a);
   }
   for (uint32_t i = tid; i < n_p; i += nthreads) {
-    MSFL_LOAD_CORR(corr_p, pp)
+    const double2 *cp = reinterpret_cast<const double2 *>(corr_p + (size_t)i * 6);
+    const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];
+    if (c1.y == 0.0 && c2.x == 0.0 && c2.y == 0.0) continue;
+    const float4 pf = pp[i];
     ++cnt_plane;
-    // r = n . d ; J = [ n^T | -n^T M ]   (lidar_factor.cc:32,38-39)
-    const double r = n0 * d0 + n1 * d1 + n2 * d2;
-    const double sc = huber_scale(r * r, huber_a, acc[27]);
-    double J[6];
-    J[0] = n0 * sc; J[1] = n1 * sc; J[2] = n2 * sc;
-    J[3] = -(n0 * m00 + n1 * m10 + n2 * m20) * sc;
-    J[4] = -(n0 * m01 + n1 * m11 + n2 * m21) * sc;
-    J[5] = -(n0 * m02 + n1 * m12 + n2 * m22) * sc;
-    acc_row(acc, J, r * sc);
+    eval_plane(acc, R, t0, t1, t2, pf.x, pf.y, pf.z, c1.y, c2.x, c2.y, c1.y * c0.x + c2.x * c0.y + c2.y * c1.x, huber_a);
   }
-#undef MSFL_LOAD_CORR
 }
 
 // Block reduction: warp shuffle tree, then warps combined in index order (deterministic).
@@ -303,6 +317,249 @@ __device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &
   tile_ctr += ts.tiles;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-private streaming (the throughput configuration).  Every warp owns a double-buffered ring of
+// tiles and its own mbarriers, issues its own bulk copies (lane 0) and consumes them after a
+// __syncwarp: there is no block-wide barrier inside a sweep, so a warp never waits for the slowest
+// warp of its CTA.  Warp w of W streams tiles w, w + W, w + 2W, ... of each class (edge entries,
+// then plane entries), i.e. the CTA as a whole still walks the scan's arrays front to back.  While a
+// warp works on the last tile of a sweep it already fetches the first tile of the next sweep (the
+// data does not depend on the pose), so the copy latency also hides behind the block reduction and
+// the thread-0 LM step.  All shared-memory traffic uses 32-bit shared-space addresses (ld.shared /
+// mbarrier on precomputed offsets): the per-tile bookkeeping is ~40 instructions.
+//
+// PC = bytes of plane constants per entry: 32 = {n, n.c} written by k_fit for the batch path,
+// 48 = {c, n} (odometry, deskew, test hooks).  A stage holds TE edge entries or TP plane entries.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarpStages = 2;     // streaming: double buffer per warp
+constexpr int kMaxWarpStages = 9;  // resident configuration (small launches): a warp's tiles stay in smem across sweeps
+constexpr uint32_t kLmWarps = kLmThreads / 32;
+template <int PB, int PC>
+struct WarpTile {
+  static constexpr uint32_t SB = PB == 16 ? 6144u : 10240u;  // bytes per stage
+  static constexpr uint32_t TE = SB / (PB + 48), TP = SB / (PB + PC);
+  static_assert((TE * PB) % 16 == 0 && (TP * PB) % 16 == 0, "constant arrays must stay 16 B aligned");
+};
+
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// per-warp pipeline state, kept in registers across the sweeps of one solve
+struct WarpPipe {
+  uint32_t ring;     // shared-space address of this warp's ring (n_stages x SB bytes)
+  uint32_t bars;     // shared-space address of this warp's mbarriers (8 B each)
+  uint32_t it;       // streaming: tiles consumed so far (stage = it & 1, phase parity = (it >> 1) & 1)
+  uint32_t my_tiles; // tiles of this warp per sweep
+  bool resident;     // all of this warp's tiles fit its ring: loaded once, re-read by every sweep
+  bool loaded;       // resident: tiles are in smem / streaming: the first tile of the next sweep is in flight
+};
+
+// class 0 = edge entries, 1 = plane entries, 2 = end of the sweep
+struct TileIt { uint32_t cls, base; };
+
+template <int PB, int PC>
+__device__ __forceinline__ TileIt tile_first(const TileSrc &ts, uint32_t warp) {
+  TileIt t{0u, warp * WarpTile<PB, PC>::TE};
+  if (t.base >= ts.n_e) {
+    t.cls = 1u;
+    t.base = warp * WarpTile<PB, PC>::TP;
+    if (t.base >= ts.n_p) t.cls = 2u;
+  }
+  return t;
+}
+template <int PB, int PC>
+__device__ __forceinline__ TileIt tile_next(const TileSrc &ts, uint32_t warp, TileIt t) {
+  if (t.cls == 0u) {
+    t.base += kLmWarps * WarpTile<PB, PC>::TE;
+    if (t.base >= ts.n_e) {
+      t.cls = 1u;
+      t.base = warp * WarpTile<PB, PC>::TP;
+      if (t.base >= ts.n_p) t.cls = 2u;
+    }
+  } else {
+    t.base += kLmWarps * WarpTile<PB, PC>::TP;
+    if (t.base >= ts.n_p) t.cls = 2u;
+  }
+  return t;
+}
+
+// lane 0: two bulk copies (points, constants) of tile t into the stage at shared address dst
+template <int PB, int PC>
+__device__ __forceinline__ void issue_warp_tile(const TileSrc &ts, TileIt t, uint32_t dst, uint32_t bar) {
+  using WT = WarpTile<PB, PC>;
+  if (t.cls == 0u) {
+    const uint32_t cnt = min(WT::TE, ts.n_e - t.base);
+    mbar_expect_tx_s(bar, cnt * (uint32_t)(PB + 48));
+    tma_load_1d_s(dst, ts.pe + (size_t)t.base * PB, cnt * (uint32_t)PB, bar);
+    tma_load_1d_s(dst + WT::TE * PB, (const unsigned char *)ts.ce + (size_t)t.base * 48, cnt * 48u, bar);
+  } else {
+    const uint32_t cnt = min(WT::TP, ts.n_p - t.base);
+    mbar_expect_tx_s(bar, cnt * (uint32_t)(PB + PC));
+    tma_load_1d_s(dst, ts.pp + (size_t)t.base * PB, cnt * (uint32_t)PB, bar);
+    tma_load_1d_s(dst + WT::TP * PB, (const unsigned char *)ts.cp + (size_t)t.base * PC, cnt * (uint32_t)PC, bar);
+  }
+}
+
+struct SweepCtx {
+  double R[9], t0, t1, t2, huber_a;
+};
+
+template <int PB>
+__device__ __forceinline__ void load_point_s(uint32_t a, double &p0, double &p1, double &p2) {
+  if (PB == 16) {
+    const float4 pf = lds_f4(a);
+    p0 = pf.x; p1 = pf.y; p2 = pf.z;
+  } else {
+    const double2 pa = lds_d2(a), pb = lds_d2(a + 16);
+    p0 = pa.x; p1 = pa.y; p2 = pb.x;
+  }
+}
+
+// all entries of one tile that sits in shared memory at `buf`
+template <int PB, int PC>
+__device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx &cx, const TileSrc &ts, TileIt t, uint32_t buf,
+                                             uint32_t lane, int &cnt_edge, int &cnt_plane) {
+  using WT = WarpTile<PB, PC>;
+  if (t.cls == 0u) {
+    const uint32_t cnt = min(WT::TE, ts.n_e - t.base);
+    uint32_t pa = buf + lane * PB, ca = buf + WT::TE * PB + lane * 48;
+#pragma unroll 1
+    for (uint32_t ent = lane; ent < cnt; ent += 32, pa += 32 * PB, ca += 32 * 48) {
+      const double2 c1 = lds_d2(ca + 16), c2 = lds_d2(ca + 32);
+      const double n0 = c1.y, n1 = c2.x, n2 = c2.y;
+      if (!(n0 == 0.0 && n1 == 0.0 && n2 == 0.0)) {
+        const double2 c0 = lds_d2(ca);
+        double p0, p1, p2;
+        load_point_s<PB>(pa, p0, p1, p2);
+        ++cnt_edge;
+        eval_edge(acc, cx.R, cx.t0, cx.t1, cx.t2, p0, p1, p2, c0.x, c0.y, c1.x, n0, n1, n2, cx.huber_a);
+      }
+    }
+  } else {
+    const uint32_t cnt = min(WT::TP, ts.n_p - t.base);
+    uint32_t pa = buf + lane * PB, ca = buf + WT::TP * PB + lane * PC;
+    // 32 B entries: lanes 4..7 (mod 8) fetch the upper half first so that a quarter-warp's eight 16 B reads
+    // cover all 32 banks
+    const uint32_t hi = PC == 32 ? ((lane >> 2) & 1u) * 16u : 0u;
+#pragma unroll 1
+    for (uint32_t ent = lane; ent < cnt; ent += 32, pa += 32 * PB, ca += 32 * PC) {
+      double n0, n1, n2, nc;
+      if (PC == 32) {
+        const double2 f = lds_d2(ca + hi), g2 = lds_d2(ca + (hi ^ 16u));
+        const double2 c0 = hi ? g2 : f, c1 = hi ? f : g2;
+        n0 = c0.x; n1 = c0.y; n2 = c1.x; nc = c1.y;
+      } else {
+        const double2 c0 = lds_d2(ca), c1 = lds_d2(ca + 16), c2 = lds_d2(ca + 32);
+        n0 = c1.y; n1 = c2.x; n2 = c2.y;
+        nc = n0 * c0.x + n1 * c0.y + n2 * c1.x;
+      }
+      if (!(n0 == 0.0 && n1 == 0.0 && n2 == 0.0)) {
+        double p0, p1, p2;
+        load_point_s<PB>(pa, p0, p1, p2);
+        ++cnt_plane;
+        eval_plane(acc, cx.R, cx.t0, cx.t1, cx.t2, p0, p1, p2, n0, n1, n2, nc, cx.huber_a);
+      }
+    }
+  }
+}
+
+template <int PB, int PC>
+__device__ __forceinline__ void sweep_warp(double (&acc)[kAcc], const TileSrc &ts, WarpPipe &wp, const double *pose, double huber_a,
+                                           int &cnt_edge, int &cnt_plane) {
+  using WT = WarpTile<PB, PC>;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+  SweepCtx cx;
+  quat_to_R(pose + 3, cx.R);
+  cx.t0 = pose[0]; cx.t1 = pose[1]; cx.t2 = pose[2];
+  cx.huber_a = huber_a;
+  cnt_edge = 0;
+  cnt_plane = 0;
+  TileIt cur = tile_first<PB, PC>(ts, warp);
+  if (cur.cls == 2u) return;  // fewer tiles than warps: nothing for this warp
+  if (wp.resident) {
+    if (!wp.loaded && lane == 0) {
+      uint32_t k = 0;
+      for (TileIt t = cur; t.cls != 2u; t = tile_next<PB, PC>(ts, warp, t), ++k)
+        issue_warp_tile<PB, PC>(ts, t, wp.ring + k * WT::SB, wp.bars + k * 8u);
+    }
+    uint32_t k = 0;
+    for (; cur.cls != 2u; cur = tile_next<PB, PC>(ts, warp, cur), ++k) {
+      if (!wp.loaded) mbar_wait_s(wp.bars + k * 8u, 0u);
+      consume_tile<PB, PC>(acc, cx, ts, cur, wp.ring + k * WT::SB, lane, cnt_edge, cnt_plane);
+    }
+    wp.loaded = true;
+    return;
+  }
+  if (!wp.loaded && lane == 0) issue_warp_tile<PB, PC>(ts, cur, wp.ring + (wp.it & 1u) * WT::SB, wp.bars + (wp.it & 1u) * 8u);
+  for (;;) {
+    TileIt nxt = tile_next<PB, PC>(ts, warp, cur);
+    const bool last = nxt.cls == 2u;
+    if (last) nxt = tile_first<PB, PC>(ts, warp);  // prefetch across the sweep boundary
+    const uint32_t s = wp.it & 1u;
+    // the other stage held the previous tile: every lane left it at the __syncwarp below
+    if (lane == 0) issue_warp_tile<PB, PC>(ts, nxt, wp.ring + (s ^ 1u) * WT::SB, wp.bars + (s ^ 1u) * 8u);
+    mbar_wait_s(wp.bars + s * 8u, (wp.it >> 1) & 1u);
+    consume_tile<PB, PC>(acc, cx, ts, cur, wp.ring + s * WT::SB, lane, cnt_edge, cnt_plane);
+    __syncwarp();
+    ++wp.it;
+    if (last) break;
+    cur = nxt;
+  }
+  wp.loaded = true;
+}
+
+// before the CTA exits: a streaming warp still has the prefetched first tile of a sweep that will never run in flight
+__device__ __forceinline__ void warp_pipe_drain(const WarpPipe &wp) {
+  if (!wp.resident && wp.loaded) mbar_wait_s(wp.bars + (wp.it & 1u) * 8u, (wp.it >> 1) & 1u);
+}
+
+template <int PB, int PC>
+__device__ __forceinline__ WarpPipe warp_pipe_init(const TileSrc &ts, unsigned char *ring_cta, uint64_t *bars_cta, uint32_t n_stages) {
+  using WT = WarpTile<PB, PC>;
+  const uint32_t warp = threadIdx.x >> 5;
+  WarpPipe wp;
+  wp.ring = smem_u32(ring_cta) + warp * n_stages * WT::SB;
+  wp.bars = smem_u32(bars_cta) + warp * kMaxWarpStages * 8u;
+  wp.it = 0;
+  const uint32_t tt_e = (ts.n_e + WT::TE - 1) / WT::TE, tt_p = (ts.n_p + WT::TP - 1) / WT::TP;
+  wp.my_tiles = (tt_e > warp ? (tt_e - warp + kLmWarps - 1) / kLmWarps : 0u) + (tt_p > warp ? (tt_p - warp + kLmWarps - 1) / kLmWarps : 0u);
+  wp.resident = n_stages > (uint32_t)kWarpStages && wp.my_tiles <= n_stages;
+  wp.loaded = false;
+  return wp;
+}
+
 __device__ inline double norm7(const double *x) {
   double s = 0;
   for (int i = 0; i < 7; ++i) s += x[i] * x[i];
@@ -440,14 +697,16 @@ __device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, Lm
   __syncthreads();
 }
 
-template <int PB>
+// PB: bytes per point (16 float4 / 32 double4), PC: bytes of plane constants per entry (32 / 48),
+// WP: warp-private streaming (sweep_warp) instead of CTA-wide tiles (sweep_tiled; PC must be 48 there)
+template <int PB, int PC, bool WP>
 __global__ void __launch_bounds__(kLmThreads, 4)
 k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
            int min_corr, uint32_t n_stages) {
   __shared__ LmShared sh;
-  __shared__ __align__(8) uint64_t bars[kMaxStages];
+  __shared__ __align__(8) uint64_t bars[WP ? (kLmThreads / 32) * kMaxWarpStages : kMaxStages];
   extern __shared__ __align__(128) unsigned char ring[];
   // One thread-block cluster per scan: G CTAs (G = 1, 2, 4 or 8) each sweep 1/G of the scan's
   // correspondences; partial sums meet in the rank-0 CTA through distributed shared memory.
@@ -464,7 +723,8 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
     po += p0; n_p = p1 - p0;
   }
   const unsigned char *pe = (const unsigned char *)qe + (size_t)eo * PB, *pp = (const unsigned char *)qp + (size_t)po * PB;
-  const double *ce_ = corr + (size_t)eo * 6, *cp_ = corr + ((size_t)n_edge_total + po) * 6;
+  const double *ce_ = corr + (size_t)eo * 6;
+  const double *cp_ = (const double *)((const unsigned char *)(corr + (size_t)n_edge_total * 6) + (size_t)po * PC);
   msfl_stats *st = (stats && rank == 0) ? stats + b : nullptr;
   msfl_lm_log *log = st ? &st->lm[outer] : nullptr;
   const uint32_t tid = threadIdx.x;
@@ -475,7 +735,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   if (tid == 0) {
     sh.done = 0;
     sh.too_few = 0;
-    for (int i = 0; i < kMaxStages; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < (WP ? (kLmThreads / 32) * kMaxWarpStages : kMaxStages); ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -485,10 +745,12 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   ts.tiles_e = (n_e + kTile - 1) / kTile;
   ts.tiles = ts.tiles_e + (n_p + kTile - 1) / kTile;
   uint32_t tile_ctr = 0;
+  WarpPipe wp = warp_pipe_init<PB, PC>(ts, ring, bars, n_stages);
 
   double acc[kAcc];
   int ce, cpl;
-  sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.x, kp.huber_a, ce, cpl);
+  if (WP) sweep_warp<PB, PC>(acc, ts, wp, sh.x, kp.huber_a, ce, cpl);
+  else sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.x, kp.huber_a, ce, cpl);
   // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
   for (int o = 16; o > 0; o >>= 1) {
     ce += __shfl_down_sync(0xffffffffu, ce, o);
@@ -541,7 +803,8 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   if (G > 1) cluster_broadcast(cluster, sh, rank);
   else __syncthreads();
   while (!sh.done) {
-    sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
+    if (WP) sweep_warp<PB, PC>(acc, ts, wp, sh.xc, kp.huber_a, ce, cpl);
+    else sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
     block_reduce(acc, sh);
     if (G > 1) cluster_reduce(cluster, sh, G, rank, false);
     if (tid == 0 && rank == 0) {
@@ -558,27 +821,28 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
     }
     if (tid < 7 && !sh.too_few) poses[(size_t)b * 7 + tid] = sh.x[tid];
   }
+  if (WP) warp_pipe_drain(wp);
   if (G > 1) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
-template <int PB>
+template <int PB, int PC, bool WP>
 static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                              const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
                              int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
-  bool &attr_set = e->lm_attr_set[PB == 16 ? 0 : 1];  // per engine: function attributes are per device
+  constexpr int sb = WP ? (int)(kLmWarps * WarpTile<PB, PC>::SB) : stage_bytes<PB>();  // smem per ring stage (whole CTA)
+  constexpr int max_stages_cfg = WP ? kMaxWarpStages : kMaxStages;
+  constexpr int max_stages = max_stages_cfg * sb <= 227 * 1024 ? max_stages_cfg : (227 * 1024) / sb;
+  bool &attr_set = e->lm_attr_set[(PB == 16 ? 0 : 1) + (PC == 32 ? 2 : 0) + (WP ? 4 : 0)];  // per engine: attributes are per device
   if (!attr_set) {
-    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (kMaxStages * stage_bytes<PB>() <= 227 * 1024 ? kMaxStages : 227 * 1024 / stage_bytes<PB>()) *
-                                          stage_bytes<PB>()));
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB, PC, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stages * sb));
     attr_set = true;
   }
   int G = e->params.lm_cluster;
   if (G != 2 && G != 4 && G != 8) G = 1;  // 0 / 1: one CTA per scan (results are then independent of the batch shape)
   // streaming ring (3 stages, 4 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
   // occupancy is irrelevant) a deep ring so that a CTA's tiles stay resident in smem across the sweeps
-  const int max_stages = kMaxStages * stage_bytes<PB>() <= 227 * 1024 ? kMaxStages : (227 * 1024) / stage_bytes<PB>();
-  const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)kStages;
-  const int smem = (int)n_stages * stage_bytes<PB>();
+  const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)(WP ? kWarpStages : kStages);
+  const int smem = (int)n_stages * sb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * G);
   cfg.blockDim = dim3(kLmThreads);
@@ -591,19 +855,26 @@ static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int3
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
+  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB, PC, WP>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
                                   d_status, d_stats, outer, min_corr, n_stages));
   e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }
 
+// plane_bytes: 48 = plane constants {c, n} (6 doubles, same layout as the edge entries), 32 = {n, n.c} (k_fit compact)
 int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                     const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
-                    msfl_stats *d_stats, int outer, int min_corr) {
+                    msfl_stats *d_stats, int outer, int min_corr, int plane_bytes) {
   if (B <= 0) return MSFL_OK;
-  return launch_lm_solve_t<16>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
-                               min_corr);
+  if (plane_bytes == 32)
+    return launch_lm_solve_t<16, 32, true>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats,
+                                           outer, min_corr);
+  if (e->dev_lm_variant == 0)
+    return launch_lm_solve_t<16, 48, false>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats,
+                                            outer, min_corr);
+  return launch_lm_solve_t<16, 48, true>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                                         min_corr);
 }
 
 // deskewed points: double4 (p' = dq p + dp in fp64, lidar_factor.cc:53), 32 B per entry
@@ -611,8 +882,11 @@ int launch_lm_solve_pd(msfl_engine *e, int B, const double *d_qe, const int32_t 
                        const double *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
                        msfl_stats *d_stats, int outer, int min_corr) {
   if (B <= 0) return MSFL_OK;
-  return launch_lm_solve_t<32>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
-                               min_corr);
+  if (e->dev_lm_variant == 0)
+    return launch_lm_solve_t<32, 48, false>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats,
+                                            outer, min_corr);
+  return launch_lm_solve_t<32, 48, true>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                                         min_corr);
 }
 
 // ---- test hook: plain accumulate at a pose (cost, H, g), one block ---------------------------

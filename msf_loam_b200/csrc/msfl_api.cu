@@ -2,6 +2,7 @@
 // marshalling of AoS cloud views, and the launch sequences of the scan-matching path.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -237,6 +238,9 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
   fill_kparams(e);
+  if (const char *v = getenv("MSFL_LM_VARIANT")) e->dev_lm_variant = atoi(v);
+  if (const char *v = getenv("MSFL_COMPACT")) e->dev_compact = atoi(v);
+  if (e->dev_lm_variant == 0) e->dev_compact = 0;  // the CTA-wide tile sweep reads 48 B plane entries
   if (stream) {
     e->stream = (cudaStream_t)stream;
     e->own_stream = false;
@@ -351,13 +355,14 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   e->a_perm_valid = 0;  // a new batch: the cell order of the previous one does not apply
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
+    const bool compact = e->dev_compact != 0;  // plane constants as 32 B {n, n.c}
     if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr,
-                                   /*reuse_order=*/false)))  // measured: re-sorting per outer iteration is faster
-                                                              // (the first solve moves points by up to ~0.3 m)
+                                   /*reuse_order=*/false, compact)))  // measured: re-sorting per outer iteration is faster
+                                                                       // (the first solve moves points by up to ~0.3 m)
       return rc;
     stage_begin(e, 1);
     rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
-                         e->d_status.as<int32_t>(), d_stats, outer, /*min_corr=*/0);
+                         e->d_status.as<int32_t>(), d_stats, outer, /*min_corr=*/0, compact ? 32 : 48);
     stage_end(e);
     if (rc) return rc;
   }

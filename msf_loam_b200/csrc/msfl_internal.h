@@ -81,7 +81,10 @@ struct msfl_engine {
   cudaStream_t copy_stream = nullptr;         // H2D of chunk c+1 overlaps the kernels of chunk c
   std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
-  bool lm_attr_set[2] = {false, false};
+  bool lm_attr_set[8] = {false, false, false, false, false, false, false, false};
+  // development switches (environment, read once in msfl_create): A/B of kernel variants on the GPU box
+  int dev_lm_variant = 1;   // MSFL_LM_VARIANT: 0 = CTA-wide tiles, 1 = warp-private streaming
+  int dev_compact = 1;      // MSFL_COMPACT: 1 = k_fit writes 32 B plane constants {n, n.c} for the batch path
   int sm_count = 148;
 
   // per-stage CUDA-event timing (msfl_set_profiling)
@@ -129,7 +132,7 @@ void submap_release(Submap &m);
 // same flat order.
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool reuse_order = false);
+                         double *d_corr, int32_t *d_knn, bool reuse_order = false, bool compact = false);
 
 int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
                           const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,
@@ -143,7 +146,7 @@ int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_
 // outer: outer-iteration index (stats slot); min_corr: 0 for mapping, params.min_correspondences for odometry
 int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                     const float4 *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
-                    msfl_stats *d_stats, int outer, int min_corr);
+                    msfl_stats *d_stats, int outer, int min_corr, int plane_bytes = 48);
 int launch_lm_solve_pd(msfl_engine *e, int B, const double *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                        const double *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
                        msfl_stats *d_stats, int outer, int min_corr);
