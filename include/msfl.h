@@ -186,6 +186,20 @@ int msfl_scan2map_batch_device(msfl_engine *e, int B,
                                const float *d_corner_xyzi, const int32_t *d_corner_off, size_t n_corner_total,
                                const float *d_surf_xyzi, const int32_t *d_surf_off, size_t n_surf_total,
                                double *d_poses_tq, msfl_stats *d_stats /* device, B entries, or NULL */);
+/* Asynchronous form of msfl_scan2map_batch for replay / multi-robot streams of batches: submit
+ * enqueues the H2D copies (copy stream), the kernels and the D2H copy of the poses (engine stream)
+ * and returns a ticket without waiting; wait blocks until that batch is done and writes its B x 7
+ * poses (and B stats entries when want_stats was set; stats may be NULL otherwise).  Up to
+ * MSFL_MAX_INFLIGHT batches may be in flight, so the upload of batch k+1 overlaps the kernels of
+ * batch k; batches complete in submission order and give bit-identical poses to the synchronous
+ * call.  The clouds must stay valid and unchanged until the matching wait returns (packed,
+ * page-locked clouds are DMA'd straight from the caller's memory).  Submitting while
+ * MSFL_MAX_INFLIGHT tickets are outstanding returns MSFL_ERR_ARG. */
+#define MSFL_MAX_INFLIGHT 2
+int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *scan_corner,
+                               const msfl_cloud *scan_surf, const double *poses_tq_in, int want_stats,
+                               int *ticket);
+int msfl_scan2map_batch_wait(msfl_engine *e, int ticket, double *poses_tq_out, msfl_stats *stats);
 /* Association only (a-6/a-7) at a given pose, for parity tests: knn_idx (n_corner+n_surf) x 5
  * original submap indices (-1 where the d5^2 gate failed), corr (n_corner+n_surf) x 6 doubles
  * [a_or_c(3), n(3)] (n = 0 where no factor was created).  Either output may be NULL. */

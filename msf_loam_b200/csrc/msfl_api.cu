@@ -277,6 +277,11 @@ void msfl_destroy(msfl_engine *e) {
                    &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp,
                    &e->k_table, &e->k_dsk, &e->k_pprime};
   for (DevBuf *b : dbs) b->release();
+  for (auto &sl : e->slots) {
+    sl.d_in.release(); sl.d_stats.release(); sl.h_stage.release(); sl.h_out.release(); sl.h_stats.release();
+    if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc};
   for (PinBuf *b : pbs) b->release();
   for (auto &s : e->stage_events) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -604,6 +609,102 @@ int msfl_scan2map_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner, co
   MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
   memcpy(poses_tq, e->h_poses.p, (size_t)B * 7 * 8);
   if (stats) memcpy(stats, e->h_stats.p, (size_t)B * sizeof(msfl_stats));
+  return MSFL_OK;
+}
+
+// ---- asynchronous batches: H2D of batch k+1 (copy stream) overlaps the kernels of batch k (engine stream) ----
+int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *corner, const msfl_cloud *surf, const double *poses_in,
+                               int want_stats, int *ticket) {
+  if (!e || B <= 0 || !corner || !surf || !poses_in || !ticket) { set_error("msfl_scan2map_batch_submit: bad argument"); return MSFL_ERR_ARG; }
+  if (!e->has_submap) { set_error("msfl_scan2map: no submap set"); return MSFL_ERR_NOSUBMAP; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  msfl_engine::BatchSlot &sl = e->slots[e->next_ticket % MSFL_MAX_INFLIGHT];
+  if (sl.busy) { set_error("msfl_scan2map_batch_submit: %d batches already in flight", MSFL_MAX_INFLIGHT); return MSFL_ERR_ARG; }
+  int rc;
+  size_t nct = 0, nst = 0;
+  bool contiguous = true;
+  for (int b = 0; b < B; ++b) {
+    if ((rc = check_cloud(&corner[b], false, "scan_corner"))) return rc;
+    if ((rc = check_cloud(&surf[b], false, "scan_surf"))) return rc;
+    const msfl_cloud *cl[2] = {&corner[b], &surf[b]};
+    const msfl_cloud *nx[2] = {b + 1 < B ? &corner[b + 1] : nullptr, b + 1 < B ? &surf[b + 1] : nullptr};
+    for (int c = 0; c < 2; ++c) {
+      if (cl[c]->stride != 16 || cl[c]->off_xyz != 0) contiguous = false;
+      if (nx[c] && (const char *)nx[c]->data != (const char *)cl[c]->data + cl[c]->n * 16) contiguous = false;
+    }
+    nct += corner[b].n;
+    nst += surf[b].n;
+  }
+  if (nct + nst > 0x7fffffffull) { set_error("batch too large"); return MSFL_ERR_ARG; }
+  if (!e->copy_stream) MSFL_CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  if (!sl.uploaded) MSFL_CUDA_OK(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+  if (!sl.done) MSFL_CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  // slot layout (host staging and device alike): [queries (nct+nst) float4 | offsets 2(B+1) int32 | poses B*7 double]
+  const size_t q_bytes = (nct + nst) * 16, q_pad = (q_bytes + 15) & ~(size_t)15;
+  const size_t off_bytes = (size_t)2 * (B + 1) * 4, off_pad = (off_bytes + 15) & ~(size_t)15;
+  const size_t pose_bytes = (size_t)B * 7 * 8;
+  if ((rc = sl.h_stage.reserve((contiguous ? 0 : q_pad) + off_pad + pose_bytes))) return rc;
+  if ((rc = sl.d_in.reserve(q_pad + off_pad + pose_bytes))) return rc;
+  if ((rc = sl.h_out.reserve(pose_bytes))) return rc;
+  char *h = sl.h_stage.as<char>(), *d = sl.d_in.as<char>();
+  char *h_tab = h + (contiguous ? 0 : q_pad);
+  int32_t *hoff = (int32_t *)h_tab;
+  size_t ci = 0, si = 0;
+  for (int b = 0; b < B; ++b) {
+    hoff[b] = (int32_t)ci;
+    hoff[B + 1 + b] = (int32_t)si;
+    if (!contiguous) {
+      pack_cloud_host(&corner[b], (float *)h + 4 * ci, nullptr);
+      pack_cloud_host(&surf[b], (float *)h + 4 * (nct + si), nullptr);
+    }
+    ci += corner[b].n;
+    si += surf[b].n;
+  }
+  hoff[B] = (int32_t)ci;
+  hoff[2 * B + 1] = (int32_t)si;
+  memcpy(h_tab + off_pad, poses_in, pose_bytes);
+  cudaStream_t cs = e->copy_stream;
+  if (contiguous) {
+    if (nct) MSFL_CUDA_OK(cudaMemcpyAsync(d, corner[0].data, nct * 16, cudaMemcpyHostToDevice, cs));
+    if (nst) MSFL_CUDA_OK(cudaMemcpyAsync(d + nct * 16, surf[0].data, nst * 16, cudaMemcpyHostToDevice, cs));
+  } else if (q_bytes) {
+    MSFL_CUDA_OK(cudaMemcpyAsync(d, h, q_bytes, cudaMemcpyHostToDevice, cs));
+  }
+  MSFL_CUDA_OK(cudaMemcpyAsync(d + q_pad, h_tab, off_pad + pose_bytes, cudaMemcpyHostToDevice, cs));
+  MSFL_CUDA_OK(cudaEventRecord(sl.uploaded, cs));
+  MSFL_CUDA_OK(cudaStreamWaitEvent(e->stream, sl.uploaded, 0));
+  msfl_stats *d_stats = nullptr;
+  if (want_stats) {
+    if ((rc = sl.d_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    if ((rc = sl.h_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    d_stats = sl.d_stats.as<msfl_stats>();
+    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, (size_t)B * sizeof(msfl_stats), e->stream));
+  }
+  const float4 *d_qc = (const float4 *)d, *d_qs = d_qc + nct;
+  const int32_t *d_c_off = (const int32_t *)(d + q_pad), *d_s_off = d_c_off + (B + 1);
+  double *d_poses = (double *)(d + q_pad + off_pad);
+  if ((rc = scan2map_enqueue(e, B, d_qc, d_c_off, (uint32_t)nct, d_qs, d_s_off, (uint32_t)nst, d_poses, d_stats))) return rc;
+  MSFL_CUDA_OK(cudaMemcpyAsync(sl.h_out.p, d_poses, pose_bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (want_stats)
+    MSFL_CUDA_OK(cudaMemcpyAsync(sl.h_stats.p, d_stats, (size_t)B * sizeof(msfl_stats), cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaEventRecord(sl.done, e->stream));
+  sl.busy = true;
+  sl.want_stats = want_stats != 0;
+  sl.B = B;
+  sl.ticket = e->next_ticket++;
+  *ticket = sl.ticket;
+  return MSFL_OK;
+}
+
+int msfl_scan2map_batch_wait(msfl_engine *e, int ticket, double *poses_out, msfl_stats *stats) {
+  if (!e || ticket < 0 || !poses_out) { set_error("msfl_scan2map_batch_wait: bad argument"); return MSFL_ERR_ARG; }
+  msfl_engine::BatchSlot &sl = e->slots[ticket % MSFL_MAX_INFLIGHT];
+  if (!sl.busy || sl.ticket != ticket) { set_error("msfl_scan2map_batch_wait: ticket %d is not in flight", ticket); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  MSFL_CUDA_OK(cudaEventSynchronize(sl.done));
+  memcpy(poses_out, sl.h_out.p, (size_t)sl.B * 7 * 8);
+  if (stats && sl.want_stats) memcpy(stats, sl.h_stats.p, (size_t)sl.B * sizeof(msfl_stats));
+  sl.busy = false;
   return MSFL_OK;
 }
 

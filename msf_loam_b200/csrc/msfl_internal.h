@@ -97,6 +97,18 @@ struct msfl_engine {
   msfl::Submap last_corner_grid, last_surf_grid;  // scan-to-scan: cell index over the last scan's features
   bool has_submap = false;
 
+  // asynchronous batches (msfl_scan2map_batch_submit / _wait): per-slot input / output buffers; the
+  // association / LM scratch below is shared because the kernels of all batches run in order on `stream`
+  struct BatchSlot {
+    msfl::DevBuf d_in, d_stats;
+    msfl::PinBuf h_stage, h_out, h_stats;
+    cudaEvent_t uploaded = nullptr, done = nullptr;
+    bool busy = false, want_stats = false;
+    int B = 0, ticket = -1;
+  };
+  BatchSlot slots[MSFL_MAX_INFLIGHT];
+  int next_ticket = 0;
+
   // batch scratch
   msfl::DevBuf d_queries, d_corr, d_poses, d_status, d_stats, d_knn, d_off, d_misc;
   msfl::PinBuf h_stage, h_poses, h_stats, h_misc;

@@ -196,6 +196,22 @@ class Engine:
             self.h, C.c_int(batch["B"]), batch["carr"], batch["sarr"],
             poses_inout.ctypes.data_as(C.POINTER(C.c_double)), None))
 
+    def scan2map_submit(self, batch, poses_in: np.ndarray) -> int:
+        """msfl_scan2map_batch_submit on a prepared batch: enqueues upload + kernels + pose download and
+        returns a ticket; up to 2 batches may be in flight (the upload of one overlaps the kernels of the other)."""
+        assert poses_in.dtype == np.float64 and poses_in.flags.c_contiguous
+        t = C.c_int(-1)
+        self._check(self.lib.msfl_scan2map_batch_submit(
+            self.h, C.c_int(batch["B"]), batch["carr"], batch["sarr"],
+            poses_in.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(0), C.byref(t)))
+        return t.value
+
+    def scan2map_wait(self, ticket: int, poses_out: np.ndarray):
+        """msfl_scan2map_batch_wait: blocks until the batch of `ticket` is done, fills poses_out (B,7)."""
+        assert poses_out.dtype == np.float64 and poses_out.flags.c_contiguous
+        return self._check(self.lib.msfl_scan2map_batch_wait(
+            self.h, C.c_int(ticket), poses_out.ctypes.data_as(C.POINTER(C.c_double)), None))
+
     def scan2map_batch_device(self, B, d_corner, d_corner_off, n_corner_total, d_surf, d_surf_off,
                               n_surf_total, d_poses, d_stats=0):
         """All arguments are raw device pointers (ints); enqueues and returns without syncing."""
