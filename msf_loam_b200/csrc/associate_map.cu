@@ -253,7 +253,9 @@ __device__ __forceinline__ float3 deskew_transform(const double pose[7], const D
 // loads).  STORED_X: read the transformed point stored by k_transform_keys (the permutation was
 // built for the current poses); otherwise transform here (the permutation of an earlier outer
 // iteration is reused -- it is only a locality hint, the result does not depend on it).
-template <bool SORTED, bool STORED_X, bool DESKEW>
+// BY_SLOT: the five indices are stored at the thread's slot (coalesced; k_fit<.., true> then walks the
+// same cell order) instead of at the query's flat index k.
+template <bool SORTED, bool STORED_X, bool DESKEW, bool BY_SLOT>
 __global__ void __launch_bounds__(128, 10)
 k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
        const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
@@ -283,7 +285,7 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
   Top5 t;
   const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);  // :125-128 / :195-198
   // 5 neighbour indices per query (-1 when the d5^2 gate fails), consumed by k_fit
-  int32_t *o = knn_out + (size_t)k * 5;
+  int32_t *o = knn_out + (size_t)(BY_SLOT ? slot : k) * 5;
 #pragma unroll
   for (int s = 0; s < 5; ++s) o[s] = gate ? t.i[s] : -1;
 }
@@ -294,17 +296,20 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
 // Jacobi / Householder code does not throttle it.
 // COMPACT: plane entries are written as 32 B {n, n.c} at corr + 48 n_corner_total + 32 i (the batch path: the LM
 // kernel only ever needs the plane's offset along its normal); otherwise 48 B {c, n} like the edge entries.
-template <bool DESKEW, bool COMPACT>
-__global__ void __launch_bounds__(128)
+// BY_SLOT: thread s handles query perm[s] and reads the neighbour indices k_knn5 stored at slot s: the lanes of a
+// warp are spatial neighbours, so they agree on the gate / validity branches and share the gathered map points.
+template <bool DESKEW, bool COMPACT, bool BY_SLOT, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB)
 k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
-      double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_total) return;
+      double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_total) return;
+  const uint32_t k = BY_SLOT ? __ldg(perm + slot) : slot;
   const bool is_corner = k < n_corner_total;
   const GridView &g = is_corner ? gc : gs;
   int idx[5];
 #pragma unroll
-  for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)k * 5 + s);
+  for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)slot * 5 + s);
   double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
   if (idx[4] >= 0) {
     double m[5][3];
@@ -378,6 +383,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
   const GridView &gc = e->map_corner.view, &gs = e->map_surf.view;
+  const bool own_knn = d_knn == nullptr;
   if (!d_knn) {  // neighbour indices travel from the search kernel to the fit kernel through this scratch
     int rck;
     if ((rck = e->d_knn.reserve((size_t)total * 5 * 4))) return rck;
@@ -387,11 +393,11 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   const bool sorted = mode == 2 || (mode == 0 && total >= 65536u);
   if (!sorted) {
     stage_begin(e, 0);
-    k_knn5<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+    k_knn5<false, false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
         gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, nullptr, d_knn,
         DeskewTable{}, nullptr);
-    if (compact) k_fit<false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
-    else k_fit<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+    if (compact) k_fit<false, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
+    else k_fit<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
     stage_end(e);
     e->launches += 2;
     MSFL_CUDA_OK(cudaGetLastError());
@@ -403,11 +409,11 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     // later outer iteration: poses moved by centimetres, the previous cell order is still a good
     // locality hint -> skip the transform/sort pass, transform inside the association kernel
     stage_begin(e, 0);
-    k_knn5<true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+    k_knn5<true, false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
         gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, e->a_perm, d_knn,
         DeskewTable{}, nullptr);
-    if (compact) k_fit<false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
-    else k_fit<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+    if (compact) k_fit<false, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
+    else k_fit<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
     stage_end(e);
     e->launches += 2;
     MSFL_CUDA_OK(cudaGetLastError());
@@ -436,14 +442,32 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   stage_end(e);
   e->a_perm = dv.Current();
   e->a_perm_valid = total;
+  // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
+  const bool by_slot = own_knn && e->dev_fit_sorted != 0;
   stage_begin(e, 0);
-  k_knn5<true, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-      gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
-      DeskewTable{}, nullptr);
+  if (by_slot)
+    k_knn5<true, true, false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
+        DeskewTable{}, nullptr);
+  else
+    k_knn5<true, true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
+        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
+        DeskewTable{}, nullptr);
   stage_end(e);
   stage_begin(e, 3);
-  if (compact) k_fit<false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
-  else k_fit<false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr);
+  {
+    const unsigned grid = (total + tb - 1) / tb;
+    const DeskewTable nt{};
+    if (by_slot) {
+      if (compact && e->dev_fit_minb == 5) k_fit<false, true, true, 5><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      else if (compact && e->dev_fit_minb == 6) k_fit<false, true, true, 6><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      else if (compact) k_fit<false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      else k_fit<false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+    } else {
+      if (compact) k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);
+      else k_fit<false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);
+    }
+  }
   stage_end(e);
   e->launches += 3 + 3;
   MSFL_CUDA_OK(cudaGetLastError());
@@ -474,10 +498,10 @@ int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_
   }
   DeskewTable tb{d_sum_dt, d_dq, d_dp, n_tab, {V[0], V[1], V[2]}, {G[0], G[1], G[2]}};
   stage_begin(e, 0);
-  k_knn5<false, false, true><<<(total + 127) / 128, 128, 0, e->stream>>>(
+  k_knn5<false, false, true, false><<<(total + 127) / 128, 128, 0, e->stream>>>(
       e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_knn, tb,
       d_dsk);
-  k_fit<true, false><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk);
+  k_fit<true, false, false><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk, nullptr);
   stage_end(e);
   e->launches += 2;
   MSFL_CUDA_OK(cudaGetLastError());

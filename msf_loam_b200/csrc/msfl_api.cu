@@ -240,6 +240,8 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   fill_kparams(e);
   if (const char *v = getenv("MSFL_LM_VARIANT")) e->dev_lm_variant = atoi(v);
   if (const char *v = getenv("MSFL_COMPACT")) e->dev_compact = atoi(v);
+  if (const char *v = getenv("MSFL_FIT_SORTED")) e->dev_fit_sorted = atoi(v);
+  if (const char *v = getenv("MSFL_FIT_MINB")) e->dev_fit_minb = atoi(v);
   if (e->dev_lm_variant == 0) e->dev_compact = 0;  // the CTA-wide tile sweep reads 48 B plane entries
   if (stream) {
     e->stream = (cudaStream_t)stream;

@@ -85,6 +85,8 @@ struct msfl_engine {
   // development switches (environment, read once in msfl_create): A/B of kernel variants on the GPU box
   int dev_lm_variant = 1;   // MSFL_LM_VARIANT: 0 = CTA-wide tiles, 1 = warp-private streaming
   int dev_compact = 1;      // MSFL_COMPACT: 1 = k_fit writes 32 B plane constants {n, n.c} for the batch path
+  int dev_fit_sorted = 1;   // MSFL_FIT_SORTED: 1 = k_fit walks the queries in cell order (batch path)
+  int dev_fit_minb = 4;     // MSFL_FIT_MINB: min CTAs/SM of k_fit (register cap 128 / 96 / 80)
   int sm_count = 148;
 
   // per-stage CUDA-event timing (msfl_set_profiling)
