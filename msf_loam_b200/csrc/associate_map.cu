@@ -8,6 +8,7 @@
 // contraction (FLANN L2_Simple<float>), candidates are ordered by (d2, original index), the fit
 // is fp64.  Output per query: 6 doubles [a_or_c(3), n(3)]; n = 0 marks "no factor".
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
@@ -132,11 +133,16 @@ __device__ __forceinline__ int cell_of(const GridView &g, float x, float y, floa
 // Pass 1 of the sorted path: transform every query by its scan's pose (mapping_scan_matcher.cc:123 /
 // :193) and emit a sort key = cell id of the transformed point (corner grid first, then surf grid; one
 // sentinel cell per class for queries with no occupied neighbourhood).
+// COUNT: counting-sort form -- the key's bin counter is bumped and the returned rank (this query's position inside
+// its bin) is stored instead of the query index; k_scatter_perm turns (key, rank) into the cell-order permutation
+// after an exclusive scan of the bins.  The order inside a bin is whatever order the atomics happened in: the
+// permutation is only a locality hint (every result is written at the query's own index), so poses do not depend on it.
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc, const int32_t *__restrict__ c_off,
                  uint32_t n_corner_total, const float4 *__restrict__ qs, const int32_t *__restrict__ s_off,
                  uint32_t n_surf_total, const double *__restrict__ poses, float4 *__restrict__ xq,
-                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ hist) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_corner_total + n_surf_total) return;
   const bool is_corner = k < n_corner_total;
@@ -163,7 +169,16 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
   }
   xq[k] = make_float4(x.x, x.y, x.z, 0.f);
   keys[k] = key;
-  vals[k] = k;
+  vals[k] = COUNT ? atomicAdd(hist + key, 1u) : k;
+}
+
+// counting sort, last pass: slot = first slot of the query's bin + its rank inside the bin
+__global__ void __launch_bounds__(256)
+k_scatter_perm(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ bin_start,
+               uint32_t n, uint32_t *__restrict__ perm) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  perm[__ldg(bin_start + __ldg(keys + k)) + __ldg(rank + k)] = k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,18 +444,40 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   while ((1ll << end_bit) < ncell) ++end_bit;
   end_bit += 6;  // 4x4x4 sub-cell index in the low bits
   if (end_bit > 32) { set_error("submap grid too large for the sorted association path"); return MSFL_ERR_GRID; }
-  cub::DoubleBuffer<uint32_t> dk(e->a_keys.as<uint32_t>(), e->a_keys_alt.as<uint32_t>()),
-      dv(e->a_vals.as<uint32_t>(), e->a_vals_alt.as<uint32_t>());
-  size_t tmp = 0;
-  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
-  if ((rc = e->a_tmp.reserve(tmp))) return rc;
-  stage_begin(e, 2);
-  k_transform_keys<<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                              n_surf_total, d_poses, e->a_xq.as<float4>(), dk.Current(),
-                                                              dv.Current());
-  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
-  stage_end(e);
-  e->a_perm = dv.Current();
+  const long long nbins = ncell << 6;
+  if (e->dev_count_sort && nbins <= (16ll << 20)) {
+    // counting sort: one atomic per query into a bin table that lives in L2, a scan of the bins, one scatter
+    size_t tmp = 0;
+    if ((rc = e->a_hist.reserve((size_t)nbins * 4))) return rc;
+    uint32_t *hist = e->a_hist.as<uint32_t>();
+    MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, hist, hist, (int)nbins, e->stream));
+    if ((rc = e->a_tmp.reserve(tmp))) return rc;
+    stage_begin(e, 2);
+    MSFL_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, e->stream));
+    k_transform_keys<true><<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                       n_surf_total, d_poses, e->a_xq.as<float4>(),
+                                                                       e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist);
+    MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(e->a_tmp.p, tmp, hist, hist, (int)nbins, e->stream));
+    k_scatter_perm<<<(total + 255) / 256, 256, 0, e->stream>>>(e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist, total,
+                                                               e->a_vals_alt.as<uint32_t>());
+    stage_end(e);
+    e->a_perm = e->a_vals_alt.as<uint32_t>();
+    e->launches += 3;  // + the cub scan kernels
+  } else {
+    cub::DoubleBuffer<uint32_t> dk(e->a_keys.as<uint32_t>(), e->a_keys_alt.as<uint32_t>()),
+        dv(e->a_vals.as<uint32_t>(), e->a_vals_alt.as<uint32_t>());
+    size_t tmp = 0;
+    MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
+    if ((rc = e->a_tmp.reserve(tmp))) return rc;
+    stage_begin(e, 2);
+    k_transform_keys<false><<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                        n_surf_total, d_poses, e->a_xq.as<float4>(), dk.Current(),
+                                                                        dv.Current(), nullptr);
+    MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
+    stage_end(e);
+    e->a_perm = dv.Current();
+    e->launches += 3;
+  }
   e->a_perm_valid = total;
   // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
   const bool by_slot = own_knn && e->dev_fit_sorted != 0;
@@ -469,7 +506,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     }
   }
   stage_end(e);
-  e->launches += 3 + 3;
+  e->launches += 3;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }

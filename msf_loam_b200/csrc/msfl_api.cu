@@ -242,6 +242,7 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   if (const char *v = getenv("MSFL_COMPACT")) e->dev_compact = atoi(v);
   if (const char *v = getenv("MSFL_FIT_SORTED")) e->dev_fit_sorted = atoi(v);
   if (const char *v = getenv("MSFL_FIT_MINB")) e->dev_fit_minb = atoi(v);
+  if (const char *v = getenv("MSFL_COUNT_SORT")) e->dev_count_sort = atoi(v);
   if (e->dev_lm_variant == 0) e->dev_compact = 0;  // the CTA-wide tile sweep reads 48 B plane entries
   if (stream) {
     e->stream = (cudaStream_t)stream;
@@ -276,7 +277,7 @@ void msfl_destroy(msfl_engine *e) {
                    &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,
                    &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
                    &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc,
-                   &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp,
+                   &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp, &e->a_hist,
                    &e->k_table, &e->k_dsk, &e->k_pprime};
   for (DevBuf *b : dbs) b->release();
   for (auto &sl : e->slots) {

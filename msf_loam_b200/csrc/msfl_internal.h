@@ -87,6 +87,7 @@ struct msfl_engine {
   int dev_compact = 1;      // MSFL_COMPACT: 1 = k_fit writes 32 B plane constants {n, n.c} for the batch path
   int dev_fit_sorted = 1;   // MSFL_FIT_SORTED: 1 = k_fit walks the queries in cell order (batch path)
   int dev_fit_minb = 4;     // MSFL_FIT_MINB: min CTAs/SM of k_fit (register cap 128 / 96 / 80)
+  int dev_count_sort = 1;   // MSFL_COUNT_SORT: 1 = counting sort of the cell keys (atomics + scan) instead of cub radix sort
   int sm_count = 148;
 
   // per-stage CUDA-event timing (msfl_set_profiling)
@@ -115,7 +116,7 @@ struct msfl_engine {
   msfl::DevBuf d_queries, d_corr, d_poses, d_status, d_stats, d_knn, d_off, d_misc;
   msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
   // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
-  msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp;
+  msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp, a_hist;
   msfl::DevBuf k_table, k_dsk, k_pprime;  // deskew branch: preintegration table, per-query (dq, dp, dt), p'
   const uint32_t *a_perm = nullptr;  // cell-order permutation of the current batch (valid for a_perm_valid queries)
   uint32_t a_perm_valid = 0;
