@@ -24,26 +24,17 @@ __device__ __forceinline__ bool cand_less(float d, int id, float bd, int bi) {
   return d < bd || (d == bd && id < bi);
 }
 
+// Sorted insertion without branches and in place: l_s = "entry s stays ahead of the candidate"; every slot is
+// rewritten by selects from the top down, so the hot candidate loop around it needs no register copies.
 __device__ __forceinline__ void top5_insert(Top5 &t, float d, int id) {
   // precondition: (d, id) < (t.d[4], t.i[4])
-  bool placed = false;
-#pragma unroll
-  for (int s = 4; s > 0; --s) {
-    if (!placed) {
-      if (cand_less(d, id, t.d[s - 1], t.i[s - 1])) {
-        t.d[s] = t.d[s - 1];
-        t.i[s] = t.i[s - 1];
-      } else {
-        t.d[s] = d;
-        t.i[s] = id;
-        placed = true;
-      }
-    }
-  }
-  if (!placed) {
-    t.d[0] = d;
-    t.i[0] = id;
-  }
+  const bool l0 = cand_less(t.d[0], t.i[0], d, id), l1 = cand_less(t.d[1], t.i[1], d, id),
+             l2 = cand_less(t.d[2], t.i[2], d, id), l3 = cand_less(t.d[3], t.i[3], d, id);
+  t.d[4] = l3 ? d : t.d[3];                    t.i[4] = l3 ? id : t.i[3];
+  t.d[3] = l3 ? t.d[3] : (l2 ? d : t.d[2]);    t.i[3] = l3 ? t.i[3] : (l2 ? id : t.i[2]);
+  t.d[2] = l2 ? t.d[2] : (l1 ? d : t.d[1]);    t.i[2] = l2 ? t.i[2] : (l1 ? id : t.i[1]);
+  t.d[1] = l1 ? t.d[1] : (l0 ? d : t.d[0]);    t.i[1] = l1 ? t.i[1] : (l0 ? id : t.i[0]);
+  t.d[0] = l0 ? t.d[0] : d;                    t.i[0] = l0 ? t.i[0] : id;
 }
 
 // 5-NN of q among the 27 cells around it, restricted to d2 < thresh.  Returns true when five
@@ -313,8 +304,8 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
 // kernel only ever needs the plane's offset along its normal); otherwise 48 B {c, n} like the edge entries.
 // BY_SLOT: thread s handles query perm[s] and reads the neighbour indices k_knn5 stored at slot s: the lanes of a
 // warp are spatial neighbours, so they agree on the gate / validity branches and share the gathered map points.
-template <bool DESKEW, bool COMPACT, bool BY_SLOT, int MINB = 4>
-__global__ void __launch_bounds__(128, MINB)
+template <bool DESKEW, bool COMPACT, bool BY_SLOT>
+__global__ void __launch_bounds__(128)
 k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
       double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,7 +436,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   end_bit += 6;  // 4x4x4 sub-cell index in the low bits
   if (end_bit > 32) { set_error("submap grid too large for the sorted association path"); return MSFL_ERR_GRID; }
   const long long nbins = ncell << 6;
-  if (e->dev_count_sort && nbins <= (16ll << 20)) {
+  if (nbins <= e->count_sort_max_bins) {
     // counting sort: one atomic per query into a bin table that lives in L2, a scan of the bins, one scatter
     size_t tmp = 0;
     if ((rc = e->a_hist.reserve((size_t)nbins * 4))) return rc;
@@ -480,7 +471,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   }
   e->a_perm_valid = total;
   // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
-  const bool by_slot = own_knn && e->dev_fit_sorted != 0;
+  const bool by_slot = own_knn;
   stage_begin(e, 0);
   if (by_slot)
     k_knn5<true, true, false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
@@ -496,9 +487,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     const unsigned grid = (total + tb - 1) / tb;
     const DeskewTable nt{};
     if (by_slot) {
-      if (compact && e->dev_fit_minb == 5) k_fit<false, true, true, 5><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
-      else if (compact && e->dev_fit_minb == 6) k_fit<false, true, true, 6><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
-      else if (compact) k_fit<false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      if (compact) k_fit<false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
       else k_fit<false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
     } else {
       if (compact) k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);

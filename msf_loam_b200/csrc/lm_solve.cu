@@ -7,8 +7,10 @@
 //
 // Every attempt is ONE sweep over the scan's correspondences: cost, H and g are evaluated together
 // at the candidate x+, so an accepted step needs no second pass (the (1+L) factor of the byte
-// formula in SURVEY.md 8d).  All factor math is fp64 (the reference's is); sums are combined in a
-// fixed order, so results are bit-reproducible run to run and independent of the batch size.
+// formula in SURVEY.md 8d).  The sweep streams the scan's points and factor constants from HBM with
+// warp-private, double-buffered TMA bulk copies (cp.async.bulk + mbarrier), see sweep_warp.  All
+// factor math is fp64 (the reference's is); sums are combined in a fixed order, so results are
+// bit-reproducible run to run and independent of the batch size.
 #include <cooperative_groups.h>
 
 #include "msfl_internal.h"
@@ -164,159 +166,19 @@ __device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) 
 
 
 // ---------------------------------------------------------------------------------------------
-// TMA (cp.async.bulk, 1-D) staging of correspondence tiles.  The per-scan arrays are contiguous, so
-// a tile of kTile entries is two bulk copies (points: 16 B/entry, constants: 48 B/entry) that land
-// in shared memory and complete on an mbarrier; a 3-stage ring keeps two tiles in flight while one
-// is consumed, which takes the L2/HBM latency off the fp64 critical path.
+// TMA (cp.async.bulk, 1-D) staging of correspondence tiles.  The per-scan arrays are contiguous, so a
+// tile is two bulk copies (points, constants) that land in shared memory and complete on an mbarrier.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPerThread = 2;              // entries per thread per tile
-constexpr int kTile = kLmThreads * kPerThread;
-constexpr int kStages = 3;      // ring depth of the streaming (throughput) configuration
-constexpr int kMaxStages = 13;  // resident configuration (clustered launches): up to 13 x 16 KB tiles stay in smem
-template <int PB> constexpr int stage_bytes() { return kTile * PB + kTile * 48; }
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 struct TileSrc {
   const unsigned char *pe, *pp;  // point arrays (PB bytes per entry)
-  const double *ce, *cp;
-  uint32_t n_e, n_p, tiles_e, tiles;
+  const double *ce, *cp;         // constants: 48 B per edge entry, PC bytes per plane entry
+  uint32_t n_e, n_p;
 };
-
-// issue the two bulk copies of tile t into stage buffer `buf`
-template <int PB>
-__device__ __forceinline__ void issue_tile(const TileSrc &ts, uint32_t t, unsigned char *buf, uint64_t *bar) {
-  const bool edge = t < ts.tiles_e;
-  const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
-  const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
-  const unsigned char *p = (edge ? ts.pe : ts.pp) + (size_t)base * PB;
-  const double *c = (edge ? ts.ce : ts.cp) + (size_t)base * 6;
-  mbar_expect_tx(bar, cnt * (uint32_t)(PB + 48));
-  tma_load_1d(buf, p, cnt * (uint32_t)PB, bar);
-  tma_load_1d(buf + kTile * PB, c, cnt * 48u, bar);
-}
-
-// One fused sweep over the scan's correspondences at `pose`, tiles streamed through the smem ring.
-// `tile_ctr` counts tiles consumed since kernel start (stage = ctr % n_stages, parity = (ctr / n_stages) & 1).
-// When all of the CTA's tiles fit in the ring (tiles <= n_stages, the clustered / small-scan case) they are
-// loaded once by the first sweep and every later sweep reads them from shared memory without any copy or
-// barrier: tile t lives in stage t.
-template <int PB>
-__device__ __forceinline__ void sweep_tiled(double (&acc)[kAcc], const TileSrc &ts, unsigned char *ring, uint64_t *bars,
-                                            uint32_t n_stages, uint32_t &tile_ctr, const double *pose, double huber_a,
-                                            int &cnt_edge, int &cnt_plane) {
-  const bool resident = ts.tiles <= n_stages;
-  const bool first_sweep = tile_ctr == 0;
-#pragma unroll
-  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-  double R[9];
-  quat_to_R(pose + 3, R);
-  const double t0 = pose[0], t1 = pose[1], t2 = pose[2];
-  cnt_edge = 0;
-  cnt_plane = 0;
-  const uint32_t tid = threadIdx.x;
-  if (tid == 0) {
-    if (resident) {
-      if (first_sweep)
-        for (uint32_t t = 0; t < ts.tiles; ++t) issue_tile<PB>(ts, t, ring + t * stage_bytes<PB>(), bars + t);
-    } else {
-      for (uint32_t t = 0; t < min(n_stages - 1, ts.tiles); ++t) {
-        const uint32_t g = tile_ctr + t;
-        issue_tile<PB>(ts, t, ring + (g % n_stages) * stage_bytes<PB>(), bars + (g % n_stages));
-      }
-    }
-  }
-  for (uint32_t t = 0; t < ts.tiles; ++t) {
-    const uint32_t g = tile_ctr + t, stage = resident ? t : g % n_stages;
-    if (!resident) {
-      if (tid == 0 && t + n_stages - 1 < ts.tiles) {
-        const uint32_t gn = g + n_stages - 1;
-        issue_tile<PB>(ts, t + n_stages - 1, ring + (gn % n_stages) * stage_bytes<PB>(), bars + (gn % n_stages));
-      }
-      mbar_wait(bars + stage, (g / n_stages) & 1u);
-    } else if (first_sweep) {
-      mbar_wait(bars + stage, 0u);
-    }
-    const bool edge = t < ts.tiles_e;
-    const uint32_t base = (edge ? t : t - ts.tiles_e) * kTile;
-    const uint32_t cnt = min((uint32_t)kTile, (edge ? ts.n_e : ts.n_p) - base);
-#pragma unroll 1
-    for (uint32_t ent = tid; ent < cnt; ent += kLmThreads) {
-      const unsigned char *buf = ring + stage * stage_bytes<PB>();
-      double p0, p1, p2;
-      if (PB == 16) {
-        const float4 pf = reinterpret_cast<const float4 *>(buf)[ent];
-        p0 = pf.x; p1 = pf.y; p2 = pf.z;
-      } else {
-        const double2 pa = reinterpret_cast<const double2 *>(buf)[2 * ent], pb = reinterpret_cast<const double2 *>(buf)[2 * ent + 1];
-        p0 = pa.x; p1 = pa.y; p2 = pb.x;
-      }
-      const double2 *cp = reinterpret_cast<const double2 *>(buf + kTile * PB + ent * 48);
-      const double2 c0 = cp[0], c1 = cp[1], c2 = cp[2];
-      const double a0 = c0.x, a1 = c0.y, a2 = c1.x, n0 = c1.y, n1 = c2.x, n2 = c2.y;
-      if (!(n0 == 0.0 && n1 == 0.0 && n2 == 0.0)) {
-        const double d0 = R[0] * p0 + R[1] * p1 + R[2] * p2 + t0 - a0;
-        const double d1 = R[3] * p0 + R[4] * p1 + R[5] * p2 + t1 - a1;
-        const double d2 = R[6] * p0 + R[7] * p1 + R[8] * p2 + t2 - a2;
-        const double m00 = R[1] * p2 - R[2] * p1, m10 = R[4] * p2 - R[5] * p1, m20 = R[7] * p2 - R[8] * p1;
-        const double m01 = R[2] * p0 - R[0] * p2, m11 = R[5] * p0 - R[3] * p2, m21 = R[8] * p0 - R[6] * p2;
-        const double m02 = R[0] * p1 - R[1] * p0, m12 = R[3] * p1 - R[4] * p0, m22 = R[6] * p1 - R[7] * p0;
-        if (edge) {
-          ++cnt_edge;
-          const double r0 = n1 * d2 - n2 * d1, r1 = n2 * d0 - n0 * d2, r2 = n0 * d1 - n1 * d0;
-          const double sc = huber_scale(r0 * r0 + r1 * r1 + r2 * r2, huber_a, acc[27]);
-          double J[6];
-          J[0] = 0.0; J[1] = -n2 * sc; J[2] = n1 * sc;
-          J[3] = -(-n2 * m10 + n1 * m20) * sc; J[4] = -(-n2 * m11 + n1 * m21) * sc; J[5] = -(-n2 * m12 + n1 * m22) * sc;
-          acc_row(acc, J, r0 * sc);
-          J[0] = n2 * sc; J[1] = 0.0; J[2] = -n0 * sc;
-          J[3] = -(n2 * m00 - n0 * m20) * sc; J[4] = -(n2 * m01 - n0 * m21) * sc; J[5] = -(n2 * m02 - n0 * m22) * sc;
-          acc_row(acc, J, r1 * sc);
-          J[0] = -n1 * sc; J[1] = n0 * sc; J[2] = 0.0;
-          J[3] = -(-n1 * m00 + n0 * m10) * sc; J[4] = -(-n1 * m01 + n0 * m11) * sc; J[5] = -(-n1 * m02 + n0 * m12) * sc;
-          acc_row(acc, J, r2 * sc);
-        } else {
-          ++cnt_plane;
-          const double r = n0 * d0 + n1 * d1 + n2 * d2;
-          const double sc = huber_scale(r * r, huber_a, acc[27]);
-          double J[6];
-          J[0] = n0 * sc; J[1] = n1 * sc; J[2] = n2 * sc;
-          J[3] = -(n0 * m00 + n1 * m10 + n2 * m20) * sc;
-          J[4] = -(n0 * m01 + n1 * m11 + n2 * m21) * sc;
-          J[5] = -(n0 * m02 + n1 * m12 + n2 * m22) * sc;
-          acc_row(acc, J, r * sc);
-        }
-      }
-    }
-    if (!resident) __syncthreads();  // every thread is done with this stage before it is refilled
-  }
-  tile_ctr += ts.tiles;
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Warp-private streaming (the throughput configuration).  Every warp owns a double-buffered ring of
@@ -697,16 +559,15 @@ __device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, Lm
   __syncthreads();
 }
 
-// PB: bytes per point (16 float4 / 32 double4), PC: bytes of plane constants per entry (32 / 48),
-// WP: warp-private streaming (sweep_warp) instead of CTA-wide tiles (sweep_tiled; PC must be 48 there)
-template <int PB, int PC, bool WP>
+// PB: bytes per point (16 float4 / 32 double4), PC: bytes of plane constants per entry (32 / 48)
+template <int PB, int PC>
 __global__ void __launch_bounds__(kLmThreads, 4)
 k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
            int min_corr, uint32_t n_stages) {
   __shared__ LmShared sh;
-  __shared__ __align__(8) uint64_t bars[WP ? (kLmThreads / 32) * kMaxWarpStages : kMaxStages];
+  __shared__ __align__(8) uint64_t bars[kLmWarps * kMaxWarpStages];
   extern __shared__ __align__(128) unsigned char ring[];
   // One thread-block cluster per scan: G CTAs (G = 1, 2, 4 or 8) each sweep 1/G of the scan's
   // correspondences; partial sums meet in the rank-0 CTA through distributed shared memory.
@@ -735,22 +596,18 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   if (tid == 0) {
     sh.done = 0;
     sh.too_few = 0;
-    for (int i = 0; i < (WP ? (kLmThreads / 32) * kMaxWarpStages : kMaxStages); ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < (int)(kLmWarps * kMaxWarpStages); ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   TileSrc ts;
   ts.pe = pe; ts.pp = pp; ts.ce = ce_; ts.cp = cp_;
   ts.n_e = n_e; ts.n_p = n_p;
-  ts.tiles_e = (n_e + kTile - 1) / kTile;
-  ts.tiles = ts.tiles_e + (n_p + kTile - 1) / kTile;
-  uint32_t tile_ctr = 0;
   WarpPipe wp = warp_pipe_init<PB, PC>(ts, ring, bars, n_stages);
 
   double acc[kAcc];
   int ce, cpl;
-  if (WP) sweep_warp<PB, PC>(acc, ts, wp, sh.x, kp.huber_a, ce, cpl);
-  else sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.x, kp.huber_a, ce, cpl);
+  sweep_warp<PB, PC>(acc, ts, wp, sh.x, kp.huber_a, ce, cpl);
   // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
   for (int o = 16; o > 0; o >>= 1) {
     ce += __shfl_down_sync(0xffffffffu, ce, o);
@@ -803,8 +660,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   if (G > 1) cluster_broadcast(cluster, sh, rank);
   else __syncthreads();
   while (!sh.done) {
-    if (WP) sweep_warp<PB, PC>(acc, ts, wp, sh.xc, kp.huber_a, ce, cpl);
-    else sweep_tiled<PB>(acc, ts, ring, bars, n_stages, tile_ctr, sh.xc, kp.huber_a, ce, cpl);
+    sweep_warp<PB, PC>(acc, ts, wp, sh.xc, kp.huber_a, ce, cpl);
     block_reduce(acc, sh);
     if (G > 1) cluster_reduce(cluster, sh, G, rank, false);
     if (tid == 0 && rank == 0) {
@@ -821,27 +677,26 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
     }
     if (tid < 7 && !sh.too_few) poses[(size_t)b * 7 + tid] = sh.x[tid];
   }
-  if (WP) warp_pipe_drain(wp);
+  warp_pipe_drain(wp);
   if (G > 1) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
-template <int PB, int PC, bool WP>
+template <int PB, int PC>
 static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
                              const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
                              int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
-  constexpr int sb = WP ? (int)(kLmWarps * WarpTile<PB, PC>::SB) : stage_bytes<PB>();  // smem per ring stage (whole CTA)
-  constexpr int max_stages_cfg = WP ? kMaxWarpStages : kMaxStages;
-  constexpr int max_stages = max_stages_cfg * sb <= 227 * 1024 ? max_stages_cfg : (227 * 1024) / sb;
-  bool &attr_set = e->lm_attr_set[(PB == 16 ? 0 : 1) + (PC == 32 ? 2 : 0) + (WP ? 4 : 0)];  // per engine: attributes are per device
+  constexpr int sb = (int)(kLmWarps * WarpTile<PB, PC>::SB);  // smem per ring stage (whole CTA)
+  constexpr int max_stages = kMaxWarpStages * sb <= 227 * 1024 ? kMaxWarpStages : (227 * 1024) / sb;
+  bool &attr_set = e->lm_attr_set[(PB == 16 ? 0 : 1) + (PC == 32 ? 2 : 0)];  // per engine: attributes are per device
   if (!attr_set) {
-    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB, PC, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stages * sb));
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stages * sb));
     attr_set = true;
   }
   int G = e->params.lm_cluster;
   if (G != 2 && G != 4 && G != 8) G = 1;  // 0 / 1: one CTA per scan (results are then independent of the batch shape)
-  // streaming ring (3 stages, 4 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
-  // occupancy is irrelevant) a deep ring so that a CTA's tiles stay resident in smem across the sweeps
-  const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)(WP ? kWarpStages : kStages);
+  // double-buffered streaming (4 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
+  // occupancy is irrelevant) a deep ring so that a warp's tiles stay resident in smem across the sweeps
+  const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)kWarpStages;
   const int smem = (int)n_stages * sb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * G);
@@ -855,7 +710,7 @@ static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int3
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB, PC, WP>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
+  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB, PC>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
                                   d_status, d_stats, outer, min_corr, n_stages));
   e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());
@@ -868,13 +723,10 @@ int launch_lm_solve(msfl_engine *e, int B, const float4 *d_qe, const int32_t *d_
                     msfl_stats *d_stats, int outer, int min_corr, int plane_bytes) {
   if (B <= 0) return MSFL_OK;
   if (plane_bytes == 32)
-    return launch_lm_solve_t<16, 32, true>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats,
-                                           outer, min_corr);
-  if (e->dev_lm_variant == 0)
-    return launch_lm_solve_t<16, 48, false>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats,
-                                            outer, min_corr);
-  return launch_lm_solve_t<16, 48, true>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
-                                         min_corr);
+    return launch_lm_solve_t<16, 32>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                                     min_corr);
+  return launch_lm_solve_t<16, 48>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                                   min_corr);
 }
 
 // deskewed points: double4 (p' = dq p + dp in fp64, lidar_factor.cc:53), 32 B per entry
@@ -882,11 +734,8 @@ int launch_lm_solve_pd(msfl_engine *e, int B, const double *d_qe, const int32_t 
                        const double *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses, int32_t *d_status,
                        msfl_stats *d_stats, int outer, int min_corr) {
   if (B <= 0) return MSFL_OK;
-  if (e->dev_lm_variant == 0)
-    return launch_lm_solve_t<32, 48, false>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats,
-                                            outer, min_corr);
-  return launch_lm_solve_t<32, 48, true>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
-                                         min_corr);
+  return launch_lm_solve_t<32, 48>(e, B, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status, d_stats, outer,
+                                   min_corr);
 }
 
 // ---- test hook: plain accumulate at a pose (cost, H, g), one block ---------------------------

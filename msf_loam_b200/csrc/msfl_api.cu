@@ -238,12 +238,7 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
   fill_kparams(e);
-  if (const char *v = getenv("MSFL_LM_VARIANT")) e->dev_lm_variant = atoi(v);
-  if (const char *v = getenv("MSFL_COMPACT")) e->dev_compact = atoi(v);
-  if (const char *v = getenv("MSFL_FIT_SORTED")) e->dev_fit_sorted = atoi(v);
-  if (const char *v = getenv("MSFL_FIT_MINB")) e->dev_fit_minb = atoi(v);
-  if (const char *v = getenv("MSFL_COUNT_SORT")) e->dev_count_sort = atoi(v);
-  if (e->dev_lm_variant == 0) e->dev_compact = 0;  // the CTA-wide tile sweep reads 48 B plane entries
+  if (const char *v = getenv("MSFL_COUNT_SORT_MAX_BINS")) e->count_sort_max_bins = atoll(v);  // tests: force the radix path
   if (stream) {
     e->stream = (cudaStream_t)stream;
     e->own_stream = false;
@@ -363,7 +358,7 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   e->a_perm_valid = 0;  // a new batch: the cell order of the previous one does not apply
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
-    const bool compact = e->dev_compact != 0;  // plane constants as 32 B {n, n.c}
+    const bool compact = true;  // plane constants as 32 B {n, n.c}
     if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr,
                                    /*reuse_order=*/false, compact)))  // measured: re-sorting per outer iteration is faster
                                                                        // (the first solve moves points by up to ~0.3 m)

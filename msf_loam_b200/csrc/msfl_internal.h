@@ -82,12 +82,9 @@ struct msfl_engine {
   std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
   bool lm_attr_set[8] = {false, false, false, false, false, false, false, false};
-  // development switches (environment, read once in msfl_create): A/B of kernel variants on the GPU box
-  int dev_lm_variant = 1;   // MSFL_LM_VARIANT: 0 = CTA-wide tiles, 1 = warp-private streaming
-  int dev_compact = 1;      // MSFL_COMPACT: 1 = k_fit writes 32 B plane constants {n, n.c} for the batch path
-  int dev_fit_sorted = 1;   // MSFL_FIT_SORTED: 1 = k_fit walks the queries in cell order (batch path)
-  int dev_fit_minb = 4;     // MSFL_FIT_MINB: min CTAs/SM of k_fit (register cap 128 / 96 / 80)
-  int dev_count_sort = 1;   // MSFL_COUNT_SORT: 1 = counting sort of the cell keys (atomics + scan) instead of cub radix sort
+  // the cell keys of a batch are counting-sorted while the bin table (64 sub-cell bins per submap cell) stays small
+  // enough to live in L2; larger (sparse, far-spread) submaps fall back to a radix sort of the keys
+  long long count_sort_max_bins = 16ll << 20;
   int sm_count = 148;
 
   // per-stage CUDA-event timing (msfl_set_profiling)

@@ -208,3 +208,24 @@ def test_requires_submap():
     with pytest.raises(MsflError):
         e.scan2map(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32), S.pose_identity())
     e.close()
+
+
+def test_radix_sort_fallback_of_the_cell_order_is_bitwise_identical(vlp16_case, monkeypatch):
+    """Large batches order their queries by submap cell: counting sort while the bin table is small, cub radix sort
+    for far-spread submaps (forced here through MSFL_COUNT_SORT_MAX_BINS).  The order is only a locality hint."""
+    qs = vlp16_case["queries"]
+    B = 40
+    res = []
+    for max_bins in ("0", None):
+        if max_bins is None:
+            monkeypatch.delenv("MSFL_COUNT_SORT_MAX_BINS", raising=False)
+        else:
+            monkeypatch.setenv("MSFL_COUNT_SORT_MAX_BINS", max_bins)
+        e = Engine(default_params(assoc_sorted=2))
+        e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+        rc, xs, st = e.scan2map_batch([qs[i % 3]["corner"] for i in range(B)], [qs[i % 3]["surf"] for i in range(B)],
+                                      [qs[i % 3]["init"] for i in range(B)], want_stats=True)
+        res.append((xs, [s["n_edge"] + s["n_plane"] for s in st]))
+        e.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    assert np.array_equal(res[0][0][0], res[0][0][3])  # replicas of one scan agree
