@@ -138,7 +138,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -216,6 +216,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     over = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
+    if os.environ.get("MSFL_BENCH_LM_CLUSTER"):  # development: thread-block cluster size of the LM kernel
+        over["lm_cluster"] = int(os.environ["MSFL_BENCH_LM_CLUSTER"])
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
         eng = Engine(default_params(**over), device=local_rank, stream=stream.cuda_stream)
@@ -325,7 +327,7 @@ def run_ours(args):
         total_bytes, assoc_bytes, solve_bytes = algorithmic_bytes(n_q, M)
         # dominant kernel = the stage with the larger share of the step
         names = {0: "k_knn5 (5-NN search over the submap cell index)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
-                 2: "k_transform_keys + cell radix sort", 3: "k_fit (fp64 line/plane fit)"}
+                 2: "k_transform_keys + counting sort of the cell keys", 3: "k_fit (fp64 line/plane fit)"}
         per_launch_ms = {s: stage_ms[s] / stage_cnt[s] for s in range(len(stage_ms)) if stage_cnt[s]}
         dom = max(per_launch_ms, key=lambda s: stage_ms[s])
         dom_bytes = assoc_bytes if dom in (0, 2, 3) else solve_bytes  # the association pass of SURVEY 8d
