@@ -85,8 +85,10 @@ typedef struct msfl_params {
   /* engine */
   int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan in the LM kernel:
                                   0 = auto, else 1/2/4/8                              */
-  int32_t assoc_sorted;        /* scan-to-map association order: 0 = auto (sort the batch's queries
-                                  by submap cell when it holds >= 65536 queries), 1 = never, 2 = always */
+  int32_t assoc_sorted;        /* scan-to-map association order: 0 = auto (order the batch's queries
+                                  by submap cell when it holds >= 65536 queries), 1 = never, 2 = always,
+                                  3 = always + search against TMA-staged shared-memory tiles of the
+                                  3x3x3 cell neighbourhood (k_knn5_tiled) */
 } msfl_params;
 
 /* Host AoS cloud view (see "Conventions"). */

@@ -296,6 +296,157 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
   for (int s = 0; s < 5; ++s) o[s] = gate ? t.i[s] : -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batch search kernel with TMA-staged submap tiles.  The slots of a batch are ordered by submap cell,
+// so the 128 queries of a CTA almost always sit in ONE cell (thousands of queries per cell at batch
+// sizes): the CTA takes the cell of its first query as anchor, warp 0 reads the 9 row ranges of the
+// anchor's 3x3x3 neighbourhood from the cell index (the three x-adjacent cells of a row are one
+// contiguous range of pts_sorted) and copies them into shared memory with cp.async.bulk (one bulk
+// copy per row, completing on an mbarrier), together with a 9-entry row table.  Every query of the
+// anchor cell then runs the same exact pruned search as knn5_grid against shared memory -- no
+// cell-index arithmetic, no L2 round trips; queries of another cell (CTAs that straddle a cell
+// boundary) or oversized neighbourhoods take the global-memory path.  Results are identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileCap = 1024;  // staged points per CTA (16 KB)
+
+__device__ __forceinline__ uint32_t a_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// same visiting order, bounds and (d2, index) candidate order as knn5_grid; rows[r] = tile indices
+// {left cell start, centre cell start, right cell start, end} of row r (nearest-first order)
+__device__ __forceinline__ bool knn5_tile(const float4 *__restrict__ tile, const uint4 *__restrict__ rows, bool exact_cells, float qx,
+                                          float qy, float qz, float fxq, float fyq, float fzq, float thresh, Top5 &t) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    t.d[s] = thresh;
+    t.i[s] = -1;
+  }
+  const float lox = exact_cells ? __fsub_rn(qx, fxq) : 0.f, hix = exact_cells ? __fsub_rn(fxq + 1.0f, qx) : 0.f;
+  const float loy = exact_cells ? __fsub_rn(qy, fyq) : 0.f, hiy = exact_cells ? __fsub_rn(fyq + 1.0f, qy) : 0.f;
+  const float loz = exact_cells ? __fsub_rn(qz, fzq) : 0.f, hiz = exact_cells ? __fsub_rn(fzq + 1.0f, qz) : 0.f;
+  const float bxl = __fmul_rn(lox, lox), bxr = __fmul_rn(hix, hix);
+  constexpr uint32_t kDyPacked = 1u | (0u << 2) | (2u << 4) | (1u << 6) | (1u << 8) | (0u << 10) | (0u << 12) | (2u << 14) | (2u << 16);
+  constexpr uint32_t kDzPacked = 1u | (1u << 2) | (1u << 4) | (0u << 6) | (2u << 8) | (0u << 10) | (2u << 12) | (0u << 14) | (2u << 16);
+#pragma unroll 1
+  for (int r = 0; r < 9; ++r) {
+    const int dy = (int)((kDyPacked >> (2 * r)) & 3u) - 1, dz = (int)((kDzPacked >> (2 * r)) & 3u) - 1;
+    const float by = dy == 0 ? 0.f : (dy < 0 ? loy : hiy), bz = dz == 0 ? 0.f : (dz < 0 ? loz : hiz);
+    const float by2 = __fmul_rn(by, by), bz2 = __fmul_rn(bz, bz);
+    const float row_lb = __fadd_rn(by2, bz2);
+    if (row_lb > t.d[4] || row_lb >= thresh) continue;
+    const uint4 rr = rows[r];
+    const float lbl = __fadd_rn(__fadd_rn(bxl, by2), bz2), lbr = __fadd_rn(__fadd_rn(bxr, by2), bz2);
+    const uint32_t js = (lbl > t.d[4] || lbl >= thresh) ? rr.y : rr.x;
+    const uint32_t je = (lbr > t.d[4] || lbr >= thresh) ? rr.z : rr.w;
+#pragma unroll 2
+    for (uint32_t j = js; j < je; ++j) {
+      const float4 m = tile[j];
+      const float dx = __fsub_rn(qx, m.x), dy2 = __fsub_rn(qy, m.y), dz2 = __fsub_rn(qz, m.z);
+      float d = __fmul_rn(dx, dx);
+      d = __fadd_rn(d, __fmul_rn(dy2, dy2));
+      d = __fadd_rn(d, __fmul_rn(dz2, dz2));
+      if (d <= t.d[4]) {
+        const int id = __float_as_int(m.w);
+        if (cand_less(d, id, t.d[4], t.i[4])) top5_insert(t, d, id);
+      }
+    }
+  }
+  return t.i[4] >= 0;
+}
+
+__global__ void __launch_bounds__(128, 10)
+k_knn5_tiled(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const float4 *__restrict__ xq,
+             const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out) {
+  __shared__ __align__(128) float4 tile[kTileCap];
+  __shared__ __align__(16) uint4 rows[9];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int anchor[5];  // is_corner, cx, cy, cz (grid-relative), staged
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = slot < n_total;
+  uint32_t k = 0;
+  float3 x = make_float3(0.f, 0.f, 0.f);
+  bool is_corner = false;
+  if (live) {
+    k = __ldg(perm + slot);
+    is_corner = k < n_corner_total;
+    const float4 xs = __ldg(xq + k);
+    x = make_float3(xs.x, xs.y, xs.z);
+  }
+  const GridView &g = is_corner ? gc : gs;
+  const float fxq = floorf(x.x * g.inv_edge), fyq = floorf(x.y * g.inv_edge), fzq = floorf(x.z * g.inv_edge);
+  const int cx = (int)fxq - g.ox, cy = (int)fyq - g.oy, cz = (int)fzq - g.oz;
+  if (threadIdx.x == 0) {  // slot of thread 0 is always live
+    const bool inside = !(cx < 1 || cy < 1 || cz < 1 || cx > g.nx - 2 || cy > g.ny - 2 || cz > g.nz - 2);
+    anchor[0] = is_corner;
+    anchor[1] = cx; anchor[2] = cy; anchor[3] = cz;
+    anchor[4] = inside;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_smem_u32(&bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && anchor[4]) {  // warp 0: row table + one bulk copy per row
+    const uint32_t lane = threadIdx.x;
+    const GridView &ga = anchor[0] ? gc : gs;
+    constexpr uint32_t kDyPacked = 1u | (0u << 2) | (2u << 4) | (1u << 6) | (1u << 8) | (0u << 10) | (0u << 12) | (2u << 14) | (2u << 16);
+    constexpr uint32_t kDzPacked = 1u | (1u << 2) | (1u << 4) | (0u << 6) | (2u << 8) | (0u << 10) | (2u << 12) | (0u << 14) | (2u << 16);
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (lane < 9) {
+      const int dy = (int)((kDyPacked >> (2 * lane)) & 3u) - 1, dz = (int)((kDzPacked >> (2 * lane)) & 3u) - 1;
+      const int row = ((anchor[3] + dz) * ga.ny + (anchor[2] + dy)) * ga.nx + anchor[1];
+      s0 = __ldg(ga.cell_start + row - 1); s1 = __ldg(ga.cell_start + row);
+      s2 = __ldg(ga.cell_start + row + 1); s3 = __ldg(ga.cell_start + row + 2);
+    }
+    const uint32_t cnt = s3 - s0;
+    uint32_t incl = cnt;  // inclusive prefix over the lanes (rows)
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 8);
+    const bool staged = total <= (uint32_t)kTileCap;
+    const uint32_t base = incl - cnt;
+    if (lane == 0) {
+      anchor[4] = staged ? 2 : 1;  // 2 = tile staged, 1 = anchor valid but neighbourhood too large
+      if (staged)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_smem_u32(&bar)), "r"(total * 16u) : "memory");
+    }
+    __syncwarp();
+    if (staged && lane < 9) {
+      rows[lane] = make_uint4(base, base + (s1 - s0), base + (s2 - s0), base + cnt);
+      if (cnt)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         a_smem_u32(tile + base)),
+                     "l"(ga.pts_sorted + s0), "r"(cnt * 16u), "r"(a_smem_u32(&bar))
+                     : "memory");
+    }
+  }
+  __syncthreads();
+  const bool staged = anchor[4] == 2;
+  if (staged) {  // every thread waits for the tile (phase 0 of the one-shot barrier)
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(a_smem_u32(&bar)),
+        "r"(0u)
+        : "memory");
+  }
+  if (!live) return;
+  Top5 t;
+  bool gate;
+  if (staged && (int)is_corner == anchor[0] && cx == anchor[1] && cy == anchor[2] && cz == anchor[3])
+    gate = knn5_tile(tile, rows, g.inv_edge == 1.0f, x.x, x.y, x.z, fxq, fyq, fzq, kp.knn_max_sq_f, t);
+  else
+    gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);
+  int32_t *o = knn_out + (size_t)slot * 5;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) o[s] = gate ? t.i[s] : -1;
+}
+
 // Line / plane fit of every gated query (fp64): thread k reads its five neighbours and writes the factor
 // constants [a_or_c(3), n(3)]; n = 0 marks "no factor".  Kept apart from the search kernel so that the
 // search runs at 40 registers / 75 % occupancy (it is L2-latency bound) while the register-hungry
@@ -304,34 +455,40 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
 // kernel only ever needs the plane's offset along its normal); otherwise 48 B {c, n} like the edge entries.
 // BY_SLOT: thread s handles query perm[s] and reads the neighbour indices k_knn5 stored at slot s: the lanes of a
 // warp are spatial neighbours, so they agree on the gate / validity branches and share the gathered map points.
-template <bool DESKEW, bool COMPACT, bool BY_SLOT>
+// CLS: -1 = one launch over all queries (class decided per thread); 0 / 1 = a launch over the corner / surf queries
+// only (the batch path: in cell order as in flat order all corner queries come first), so the Jacobi eigen-solver
+// and the Householder QR each get their own register allocation and a warp never holds both classes.
+template <bool DESKEW, bool COMPACT, bool BY_SLOT, int CLS = -1>
 __global__ void __launch_bounds__(128)
 k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
       double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_total) return;
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (CLS == 1 ? n_corner_total : 0u);
+  if (slot >= (CLS == 0 ? n_corner_total : n_total)) return;
   const uint32_t k = BY_SLOT ? __ldg(perm + slot) : slot;
-  const bool is_corner = k < n_corner_total;
+  const bool is_corner = CLS < 0 ? k < n_corner_total : CLS == 0;
   const GridView &g = is_corner ? gc : gs;
   int idx[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)slot * 5 + s);
   double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
   if (idx[4] >= 0) {
-    double m[5][3];
+    // the five neighbours stay in registers as the fp32 values they are (15 registers, not 30) and are widened
+    // where they are used -- the conversion is exact
+    float mf[5][3];
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
       const float4 mp = __ldg(g.pts_orig + idx[s]);
-      m[s][0] = (double)mp.x; m[s][1] = (double)mp.y; m[s][2] = (double)mp.z;
+      mf[s][0] = mp.x; mf[s][1] = mp.y; mf[s][2] = mp.z;
     }
+#define M(s, d) ((double)mf[s][d])
     double c[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) c[d] = ((((m[0][d] + m[1][d]) + m[2][d]) + m[3][d]) + m[4][d]) / 5.0;  // :137 / :212
+    for (int d = 0; d < 3; ++d) c[d] = ((((M(0, d) + M(1, d)) + M(2, d)) + M(3, d)) + M(4, d)) / 5.0;  // :137 / :212
     if (is_corner) {
       double cov[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int s = 0; s < 5; ++s) {  // :138-139 (S = sum (p-c)(p-c)^T, not divided by 5)
-        const double e0 = m[s][0] - c[0], e1 = m[s][1] - c[1], e2 = m[s][2] - c[2];
+        const double e0 = M(s, 0) - c[0], e1 = M(s, 1) - c[1], e2 = M(s, 2) - c[2];
         cov[0] += e0 * e0; cov[1] += e0 * e1; cov[2] += e0 * e2;
         cov[3] += e1 * e1; cov[4] += e1 * e2; cov[5] += e2 * e2;
       }
@@ -351,14 +508,14 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
     } else {
       double A[5][3], bb[5] = {-1, -1, -1, -1, -1}, nrm[3];
 #pragma unroll
-      for (int s = 0; s < 5; ++s) { A[s][0] = m[s][0]; A[s][1] = m[s][1]; A[s][2] = m[s][2]; }
+      for (int s = 0; s < 5; ++s) { A[s][0] = M(s, 0); A[s][1] = M(s, 1); A[s][2] = M(s, 2); }
       lstsq_5x3(A, bb, nrm);  // :210
       const double inv_nn = 1.0 / sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
       nrm[0] *= inv_nn; nrm[1] *= inv_nn; nrm[2] *= inv_nn;  // norm.normalize() :211
       bool valid = true;
 #pragma unroll
       for (int s = 0; s < 5; ++s) {  // :214-220
-        const double dd = nrm[0] * (m[s][0] - c[0]) + nrm[1] * (m[s][1] - c[1]) + nrm[2] * (m[s][2] - c[2]);
+        const double dd = nrm[0] * (M(s, 0) - c[0]) + nrm[1] * (M(s, 1) - c[1]) + nrm[2] * (M(s, 2) - c[2]);
         if (!(fabs(dd) <= kp.plane_tol)) valid = false;
       }
       if (valid) {
@@ -366,6 +523,7 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
         for (int d = 0; d < 3; ++d) { a[d] = c[d]; n[d] = nrm[d]; }
       }
     }
+#undef M
   }
   if (DESKEW && (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0)) {  // fold the constant offset: C' = C - o, o = V dt - g dt^2 / 2
     const double dt = dsk[(size_t)k * 8 + 7];
@@ -396,7 +554,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     d_knn = e->d_knn.as<int32_t>();
   }
   const int mode = e->params.assoc_sorted;  // 0 auto, 1 never, 2 always
-  const bool sorted = mode == 2 || (mode == 0 && total >= 65536u);
+  const bool sorted = mode == 2 || mode == 3 || (mode == 0 && total >= 65536u);
   if (!sorted) {
     stage_begin(e, 0);
     k_knn5<false, false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
@@ -473,7 +631,10 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
   const bool by_slot = own_knn;
   stage_begin(e, 0);
-  if (by_slot)
+  if (by_slot && mode == 3)  // measured on B200 (VLP-16, 2048 scans): 0.523 ms staged vs 0.507 ms direct -- the search is
+                             // instruction-issue-bound (78 % of issue slots), not latency-bound, so staging is opt-in
+    k_knn5_tiled<<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, e->a_xq.as<float4>(), e->a_perm, d_knn);
+  else if (by_slot)
     k_knn5<true, true, false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
         gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
         DeskewTable{}, nullptr);
@@ -486,9 +647,13 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   {
     const unsigned grid = (total + tb - 1) / tb;
     const DeskewTable nt{};
-    if (by_slot) {
-      if (compact) k_fit<false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
-      else k_fit<false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+    if (by_slot && compact) {
+      const unsigned grid_c = (n_corner_total + tb - 1) / tb, grid_s = (n_surf_total + tb - 1) / tb;
+      if (grid_c) k_fit<false, true, true, 0><<<grid_c, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      if (grid_s) k_fit<false, true, true, 1><<<grid_s, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      e->launches += 1;
+    } else if (by_slot) {
+      k_fit<false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
     } else {
       if (compact) k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);
       else k_fit<false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);

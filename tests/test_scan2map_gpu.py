@@ -111,7 +111,7 @@ def test_sorted_association_path_is_bitwise_identical(vlp16_case):
     P = O.default_params()
     qs = vlp16_case["queries"]
     res = {}
-    for mode in (1, 2):
+    for mode in (1, 2, 3):  # 3: cell order + TMA-staged shared-memory tiles (k_knn5_tiled)
         e = Engine(default_params(assoc_sorted=mode))
         e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
         knn, corr = e.associate_map(qs[0]["corner"], qs[0]["surf"], qs[0]["init"])
@@ -121,8 +121,9 @@ def test_sorted_association_path_is_bitwise_identical(vlp16_case):
                                       [q["init"] for q in qs] + [far], want_stats=True)
         res[mode] = (knn, corr, xs, [s["n_edge"] + s["n_plane"] for s in st])
         e.close()
-    assert np.array_equal(res[1][0], res[2][0]) and np.array_equal(res[1][1], res[2][1])
-    assert np.array_equal(res[1][2], res[2][2]) and res[1][3] == res[2][3]
+    for mode in (2, 3):
+        assert np.array_equal(res[1][0], res[mode][0]) and np.array_equal(res[1][1], res[mode][1])
+        assert np.array_equal(res[1][2], res[mode][2]) and res[1][3] == res[mode][3]
     _, _, _, kidx = _oracle_corr_full(P, vlp16_case, qs[0], qs[0]["init"])
     assert np.array_equal(res[2][0], kidx)
 
@@ -229,3 +230,21 @@ def test_radix_sort_fallback_of_the_cell_order_is_bitwise_identical(vlp16_case, 
         e.close()
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
     assert np.array_equal(res[0][0][0], res[0][0][3])  # replicas of one scan agree
+
+
+def test_tma_staged_tile_search_matches_direct_search_on_a_dense_batch(vlp16_case):
+    """assoc_sorted = 3 (k_knn5_tiled: the CTA's 3x3x3 neighbourhood staged in shared memory by cp.async.bulk) on a
+    batch dense enough that most CTAs sit inside one cell, incl. perturbed replicas that straddle cell borders."""
+    qs = vlp16_case["queries"]
+    rng = np.random.default_rng(5)
+    B = 96
+    inits = np.stack([S.perturb_pose(qs[i % 3]["gt"], rng) for i in range(B)])
+    out = {}
+    for mode in (2, 3):
+        e = Engine(default_params(assoc_sorted=mode))
+        e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+        rc, xs, st = e.scan2map_batch([qs[i % 3]["corner"] for i in range(B)], [qs[i % 3]["surf"] for i in range(B)], inits,
+                                      want_stats=True)
+        out[mode] = (xs, [s["n_edge"] + s["n_plane"] for s in st])
+        e.close()
+    assert np.array_equal(out[2][0], out[3][0]) and out[2][1] == out[3][1]
