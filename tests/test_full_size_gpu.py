@@ -1,0 +1,103 @@
+"""Parity at BASELINE.json's larger shapes and through size-independent properties:
+HDL-64E-shape scan-to-map against the oracle, exact 5-NN on a million-point submap against brute force,
+and a full 2048-scan batch: replicas bitwise equal, poses near ground truth, idempotence of the converged pose."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import make_map_case
+from msf_loam_b200 import Engine, default_params
+from msf_loam_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hdl64_scan2map_matches_oracle():
+    case = make_map_case("hdl64", "room80", 5, 200)
+    P = O.default_params()
+    e = Engine(default_params(assoc_sorted=2))  # the batch (cell-ordered) association path
+    e.set_submap(case["map_corner"], case["map_surf"])
+    q = case["queries"][0]
+    knn, _ = e.associate_map(q["corner"], q["surf"], q["init"])
+    _, _, _, kidx = O.associate_map(P, case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"])
+    assert np.array_equal(knn, kidx) and (knn[:, 0] >= 0).sum() > 5000
+    x_ref, logs, counts = O.scan2map(P, case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"])
+    rc, x, st = e.scan2map(q["corner"], q["surf"], q["init"])
+    dt, dr = S.pose_error(x, x_ref)
+    assert rc == 0 and dt <= 1e-4 and dr <= 1e-4  # north_star tolerance
+    assert dt < 1e-7 and dr < 1e-8                # what the fp64 path achieves
+    assert st["n_edge"] == list(counts[:, 0]) and st["n_plane"] == list(counts[:, 1])
+    e.close()
+
+
+def _brute_knn5(m, q):
+    """exact 5-NN in FLANN's arithmetic: fp32 ((dx*dx + dy*dy) + dz*dz), order (d2, index); d5^2 < 1 gate"""
+    d = q[None, :3].astype(np.float32) - m[:, :3]
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    order = np.lexsort((np.arange(m.shape[0]), d2))[:5]
+    return order if d2[order[4]] < np.float32(1.0) else np.full(5, -1)
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_million_point_submap_knn_equals_brute_force(mode):
+    rng = np.random.default_rng(11)
+    n_c, n_s = 250_000, 750_000  # BASELINE config 5: ~1 M-point (50-scan) submap
+    def cloud(n):
+        # a mix of uniform clutter and dense planar patches in a 120 x 90 x 12 m volume, negative coordinates included
+        u = rng.uniform([-60, -45, -2], [60, 45, 10], size=(n // 2, 3))
+        c = rng.uniform([-55, -40, 0], [55, 40, 8], size=(64, 3))
+        p = c[rng.integers(0, 64, n - n // 2)] + rng.normal(0, [1.5, 1.5, 0.02], size=(n - n // 2, 3))
+        xyz = np.concatenate([u, p]).astype(np.float32)
+        return np.concatenate([xyz, np.zeros((n, 1), np.float32)], axis=1)
+    mc, ms = cloud(n_c), cloud(n_s)
+    qc = cloud(4000)
+    qs = cloud(70_000)  # > 65536 queries: a real cell-ordered launch
+    qc[:, :3] += rng.normal(0, 0.05, size=(qc.shape[0], 3)).astype(np.float32)
+    qs[:, :3] += rng.normal(0, 0.05, size=(qs.shape[0], 3)).astype(np.float32)
+    e = Engine(default_params(assoc_sorted=mode))
+    e.set_submap(mc, ms)
+    pose = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0])  # identity: the transformed query is the query, bit for bit
+    knn, _ = e.associate_map(qc, qs, pose)
+    xc, xs = qc, qs
+    gated = 0
+    for i in rng.integers(0, qc.shape[0], 100):
+        ref = _brute_knn5(mc, xc[i])
+        assert np.array_equal(knn[i], ref)
+        gated += ref[0] >= 0
+    for i in rng.integers(0, qs.shape[0], 200):
+        ref = _brute_knn5(ms, xs[i])
+        assert np.array_equal(knn[qc.shape[0] + i], ref)
+        gated += ref[0] >= 0
+    assert gated > 100  # the sample exercises real neighbourhoods, not only failed gates
+    e.close()
+
+
+def test_full_batch_2048_replicas_bitwise_near_gt_and_idempotent(vlp16_case):
+    qs = vlp16_case["queries"]
+    B = 2048
+    rng = np.random.default_rng(3)
+    base = [S.perturb_pose(q["gt"], rng) for q in qs]
+    cat_c = np.concatenate([qs[i % 3]["corner"] for i in range(B)])
+    cat_s = np.concatenate([qs[i % 3]["surf"] for i in range(B)])
+    co = np.concatenate([[0], np.cumsum([qs[i % 3]["corner"].shape[0] for i in range(B)])])
+    so = np.concatenate([[0], np.cumsum([qs[i % 3]["surf"].shape[0] for i in range(B)])])
+    corners = [cat_c[co[i]:co[i + 1]] for i in range(B)]
+    surfs = [cat_s[so[i]:so[i + 1]] for i in range(B)]
+    inits = np.stack([base[i % 3] for i in range(B)])
+    e = Engine(default_params())
+    e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+    rc, xs, _ = e.scan2map_batch(corners, surfs, inits)
+    assert rc == 0
+    for i in range(3, B):
+        assert np.array_equal(xs[i], xs[i % 3])          # position in the batch does not matter
+    for i in range(3):
+        single = e.scan2map(qs[i]["corner"], qs[i]["surf"], base[i])[1]
+        assert np.array_equal(xs[i], single)             # nor does the batch size
+        dt, dr = S.pose_error(xs[i], qs[i]["gt"])
+        assert dt < 0.03 and dr < 0.005                  # 1 cm range noise
+    # idempotence: matching again from the converged poses moves them by far less than the noise floor
+    rc, xs2, _ = e.scan2map_batch(corners[:3], surfs[:3], xs[:3])
+    for i in range(3):
+        dt, dr = S.pose_error(xs2[i], xs[i])
+        assert dt < 2e-3 and dr < 2e-4
+    e.close()
