@@ -6,8 +6,8 @@
 //   another ring within +-2.5 rings                            -> LidarPlaneFactorSE3(p, a, b, c)
 // The reference walks the ring-sorted arrays linearly; given ring-sorted input (which its own
 // extraction guarantees and this entry point checks) those walks are "nearest point subject to a
-// ring filter", evaluated here on the 1 m cell index by expanding Chebyshev shells until the best
-// candidate is provably nearest or the 5 m radius is exhausted.  Ties (equal fp32 distance) follow
+// ring filter", evaluated here on the 1 m cell index by expanding Chebyshev shells (one warp per query) until the
+// best candidate is provably nearest or the 5 m radius is exhausted.  Ties (equal fp32 distance) follow
 // the reference's visiting order: forward indices ascending, then backward indices descending.
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
@@ -38,86 +38,142 @@ struct Best {
   uint32_t prio;
 };
 
-// mode 0: plain 1-NN (ties -> lowest index); mode 1: ring != id within nearby; mode 2: ring == id, j != closest
-template <int MODE>
-__device__ __forceinline__ void consider(const ScanGrid &sg, float qx, float qy, float qz, uint32_t j, int closest, int id,
-                                         double nearby, Best &b) {
-  const float4 m = __ldg(sg.g.pts_sorted + j);
-  const int idx = __float_as_int(m.w);
-  if (MODE != 0) {
-    if (idx == closest) return;
-    const int r = (int)__ldg(sg.ring + idx);
-    if (MODE == 1) {
-      if (r == id || (double)r > id + nearby || (double)r < id - nearby) return;
-    } else {
-      if (r != id) return;
-    }
-  }
-  const float d = sqdist_f(qx, qy, qz, m);
-  if (MODE == 0) {
-    if (d < b.d || (d == b.d && idx < b.idx)) { b.d = d; b.idx = idx; }
-  } else {
-    const uint32_t pr = visit_prio(idx, closest, sg.n);
-    if (d < b.d || (d == b.d && b.idx >= 0 && pr < b.prio)) { b.d = d; b.idx = idx; b.prio = pr; }
-  }
-}
-
-// Nearest candidate with d2 < thresh under the MODE filter; expanding shells on the cell grid.
-template <int MODE>
-__device__ void shell_search(const ScanGrid &sg, float qx, float qy, float qz, float thresh, int closest, int id,
-                             double nearby, Best &b) {
-  const GridView &g = sg.g;
-  b.d = thresh;
-  b.idx = -1;
-  b.prio = 0xffffffffu;
-  const float edge = 1.0f / g.inv_edge;
-  const int cx = (int)floorf(qx * g.inv_edge) - g.ox, cy = (int)floorf(qy * g.inv_edge) - g.oy,
-            cz = (int)floorf(qz * g.inv_edge) - g.oz;
-  const int smax = (int)ceilf(sqrtf(thresh) * g.inv_edge) + 1;
-  for (int s = 0; s <= smax; ++s) {
-    for (int dz = -s; dz <= s; ++dz) {
-      const int z = cz + dz;
-      if (z < 0 || z >= g.nz) continue;
-      for (int dy = -s; dy <= s; ++dy) {
-        const int y = cy + dy;
-        if (y < 0 || y >= g.ny) continue;
-        const bool full_row = (dz == -s || dz == s || dy == -s || dy == s);
-        const int row = (z * g.ny + y) * g.nx;
-        if (full_row) {
-          const int x0 = max(cx - s, 0), x1 = min(cx + s, g.nx - 1);
-          if (x0 > x1) continue;
-          const uint32_t js = __ldg(g.cell_start + row + x0), je = __ldg(g.cell_start + row + x1 + 1);
-          for (uint32_t j = js; j < je; ++j) consider<MODE>(sg, qx, qy, qz, j, closest, id, nearby, b);
-        } else {
-          const int xs[2] = {cx - s, cx + s};
-          for (int t = 0; t < 2; ++t) {
-            const int x = xs[t];
-            if (x < 0 || x >= g.nx) continue;
-            const uint32_t js = __ldg(g.cell_start + row + x), je = __ldg(g.cell_start + row + x + 1);
-            for (uint32_t j = js; j < je; ++j) consider<MODE>(sg, qx, qy, qz, j, closest, id, nearby, b);
-          }
-        }
-      }
-    }
-    // every unvisited point lies outside the (2s+1)^3 block, i.e. at least s*edge away on some axis;
-    // squaring and fp32 rounding are monotone, so its fp32 distance is >= fl((s*edge)^2).
-    const float reach = (float)s * edge;
-    const float reach2 = __fmul_rn(reach, reach);
-    if (b.idx >= 0 && b.d < reach2) break;
-    if (reach2 >= thresh) break;
-  }
-}
-
 __device__ __forceinline__ void store6(double *corr, size_t q, const double a[3], const double n[3]) {
   double *o = corr + q * 6;
   o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = n[0]; o[4] = n[1]; o[5] = n[2];
 }
 
+// ---------------------------------------------------------------------------------------------
+// One WARP per query.  A query's searches walk hundreds to thousands of candidates (5 m radius on
+// a 1 m cell index), far too many for one thread: the lanes of the warp look up the row ranges of a
+// shell in parallel, then stride together over every range, each lane keeping its own best under the
+// exact (distance, tie-rule) order; a shuffle reduction with the same order merges the lanes after
+// every shell, which is also where the termination test of shell_search is evaluated.  The two
+// ring-filtered searches of a flat point share one shell walk (a search that is already decided
+// cannot change any more: every later candidate is strictly farther).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better_nn(float d, int idx, const Best &b) { return d < b.d || (d == b.d && idx < b.idx); }
+__device__ __forceinline__ bool better_ring(float d, uint32_t pr, const Best &b) {
+  return d < b.d || (d == b.d && b.idx >= 0 && pr < b.prio);
+}
+
+__device__ __forceinline__ void warp_merge_nn(Best &b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float d = __shfl_xor_sync(0xffffffffu, b.d, o);
+    const int idx = __shfl_xor_sync(0xffffffffu, b.idx, o);
+    if (idx >= 0 && (b.idx < 0 || better_nn(d, idx, b))) { b.d = d; b.idx = idx; }
+  }
+}
+__device__ __forceinline__ void warp_merge_ring(Best &b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float d = __shfl_xor_sync(0xffffffffu, b.d, o);
+    const int idx = __shfl_xor_sync(0xffffffffu, b.idx, o);
+    const uint32_t pr = __shfl_xor_sync(0xffffffffu, b.prio, o);
+    if (idx >= 0 && (b.idx < 0 || better_ring(d, pr, b))) { b.d = d; b.idx = idx; b.prio = pr; }
+  }
+}
+
+// PHASE 0: plain 1-NN into b0.  PHASE 1: ring-filtered searches around `closest` (ring `id`): b_other = nearest point
+// of another ring within +-nearby rings; b_same (only when WANT_SAME) = nearest other point of the same ring.
+template <int PHASE, bool WANT_SAME>
+__device__ __forceinline__ void warp_shell_search(const ScanGrid &sg, const uint16_t *__restrict__ ring_sorted, float qx, float qy,
+                                                  float qz, float thresh, int closest, int id, double nearby, Best &b0,
+                                                  Best &b_other, Best &b_same) {
+  const GridView &g = sg.g;
+  const uint32_t lane = threadIdx.x & 31;
+  if (PHASE == 0) { b0.d = thresh; b0.idx = -1; b0.prio = 0xffffffffu; }
+  else {
+    b_other.d = thresh; b_other.idx = -1; b_other.prio = 0xffffffffu;
+    b_same.d = thresh; b_same.idx = -1; b_same.prio = 0xffffffffu;
+  }
+  const float edge = 1.0f / g.inv_edge;
+  const int cx = (int)floorf(qx * g.inv_edge) - g.ox, cy = (int)floorf(qy * g.inv_edge) - g.oy,
+            cz = (int)floorf(qz * g.inv_edge) - g.oz;
+  const int smax = (int)ceilf(sqrtf(thresh) * g.inv_edge) + 1;
+  for (int s = 0; s <= smax; ++s) {
+    const int side = 2 * s + 1, n_rows = side * side;
+    for (int r0 = 0; r0 < n_rows; r0 += 32) {
+      // lane-parallel lookup: the (up to two) candidate ranges of row r0 + lane of this shell
+      const int r = r0 + (int)lane;
+      uint32_t js0 = 0, je0 = 0, js1 = 0, je1 = 0;
+      if (r < n_rows) {
+        const int dz = r / side - s, dy = r % side - s;
+        const int z = cz + dz, y = cy + dy;
+        if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
+          const int row = (z * g.ny + y) * g.nx;
+          if (dz == -s || dz == s || dy == -s || dy == s) {  // a face row of the shell: the whole x range
+            const int x0 = max(cx - s, 0), x1 = min(cx + s, g.nx - 1);
+            if (x0 <= x1) { js0 = __ldg(g.cell_start + row + x0); je0 = __ldg(g.cell_start + row + x1 + 1); }
+          } else {                                           // interior row: only the two end cells
+            const int xa = cx - s, xb = cx + s;
+            if (xa >= 0 && xa < g.nx) { js0 = __ldg(g.cell_start + row + xa); je0 = __ldg(g.cell_start + row + xa + 1); }
+            if (xb >= 0 && xb < g.nx) { js1 = __ldg(g.cell_start + row + xb); je1 = __ldg(g.cell_start + row + xb + 1); }
+          }
+        }
+      }
+      uint32_t live = __ballot_sync(0xffffffffu, je0 > js0 || je1 > js1);
+      while (live) {
+        const int l = __ffs(live) - 1;
+        live &= live - 1;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          const uint32_t js = __shfl_sync(0xffffffffu, part ? js1 : js0, l), je = __shfl_sync(0xffffffffu, part ? je1 : je0, l);
+          for (uint32_t j = js + lane; j < je; j += 32) {
+            const float4 m = __ldg(g.pts_sorted + j);
+            const int idx = __float_as_int(m.w);
+            if (PHASE == 0) {
+              const float d = sqdist_f(qx, qy, qz, m);
+              if (better_nn(d, idx, b0)) { b0.d = d; b0.idx = idx; }
+            } else {
+              if (idx == closest) continue;
+              const int rg = (int)__ldg(ring_sorted + j);
+              const bool same = rg == id;
+              if (same ? !WANT_SAME : ((double)rg > id + nearby || (double)rg < id - nearby)) continue;
+              const float d = sqdist_f(qx, qy, qz, m);
+              const uint32_t pr = visit_prio(idx, closest, sg.n);
+              Best &b = same ? b_same : b_other;
+              if (better_ring(d, pr, b)) { b.d = d; b.idx = idx; b.prio = pr; }
+            }
+          }
+        }
+      }
+    }
+    // merge the lanes; every unvisited point lies outside the (2s+1)^3 block, i.e. at least s*edge away on some
+    // axis, and squaring / fp32 rounding are monotone, so its fp32 distance is >= fl((s*edge)^2)
+    const float reach = (float)s * edge;
+    const float reach2 = __fmul_rn(reach, reach);
+    bool done;
+    if (PHASE == 0) {
+      Best t = b0;
+      warp_merge_nn(t);
+      done = t.idx >= 0 && t.d < reach2;
+    } else {
+      Best t = b_other;
+      warp_merge_ring(t);
+      done = t.idx >= 0 && t.d < reach2;
+      if (WANT_SAME) {
+        Best u = b_same;
+        warp_merge_ring(u);
+        done = done && u.idx >= 0 && u.d < reach2;
+      }
+    }
+    if (done || reach2 >= thresh) break;
+  }
+  if (PHASE == 0) warp_merge_nn(b0);
+  else {
+    warp_merge_ring(b_other);
+    if (WANT_SAME) warp_merge_ring(b_same);
+  }
+}
+
 __global__ void __launch_bounds__(128)
-k_associate_scan(ScanGrid gc, ScanGrid gs, KParams kp, const float4 *__restrict__ q_sharp, uint32_t n_sharp,
-                 const float4 *__restrict__ q_flat, uint32_t n_flat, const double *__restrict__ pose_g,
-                 double *__restrict__ corr, int32_t *__restrict__ assoc) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+k_associate_scan(ScanGrid gc, ScanGrid gs, const uint16_t *__restrict__ ring_sorted_c, const uint16_t *__restrict__ ring_sorted_s,
+                 KParams kp, const float4 *__restrict__ q_sharp, uint32_t n_sharp, const float4 *__restrict__ q_flat,
+                 uint32_t n_flat, const double *__restrict__ pose_g, double *__restrict__ corr, int32_t *__restrict__ assoc) {
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per query
+  const uint32_t lane = threadIdx.x & 31;
   if (k >= n_sharp + n_flat) return;
   double pose[7];
 #pragma unroll
@@ -126,16 +182,19 @@ k_associate_scan(ScanGrid gc, ScanGrid gs, KParams kp, const float4 *__restrict_
   const float4 p = is_sharp ? q_sharp[k] : q_flat[k - n_sharp];
   const float3 x = transform_point_f(pose, p.x, p.y, p.z);  // TransformToStart, s = 1 (:21-33)
   const ScanGrid &sg = is_sharp ? gc : gs;
+  const uint16_t *ring_sorted = is_sharp ? ring_sorted_c : ring_sorted_s;
   double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
   Best nn, b2, b3;
   b2.idx = b3.idx = -1;
-  shell_search<0>(sg, x.x, x.y, x.z, kp.dist_sq_thresh_f, -1, 0, 0.0, nn);  // :84-87 / :169-173
+  warp_shell_search<0, false>(sg, ring_sorted, x.x, x.y, x.z, kp.dist_sq_thresh_f, -1, 0, 0.0, nn, b2, b3);  // :84-87 / :169-173
   if (nn.idx >= 0) {
     const int closest = nn.idx;
     const int id = (int)__ldg(sg.ring + closest);
     const float4 pa = __ldg(sg.g.pts_orig + closest);
     if (is_sharp) {
-      shell_search<1>(sg, x.x, x.y, x.z, kp.dist_sq_thresh_f, closest, id, kp.nearby_scan, b2);  // :93-140
+      Best unused;
+      warp_shell_search<1, false>(sg, ring_sorted, x.x, x.y, x.z, kp.dist_sq_thresh_f, closest, id, kp.nearby_scan, nn, b2,
+                                  unused);  // :93-140
       if (b2.idx >= 0) {  // :143-162
         const float4 pb = __ldg(sg.g.pts_orig + b2.idx);
         a[0] = pa.x; a[1] = pa.y; a[2] = pa.z;
@@ -144,8 +203,8 @@ k_associate_scan(ScanGrid gc, ScanGrid gs, KParams kp, const float4 *__restrict_
         if (nn2 > 0) { n[0] /= nn2; n[1] /= nn2; n[2] /= nn2; }
       }
     } else {
-      shell_search<2>(sg, x.x, x.y, x.z, kp.dist_sq_thresh_f, closest, id, kp.nearby_scan, b2);  // same ring
-      shell_search<1>(sg, x.x, x.y, x.z, kp.dist_sq_thresh_f, closest, id, kp.nearby_scan, b3);  // other rings
+      // b2 = nearest in the same ring, b3 = nearest in another ring (one shared shell walk)
+      warp_shell_search<1, true>(sg, ring_sorted, x.x, x.y, x.z, kp.dist_sq_thresh_f, closest, id, kp.nearby_scan, nn, b3, b2);
       if (b2.idx >= 0 && b3.idx >= 0) {  // :234-256, LidarPlaneFactorSE3 4-point ctor (lidar_factor.h:70-78)
         const float4 pb = __ldg(sg.g.pts_orig + b2.idx), pc = __ldg(sg.g.pts_orig + b3.idx);
         const double A[3] = {pa.x, pa.y, pa.z}, Bv[3] = {pb.x, pb.y, pb.z}, Cv[3] = {pc.x, pc.y, pc.z};
@@ -159,6 +218,7 @@ k_associate_scan(ScanGrid gc, ScanGrid gs, KParams kp, const float4 *__restrict_
       }
     }
   }
+  if (lane != 0) return;
   store6(corr, k, a, n);
   if (assoc) {
     if (is_sharp) {
@@ -169,6 +229,13 @@ k_associate_scan(ScanGrid gc, ScanGrid gs, KParams kp, const float4 *__restrict_
       o[0] = nn.idx; o[1] = b2.idx; o[2] = b3.idx;
     }
   }
+}
+
+// ring of every point in cell order (coalesced beside pts_sorted)
+__global__ void k_gather_ring(const float4 *__restrict__ pts_sorted, const uint16_t *__restrict__ ring, uint32_t n,
+                              uint16_t *__restrict__ ring_sorted) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) ring_sorted[j] = ring[__float_as_int(pts_sorted[j].w)];
 }
 
 }  // namespace msfl
@@ -263,6 +330,11 @@ static int scan2scan_impl(msfl_engine *e, const msfl_cloud *lc, const msfl_cloud
   if ((rc = submap_build(e, g_surf, e->d_last_surf.as<float4>(), ls->n, 1.0f))) return rc;
   ScanGrid gc{g_corner.view, e->d_last_corner_ring.as<uint16_t>(), (uint32_t)lc->n};
   ScanGrid gs{g_surf.view, e->d_last_surf_ring.as<uint16_t>(), (uint32_t)ls->n};
+  if ((rc = e->d_ring_tab.reserve((lc->n + ls->n) * 2 + 64))) return rc;
+  uint16_t *ring_sorted_c = e->d_ring_tab.as<uint16_t>(), *ring_sorted_s = ring_sorted_c + ((lc->n + 7) & ~(size_t)7);
+  k_gather_ring<<<((unsigned)lc->n + 255) / 256, 256, 0, st>>>(g_corner.view.pts_sorted, gc.ring, (uint32_t)lc->n, ring_sorted_c);
+  k_gather_ring<<<((unsigned)ls->n + 255) / 256, 256, 0, st>>>(g_surf.view.pts_sorted, gs.ring, (uint32_t)ls->n, ring_sorted_s);
+  e->launches += 2;
   char *d = e->d_queries.as<char>();
   const float4 *d_sharp = (const float4 *)d, *d_flat = d_sharp + n_sharp;
   const int32_t *d_e_off = (const int32_t *)(d + q_bytes), *d_p_off = d_e_off + 2;
@@ -279,7 +351,7 @@ static int scan2scan_impl(msfl_engine *e, const msfl_cloud *lc, const msfl_cloud
   const int tb = 128;
   const int n_outer = assoc_only ? 1 : e->params.num_outer;
   for (int outer = 0; outer < n_outer; ++outer) {  // :64
-    k_associate_scan<<<(nq + tb - 1) / tb, tb, 0, st>>>(gc, gs, e->kp, d_sharp, n_sharp, d_flat, n_flat, d_pose,
+    k_associate_scan<<<(nq * 32 + tb - 1) / tb, tb, 0, st>>>(gc, gs, ring_sorted_c, ring_sorted_s, e->kp, d_sharp, n_sharp, d_flat, n_flat, d_pose,
                                                         e->d_corr.as<double>(),
                                                         (assoc_out && outer == 0) ? e->d_assoc.as<int32_t>() : nullptr);
     e->launches += 1;
