@@ -6,8 +6,9 @@
 //        4 flat with +-5 neighbour suppression, everything FLAT/UNKNOWN -> less-flat (:251-351)
 //   a-4  extrinsic applied to every output cloud (:367-371)
 // The greedy pick is sequential inside a ring (flags leak across sector borders), so the pick
-// kernel runs one CTA per ring: the sector sort is a block-wide bitonic sort in shared memory,
-// lane 0 does the order-dependent sweeps, warp 0 compacts the less-flat list.
+// kernel runs one CTA per ring: the ring is staged in shared memory, its sectors are sorted by one segmented
+// block-wide bitonic sort, warp 0 does the order-dependent sweeps (lane-parallel candidate scan and neighbour
+// suppression) and compacts the less-flat list.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <limits.h>
@@ -17,8 +18,8 @@
 
 namespace msfl {
 
-constexpr int kMaxSectorPts = 4096;
-constexpr int kPickThreads = 256;
+constexpr int kMaxSectorPts = 8192;  // = kKeysCap of k_feat_pick
+constexpr int kPickThreads = 1024;
 constexpr double kTwoPi = 2 * 3.14159265358979323846;
 
 struct FeatMeta {
@@ -174,143 +175,222 @@ __device__ __forceinline__ float gap_sq(const float4 a, const float4 b) {  // Ve
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// a-3: one CTA per ring.
+// a-3: one CTA per ring.  The ring's points, labels and picked flags are staged in shared memory (rings of up to
+// kRingCap points; longer rings work on the global arrays), all sectors of the ring are sorted by ONE segmented
+// bitonic sort (the sort keys -- curvature bits, index -- do not depend on the picking), and warp 0 then runs the
+// order-dependent sweeps sector by sector: the lanes scan 32 sorted candidates at a time for "above the threshold and
+// not yet picked", the picks of a chunk are taken in order, and the +-5 neighbour suppression of a pick is evaluated
+// by ten lanes at once.  Same decisions, same output order as the sequential loops of :263-350.
+constexpr int kRingCap = 4096;   // ring points staged in shared memory
+constexpr int kKeysCap = 8192;   // sort keys in shared memory (all sectors of a ring, padded to powers of two)
+constexpr size_t kPickSmem = (size_t)kKeysCap * 8 + (size_t)kRingCap * (16 + 4 + 1);
+
 __global__ void __launch_bounds__(kPickThreads)
 k_feat_pick(const float4 *__restrict__ full, const float *__restrict__ curv, int32_t *__restrict__ label,
             uint8_t *__restrict__ picked, FeatMeta *m, double curv_thr, double gap_thr, int n_sectors, int n_sharp,
             int n_less, int n_flat, int32_t *__restrict__ slot_sharp, int32_t *__restrict__ slot_less,
             int32_t *__restrict__ slot_flat, int32_t *__restrict__ lessflat_tmp) {
-  __shared__ unsigned long long keys[kMaxSectorPts];
-  __shared__ int s_lf;
+  extern __shared__ __align__(16) unsigned char pick_smem[];
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(pick_smem);
+  float4 *s_full = reinterpret_cast<float4 *>(pick_smem + (size_t)kKeysCap * 8);
+  int32_t *s_label = reinterpret_cast<int32_t *>(pick_smem + (size_t)kKeysCap * 8 + (size_t)kRingCap * 16);
+  uint8_t *s_picked = pick_smem + (size_t)kKeysCap * 8 + (size_t)kRingCap * 20;
   const int r = blockIdx.x;
   const int rs = (int)m->ring_start[r], re = (int)m->ring_start[r + 1];
   const int start = rs + 5, end = re - 6;  // :192-194
   if (end - start < 6) return;             // :252
-  const int tid = threadIdx.x;
-  int ns = 0, nl = 0, nf = 0;
-  if (tid == 0) s_lf = 0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ring_len = re - rs;
+  const bool staged = ring_len <= kRingCap;
+  // F / LB / PK are indexed by (absolute point index - ob)
+  const float4 *F = staged ? s_full : full;
+  int32_t *LB = staged ? s_label : label;
+  uint8_t *PK = staged ? s_picked : picked;
+  const int ob = staged ? rs : 0;
+  if (staged)
+    for (int i = tid; i < ring_len; i += kPickThreads) {
+      s_full[i] = full[rs + i];
+      s_label[i] = 0;
+      s_picked[i] = 0;
+    }
+  // sector geometry (:256-259) and the common padded size of the segmented sort
+  int max_cnt = 0;
+  for (int j = 0; j < n_sectors; ++j) {
+    const int sp = start + (end - start) * j / n_sectors, ep = start + (end - start) * (j + 1) / n_sectors - 1;
+    max_cnt = max(max_cnt, ep - sp + 1);
+  }
+  int P = 1;
+  while (P < max_cnt) P <<= 1;
+  if (P > kKeysCap) {
+    if (tid == 0) atomicOr(&m->sector_overflow, 1);
+    return;
+  }
+  const int batch = min(n_sectors, kKeysCap / P);  // sectors sorted together
+  int ns = 0, nl = 0, nf = 0, n_lf = 0;            // list lengths (meaningful in warp 0)
   int32_t *my_sharp = slot_sharp + (size_t)r * n_sectors * n_sharp;
   int32_t *my_less = slot_less + (size_t)r * n_sectors * n_less;
   int32_t *my_flat = slot_flat + (size_t)r * n_sectors * n_flat;
   int32_t *my_lf = lessflat_tmp + rs;
-  for (int j = 0; j < n_sectors; ++j) {
-    const int sp = start + (end - start) * j / n_sectors;           // :256-259
-    const int ep = start + (end - start) * (j + 1) / n_sectors - 1;
-    const int cnt = ep - sp + 1;
-    if (cnt <= 0) continue;
-    if (cnt > kMaxSectorPts) {
-      if (tid == 0) atomicOr(&m->sector_overflow, 1);
-      return;
+  for (int j0 = 0; j0 < n_sectors; j0 += batch) {
+    const int j1 = min(n_sectors, j0 + batch), nb = j1 - j0;
+    __syncthreads();  // staging done / previous batch's keys no longer needed
+    // std::sort by curvature (:263) -> bitonic sort on (curvature bits, index): curvature >= 0 so the uint order of the
+    // bits is the float order; ties resolved by index (deterministic).  Segment q of the batch lives in keys[q P .. q P + P).
+    for (int t = tid; t < nb * P; t += kPickThreads) {
+      const int q = t / P, k = t - q * P, j = j0 + q;
+      const int sp = start + (end - start) * j / n_sectors, ep = start + (end - start) * (j + 1) / n_sectors - 1;
+      keys[t] = (k <= ep - sp) ? (((unsigned long long)__float_as_uint(curv[sp + k]) << 32) | (unsigned)(sp + k)) : ~0ull;
     }
-    int P = 1;
-    while (P < cnt) P <<= 1;
-    for (int k = tid; k < P; k += kPickThreads)
-      keys[k] = (k < cnt) ? (((unsigned long long)__float_as_uint(curv[sp + k]) << 32) | (unsigned)(sp + k)) : ~0ull;
     __syncthreads();
-    // std::sort by curvature (:263) -> bitonic sort on (curvature bits, index): curvature >= 0 so
-    // the uint order of the bits is the float order; ties resolved by index (deterministic).
+    const int lp = __ffs(P) - 1;  // P = 1 << lp; all index arithmetic below is shifts and masks
     for (int size = 2; size <= P; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = tid; t < (P >> 1); t += kPickThreads) {
-          const int lo = (t / stride) * (stride << 1) + (t % stride);
+      for (int ls = __ffs(size) - 2; ls >= 0; --ls) {  // stride = 1 << ls
+        const int stride = 1 << ls;
+        for (int t = tid; t < (nb << (lp - 1)); t += kPickThreads) {
+          const int q = lp > 0 ? t >> (lp - 1) : t, u = t & ((P >> 1) - 1);
+          const int lo = ((u >> ls) << (ls + 1)) | (u & (stride - 1));
           const int hi = lo + stride;
           const bool up = ((lo & size) == 0);
-          const unsigned long long a = keys[lo], b = keys[hi];
-          if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+          unsigned long long *K = keys + ((size_t)q << lp);
+          const unsigned long long a = K[lo], b = K[hi];
+          if ((a > b) == up) { K[lo] = b; K[hi] = a; }
         }
         __syncthreads();
       }
     }
-    if (tid == 0) {
-      int largest = 0;
-      for (int k = cnt - 1; k >= 0; --k) {  // :272-305
-        const int ind = (int)(unsigned)(keys[k] & 0xffffffffull);
-        if (!picked[ind] && (double)curv[ind] > curv_thr) {
-          ++largest;
-          if (largest <= n_sharp) {
-            label[ind] = 1;
-            my_sharp[ns++] = ind;
-            my_less[nl++] = ind;
-          } else if (largest <= n_less) {
-            label[ind] = 2;
-            my_less[nl++] = ind;
-          } else {
-            break;
-          }
-          picked[ind] = 1;
-          for (int l = 1; l <= 5; ++l) {
-            if ((double)gap_sq(full[ind + l], full[ind + l - 1]) > gap_thr) break;
-            picked[ind + l] = 1;
-            label[ind + l] = 2;
-          }
-          for (int l = -1; l >= -5; --l) {
-            if ((double)gap_sq(full[ind + l], full[ind + l + 1]) > gap_thr) break;
-            picked[ind + l] = 1;
-            label[ind + l] = 2;
+    if (tid < 32) {  // warp 0: the order-dependent part, sector after sector
+      for (int j = j0; j < j1; ++j) {
+        const int sp = start + (end - start) * j / n_sectors, ep = start + (end - start) * (j + 1) / n_sectors - 1;
+        const int cnt = ep - sp + 1;
+        if (cnt <= 0) continue;
+        const unsigned long long *K = keys + (size_t)(j - j0) * P;
+        // --- largest curvature first: 2 sharp, up to 20 less-sharp (:272-305)
+        int largest = 0;
+        bool stop = false;
+        for (int k0 = cnt - 1; k0 >= 0 && !stop; k0 -= 32) {
+          const int kk = k0 - lane;
+          const unsigned long long key = kk >= 0 ? K[kk] : 0ull;
+          const int ind = (int)(unsigned)(key & 0xffffffffull);
+          const bool above = kk >= 0 && (double)__uint_as_float((unsigned)(key >> 32)) > curv_thr;
+          unsigned pend = __ballot_sync(0xffffffffu, above);
+          if (!pend) break;  // sorted: nothing further exceeds the threshold
+          while (pend) {
+            const int l = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const int ci = __shfl_sync(0xffffffffu, ind, l);
+            if (PK[ci - ob]) continue;
+            ++largest;
+            if (largest > n_less) { stop = true; break; }
+            if (lane == 0) {
+              if (largest <= n_sharp) {
+                LB[ci - ob] = 1;
+                my_sharp[ns++] = ci;
+                my_less[nl++] = ci;
+              } else {
+                LB[ci - ob] = 2;
+                my_less[nl++] = ci;
+              }
+              PK[ci - ob] = 1;
+            }
+            // neighbour suppression: lanes 0-4 test the forward gaps 1..5, lanes 8-12 the backward gaps 1..5 (:289-303)
+            bool fail = false;
+            if (lane < 5) fail = (double)gap_sq(F[ci + lane + 1 - ob], F[ci + lane - ob]) > gap_thr;
+            else if (lane >= 8 && lane < 13) fail = (double)gap_sq(F[ci - (lane - 7) - ob], F[ci - (lane - 8) - ob]) > gap_thr;
+            const unsigned fm = __ballot_sync(0xffffffffu, fail);
+            const int nfw = (fm & 0x1fu) ? __ffs(fm & 0x1fu) - 1 : 5, nbw = ((fm >> 8) & 0x1fu) ? __ffs((fm >> 8) & 0x1fu) - 1 : 5;
+            if (lane < nfw) { PK[ci + lane + 1 - ob] = 1; LB[ci + lane + 1 - ob] = 2; }
+            if (lane >= 8 && lane - 8 < nbw) { PK[ci - (lane - 7) - ob] = 1; LB[ci - (lane - 7) - ob] = 2; }
+            __syncwarp();
           }
         }
-      }
-      int smallest = 0;
-      for (int k = 0; k < cnt; ++k) {  // :309-336
-        const int ind = (int)(unsigned)(keys[k] & 0xffffffffull);
-        if (!picked[ind] && (double)curv[ind] < curv_thr) {
-          label[ind] = 3;
-          my_flat[nf++] = ind;
-          if (++smallest >= n_flat) break;
-          picked[ind] = 1;
-          for (int l = 1; l <= 5; ++l) {
-            if ((double)gap_sq(full[ind + l], full[ind + l - 1]) > gap_thr) break;
-            picked[ind + l] = 1;
-          }
-          for (int l = -1; l >= -5; --l) {
-            if ((double)gap_sq(full[ind + l], full[ind + l + 1]) > gap_thr) break;
-            picked[ind + l] = 1;
+        __syncwarp();
+        // --- smallest curvature first: 4 flat (:309-336)
+        int smallest = 0;
+        stop = false;
+        for (int k0 = 0; k0 < cnt && !stop; k0 += 32) {
+          const int kk = k0 + lane;
+          const unsigned long long key = kk < cnt ? K[kk] : 0ull;
+          const int ind = (int)(unsigned)(key & 0xffffffffull);
+          const bool below = kk < cnt && (double)__uint_as_float((unsigned)(key >> 32)) < curv_thr;
+          unsigned pend = __ballot_sync(0xffffffffu, below);
+          if (!pend) break;  // sorted: everything further is at or above the threshold
+          while (pend) {
+            const int l = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const int ci = __shfl_sync(0xffffffffu, ind, l);
+            if (PK[ci - ob]) continue;
+            if (lane == 0) {
+              LB[ci - ob] = 3;
+              my_flat[nf++] = ci;
+            }
+            if (++smallest >= n_flat) { stop = true; break; }
+            bool fail = false;
+            if (lane < 5) fail = (double)gap_sq(F[ci + lane + 1 - ob], F[ci + lane - ob]) > gap_thr;
+            else if (lane >= 8 && lane < 13) fail = (double)gap_sq(F[ci - (lane - 7) - ob], F[ci - (lane - 8) - ob]) > gap_thr;
+            const unsigned fm = __ballot_sync(0xffffffffu, fail);
+            const int nfw = (fm & 0x1fu) ? __ffs(fm & 0x1fu) - 1 : 5, nbw = ((fm >> 8) & 0x1fu) ? __ffs((fm >> 8) & 0x1fu) - 1 : 5;
+            if (lane == 16) PK[ci - ob] = 1;
+            if (lane < nfw) PK[ci + lane + 1 - ob] = 1;
+            if (lane >= 8 && lane - 8 < nbw) PK[ci - (lane - 7) - ob] = 1;
+            __syncwarp();
           }
         }
+        __syncwarp();
+        // --- everything FLAT or UNKNOWN of this sector -> less-flat, in scan order (:339-344)
+        for (int k0 = sp; k0 <= ep; k0 += 32) {
+          const int k = k0 + lane;
+          const bool take = (k <= ep) && (LB[k - ob] == 3 || LB[k - ob] == 0);
+          const unsigned bal = __ballot_sync(0xffffffffu, take);
+          if (take) my_lf[n_lf + __popc(bal & ((1u << lane) - 1u))] = k;
+          n_lf += __popc(bal);
+        }
+        __syncwarp();
       }
     }
-    __syncthreads();
-    if (tid < 32) {  // :339-344, order-preserving compaction by warp 0
-      int base = s_lf;
-      for (int k0 = sp; k0 <= ep; k0 += 32) {
-        const int k = k0 + tid;
-        const bool take = (k <= ep) && (label[k] == 3 || label[k] == 0);
-        const unsigned bal = __ballot_sync(0xffffffffu, take);
-        if (take) my_lf[base + __popc(bal & ((1u << tid) - 1u))] = k;
-        base += __popc(bal);
-      }
-      if (tid == 0) s_lf = base;
-    }
-    __syncthreads();
   }
+  __syncthreads();
+  if (staged)
+    for (int i = tid; i < ring_len; i += kPickThreads) label[rs + i] = s_label[i];
   if (tid == 0) {
     m->cnt[0][r] = ns;
     m->cnt[1][r] = nl;
     m->cnt[2][r] = nf;
-    m->cnt[3][r] = s_lf;
+    m->cnt[3][r] = n_lf;
   }
 }
 
-// ring-major concatenation of the per-ring lists (the push_back order of :279-283, :314, :350)
-__global__ void k_feat_compact(FeatMeta *m, int n_sectors, int n_sharp, int n_less, int n_flat,
-                               const int32_t *__restrict__ slot_sharp, const int32_t *__restrict__ slot_less,
-                               const int32_t *__restrict__ slot_flat, const int32_t *__restrict__ lessflat_tmp,
-                               int32_t *__restrict__ out_sharp, int32_t *__restrict__ out_less,
-                               int32_t *__restrict__ out_flat, int32_t *__restrict__ out_lf) {
-  __shared__ int off[4][MSFL_MAX_RINGS + 1];
-  if (threadIdx.x < 4) {
-    int s = 0;
-    for (int r = 0; r < MSFL_MAX_RINGS; ++r) { off[threadIdx.x][r] = s; s += m->cnt[threadIdx.x][r]; }
-    off[threadIdx.x][MSFL_MAX_RINGS] = s;
-    m->tot[threadIdx.x] = s;
+// ring-major concatenation of the per-ring lists (the push_back order of :279-283, :314, :350): one CTA per ring,
+// its four output offsets are the exclusive prefix sums of the per-ring counts (warp w scans list w)
+__global__ void __launch_bounds__(128)
+k_feat_compact(FeatMeta *m, int n_sectors, int n_sharp, int n_less, int n_flat,
+               const int32_t *__restrict__ slot_sharp, const int32_t *__restrict__ slot_less,
+               const int32_t *__restrict__ slot_flat, const int32_t *__restrict__ lessflat_tmp,
+               int32_t *__restrict__ out_sharp, int32_t *__restrict__ out_less,
+               int32_t *__restrict__ out_flat, int32_t *__restrict__ out_lf) {
+  __shared__ int off[4], cnt[4];
+  const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    int before = 0, total = 0;
+    for (int q = lane; q < MSFL_MAX_RINGS; q += 32) {
+      const int c = m->cnt[w][q];
+      total += c;
+      if (q < r) before += c;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, o);
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if (lane == 0) {
+      off[w] = before;
+      cnt[w] = m->cnt[w][r];
+      if (r == 0) m->tot[w] = total;
+    }
   }
   __syncthreads();
-  for (int r = 0; r < MSFL_MAX_RINGS; ++r) {
-    for (int k = threadIdx.x; k < m->cnt[0][r]; k += blockDim.x) out_sharp[off[0][r] + k] = slot_sharp[(size_t)r * n_sectors * n_sharp + k];
-    for (int k = threadIdx.x; k < m->cnt[1][r]; k += blockDim.x) out_less[off[1][r] + k] = slot_less[(size_t)r * n_sectors * n_less + k];
-    for (int k = threadIdx.x; k < m->cnt[2][r]; k += blockDim.x) out_flat[off[2][r] + k] = slot_flat[(size_t)r * n_sectors * n_flat + k];
-    for (int k = threadIdx.x; k < m->cnt[3][r]; k += blockDim.x) out_lf[off[3][r] + k] = lessflat_tmp[m->ring_start[r] + k];
-  }
+  for (int k = threadIdx.x; k < cnt[0]; k += blockDim.x) out_sharp[off[0] + k] = slot_sharp[(size_t)r * n_sectors * n_sharp + k];
+  for (int k = threadIdx.x; k < cnt[1]; k += blockDim.x) out_less[off[1] + k] = slot_less[(size_t)r * n_sectors * n_less + k];
+  for (int k = threadIdx.x; k < cnt[2]; k += blockDim.x) out_flat[off[2] + k] = slot_flat[(size_t)r * n_sectors * n_flat + k];
+  for (int k = threadIdx.x; k < cnt[3]; k += blockDim.x) out_lf[off[3] + k] = lessflat_tmp[m->ring_start[r] + k];
 }
 
 // a-4 TransformPointCloudInPlace (:367-371; rigid_transform.h:140-145)
@@ -379,10 +459,15 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
   k_feat_first_dec<<<gb, tb, 0, st>>>(ks, rel, meta);
   k_feat_full<<<gb, tb, 0, st>>>(d_raw, ks, vs, rel, meta, P.scan_period, full_pre, d_ring);
   k_feat_curv<<<gb, tb, 0, st>>>(full_pre, meta, curv, label, picked);
-  k_feat_pick<<<MSFL_MAX_RINGS, kPickThreads, 0, st>>>(full_pre, curv, label, picked, meta, P.curvature_thresh,
+  static bool pick_attr_set[64] = {};
+  if (e->device < 64 && !pick_attr_set[e->device]) {
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_feat_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPickSmem));
+    pick_attr_set[e->device] = true;
+  }
+  k_feat_pick<<<MSFL_MAX_RINGS, kPickThreads, kPickSmem, st>>>(full_pre, curv, label, picked, meta, P.curvature_thresh,
                                                        P.neighbor_gap_sq, S, P.n_sharp, P.n_less_sharp, P.n_flat,
                                                        slot_sharp, slot_less, slot_flat, lf_tmp);
-  k_feat_compact<<<1, 256, 0, st>>>(meta, S, P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat,
+  k_feat_compact<<<MSFL_MAX_RINGS, 128, 0, st>>>(meta, S, P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat,
                                     lf_tmp, o_sharp, o_less, o_flat, o_lf);
   Pose7 T7;
   for (int i = 0; i < 7; ++i) T7.v[i] = T ? T[i] : (i == 6 ? 1.0 : 0.0);

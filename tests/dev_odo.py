@@ -22,3 +22,18 @@ x0, r0 = scans[1]
 t0 = time.perf_counter()
 for _ in range(n): e.extract_features(x0, r0, None)
 print("extract us/call", (time.perf_counter() - t0) / n * 1e6)
+# raw C-ABI call with preallocated outputs (no Python marshalling inside the timed loop)
+import ctypes as C
+from msf_loam_b200._lib import Features
+from msf_loam_b200.engine import _View
+v = _View(to_pcl(x0, r0))
+nn_ = v.n
+full = np.zeros((nn_, 4), np.float32); fring = np.zeros(nn_, np.uint16); idx = [np.zeros(nn_, np.int32) for _ in range(4)]
+ft = Features()
+ft.full_xyzi = full.ctypes.data_as(C.POINTER(C.c_float)); ft.full_ring = fring.ctypes.data_as(C.POINTER(C.c_uint16))
+ft.idx_sharp, ft.idx_less_sharp, ft.idx_flat, ft.idx_less_flat = [a.ctypes.data_as(C.POINTER(C.c_int32)) for a in idx]
+for _ in range(3): e.lib.msfl_extract_features(e.h, C.byref(v.cloud), None, C.byref(ft))
+t0 = time.perf_counter()
+for _ in range(n): e.lib.msfl_extract_features(e.h, C.byref(v.cloud), None, C.byref(ft))
+print("extract (C ABI, preallocated outputs: full cloud + rings + 4 index lists) us/call", (time.perf_counter() - t0) / n * 1e6)
+e.set_profiling(True)
