@@ -141,19 +141,31 @@ __device__ __forceinline__ void sweep(double (&acc)[kAcc], const float4 *__restr
 }
 
 // Block reduction: warp shuffle tree, then warps combined in index order (deterministic).
+// one butterfly level of the warp reduce-scatter: lanes whose `bit` is clear keep the lower half of v[0 .. 2 HALF)
+// and receive the partner's lower half, the others the upper half; HALF sums remain
+template <int HALF>
+__device__ __forceinline__ void reduce_scatter_level(double (&v)[32], uint32_t lane, uint32_t bit) {
+  const bool upper = (lane & bit) != 0;
+#pragma unroll
+  for (int k = 0; k < HALF; ++k) {
+    const double keep = upper ? v[HALF + k] : v[k], send = upper ? v[k] : v[HALF + k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+  }
+}
+
 __device__ __forceinline__ void block_reduce(double (&acc)[kAcc], LmShared &sh) {
+  // warp level: a reduce-scatter (31 shuffles of a double instead of 28 x 5) that leaves the warp total of
+  // accumulator l in lane l; every level adds in a fixed order, so the sums are reproducible
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double v[32];
 #pragma unroll
-  for (int k = 0; k < kAcc; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    acc[k] = v;
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kAcc; ++k) sh.red[warp][k] = acc[k];
-  }
+  for (int k = 0; k < 32; ++k) v[k] = k < kAcc ? acc[k] : 0.0;
+  reduce_scatter_level<16>(v, lane, 16);
+  reduce_scatter_level<8>(v, lane, 8);
+  reduce_scatter_level<4>(v, lane, 4);
+  reduce_scatter_level<2>(v, lane, 2);
+  reduce_scatter_level<1>(v, lane, 1);
+  if (lane < kAcc) sh.red[warp][lane] = v[0];
   __syncthreads();
   if (threadIdx.x < kAcc) {
     double v = 0.0;
@@ -448,28 +460,38 @@ __device__ void lm_prepare_step(LmShared &sh, const KParams &kp, msfl_lm_log *lo
     msfl_lm_iter *L = log ? &log->it[sh.iteration - 1] : nullptr;
     if (log) log->n_attempts = sh.iteration;
     if (L) { L->cost = sh.cost; L->cost_candidate = sh.cost; L->model_change = 0; L->rho = 0; L->radius = sh.radius; L->valid = 0; L->accepted = 0; }
-    double Hs[36], gs[6], A[36], nb[6], y[6];
+    // everything below lives in registers: packed upper triangles (tri6), every loop unrolled
+    double Hs[21], gs[6], A[21], nb[6], y[6], S[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) S[u] = sh.S[u];
+#pragma unroll
     for (int u = 0; u < 6; ++u) {
-      gs[u] = sh.S[u] * sh.g[u];
-      for (int v = u; v < 6; ++v) {
-        const double h = sh.S[u] * sh.H[tri6(u, v)] * sh.S[v];
-        Hs[u * 6 + v] = h;
-        Hs[v * 6 + u] = h;
-      }
+      gs[u] = S[u] * sh.g[u];
+#pragma unroll
+      for (int v = u; v < 6; ++v) Hs[tri6(u, v)] = S[u] * sh.H[tri6(u, v)] * S[v];
     }
-    if (!sh.reuse)
-      for (int k = 0; k < 6; ++k) sh.diag[k] = fmin(fmax(Hs[k * 6 + k], kp.min_diag), kp.max_diag);
-    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
-    for (int k = 0; k < 6; ++k) { A[k * 6 + k] += sh.diag[k] / sh.radius; nb[k] = -gs[k]; }
-    const bool ok = chol_solve6(A, nb, y);
+    if (!sh.reuse) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sh.diag[k] = fmin(fmax(Hs[tri6(k, k)], kp.min_diag), kp.max_diag);
+    }
+#pragma unroll
+    for (int i = 0; i < 21; ++i) A[i] = Hs[i];
+    {
+      const double radius = sh.radius;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { A[tri6(k, k)] += sh.diag[k] / radius; nb[k] = -gs[k]; }
+    }
+    const bool ok = chol_solve6_packed(A, nb, y);
     sh.reuse = 1;  // LevenbergMarquardtStrategy::ComputeStep
     double model = 0;
     if (ok) {
       double yg = 0, yHy = 0;
+#pragma unroll
       for (int u = 0; u < 6; ++u) {
         yg += y[u] * gs[u];
         double t = 0;
-        for (int v = 0; v < 6; ++v) t += Hs[u * 6 + v] * y[v];
+#pragma unroll
+        for (int v = 0; v < 6; ++v) t += Hs[u <= v ? tri6(u, v) : tri6(v, u)] * y[v];
         yHy += y[u] * t;
       }
       model = -(yg + 0.5 * yHy);
@@ -484,9 +506,14 @@ __device__ void lm_prepare_step(LmShared &sh, const KParams &kp, msfl_lm_log *lo
     }
     sh.n_invalid = 0;
     sh.model = model;
-    double delta[6];
-    for (int k = 0; k < 6; ++k) delta[k] = y[k] * sh.S[k];
-    pose_plus(sh.x, delta, sh.xc);
+    double delta[6], x0[7], xc[7];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) delta[k] = y[k] * S[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x0[k] = sh.x[k];
+    pose_plus(x0, delta, xc);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) sh.xc[k] = xc[k];
     if (L) { L->valid = 1; L->model_change = model; }
     return;
   }
@@ -659,17 +686,36 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   }
   if (G > 1) cluster_broadcast(cluster, sh, rank);
   else __syncthreads();
+#ifdef MSFL_LM_TIMING  // development (-DMSFL_LM_TIMING): cycles per phase of CTA 0, printed at exit
+  long long t_sweep = 0, t_red = 0, t_step = 0, t_sync = 0;
+#define MSFL_TICK(v) const long long v = clock64()
+#else
+#define MSFL_TICK(v)
+#endif
   while (!sh.done) {
+    MSFL_TICK(c0);
     sweep_warp<PB, PC>(acc, ts, wp, sh.xc, kp.huber_a, ce, cpl);
+    MSFL_TICK(c1);
     block_reduce(acc, sh);
     if (G > 1) cluster_reduce(cluster, sh, G, rank, false);
+    MSFL_TICK(c2);
     if (tid == 0 && rank == 0) {
       lm_finish_step(sh, kp, log);
       if (!sh.done) lm_prepare_step(sh, kp, log);
     }
+    MSFL_TICK(c3);
     if (G > 1) cluster_broadcast(cluster, sh, rank);
     else __syncthreads();
+#ifdef MSFL_LM_TIMING
+    t_sweep += c1 - c0; t_red += c2 - c1; t_step += c3 - c2; t_sync += clock64() - c3;
+#endif
   }
+#ifdef MSFL_LM_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64))
+    printf("LM timing CTA 0 tid %d: sweep %lld reduce %lld step %lld sync %lld cycles (n_e %u n_p %u)\n", (int)tid, t_sweep, t_red,
+           t_step, t_sync, n_e, n_p);
+#endif
+#undef MSFL_TICK
   if (rank == 0) {
     if (tid == 0 && log && !sh.too_few && sh.n_edge + sh.n_plane > 0) {
       log->termination = sh.termination;

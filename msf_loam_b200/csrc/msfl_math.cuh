@@ -214,6 +214,58 @@ __device__ __forceinline__ void lstsq_5x3(double (&A)[5][3], double (&b)[5], dou
   for (int c = 0; c < 3; ++c) x[c] = perm[0] == c ? y[0] : (perm[1] == c ? y[1] : y[2]);
 }
 
+// index of the (u,v) entry, u <= v, in the packed upper triangle of a 6x6 (row-major)
+__host__ __device__ __forceinline__ constexpr int tri6(int u, int v) { return u * 6 - (u * (u - 1)) / 2 + (v - u); }
+
+// The same Cholesky solve as chol_solve6 (same operation order, hence the same bits) on the packed upper triangle:
+// A[tri6(j, i)] = A_ij for j <= i.  21 + 21 doubles instead of 36 + 36, every index a compile-time constant.
+__device__ __forceinline__ bool chol_solve6_packed(const double (&A)[21], const double (&b)[6], double (&y)[6]) {
+  double L[21], inv[6];  // L[tri6(j, i)] = L_ij, i >= j
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[tri6(j, j)];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < j) d -= L[tri6(k, j)] * L[tri6(k, j)];
+    if (!(d > 0) || !isfinite(d)) ok = false;
+    inv[j] = rsqrt(d);
+    L[tri6(j, j)] = d * inv[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double s = A[tri6(j, i)];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < j) s -= L[tri6(k, i)] * L[tri6(k, j)];
+        L[tri6(j, i)] = s * inv[j];
+      }
+    }
+  }
+  if (!ok) return false;
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < i) s -= L[tri6(k, i)] * z[k];
+    z[i] = s * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = z[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k > i) s -= L[tri6(i, k)] * y[k];
+    y[i] = s * inv[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (!isfinite(y[i])) ok = false;
+  return ok;
+}
+
 // 6x6 SPD solve by Cholesky (the LM normal equations).  Returns false when not positive
 // definite / non-finite (Ceres LINEAR_SOLVER_FAILURE -> invalid step).
 __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6], double y[6]) {
@@ -272,7 +324,5 @@ __host__ __device__ inline bool chol_solve6(const double A[36], const double b[6
   return ok;
 }
 
-// index of the (u,v) entry, u <= v, in the packed upper triangle of a 6x6 (row-major)
-__host__ __device__ __forceinline__ int tri6(int u, int v) { return u * 6 - (u * (u - 1)) / 2 + (v - u); }
 
 }  // namespace msfl
