@@ -49,6 +49,37 @@ def test_extract_features_bit_exact(eng, sensor, scene):
         _check_features(f, g)
 
 
+def test_extract_features_os1_128_all_rings_bit_exact(eng):
+    """128 rings = kMaxScanNum (msf_loam_node.cc:79): every CTA of the pick kernel is busy, ring 127 included."""
+    P = O.default_params()
+    xyzi, ring = S.raycast_scan(S.make_scene("room80"), "os1-128", S.trajectory(1)[0], seed=77)
+    assert ring.max() == 127
+    f = O.extract_features(P, xyzi, ring, None)
+    g = eng.extract_features(xyzi, ring, None)
+    _check_features(f, g)
+
+
+@pytest.mark.parametrize("n_ring0", [5000, 13000, 30000])
+def test_extract_long_rings_take_the_unstaged_and_batched_sort_paths(eng, n_ring0):
+    """The pick kernel stages rings of <= 4096 points in shared memory and sorts all sectors of a ring at once when
+    they fit 8192 keys: 5000 points -> global-memory flags, one sort batch; 13000 -> sectors of 2165 points sorted in
+    batches of 4 + 2; 30000 -> sectors of 4998 points, one sector per batch.  A second, ordinary ring rides along."""
+    rng = np.random.default_rng(n_ring0)
+    def ring_cloud(n, rad, z):
+        # clockwise azimuth (README.md:56-58), noisy radius with corners (a rounded square) so both feature kinds exist
+        az = -np.linspace(0.0, 2 * np.pi, n, endpoint=False)
+        sigma = np.where((np.floor(-az * 16 / (2 * np.pi)).astype(int) % 2) == 0, 0.04, 0.002)  # rough and smooth stretches
+        rr = rad / np.maximum(np.abs(np.cos(az)), np.abs(np.sin(az))) + rng.normal(0, 1.0, n) * sigma
+        return np.stack([rr * np.cos(az), rr * np.sin(az), np.full(n, z), np.zeros(n)], axis=1).astype(np.float32)
+    xyzi = np.concatenate([ring_cloud(n_ring0, 8.0, -0.5), ring_cloud(1800, 6.0, 0.4)])
+    ring = np.concatenate([np.zeros(n_ring0, np.uint16), np.ones(1800, np.uint16)])
+    P = O.default_params()
+    f = O.extract_features(P, xyzi, ring, None)
+    g = eng.extract_features(xyzi, ring, None)
+    assert len(f["idx_less_sharp"]) > 100 and len(f["idx_flat"]) > 24
+    _check_features(f, g)
+
+
 def test_extract_ring_major_input_invalid_points_and_ragged_rings(eng):
     """ring-major input, NaN / too-close points removed, rings with < 12 points skipped."""
     P = O.default_params()
