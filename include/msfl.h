@@ -83,8 +83,10 @@ typedef struct msfl_params {
   int32_t early_exit;          /* 1 = Ceres termination tests; 0 = fixed attempt count
                                   (throughput schedule)                 */
   /* engine */
-  int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan in the LM kernel:
-                                  0 = auto, else 1/2/4/8                              */
+  int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan in the LM kernel: 0 / 1 = one
+                                  CTA per scan (a scan's pose is then bit-identical alone and in any
+                                  batch), 2/4/8 = partial sums meet over distributed shared memory:
+                                  lower latency for single scans and for small batches of large scans */
   int32_t assoc_sorted;        /* scan-to-map association order: 0 = auto (order the batch's queries
                                   by submap cell when it holds >= 65536 queries), 1 = never, 2 = always,
                                   3 = always + search against TMA-staged shared-memory tiles of the
