@@ -20,7 +20,10 @@ namespace cg = cooperative_groups;
 
 namespace msfl {
 
-constexpr int kLmThreads = 128;
+#ifndef MSFL_LM_THREADS
+#define MSFL_LM_THREADS 128
+#endif
+constexpr int kLmThreads = MSFL_LM_THREADS;
 constexpr int kAcc = 28;  // 21 upper-tri H + 6 g + 1 cost
 
 struct LmShared {
@@ -588,7 +591,7 @@ __device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, Lm
 
 // PB: bytes per point (16 float4 / 32 double4), PC: bytes of plane constants per entry (32 / 48)
 template <int PB, int PC>
-__global__ void __launch_bounds__(kLmThreads, 4)
+__global__ void __launch_bounds__(kLmThreads, 512 / kLmThreads)
 k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
