@@ -256,9 +256,8 @@ __device__ __forceinline__ float3 deskew_transform(const double pose[7], const D
 // Search kernel.  SORTED = false: thread k handles flat query k and transforms it itself.
 // SORTED = true: thread s handles query perm[s] (queries ordered by the cell of their transformed
 // point, so the lanes of a warp walk the same candidate ranges: uniform trip counts and broadcast
-// loads).  STORED_X: read the transformed point stored by k_transform_keys (the permutation was
-// built for the current poses); otherwise transform here (the permutation of an earlier outer
-// iteration is reused -- it is only a locality hint, the result does not depend on it).
+// loads; the order is only a locality hint, the result does not depend on it).  STORED_X: read the
+// transformed point stored by k_transform_keys instead of transforming here.
 // BY_SLOT: the five indices are stored at the thread's slot (coalesced; k_fit<.., true> then walks the
 // same cell order) instead of at the query's flat index k.
 template <bool SORTED, bool STORED_X, bool DESKEW, bool BY_SLOT>
@@ -542,7 +541,7 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
 
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool reuse_order, bool compact) {
+                         double *d_corr, int32_t *d_knn, bool compact) {
   const uint32_t total = n_corner_total + n_surf_total;
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
@@ -569,20 +568,6 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   }
   // sorted path: transform + cell keys -> radix sort -> association in cell order
   int rc;
-  if (reuse_order && e->a_perm_valid == total && e->a_perm != nullptr) {
-    // later outer iteration: poses moved by centimetres, the previous cell order is still a good
-    // locality hint -> skip the transform/sort pass, transform inside the association kernel
-    stage_begin(e, 0);
-    k_knn5<true, false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, e->a_perm, d_knn,
-        DeskewTable{}, nullptr);
-    if (compact) k_fit<false, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
-    else k_fit<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
-    stage_end(e);
-    e->launches += 2;
-    MSFL_CUDA_OK(cudaGetLastError());
-    return MSFL_OK;
-  }
   if ((rc = e->a_xq.reserve((size_t)total * 16))) return rc;
   if ((rc = e->a_keys.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_keys_alt.reserve((size_t)total * 4))) return rc;
@@ -627,7 +612,6 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     e->a_perm = dv.Current();
     e->launches += 3;
   }
-  e->a_perm_valid = total;
   // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
   const bool by_slot = own_knn;
   stage_begin(e, 0);

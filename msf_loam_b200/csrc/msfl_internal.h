@@ -115,8 +115,7 @@ struct msfl_engine {
   // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp, a_hist;
   msfl::DevBuf k_table, k_dsk, k_pprime;  // deskew branch: preintegration table, per-query (dq, dp, dt), p'
-  const uint32_t *a_perm = nullptr;  // cell-order permutation of the current batch (valid for a_perm_valid queries)
-  uint32_t a_perm_valid = 0;
+  const uint32_t *a_perm = nullptr;  // cell-order permutation of the batch being associated
 
   // odometry scratch
   msfl::DevBuf d_last_corner, d_last_surf, d_last_corner_ring, d_last_surf_ring, d_ring_tab, d_assoc;
@@ -144,7 +143,7 @@ void submap_release(Submap &m);
 // same flat order.
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool reuse_order = false, bool compact = false);
+                         double *d_corr, int32_t *d_knn, bool compact = false);
 
 int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
                           const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,

@@ -217,8 +217,11 @@ __device__ __forceinline__ void lstsq_5x3(double (&A)[5][3], double (&b)[5], dou
 // index of the (u,v) entry, u <= v, in the packed upper triangle of a 6x6 (row-major)
 __host__ __device__ __forceinline__ constexpr int tri6(int u, int v) { return u * 6 - (u * (u - 1)) / 2 + (v - u); }
 
-// The same Cholesky solve as chol_solve6 (same operation order, hence the same bits) on the packed upper triangle:
-// A[tri6(j, i)] = A_ij for j <= i.  21 + 21 doubles instead of 36 + 36, every index a compile-time constant.
+// 6x6 SPD solve by Cholesky (the LM normal equations) on the packed upper triangle: A[tri6(j, i)] = A_ij for j <= i.
+// Returns false when not positive definite / non-finite (Ceres LINEAR_SOLVER_FAILURE -> invalid step).  Every index is
+// a compile-time constant, so A, L and the right-hand sides live in registers; one reciprocal square root per pivot
+// replaces the sqrt + divisions of the textbook form (this runs on a single thread between two sweeps: its latency is
+// exposed).
 __device__ __forceinline__ bool chol_solve6_packed(const double (&A)[21], const double (&b)[6], double (&y)[6]) {
   double L[21], inv[6];  // L[tri6(j, i)] = L_ij, i >= j
   bool ok = true;
@@ -265,64 +268,5 @@ __device__ __forceinline__ bool chol_solve6_packed(const double (&A)[21], const 
     if (!isfinite(y[i])) ok = false;
   return ok;
 }
-
-// 6x6 SPD solve by Cholesky (the LM normal equations).  Returns false when not positive
-// definite / non-finite (Ceres LINEAR_SOLVER_FAILURE -> invalid step).
-__host__ __device__ inline bool chol_solve6(const double A[36], const double b[6], double y[6]) {
-  // every loop has compile-time bounds and is fully unrolled, so L, z live in registers; one reciprocal
-  // square root per pivot replaces the sqrt + 4 divisions per column of the textbook form (this runs on
-  // a single thread between two sweeps, so its latency is exposed)
-  double L[36], inv[6];
-#pragma unroll
-  for (int i = 0; i < 36; ++i) L[i] = 0;
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double d = A[j * 6 + j];
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (k < j) d -= L[j * 6 + k] * L[j * 6 + k];
-    if (!(d > 0) || !isfinite(d)) ok = false;
-#ifdef __CUDA_ARCH__
-    inv[j] = rsqrt(d);
-#else
-    inv[j] = 1.0 / sqrt(d);
-#endif
-    L[j * 6 + j] = d * inv[j];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      if (i > j) {
-        double s = A[i * 6 + j];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-          if (k < j) s -= L[i * 6 + k] * L[j * 6 + k];
-        L[i * 6 + j] = s * inv[j];
-      }
-    }
-  }
-  if (!ok) return false;
-  double z[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double s = b[i];
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (k < i) s -= L[i * 6 + k] * z[k];
-    z[i] = s * inv[i];
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    double s = z[i];
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (k > i) s -= L[k * 6 + i] * y[k];
-    y[i] = s * inv[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (!isfinite(y[i])) ok = false;
-  return ok;
-}
-
 
 }  // namespace msfl
