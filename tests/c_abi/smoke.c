@@ -56,6 +56,28 @@ int main(void) {
   const double et = sqrt((pose[0] - t[0]) * (pose[0] - t[0]) + (pose[1] - t[1]) * (pose[1] - t[1]) + (pose[2] - t[2]) * (pose[2] - t[2]));
   printf("pose t = %.5f %.5f %.5f yaw = %.6f | err %.2e m %.2e rad | corr %d edge %d plane | launches %llu\n", pose[0], pose[1],
          pose[2], est_yaw, et, fabs(est_yaw - yaw), st.n_edge[1], st.n_plane[1], (unsigned long long)msfl_launch_count(e));
+  /* the asynchronous batch form: two tickets in flight, each batch = the same scan three times from the identity
+   * guess; every pose must equal the synchronous result bit for bit */
+  int async_ok = 1;
+  {
+    msfl_cloud bc[3] = {qc, qc, qc}, bs[3] = {qs, qs, qs};
+    double init[21], out0[21], out1[21];
+    for (int b = 0; b < 3; ++b)
+      for (int k = 0; k < 7; ++k) init[7 * b + k] = k == 6 ? 1.0 : 0.0;
+    int t0 = -1, t1 = -1, t2 = -1;
+    if (msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t0) != MSFL_OK || msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t1) != MSFL_OK) {
+      fprintf(stderr, "submit: %s\n", msfl_last_error());
+      return 5;
+    }
+    if (msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t2) == MSFL_OK) async_ok = 0; /* a third ticket must be refused */
+    if (msfl_scan2map_batch_wait(e, t0, out0, NULL) != MSFL_OK || msfl_scan2map_batch_wait(e, t1, out1, NULL) != MSFL_OK) {
+      fprintf(stderr, "wait: %s\n", msfl_last_error());
+      return 6;
+    }
+    for (int b = 0; b < 3; ++b)
+      if (memcmp(out0 + 7 * b, pose, sizeof pose) != 0 || memcmp(out1 + 7 * b, pose, sizeof pose) != 0) async_ok = 0;
+    printf("async batches %s\n", async_ok ? "match the synchronous pose bit for bit" : "MISMATCH");
+  }
   msfl_destroy(e);
-  return (et < 5e-3 && fabs(est_yaw - yaw) < 5e-4 && st.n_plane[1] > 1000) ? 0 : 1;
+  return (async_ok && et < 5e-3 && fabs(est_yaw - yaw) < 5e-4 && st.n_plane[1] > 1000) ? 0 : 1;
 }

@@ -1,12 +1,13 @@
-run() { echo "== $*"; python bench.py --steps 10 --warmup 3 --cpu-sample 64 2>&1 | python -c "
+python -m pytest tests/test_c_abi_program.py -m gpu -x -q -s 2>&1 | grep -E "async|passed|failed|pose t" | head -5
+run() { echo "== $*"; env "$@" python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); r=d['roofline']; print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], r['kernel'][:12], r['avg_launch_ms'], r['frac'], {k[:10]:v for k,v in r['stage_share'].items()}, d['pose_err_vs_oracle']['max_trans_m'])
+        d=json.loads(l); print(d['value'], 'e2e', d['e2e']['value'], 'sync', d['e2e']['synchronous_call_value'])
     else: print(l.rstrip())
 "; }
-MSFL_NVCC_EXTRA=-DMSFL_LM_THREADS=64 python -m msf_loam_b200.build --force > /dev/null
-run threads64
-python -m pytest tests/test_scan2map_gpu.py -m gpu -x -q 2>&1 | tail -2
-MSFL_NVCC_EXTRA=-DMSFL_LM_THREADS=256 python -m msf_loam_b200.build --force > /dev/null
-run threads256
+run MSFL_X=geo4
+run MSFL_CHUNK_SCHED=eq4
+run MSFL_CHUNK_SCHED=3
+run MSFL_CHUNK_SCHED=2
+run MSFL_CHUNK_SCHED=b

@@ -188,6 +188,36 @@ def test_lm_agrees_with_independent_numpy_lm():
     assert log["n_attempts"] <= P.max_num_iterations
 
 
+def test_lm_converged_minimiser_matches_scipy_least_squares_with_huber_loss():
+    """A different solver on the same objective: scipy.optimize.least_squares (trust-region reflective, its own Huber
+    loss, finite-difference Jacobian) over a minimal 6-vector around the oracle's answer.  Ceres applies the loss per
+    residual BLOCK (s = |r|^2 of the 3-vector edge residual), so an edge block enters scipy as the single residual |r|.
+    The converged poses must agree far below the 1e-4 parity bound."""
+    from scipy.optimize import least_squares
+    rng = np.random.default_rng(16)
+    P = O.default_params(max_num_iterations=30, early_exit=0)
+    truth = rand_pose(rng, 2.0, 0.3)
+    corr = _synthetic_corr(rng, truth, n_edge=60, n_plane=200, noise=0.03, outliers=1)
+    x, log = O.lm_solve(P, corr, S.perturb_pose(truth, rng, 0.2, 2.0))
+
+    def residuals(d):
+        xd = O.pose_plus(x, d)
+        out = []
+        for c in corr:
+            r, _ = (O.edge_factor if c[0] == 0 else O.plane_factor)(xd, c[1:4], c[4:7], c[7:10])
+            out.append(np.linalg.norm(r) if c[0] == 0 else r[0])
+        return np.array(out)
+
+    sol = least_squares(residuals, np.zeros(6), loss="huber", f_scale=P.huber_a, xtol=1e-15, ftol=1e-15, gtol=1e-15,
+                        x_scale=1.0, diff_step=1e-7)
+    assert sol.cost <= log["final_cost"] * (1 + 1e-9)           # scipy may polish, never by much
+    assert abs(sol.cost - log["final_cost"]) <= 1e-7 * log["final_cost"]
+    dt, dr = S.pose_error(O.pose_plus(x, sol.x), x)
+    assert dt < 2e-6 and dr < 2e-6
+    n_out = int((np.abs(residuals(np.zeros(6))) > P.huber_a).sum())
+    assert n_out >= 3  # the loss is actually active at the optimum
+
+
 def test_lm_recovers_known_transform_noise_free():
     rng = np.random.default_rng(7)
     P = O.default_params(max_num_iterations=15, early_exit=0)
