@@ -33,6 +33,34 @@ def test_knn_matches_brute_force_and_ckdtree():
         assert np.allclose(np.sqrt(d2), dd, rtol=1e-5, atol=1e-5)
 
 
+def test_map_association_knn_matches_real_flann_kdtree_single(vlp16_case):
+    """Pins the 5-NN of rows a-6/a-7 against an actual FLANN build: OpenCV bundles FLANN and exposes
+    KDTreeSingleIndex (algorithm 4, the index pcl::KdTreeFLANN uses; leaf size 15 as in PCL) with the fp32
+    ((dx^2 + dy^2) + dz^2) distance.  Same neighbours in the same order, and the same d5^2 < 1 gate
+    (mapping_scan_matcher.cc:125-128 / :195-198), on the real VLP-16 case."""
+    cv2 = pytest.importorskip("cv2")
+    P = O.default_params()
+    q = vlp16_case["queries"][0]
+    _, _, _, kidx = O.associate_map(P, vlp16_case["map_corner"], vlp16_case["map_surf"], q["corner"], q["surf"], q["init"])
+    n_c = q["corner"].shape[0]
+    checked = 0
+    for cloud_map, scan, rows in ((vlp16_case["map_corner"], q["corner"], kidx[:n_c]), (vlp16_case["map_surf"], q["surf"], kidx[n_c:])):
+        m = np.ascontiguousarray(cloud_map[:, :3])
+        x = np.ascontiguousarray(S.transform_cloud(q["init"], scan)[:, :3])  # TransformPoint: fp64 math, fp32 store
+        index = cv2.flann_Index(m, dict(algorithm=4, leaf_max_size=15))
+        idx, d2 = index.knnSearch(x, 5, params=dict(checks=-1, eps=0.0, sorted=True))
+        gate = d2[:, 4] < np.float32(1.0)
+        assert np.array_equal(gate, rows[:, 0] >= 0)
+        # equal distances may come back in either order from a kd-tree: compare as sets there, exactly elsewhere
+        tie = (np.diff(d2, axis=1) == 0).any(axis=1)
+        ok = gate & ~tie
+        assert np.array_equal(rows[ok], idx[ok])
+        for i in np.nonzero(gate & tie)[0]:
+            assert sorted(rows[i]) == sorted(idx[i])
+        checked += int(ok.sum())
+    assert checked > 3000
+
+
 def test_knn_fewer_points_than_k():
     pts = np.zeros((3, 4), np.float32)
     pts[:, 0] = [0, 1, 2]
