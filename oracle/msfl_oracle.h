@@ -21,8 +21,11 @@
  *   - ceres::Solve (TRUST_REGION / LEVENBERG_MARQUARDT, HuberLoss(0.1), jacobi scaling,
  *     max_num_iterations=6) -> trust_region_minimizer.cc / levenberg_marquardt_strategy.cc /
  *     corrector.cc / loss_function.cc semantics (see msflo_lm_solve).
- * It is validated in tests/ against numpy / scipy (cKDTree, eigh, lstsq), finite-difference
- * Jacobians, an independent numpy LM and known-transform recovery.
+ * It is validated in tests/ against an actual FLANN KDTreeSingleIndex (the copy OpenCV bundles:
+ * same neighbours, order, fp32 distances and gate on the VLP-16 case), numpy / scipy (cKDTree, eigh,
+ * lstsq), finite-difference Jacobians, an independent numpy LM, scipy's least_squares with Huber
+ * loss at convergence, and known-transform recovery.  That pins the k-NN row against third-party
+ * code; the other rows stay pinned only by these independent restatements.
  */
 #ifndef MSFL_ORACLE_H
 #define MSFL_ORACLE_H
