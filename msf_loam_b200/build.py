@@ -34,11 +34,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = os.environ.get("MSFL_NVCC_EXTRA", "").split()  # development: e.g. -DFIT_MINB=5
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    # build into a private file and rename: several ranks of one torchrun may find the library stale at once, and a
+    # reader must never see a half-written .so
+    tmp = f"{LIB}.tmp.{os.getpid()}"
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed building libmsfl.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(r.stderr)
     return LIB
