@@ -140,7 +140,7 @@ class ClockSampler:
             return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
