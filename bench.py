@@ -313,6 +313,22 @@ def run_ours(args):
             eng.scan2map_prepared(prepared, h_p)
         e2e_sync_s = time.perf_counter() - t0
         clocks = sampler.stop()
+        # BASELINE config 2 as the ROS node runs it: ONE scan per call through the synchronous C ABI (pageable host
+        # buffers, stream sync per call); lm_cluster = 8 spreads the solve over an 8-CTA thread-block cluster
+        single = None
+        if rank == 0:
+            single = {}
+            c0, s0 = qc[c_off[0]:c_off[1]], qs[s_off[0]:s_off[1]]
+            for G in (1, 8):
+                e1 = Engine(default_params(lm_cluster=G, **over), device=local_rank)
+                e1.set_submap(map_corner, map_surf)
+                for _ in range(5):
+                    e1.scan2map(c0, s0, inits[0], want_stats=False)
+                t0 = time.perf_counter()
+                for _ in range(40):
+                    e1.scan2map(c0, s0, inits[0], want_stats=False)
+                single[f"lm_cluster_{G}_us_per_scan"] = round((time.perf_counter() - t0) / 40 * 1e6, 1)
+                e1.close()
     assert np.array_equal(h_out[0], poses_dev) and (args.steps < 2 or np.array_equal(h_out[1], poses_dev)), \
         "pipelined host-buffer path and device-resident path disagree"
 
@@ -373,6 +389,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "pose_err_vs_oracle": pose_err,
+            "single_scan_latency": single,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
         }
