@@ -142,6 +142,10 @@ typedef struct msfl_engine msfl_engine;
 void msfl_default_params(msfl_params *p);
 const char *msfl_last_error(void);
 const char *msfl_version(void);
+/* Binding self-check: pass the caller's sizeof() of the five structs above/below; MSFL_ERR_ARG (and the sizes this
+ * library was compiled with in msfl_last_error()) when a binding generated from another msfl.h is in use. */
+int msfl_abi_check(size_t sizeof_params, size_t sizeof_stats, size_t sizeof_cloud, size_t sizeof_features,
+                   size_t sizeof_deskew);
 
 /* One engine per matcher object (replaces the members of OdometryScanMatcher /
  * MappingScanMatcher, laser_odometry.cc:56, laser_mapping.cc:42).  `stream` (a cudaStream_t)

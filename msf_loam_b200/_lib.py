@@ -20,7 +20,7 @@ NO_FIELD = C.c_size_t(-1).value
 
 # every symbol include/msfl.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "msfl_default_params", "msfl_last_error", "msfl_version", "msfl_create", "msfl_create_on_stream",
+    "msfl_default_params", "msfl_last_error", "msfl_version", "msfl_abi_check", "msfl_create", "msfl_create_on_stream",
     "msfl_destroy", "msfl_sync", "msfl_stream", "msfl_launch_count", "msfl_set_profiling",
     "msfl_get_profile", "msfl_set_submap",
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
@@ -119,11 +119,8 @@ def load_library(build_if_needed: bool = True):
         return _lib
     if build_if_needed:
         from . import build as _build
-        try:
-            _build.build()
-        except Exception:
-            if not os.path.exists(LIB_PATH):
-                raise
+        # a stale binary must never be loaded silently: the ctypes struct layouts below follow the CURRENT msfl.h
+        _build.build()
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -m msf_loam_b200.build` "
                           "(there is no CPU fallback)")
@@ -139,5 +136,11 @@ def load_library(build_if_needed: bool = True):
     lib.msfl_default_params.restype = None
     lib.msfl_map_destroy.restype = None
     lib.msfl_map_destroy.argtypes = [C.c_void_p]
+    # the .so reports the struct sizes it was compiled with; a mismatch means msfl.h and this binding disagree
+    lib.msfl_abi_check.argtypes = [C.c_size_t] * 5
+    rc = lib.msfl_abi_check(C.sizeof(Params), C.sizeof(Stats), C.sizeof(Cloud), C.sizeof(Features), C.sizeof(Deskew))
+    if rc != MSFL_OK:
+        raise ImportError(f"{LIB_PATH}: ABI mismatch with the ctypes binding ({lib.msfl_last_error().decode()}); "
+                          "rebuild with `python -m msf_loam_b200.build --force`")
     _lib = lib
     return lib

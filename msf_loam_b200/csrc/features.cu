@@ -459,10 +459,9 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
   k_feat_first_dec<<<gb, tb, 0, st>>>(ks, rel, meta);
   k_feat_full<<<gb, tb, 0, st>>>(d_raw, ks, vs, rel, meta, P.scan_period, full_pre, d_ring);
   k_feat_curv<<<gb, tb, 0, st>>>(full_pre, meta, curv, label, picked);
-  static bool pick_attr_set[64] = {};
-  if (e->device < 64 && !pick_attr_set[e->device]) {
+  if (!e->pick_attr_set) {
     MSFL_CUDA_OK(cudaFuncSetAttribute(k_feat_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPickSmem));
-    pick_attr_set[e->device] = true;
+    e->pick_attr_set = true;
   }
   k_feat_pick<<<MSFL_MAX_RINGS, kPickThreads, kPickSmem, st>>>(full_pre, curv, label, picked, meta, P.curvature_thresh,
                                                        P.neighbor_gap_sq, S, P.n_sharp, P.n_less_sharp, P.n_flat,

@@ -85,12 +85,20 @@ static void fill_kparams(msfl_engine *e) {
   k.ptol = p.parameter_tolerance;
 }
 
-static int check_cloud(const msfl_cloud *c, bool need_ring, const char *what) {
+// One validation for every entry point that takes an msfl_cloud: every field the call will read has to lie inside
+// the point stride, so the last point can never be read past the caller's buffer.
+int check_cloud(const msfl_cloud *c, bool need_ring, const char *what) {
   if (!c) { set_error("%s: null cloud", what); return MSFL_ERR_ARG; }
-  if (c->n > 0 && !c->data) { set_error("%s: null data with n=%zu", what, c->n); return MSFL_ERR_ARG; }
-  if (c->n > 0 && (c->stride < 12 || c->off_xyz + 12 > c->stride)) { set_error("%s: bad stride/offset", what); return MSFL_ERR_ARG; }
+  if (c->n == 0) return MSFL_OK;
+  if (!c->data) { set_error("%s: null data with n=%zu", what, c->n); return MSFL_ERR_ARG; }
+  if (c->stride < 12 || c->off_xyz > c->stride - 12) { set_error("%s: xyz outside the point stride", what); return MSFL_ERR_ARG; }
+  if (c->off_intensity != MSFL_NO_FIELD && (c->stride < 4 || c->off_intensity > c->stride - 4)) {
+    set_error("%s: intensity outside the point stride", what);
+    return MSFL_ERR_ARG;
+  }
+  if (c->off_ring != MSFL_NO_FIELD && c->off_ring > c->stride - 2) { set_error("%s: ring outside the point stride", what); return MSFL_ERR_ARG; }
   if (need_ring && c->off_ring == MSFL_NO_FIELD) { set_error("%s: ring field required", what); return MSFL_ERR_ARG; }
-  if (c->n > 0x7fffffffull) { set_error("%s: too many points", what); return MSFL_ERR_ARG; }
+  if (c->n > 0x3fffffffull) { set_error("%s: too many points", what); return MSFL_ERR_ARG; }
   return MSFL_OK;
 }
 
@@ -170,7 +178,16 @@ int msfl_get_profile(msfl_engine *e, double ms[MSFL_N_STAGES], int32_t count[MSF
 }
 
 const char *msfl_last_error(void) { return g_err; }
-const char *msfl_version(void) { return "msfl 0.1 (sm_100a)"; }
+const char *msfl_version(void) { return "msfl 0.2 (sm_100a)"; }
+
+int msfl_abi_check(size_t sp, size_t ss, size_t sc, size_t sf, size_t sd) {
+  if (sp == sizeof(msfl_params) && ss == sizeof(msfl_stats) && sc == sizeof(msfl_cloud) && sf == sizeof(msfl_features) &&
+      sd == sizeof(msfl_deskew))
+    return MSFL_OK;
+  set_error("struct sizes differ: library has params %zu stats %zu cloud %zu features %zu deskew %zu, caller passed %zu %zu %zu %zu %zu",
+            sizeof(msfl_params), sizeof(msfl_stats), sizeof(msfl_cloud), sizeof(msfl_features), sizeof(msfl_deskew), sp, ss, sc, sf, sd);
+  return MSFL_ERR_ARG;
+}
 
 void msfl_default_params(msfl_params *p) {
   memset(p, 0, sizeof *p);

@@ -82,6 +82,7 @@ struct msfl_engine {
   std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
   bool lm_attr_set[8] = {false, false, false, false, false, false, false, false};
+  bool pick_attr_set = false;  // k_feat_pick's dynamic shared-memory attribute (per device, so kept per engine)
   // the cell keys of a batch are counting-sorted while the bin table (64 sub-cell bins per submap cell) stays small
   // enough to live in L2; larger (sparse, far-spread) submaps fall back to a radix sort of the keys
   long long count_sort_max_bins = 16ll << 20;
@@ -177,7 +178,8 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
 // ---- voxel_grid.cu
 int run_voxel_grid(msfl_engine *e, const float4 *d_in, size_t n, float leaf, float4 *d_out, size_t *n_out);
 
-// ---- repack (msfl_api.cu)
+// ---- cloud-view validation and repack (msfl_api.cu)
+int check_cloud(const msfl_cloud *c, bool need_ring, const char *what);
 int upload_cloud_packed(msfl_engine *e, const msfl_cloud *c, float4 *d_dst, uint16_t *d_ring_dst);
 
 }  // namespace msfl

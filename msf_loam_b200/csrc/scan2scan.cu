@@ -278,12 +278,13 @@ static int upload_with_rings(msfl_engine *e, const msfl_cloud *c, DevBuf &d_pts,
 static int scan2scan_impl(msfl_engine *e, const msfl_cloud *lc, const msfl_cloud *ls, const msfl_cloud *cs,
                           const msfl_cloud *cf, double pose_tq[7], msfl_stats *stats, int32_t *assoc_out, bool assoc_only) {
   const msfl_cloud *cl[4] = {lc, ls, cs, cf};
+  static const char *const names[4] = {"scan2scan last_corner_less_sharp", "scan2scan last_surf_less_flat",
+                                       "scan2scan curr_corner_sharp", "scan2scan curr_surf_flat"};
   for (int i = 0; i < 4; ++i) {
     if (!cl[i]) { set_error("scan2scan: null cloud"); return MSFL_ERR_ARG; }
-    if (cl[i]->n > 0 && (!cl[i]->data || cl[i]->stride < 12)) { set_error("scan2scan: bad cloud"); return MSFL_ERR_ARG; }
-    if (cl[i]->n > 0x3fffffffull) { set_error("scan2scan: cloud too large"); return MSFL_ERR_ARG; }
+    int rck;
+    if ((rck = check_cloud(cl[i], /*need_ring=*/i < 2, names[i]))) return rck;
   }
-  if (lc->off_ring == MSFL_NO_FIELD || ls->off_ring == MSFL_NO_FIELD) { set_error("scan2scan: last-scan clouds need the ring field"); return MSFL_ERR_ARG; }
   MSFL_CUDA_OK(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
   const uint32_t n_sharp = (uint32_t)cs->n, n_flat = (uint32_t)cf->n, nq = n_sharp + n_flat;

@@ -449,9 +449,9 @@ void msfl_map_destroy(msfl_map *m) {
 int msfl_map_insert(msfl_map *m, const msfl_cloud *scan, const double pose_tq[7]) {
   if (!m || !scan) { set_error("msfl_map_insert: bad argument"); return MSFL_ERR_ARG; }
   if (scan->n == 0) return MSFL_OK;  // hybrid_grid.cc:504
-  if (!scan->data || scan->stride < 12 || scan->n > 0x3fffffffull) { set_error("msfl_map_insert: bad cloud"); return MSFL_ERR_ARG; }
-  MSFL_CUDA_OK(cudaSetDevice(m->e->device));
   int rc;
+  if ((rc = check_cloud(scan, false, "msfl_map_insert"))) return rc;
+  MSFL_CUDA_OK(cudaSetDevice(m->e->device));
   if ((rc = upload_packed(m->e, scan, m->in))) return rc;
   return map_insert_device(m, (uint32_t)scan->n, pose_tq != nullptr, pose_tq);
 }
@@ -472,6 +472,7 @@ int msfl_map_surround(msfl_map *m, const msfl_cloud *scan, const double pose_tq[
   if (n_out) *n_out = 0;
   if (m->n_cells == 0 || scan->n == 0) return MSFL_OK;
   int rc;
+  if ((rc = check_cloud(scan, false, "msfl_map_surround"))) return rc;
   if ((rc = upload_packed(e, scan, m->in))) return rc;
   const int nc = (int)m->n_cells, tb = 256;
   const uint32_t n = (uint32_t)scan->n;
@@ -514,6 +515,9 @@ int msfl_map_download(msfl_map *m, int which, float *out_xyzi, size_t capacity, 
 int msfl_set_submap_from_maps(msfl_engine *e, msfl_map *corner, msfl_map *surf) {
   if (!e || !corner || !surf) { set_error("msfl_set_submap_from_maps: bad argument"); return MSFL_ERR_ARG; }
   if (corner->sur_n == 0 || surf->sur_n == 0) { set_error("msfl_set_submap_from_maps: empty surround cloud"); return MSFL_ERR_ARG; }
+  // the surround gathers are enqueued (unsynchronised) on the maps' own engine stream: only that engine's stream is
+  // ordered behind them
+  if (corner->e != e || surf->e != e) { set_error("msfl_set_submap_from_maps: the maps belong to another engine"); return MSFL_ERR_ARG; }
   return msfl_set_submap_device(e, corner->sur.as<float>(), corner->sur_n, surf->sur.as<float>(), surf->sur_n);
 }
 

@@ -154,9 +154,9 @@ extern "C" int msfl_voxel_grid(msfl_engine *e, const msfl_cloud *in, float leaf,
   if (!e || !in || !out_xyzi || !n_out) { set_error("msfl_voxel_grid: bad argument"); return MSFL_ERR_ARG; }
   *n_out = 0;
   if (in->n == 0) return MSFL_OK;
-  if (in->n > 0x7fffffffull || !in->data || in->stride < 12) { set_error("msfl_voxel_grid: bad cloud"); return MSFL_ERR_ARG; }
-  MSFL_CUDA_OK(cudaSetDevice(e->device));
   int rc;
+  if ((rc = check_cloud(in, false, "msfl_voxel_grid"))) return rc;
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
   const size_t n = in->n;
   if ((rc = e->h_stage.reserve(n * 16))) return rc;
   if ((rc = e->v_in.reserve(n * 16))) return rc;

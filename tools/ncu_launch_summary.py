@@ -1,6 +1,6 @@
 """Dev helper: per-kernel totals of an ncu launch list (gpu__time_duration.sum CSV) for the launches of the
 device-timed steps of bench.py: the full-batch steps (largest k_transform_keys grid) number warmup .. warmup+steps-1.
-usage: python tests/ncu_launch_summary.py launches.csv [steps=3] [outer=2] [warmup=3]"""
+usage: python tools/ncu_launch_summary.py launches.csv [steps=3] [outer=2] [warmup=3]"""
 import csv
 import sys
 from collections import OrderedDict

@@ -1,5 +1,5 @@
 """Dev helper: per-source-line hot spots (samples, executed instructions) for one kernel from an .ncu-rep.
-usage: python tests/ncu_source_hot.py rep.ncu-rep kernel_regex [top]"""
+usage: python tools/ncu_source_hot.py rep.ncu-rep kernel_regex [top]"""
 import csv, subprocess, sys
 rep, kre = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25

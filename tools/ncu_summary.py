@@ -1,5 +1,5 @@
 """Dev helper: condensed text summary of an .ncu-rep (per kernel: time, regs, occupancy, IPC, lanes,
-DRAM bytes, fp64 pipe, warp-stall breakdown).  usage: python tests/ncu_summary.py rep.ncu-rep > profiles/x.txt"""
+DRAM bytes, fp64 pipe, warp-stall breakdown).  usage: python tools/ncu_summary.py rep.ncu-rep > profiles/x.txt"""
 import csv
 import subprocess
 import sys
