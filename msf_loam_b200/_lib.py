@@ -117,6 +117,9 @@ def load_library(build_if_needed: bool = True):
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("MSFL_LIB_PATH"):  # development: A/B an older build of the library against the tree's
+        LIB_PATH, build_if_needed = os.environ["MSFL_LIB_PATH"], False
     if build_if_needed:
         from . import build as _build
         # a stale binary must never be loaded silently: the ctypes struct layouts below follow the CURRENT msfl.h
@@ -137,6 +140,9 @@ def load_library(build_if_needed: bool = True):
     lib.msfl_map_destroy.restype = None
     lib.msfl_map_destroy.argtypes = [C.c_void_p]
     # the .so reports the struct sizes it was compiled with; a mismatch means msfl.h and this binding disagree
+    if os.environ.get("MSFL_LIB_PATH") and not hasattr(lib, "msfl_abi_check"):
+        _lib = lib  # an older development build without the self-check
+        return lib
     lib.msfl_abi_check.argtypes = [C.c_size_t] * 5
     rc = lib.msfl_abi_check(C.sizeof(Params), C.sizeof(Stats), C.sizeof(Cloud), C.sizeof(Features), C.sizeof(Deskew))
     if rc != MSFL_OK:

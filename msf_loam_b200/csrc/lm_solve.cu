@@ -48,15 +48,35 @@ __device__ __forceinline__ void acc_row(double (&acc)[kAcc], const double J[6], 
   for (int u = 0; u < 6; ++u) acc[21 + u] += J[u] * r;
 }
 
+// s^(-1/4) for the Huber outlier path: two MUFU.RSQ give a 22-bit fp32 seed, two Newton steps of
+// y <- y (1 + (1 - s y^4) / 4) (error e -> 2.5 e^2) bring it to fp64 round-off.  12 fp64 instructions instead of the
+// ~45 of rsqrt(double) followed by sqrt(double); only a few lanes of a warp take this path, so its length is what
+// the whole warp pays.
+__device__ __forceinline__ double inv_fourth_root(double s) {
+  float r, q;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)s));  // s^(-1/2), one MUFU.RSQ
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(r));         // r^(-1/2)
+  double y = (double)(r * q);                                      // sqrt(r) = s^(-1/4)
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double y2 = y * y;
+    const double e = fma(-s, y2 * y2, 1.0);
+    y = fma(y, 0.25 * e, y);
+  }
+  return y;
+}
+
 // Huber loss + Ceres corrector (loss_function.cc HuberLoss::Evaluate; corrector.cc: rho'' <= 0 so
 // residual and Jacobian are both scaled by sqrt(rho')).  Returns the scale, adds 0.5 rho to cost.
-__device__ __forceinline__ double huber_scale(double s, double a, double &cost) {
-  const double b = a * a;
-  if (s > b) {
-    // rho = 2 a sqrt(s) - a^2, rho' = a / sqrt(s); one rsqrt feeds both (sqrt(s) = s * rsqrt(s))
-    const double rs = rsqrt(s);
-    cost += 0.5 * (2.0 * a * (s * rs) - b);
-    return sqrt(fmax(2.2250738585072014e-308, a * rs));
+// hub = {a, a^2, sqrt(a)}.
+struct Huber { double a, b, sqrt_a; };
+__device__ __forceinline__ double huber_scale(double s, const Huber &hub, double &cost) {
+  if (s > hub.b) {
+    // rho = 2 a sqrt(s) - a^2, rho' = a / sqrt(s); with y = s^(-1/4): sqrt(s) = s y^2, sqrt(rho') = sqrt(a) y
+    // (beyond the fp32 range of the seed -- |r| > 1e15 m -- the library routines take over)
+    const double y = s < 1e30 ? inv_fourth_root(s) : sqrt(rsqrt(s));
+    cost += 0.5 * (2.0 * hub.a * (s * (y * y)) - hub.b);
+    return hub.sqrt_a * y;
   }
   cost += 0.5 * s;
   return 1.0;
@@ -72,7 +92,7 @@ __device__ __forceinline__ double huber_scale(double s, double a, double &cost) 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void eval_edge(double (&acc)[kAcc], const double (&R)[9], double t0, double t1, double t2, double p0,
                                           double p1, double p2, double a0, double a1, double a2, double n0, double n1,
-                                          double n2, double huber_a) {
+                                          double n2, const Huber &huber_a) {
   const double q0 = R[0] * p0 + R[1] * p1 + R[2] * p2, q1 = R[3] * p0 + R[4] * p1 + R[5] * p2,
                q2 = R[6] * p0 + R[7] * p1 + R[8] * p2;  // R p
   const double d0 = q0 + (t0 - a0), d1 = q1 + (t1 - a1), d2 = q2 + (t2 - a2);
@@ -99,7 +119,7 @@ __device__ __forceinline__ void eval_edge(double (&acc)[kAcc], const double (&R)
 
 // nc = n . c (the plane offset along its normal)
 __device__ __forceinline__ void eval_plane(double (&acc)[kAcc], const double (&R)[9], double t0, double t1, double t2, double p0,
-                                           double p1, double p2, double n0, double n1, double n2, double nc, double huber_a) {
+                                           double p1, double p2, double n0, double n1, double n2, double nc, const Huber &huber_a) {
   const double w0 = R[0] * n0 + R[3] * n1 + R[6] * n2, w1 = R[1] * n0 + R[4] * n1 + R[7] * n2,
                w2 = R[2] * n0 + R[5] * n1 + R[8] * n2;  // R^T n
   const double r = (w0 * p0 + w1 * p1 + w2 * p2) + ((n0 * t0 + n1 * t1 + n2 * t2) - nc);  // lidar_factor.cc:32
@@ -116,8 +136,9 @@ __device__ __forceinline__ void eval_plane(double (&acc)[kAcc], const double (&R
 // per query [a_or_c(3), n(3)], n = 0 where no factor exists.
 __device__ __forceinline__ void sweep(double (&acc)[kAcc], const float4 *__restrict__ pe, const double *__restrict__ corr_e,
                                       uint32_t n_e, const float4 *__restrict__ pp, const double *__restrict__ corr_p,
-                                      uint32_t n_p, const double *pose, double huber_a, uint32_t tid, uint32_t nthreads,
+                                      uint32_t n_p, const double *pose, double huber_a_, uint32_t tid, uint32_t nthreads,
                                       int &cnt_edge, int &cnt_plane) {
+  const Huber huber_a{huber_a_, huber_a_ * huber_a_, sqrt(huber_a_)};
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
   double R[9];
@@ -199,8 +220,9 @@ struct TileSrc {
 // Warp-private streaming (the throughput configuration).  Every warp owns a double-buffered ring of
 // tiles and its own mbarriers, issues its own bulk copies (lane 0) and consumes them after a
 // __syncwarp: there is no block-wide barrier inside a sweep, so a warp never waits for the slowest
-// warp of its CTA.  Warp w of W streams tiles w, w + W, w + 2W, ... of each class (edge entries,
-// then plane entries), i.e. the CTA as a whole still walks the scan's arrays front to back.  While a
+// warp of its CTA.  Warp w of W owns the w-th of W equal contiguous shares of each class (edge entries, then plane
+// entries; the shares differ by at most one entry, so the four warps reach the block reduction together -- with
+// round-robin tiles warp 0 carried the odd tile of both classes and the others waited ~20 % of every sweep).  While a
 // warp works on the last tile of a sweep it already fetches the first tile of the next sweep (the
 // data does not depend on the pose), so the copy latency also hides behind the block reduction and
 // the thread-0 LM step.  All shared-memory traffic uses 32-bit shared-space addresses (ld.shared /
@@ -253,6 +275,7 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
 
 // per-warp pipeline state, kept in registers across the sweeps of one solve
 struct WarpPipe {
+  uint32_t e_lo, e_hi, p_lo, p_hi;  // this warp's share of the edge / plane entries of the CTA's arrays
   uint32_t ring;     // shared-space address of this warp's ring (n_stages x SB bytes)
   uint32_t bars;     // shared-space address of this warp's mbarriers (8 B each)
   uint32_t it;       // streaming: tiles consumed so far (stage = it & 1, phase parity = (it >> 1) & 1)
@@ -265,42 +288,46 @@ struct WarpPipe {
 struct TileIt { uint32_t cls, base; };
 
 template <int PB, int PC>
-__device__ __forceinline__ TileIt tile_first(const TileSrc &ts, uint32_t warp) {
-  TileIt t{0u, warp * WarpTile<PB, PC>::TE};
-  if (t.base >= ts.n_e) {
+__device__ __forceinline__ TileIt tile_first(const WarpPipe &wp) {
+  TileIt t{0u, wp.e_lo};
+  if (t.base >= wp.e_hi) {
     t.cls = 1u;
-    t.base = warp * WarpTile<PB, PC>::TP;
-    if (t.base >= ts.n_p) t.cls = 2u;
+    t.base = wp.p_lo;
+    if (t.base >= wp.p_hi) t.cls = 2u;
   }
   return t;
 }
 template <int PB, int PC>
-__device__ __forceinline__ TileIt tile_next(const TileSrc &ts, uint32_t warp, TileIt t) {
+__device__ __forceinline__ TileIt tile_next(const WarpPipe &wp, TileIt t) {
   if (t.cls == 0u) {
-    t.base += kLmWarps * WarpTile<PB, PC>::TE;
-    if (t.base >= ts.n_e) {
+    t.base += WarpTile<PB, PC>::TE;
+    if (t.base >= wp.e_hi) {
       t.cls = 1u;
-      t.base = warp * WarpTile<PB, PC>::TP;
-      if (t.base >= ts.n_p) t.cls = 2u;
+      t.base = wp.p_lo;
+      if (t.base >= wp.p_hi) t.cls = 2u;
     }
   } else {
-    t.base += kLmWarps * WarpTile<PB, PC>::TP;
-    if (t.base >= ts.n_p) t.cls = 2u;
+    t.base += WarpTile<PB, PC>::TP;
+    if (t.base >= wp.p_hi) t.cls = 2u;
   }
   return t;
+}
+// entries of tile t (the last tile of a share is short)
+template <int PB, int PC>
+__device__ __forceinline__ uint32_t tile_count(const WarpPipe &wp, TileIt t) {
+  return t.cls == 0u ? min(WarpTile<PB, PC>::TE, wp.e_hi - t.base) : min(WarpTile<PB, PC>::TP, wp.p_hi - t.base);
 }
 
 // lane 0: two bulk copies (points, constants) of tile t into the stage at shared address dst
 template <int PB, int PC>
-__device__ __forceinline__ void issue_warp_tile(const TileSrc &ts, TileIt t, uint32_t dst, uint32_t bar) {
+__device__ __forceinline__ void issue_warp_tile(const TileSrc &ts, const WarpPipe &wp, TileIt t, uint32_t dst, uint32_t bar) {
   using WT = WarpTile<PB, PC>;
+  const uint32_t cnt = tile_count<PB, PC>(wp, t);
   if (t.cls == 0u) {
-    const uint32_t cnt = min(WT::TE, ts.n_e - t.base);
     mbar_expect_tx_s(bar, cnt * (uint32_t)(PB + 48));
     tma_load_1d_s(dst, ts.pe + (size_t)t.base * PB, cnt * (uint32_t)PB, bar);
     tma_load_1d_s(dst + WT::TE * PB, (const unsigned char *)ts.ce + (size_t)t.base * 48, cnt * 48u, bar);
   } else {
-    const uint32_t cnt = min(WT::TP, ts.n_p - t.base);
     mbar_expect_tx_s(bar, cnt * (uint32_t)(PB + PC));
     tma_load_1d_s(dst, ts.pp + (size_t)t.base * PB, cnt * (uint32_t)PB, bar);
     tma_load_1d_s(dst + WT::TP * PB, (const unsigned char *)ts.cp + (size_t)t.base * PC, cnt * (uint32_t)PC, bar);
@@ -308,7 +335,8 @@ __device__ __forceinline__ void issue_warp_tile(const TileSrc &ts, TileIt t, uin
 }
 
 struct SweepCtx {
-  double R[9], t0, t1, t2, huber_a;
+  double R[9], t0, t1, t2;
+  Huber huber_a;
 };
 
 template <int PB>
@@ -324,11 +352,11 @@ __device__ __forceinline__ void load_point_s(uint32_t a, double &p0, double &p1,
 
 // all entries of one tile that sits in shared memory at `buf`
 template <int PB, int PC>
-__device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx &cx, const TileSrc &ts, TileIt t, uint32_t buf,
+__device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx &cx, const WarpPipe &wp, TileIt t, uint32_t buf,
                                              uint32_t lane, int &cnt_edge, int &cnt_plane) {
   using WT = WarpTile<PB, PC>;
+  const uint32_t cnt = tile_count<PB, PC>(wp, t);
   if (t.cls == 0u) {
-    const uint32_t cnt = min(WT::TE, ts.n_e - t.base);
     uint32_t pa = buf + lane * PB, ca = buf + WT::TE * PB + lane * 48;
 #pragma unroll 1
     for (uint32_t ent = lane; ent < cnt; ent += 32, pa += 32 * PB, ca += 32 * 48) {
@@ -343,7 +371,6 @@ __device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx
       }
     }
   } else {
-    const uint32_t cnt = min(WT::TP, ts.n_p - t.base);
     uint32_t pa = buf + lane * PB, ca = buf + WT::TP * PB + lane * PC;
     // 32 B entries: lanes 4..7 (mod 8) fetch the upper half first so that a quarter-warp's eight 16 B reads
     // cover all 32 banks
@@ -372,43 +399,43 @@ __device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx
 
 template <int PB, int PC>
 __device__ __forceinline__ void sweep_warp(double (&acc)[kAcc], const TileSrc &ts, WarpPipe &wp, const double *pose, double huber_a,
-                                           int &cnt_edge, int &cnt_plane) {
+                                           double sqrt_huber_a, int &cnt_edge, int &cnt_plane) {
   using WT = WarpTile<PB, PC>;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
   SweepCtx cx;
   quat_to_R(pose + 3, cx.R);
   cx.t0 = pose[0]; cx.t1 = pose[1]; cx.t2 = pose[2];
-  cx.huber_a = huber_a;
+  cx.huber_a = Huber{huber_a, huber_a * huber_a, sqrt_huber_a};
   cnt_edge = 0;
   cnt_plane = 0;
-  TileIt cur = tile_first<PB, PC>(ts, warp);
-  if (cur.cls == 2u) return;  // fewer tiles than warps: nothing for this warp
+  TileIt cur = tile_first<PB, PC>(wp);
+  if (cur.cls == 2u) return;  // fewer entries than warps: nothing for this warp
   if (wp.resident) {
     if (!wp.loaded && lane == 0) {
       uint32_t k = 0;
-      for (TileIt t = cur; t.cls != 2u; t = tile_next<PB, PC>(ts, warp, t), ++k)
-        issue_warp_tile<PB, PC>(ts, t, wp.ring + k * WT::SB, wp.bars + k * 8u);
+      for (TileIt t = cur; t.cls != 2u; t = tile_next<PB, PC>(wp, t), ++k)
+        issue_warp_tile<PB, PC>(ts, wp, t, wp.ring + k * WT::SB, wp.bars + k * 8u);
     }
     uint32_t k = 0;
-    for (; cur.cls != 2u; cur = tile_next<PB, PC>(ts, warp, cur), ++k) {
+    for (; cur.cls != 2u; cur = tile_next<PB, PC>(wp, cur), ++k) {
       if (!wp.loaded) mbar_wait_s(wp.bars + k * 8u, 0u);
-      consume_tile<PB, PC>(acc, cx, ts, cur, wp.ring + k * WT::SB, lane, cnt_edge, cnt_plane);
+      consume_tile<PB, PC>(acc, cx, wp, cur, wp.ring + k * WT::SB, lane, cnt_edge, cnt_plane);
     }
     wp.loaded = true;
     return;
   }
-  if (!wp.loaded && lane == 0) issue_warp_tile<PB, PC>(ts, cur, wp.ring + (wp.it & 1u) * WT::SB, wp.bars + (wp.it & 1u) * 8u);
+  if (!wp.loaded && lane == 0) issue_warp_tile<PB, PC>(ts, wp, cur, wp.ring + (wp.it & 1u) * WT::SB, wp.bars + (wp.it & 1u) * 8u);
   for (;;) {
-    TileIt nxt = tile_next<PB, PC>(ts, warp, cur);
+    TileIt nxt = tile_next<PB, PC>(wp, cur);
     const bool last = nxt.cls == 2u;
-    if (last) nxt = tile_first<PB, PC>(ts, warp);  // prefetch across the sweep boundary
+    if (last) nxt = tile_first<PB, PC>(wp);  // prefetch across the sweep boundary
     const uint32_t s = wp.it & 1u;
     // the other stage held the previous tile: every lane left it at the __syncwarp below
-    if (lane == 0) issue_warp_tile<PB, PC>(ts, nxt, wp.ring + (s ^ 1u) * WT::SB, wp.bars + (s ^ 1u) * 8u);
+    if (lane == 0) issue_warp_tile<PB, PC>(ts, wp, nxt, wp.ring + (s ^ 1u) * WT::SB, wp.bars + (s ^ 1u) * 8u);
     mbar_wait_s(wp.bars + s * 8u, (wp.it >> 1) & 1u);
-    consume_tile<PB, PC>(acc, cx, ts, cur, wp.ring + s * WT::SB, lane, cnt_edge, cnt_plane);
+    consume_tile<PB, PC>(acc, cx, wp, cur, wp.ring + s * WT::SB, lane, cnt_edge, cnt_plane);
     __syncwarp();
     ++wp.it;
     if (last) break;
@@ -430,8 +457,11 @@ __device__ __forceinline__ WarpPipe warp_pipe_init(const TileSrc &ts, unsigned c
   wp.ring = smem_u32(ring_cta) + warp * n_stages * WT::SB;
   wp.bars = smem_u32(bars_cta) + warp * kMaxWarpStages * 8u;
   wp.it = 0;
-  const uint32_t tt_e = (ts.n_e + WT::TE - 1) / WT::TE, tt_p = (ts.n_p + WT::TP - 1) / WT::TP;
-  wp.my_tiles = (tt_e > warp ? (tt_e - warp + kLmWarps - 1) / kLmWarps : 0u) + (tt_p > warp ? (tt_p - warp + kLmWarps - 1) / kLmWarps : 0u);
+  wp.e_lo = (uint32_t)(((uint64_t)ts.n_e * warp) / kLmWarps);
+  wp.e_hi = (uint32_t)(((uint64_t)ts.n_e * (warp + 1)) / kLmWarps);
+  wp.p_lo = (uint32_t)(((uint64_t)ts.n_p * warp) / kLmWarps);
+  wp.p_hi = (uint32_t)(((uint64_t)ts.n_p * (warp + 1)) / kLmWarps);
+  wp.my_tiles = (wp.e_hi - wp.e_lo + WT::TE - 1) / WT::TE + (wp.p_hi - wp.p_lo + WT::TP - 1) / WT::TP;
   wp.resident = n_stages > (uint32_t)kWarpStages && wp.my_tiles <= n_stages;
   wp.loaded = false;
   return wp;
@@ -637,7 +667,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
 
   double acc[kAcc];
   int ce, cpl;
-  sweep_warp<PB, PC>(acc, ts, wp, sh.x, kp.huber_a, ce, cpl);
+  sweep_warp<PB, PC>(acc, ts, wp, sh.x, kp.huber_a, kp.huber_sqrt_a, ce, cpl);
   // correspondence counts (corner_num / surf_num, mapping_scan_matcher.cc:173,243)
   for (int o = 16; o > 0; o >>= 1) {
     ce += __shfl_down_sync(0xffffffffu, ce, o);
@@ -697,7 +727,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
 #endif
   while (!sh.done) {
     MSFL_TICK(c0);
-    sweep_warp<PB, PC>(acc, ts, wp, sh.xc, kp.huber_a, ce, cpl);
+    sweep_warp<PB, PC>(acc, ts, wp, sh.xc, kp.huber_a, kp.huber_sqrt_a, ce, cpl);
     MSFL_TICK(c1);
     block_reduce(acc, sh);
     if (G > 1) cluster_reduce(cluster, sh, G, rank, false);

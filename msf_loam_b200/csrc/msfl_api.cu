@@ -74,6 +74,7 @@ static void fill_kparams(msfl_engine *e) {
   k.max_invalid = p.max_consecutive_invalid_steps;
   k.min_corr = p.min_correspondences;
   k.huber_a = p.huber_a;
+  k.huber_sqrt_a = sqrt(p.huber_a);
   k.initial_radius = p.initial_radius;
   k.max_radius = p.max_radius;
   k.min_radius = p.min_radius;

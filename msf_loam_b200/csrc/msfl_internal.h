@@ -66,7 +66,7 @@ struct KParams {
   double nearby_scan;
   double line_eig_ratio, line_half_len, plane_tol;
   int max_it, early_exit, max_invalid, min_corr;
-  double huber_a, initial_radius, max_radius, min_radius, min_rel_decrease;
+  double huber_a, huber_sqrt_a, initial_radius, max_radius, min_radius, min_rel_decrease;
   double min_diag, max_diag, ftol, gtol, ptol;
 };
 
