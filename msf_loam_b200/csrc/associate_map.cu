@@ -10,6 +10,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
 
@@ -45,10 +47,12 @@ __device__ __forceinline__ void top5_insert(Top5 &t, float d, int id) {
 // fp32: with 1 m cells the cell boundaries are integers, float subtraction / squaring / addition
 // are monotone, and the bound is accumulated in the same order as the distance itself
 // ((bx^2 + by^2) + bz^2), so  bound > worst  implies  d > worst  for every point of that cell.
-__device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy, float qz, float thresh, Top5 &t) {
+// `seed` (<= thresh) is an upper bound, exclusive, on the 5th-nearest distance when one is known (seed_bound below):
+// the five sentinels start there instead of at the gate, so rows, cells and candidates beyond it are never touched.
+__device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy, float qz, float thresh, float seed, Top5 &t) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    t.d[s] = thresh;
+    t.d[s] = seed;
     t.i[s] = -1;
   }
   const float fxq = floorf(qx * g.inv_edge), fyq = floorf(qy * g.inv_edge), fzq = floorf(qz * g.inv_edge);
@@ -95,6 +99,23 @@ __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy,
   return t.i[4] >= 0;
 }
 
+// Outer iteration >= 1: the five neighbours found at the previous pose are still five distinct map points, so the
+// largest of their (exactly recomputed) distances to the moved query bounds the new 5th-nearest distance from above.
+// Returns the smallest float above that maximum, capped at the gate: every member of the new exact top five is
+// strictly below it, and so beats the sentinels in the (d2, index) order.
+__device__ __forceinline__ float seed_bound(const GridView &g, const int32_t *__restrict__ prev5, float qx, float qy, float qz,
+                                            float thresh) {
+  if (__ldg(prev5 + 4) < 0) return thresh;  // the gate failed last time: no bound
+  float u = 0.f;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const float4 m = __ldg(g.pts_orig + __ldg(prev5 + s));
+    const float dx = __fsub_rn(qx, m.x), dy = __fsub_rn(qy, m.y), dz = __fsub_rn(qz, m.z);
+    u = fmaxf(u, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  }
+  return fminf(__uint_as_float(__float_as_uint(u) + 1u), thresh);
+}
+
 __device__ __forceinline__ void store_corr(double *corr, size_t q, const double a[3], const double n[3]) {
   double2 *o = reinterpret_cast<double2 *>(corr + q * 6);
   o[0] = make_double2(a[0], a[1]);
@@ -133,7 +154,7 @@ __global__ void __launch_bounds__(256)
 k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc, const int32_t *__restrict__ c_off,
                  uint32_t n_corner_total, const float4 *__restrict__ qs, const int32_t *__restrict__ s_off,
                  uint32_t n_surf_total, const double *__restrict__ poses, float4 *__restrict__ xq,
-                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ hist) {
+                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ hist, int sub_log2) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_corner_total + n_surf_total) return;
   const bool is_corner = k < n_corner_total;
@@ -149,14 +170,16 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
   uint32_t key;
   if (is_corner) key = c < 0 ? ncell_c : (uint32_t)c;
   else key = ncell_c + 1u + (c < 0 ? ncell_s : (uint32_t)c);
-  // refine the order inside a cell by a 4x4x4 sub-cell index so the lanes of a warp are spatial
-  // neighbours (<= 0.25 m apart): their row / cell pruning decisions in knn5_grid then agree
-  {
+  // refine the order inside a cell by a sub-cell index (4x4x4 when the key has room: sub_log2 = 2) so the lanes of a
+  // warp are spatial neighbours (<= 0.25 m apart): their row / cell pruning decisions in knn5_grid then agree
+  if (sub_log2 > 0) {
     const GridView &g = is_corner ? gc : gs;
+    const int ns = 1 << sub_log2;
+    const float fs = (float)ns;
     const float ux = x.x * g.inv_edge, uy = x.y * g.inv_edge, uz = x.z * g.inv_edge;
-    const int sx = min(3, max(0, (int)((ux - floorf(ux)) * 4.0f))), sy = min(3, max(0, (int)((uy - floorf(uy)) * 4.0f))),
-              sz = min(3, max(0, (int)((uz - floorf(uz)) * 4.0f)));
-    key = (key << 6) | (uint32_t)((sz * 4 + sy) * 4 + sx);
+    const int sx = min(ns - 1, max(0, (int)((ux - floorf(ux)) * fs))), sy = min(ns - 1, max(0, (int)((uy - floorf(uy)) * fs))),
+              sz = min(ns - 1, max(0, (int)((uz - floorf(uz)) * fs)));
+    key = (key << (3 * sub_log2)) | (uint32_t)((((sz << sub_log2) + sy) << sub_log2) + sx);
   }
   xq[k] = make_float4(x.x, x.y, x.z, 0.f);
   keys[k] = key;
@@ -166,10 +189,18 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
 // counting sort, last pass: slot = first slot of the query's bin + its rank inside the bin
 __global__ void __launch_bounds__(256)
 k_scatter_perm(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ bin_start,
-               uint32_t n, uint32_t *__restrict__ perm) {
+               uint32_t n, uint32_t *__restrict__ perm, uint32_t *__restrict__ inv) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  perm[__ldg(bin_start + __ldg(keys + k)) + __ldg(rank + k)] = k;
+  const uint32_t slot = __ldg(bin_start + __ldg(keys + k)) + __ldg(rank + k);
+  perm[slot] = k;
+  inv[k] = slot;  // where query k's neighbour list will sit: the next outer iteration seeds its search from it
+}
+
+// radix-sort path: the inverse of the sorted permutation
+__global__ void __launch_bounds__(256) k_invert_perm(const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ inv) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < n) inv[__ldg(perm + slot)] = slot;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,13 +291,16 @@ __device__ __forceinline__ float3 deskew_transform(const double pose[7], const D
 // transformed point stored by k_transform_keys instead of transforming here.
 // BY_SLOT: the five indices are stored at the thread's slot (coalesced; k_fit<.., true> then walks the
 // same cell order) instead of at the query's flat index k.
-template <bool SORTED, bool STORED_X, bool DESKEW, bool BY_SLOT>
+// SEED: prev_knn holds the neighbour lists of the previous outer iteration (at slot prev_inv[k], or at k when prev_inv
+// is null); they bound the search at the new pose (seed_bound).
+template <bool SORTED, bool STORED_X, bool DESKEW, bool BY_SLOT, bool SEED = false>
 __global__ void __launch_bounds__(128, 10)
 k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
        const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
        const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
        const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, DeskewTable tb,
-       const double *__restrict__ dsk) {
+       const double *__restrict__ dsk, const int32_t *__restrict__ prev_knn = nullptr,
+       const uint32_t *__restrict__ prev_inv = nullptr) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_corner_total + n_surf_total) return;
   const uint32_t k = SORTED ? __ldg(perm + slot) : slot;
@@ -288,7 +322,9 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
   }
   const GridView &g = is_corner ? gc : gs;
   Top5 t;
-  const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);  // :125-128 / :195-198
+  float seed = kp.knn_max_sq_f;
+  if (SEED) seed = seed_bound(g, prev_knn + (size_t)(prev_inv ? __ldg(prev_inv + k) : k) * 5, x.x, x.y, x.z, kp.knn_max_sq_f);
+  const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, seed, t);  // :125-128 / :195-198
   // 5 neighbour indices per query (-1 when the d5^2 gate fails), consumed by k_fit
   int32_t *o = knn_out + (size_t)(BY_SLOT ? slot : k) * 5;
 #pragma unroll
@@ -440,32 +476,76 @@ k_knn5_tiled(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint
   if (staged && (int)is_corner == anchor[0] && cx == anchor[1] && cy == anchor[2] && cz == anchor[3])
     gate = knn5_tile(tile, rows, g.inv_edge == 1.0f, x.x, x.y, x.z, fxq, fyq, fzq, kp.knn_max_sq_f, t);
   else
-    gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);
+    gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, kp.knn_max_sq_f, t);
   int32_t *o = knn_out + (size_t)slot * 5;
 #pragma unroll
   for (int s = 0; s < 5; ++s) o[s] = gate ? t.i[s] : -1;
 }
 
-// Line / plane fit of every gated query (fp64): thread k reads its five neighbours and writes the factor
-// constants [a_or_c(3), n(3)]; n = 0 marks "no factor".  Kept apart from the search kernel so that the
-// search runs at 40 registers / 75 % occupancy (it is L2-latency bound) while the register-hungry
-// Jacobi / Householder code does not throttle it.
+// ---------------------------------------------------------------------------------------------
+// Plane fit without the QR.  The reference solves the 5x3 least-squares system A x = -1 (rows = the five
+// neighbours) and normalises x (mapping_scan_matcher.cc:199-211).  With c = the mean row and S = sum (p-c)(p-c)^T
+// the normal equations are (S + 5 c c^T) x = -5 c, so by Sherman-Morrison x is a positive multiple of -S^-1 c =
+// -adj(S) c / det(S): the unit normal is  n = -adj(S) c / |adj(S) c|  -- six 2x2 minors of a CENTRED 3x3 matrix,
+// one matrix-vector product and one reciprocal square root (~100 fp64 instructions, 64 registers) instead of three
+// Householder reflections with their square roots and divisions (~250, 128 registers).  It is the same least-squares
+// solution, not an approximation; centring removes the |c|^2 / spread^2 conditioning of the raw system, so it
+// agrees with the pivoted-Householder solve to ~5e-12 on the bench clouds (tools/dev_fit_study.py).
+// Round-off is amplified by tr(S)^2 |c| / |adj(S) c| (five nearly collinear neighbours): beyond 1e5, or when a
+// neighbour sits within 1e-7 m of the validity bound, the query is handed to the Householder kernel instead
+// (0.3 % / 1.4 % of the VLP-16 / HDL-64E queries).  Explicit round-to-nearest intrinsics: every kernel that hosts
+// this function produces the same bits.
+// Returns true when the query needs the Householder path; otherwise nrm (zero when the plane is invalid).
+// ---------------------------------------------------------------------------------------------
+constexpr double kFastFitMinRatioSq = 1e-10;  // (|adj(S) c| / (tr(S)^2 |c|))^2 below this: ill-conditioned
+constexpr double kFastFitBorder = 1e-7;       // metres around plane_tol
+__device__ __forceinline__ bool plane_fit_fast(const float (&mf)[5][3], const double (&c)[3], double plane_tol, double (&nrm)[3]) {
+  double S00 = 0, S01 = 0, S02 = 0, S11 = 0, S12 = 0, S22 = 0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const double e0 = __dsub_rn((double)mf[s][0], c[0]), e1 = __dsub_rn((double)mf[s][1], c[1]), e2 = __dsub_rn((double)mf[s][2], c[2]);
+    S00 = __fma_rn(e0, e0, S00); S01 = __fma_rn(e0, e1, S01); S02 = __fma_rn(e0, e2, S02);
+    S11 = __fma_rn(e1, e1, S11); S12 = __fma_rn(e1, e2, S12); S22 = __fma_rn(e2, e2, S22);
+  }
+  // adj(S) (symmetric): the 2x2 minors
+  const double A00 = __fma_rn(S11, S22, -__dmul_rn(S12, S12)), A01 = __fma_rn(S02, S12, -__dmul_rn(S01, S22)),
+               A02 = __fma_rn(S01, S12, -__dmul_rn(S02, S11)), A11 = __fma_rn(S00, S22, -__dmul_rn(S02, S02)),
+               A12 = __fma_rn(S01, S02, -__dmul_rn(S00, S12)), A22 = __fma_rn(S00, S11, -__dmul_rn(S01, S01));
+  const double v0 = -__fma_rn(A02, c[2], __fma_rn(A01, c[1], __dmul_rn(A00, c[0]))),
+               v1 = -__fma_rn(A12, c[2], __fma_rn(A11, c[1], __dmul_rn(A01, c[0]))),
+               v2 = -__fma_rn(A22, c[2], __fma_rn(A12, c[1], __dmul_rn(A02, c[0])));
+  const double vv = __fma_rn(v2, v2, __fma_rn(v1, v1, __dmul_rn(v0, v0)));
+  const double tr = __dadd_rn(__dadd_rn(S00, S11), S22), tr2 = __dmul_rn(tr, tr);
+  const double cc = __fma_rn(c[2], c[2], __fma_rn(c[1], c[1], __dmul_rn(c[0], c[0])));
+  if (!(vv > __dmul_rn(__dmul_rn(kFastFitMinRatioSq, __dmul_rn(tr2, tr2)), cc))) return true;
+  const double inv = rsqrt(vv);
+  const double n0 = __dmul_rn(v0, inv), n1 = __dmul_rn(v1, inv), n2 = __dmul_rn(v2, inv);
+  bool valid = true, border = false;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {  // :214-220
+    const double e0 = __dsub_rn((double)mf[s][0], c[0]), e1 = __dsub_rn((double)mf[s][1], c[1]), e2 = __dsub_rn((double)mf[s][2], c[2]);
+    const double dd = fabs(__fma_rn(n2, e2, __fma_rn(n1, e1, __dmul_rn(n0, e0))));
+    if (!(dd <= plane_tol)) valid = false;
+    if (fabs(__dsub_rn(dd, plane_tol)) < kFastFitBorder) border = true;
+  }
+  if (border) return true;
+  nrm[0] = valid ? n0 : 0.0; nrm[1] = valid ? n1 : 0.0; nrm[2] = valid ? n2 : 0.0;
+  return false;
+}
+
+// Line / plane fit of one gated query (fp64): reads its five neighbours and writes the factor constants
+// [a_or_c(3), n(3)]; n = 0 marks "no factor".
 // COMPACT: plane entries are written as 32 B {n, n.c} at corr + 48 n_corner_total + 32 i (the batch path: the LM
 // kernel only ever needs the plane's offset along its normal); otherwise 48 B {c, n} like the edge entries.
-// BY_SLOT: thread s handles query perm[s] and reads the neighbour indices k_knn5 stored at slot s: the lanes of a
-// warp are spatial neighbours, so they agree on the gate / validity branches and share the gathered map points.
-// CLS: -1 = one launch over all queries (class decided per thread); 0 / 1 = a launch over the corner / surf queries
-// only (the batch path: in cell order as in flat order all corner queries come first), so the Jacobi eigen-solver
-// and the Householder QR each get their own register allocation and a warp never holds both classes.
-template <bool DESKEW, bool COMPACT, bool BY_SLOT, int CLS = -1>
-__global__ void __launch_bounds__(128)
-k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
-      double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (CLS == 1 ? n_corner_total : 0u);
-  if (slot >= (CLS == 0 ? n_corner_total : n_total)) return;
+// BY_SLOT: slot s holds query perm[s] and the neighbour indices k_knn5 stored at slot s.
+// QR: planes take the pivoted-Householder solve (the fallback kernel); otherwise plane_fit_fast, and a query that
+// needs the Householder path is appended to fb_list instead of being written.
+template <bool DESKEW, bool COMPACT, bool BY_SLOT, bool QR>
+__device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, bool is_corner, uint32_t slot, uint32_t n_corner_total,
+                                          const int32_t *__restrict__ knn, double *__restrict__ corr, const DeskewTable &tb,
+                                          const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
+                                          uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
   const uint32_t k = BY_SLOT ? __ldg(perm + slot) : slot;
-  const bool is_corner = CLS < 0 ? k < n_corner_total : CLS == 0;
-  const GridView &g = is_corner ? gc : gs;
   int idx[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)slot * 5 + s);
@@ -482,7 +562,8 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
 #define M(s, d) ((double)mf[s][d])
     double c[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) c[d] = ((((M(0, d) + M(1, d)) + M(2, d)) + M(3, d)) + M(4, d)) / 5.0;  // :137 / :212
+    for (int d = 0; d < 3; ++d)  // :137 / :212
+      c[d] = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(M(0, d), M(1, d)), M(2, d)), M(3, d)), M(4, d)), 5.0);
     if (is_corner) {
       double cov[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -504,7 +585,7 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
         const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);  // (point_a - point_b).normalized() :168
         if (nn > 0) { n[0] /= nn; n[1] /= nn; n[2] /= nn; }
       }
-    } else {
+    } else if (QR) {
       double A[5][3], bb[5] = {-1, -1, -1, -1, -1}, nrm[3];
 #pragma unroll
       for (int s = 0; s < 5; ++s) { A[s][0] = M(s, 0); A[s][1] = M(s, 1); A[s][2] = M(s, 2); }
@@ -521,6 +602,13 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
 #pragma unroll
         for (int d = 0; d < 3; ++d) { a[d] = c[d]; n[d] = nrm[d]; }
       }
+    } else {
+      if (plane_fit_fast(mf, c, kp.plane_tol, n)) {
+        fb_list[atomicAdd(fb_count, 1u)] = slot;  // the Householder kernel writes this entry
+        return;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) a[d] = c[d];
     }
 #undef M
   }
@@ -533,119 +621,210 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
     double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(corr + (size_t)n_corner_total * 6) +
                                              (size_t)(k - n_corner_total) * 32);
     o[0] = make_double2(n[0], n[1]);
-    o[1] = make_double2(n[2], n[0] * a[0] + n[1] * a[1] + n[2] * a[2]);
+    o[1] = make_double2(n[2], __fma_rn(n[2], a[2], __fma_rn(n[1], a[1], __dmul_rn(n[0], a[0]))));
   } else {
     store_corr(corr, k, a, n);
   }
 }
 
+// One thread per query.  Kept apart from the search kernel so that the search runs at 40 registers / 75 %
+// occupancy while the fits do not throttle it.
+// CLS: -1 = one launch over all queries (class decided per thread); 0 / 1 = a launch over the corner / surf queries
+// only (the batch path: in cell order as in flat order all corner queries come first), so the Jacobi eigen-solver
+// and the plane fit each get their own register allocation and a warp never holds both classes.
+template <bool DESKEW, bool COMPACT, bool BY_SLOT, int CLS = -1>
+__global__ void __launch_bounds__(128)
+k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
+      double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
+      uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (CLS == 1 ? n_corner_total : 0u);
+  if (slot >= (CLS == 0 ? n_corner_total : n_total)) return;
+  // corner slots come first in cell order as in flat order, so the class follows from the slot in both
+  const bool is_corner = CLS < 0 ? slot < n_corner_total : CLS == 0;
+  fit_query<DESKEW, COMPACT, BY_SLOT, false>(is_corner ? gc : gs, kp, is_corner, slot, n_corner_total, knn, corr, tb, dsk, perm,
+                                             fb_list, fb_count);
+}
+
+// The Householder path for the plane queries plane_fit_fast declined (grid-stride over the list; its length is only
+// known on the device).  The list order is arbitrary, but every entry is written at its own query's place.
+template <bool DESKEW, bool COMPACT, bool BY_SLOT>
+__global__ void __launch_bounds__(128)
+k_fit_qr_list(GridView gs, KParams kp, uint32_t n_corner_total, const int32_t *__restrict__ knn, double *__restrict__ corr,
+              DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
+              const uint32_t *__restrict__ fb_list, const uint32_t *__restrict__ fb_count) {
+  const uint32_t cnt = *fb_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+    fit_query<DESKEW, COMPACT, BY_SLOT, true>(gs, kp, false, fb_list[i], n_corner_total, knn, corr, tb, dsk, perm, nullptr, nullptr);
+}
+
+// grid of the Householder fallback kernel: it strides over a list whose length the host does not know
+static unsigned qr_list_grid(const msfl_engine *e, uint32_t n_plane_queries) {
+  const unsigned want = (n_plane_queries / 64u + 127u) / 128u + 1u;  // ~1.5 % of the queries land on the list
+  return std::min(want, (unsigned)e->sm_count * 4u);
+}
+
+// outer: outer-iteration index of the calling solve.  For outer > 0 the neighbour lists of the previous call (same
+// queries, same submap, previous pose) seed the search; the caller guarantees that calls with outer > 0 follow the
+// outer - 1 call of the same batch on the same stream.
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool compact) {
+                         double *d_corr, int32_t *d_knn, bool compact, int outer) {
   const uint32_t total = n_corner_total + n_surf_total;
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
   const GridView &gc = e->map_corner.view, &gs = e->map_surf.view;
   const bool own_knn = d_knn == nullptr;
-  if (!d_knn) {  // neighbour indices travel from the search kernel to the fit kernel through this scratch
-    int rck;
-    if ((rck = e->d_knn.reserve((size_t)total * 5 * 4))) return rck;
-    d_knn = e->d_knn.as<int32_t>();
+  int rc;
+  // neighbour indices travel from the search kernel to the fit kernel through this scratch; two buffers, so that the
+  // lists of outer iteration o - 1 are still there when iteration o searches
+  const int32_t *prev_knn = nullptr;
+  const uint32_t *prev_inv = nullptr;
+  const bool seeded = own_knn && outer > 0 && e->assoc_prev_total == total && e->assoc_prev_knn != nullptr && e->seed_knn;
+  if (seeded) { prev_knn = e->assoc_prev_knn; prev_inv = e->assoc_prev_inv; }
+  if (own_knn) {
+    DevBuf &kb = (outer & 1) ? e->d_knn2 : e->d_knn;
+    if ((rc = kb.reserve((size_t)total * 5 * 4))) return rc;
+    d_knn = kb.as<int32_t>();
   }
+  if ((rc = e->a_fb.reserve(((size_t)n_surf_total + 2) * 4))) return rc;
+  uint32_t *fb_count = e->a_fb.as<uint32_t>(), *fb_list = fb_count + 1;
+  MSFL_CUDA_OK(cudaMemsetAsync(fb_count, 0, 4, e->stream));
+  const DeskewTable nt{};
   const int mode = e->params.assoc_sorted;  // 0 auto, 1 never, 2 always
   const bool sorted = mode == 2 || mode == 3 || (mode == 0 && total >= 65536u);
   if (!sorted) {
     stage_begin(e, 0);
-    k_knn5<false, false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, nullptr, nullptr, d_knn,
-        DeskewTable{}, nullptr);
-    if (compact) k_fit<false, true, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
-    else k_fit<false, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, DeskewTable{}, nullptr, nullptr);
+    const unsigned grid = (total + tb - 1) / tb;
+    if (seeded)
+      k_knn5<false, false, false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                          n_surf_total, d_poses, nullptr, nullptr, d_knn, nt, nullptr,
+                                                                          prev_knn, prev_inv);
+    else
+      k_knn5<false, false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                    n_surf_total, d_poses, nullptr, nullptr, d_knn, nt, nullptr);
+    if (compact) {
+      k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+      k_fit_qr_list<false, true, false><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+    } else {
+      k_fit<false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+      k_fit_qr_list<false, false, false><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+    }
     stage_end(e);
-    e->launches += 2;
+    e->launches += 3;
     MSFL_CUDA_OK(cudaGetLastError());
+    e->assoc_prev_knn = own_knn ? d_knn : nullptr;
+    e->assoc_prev_inv = nullptr;  // lists sit at the query's own index
+    e->assoc_prev_total = total;
     return MSFL_OK;
   }
-  // sorted path: transform + cell keys -> radix sort -> association in cell order
-  int rc;
+  // sorted path: transform + cell keys -> counting / radix sort -> association in cell order
   if ((rc = e->a_xq.reserve((size_t)total * 16))) return rc;
   if ((rc = e->a_keys.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_keys_alt.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_vals.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_vals_alt.reserve((size_t)total * 4))) return rc;
-  const long long ncell = (long long)gc.nx * gc.ny * gc.nz + (long long)gs.nx * gs.ny * gs.nz + 2;
-  int end_bit = 1;
-  while ((1ll << end_bit) < ncell) ++end_bit;
-  end_bit += 6;  // 4x4x4 sub-cell index in the low bits
-  if (end_bit > 32) { set_error("submap grid too large for the sorted association path"); return MSFL_ERR_GRID; }
-  const long long nbins = ncell << 6;
-  if (nbins <= e->count_sort_max_bins) {
-    // counting sort: one atomic per query into a bin table that lives in L2, a scan of the bins, one scatter
-    size_t tmp = 0;
-    if ((rc = e->a_hist.reserve((size_t)nbins * 4))) return rc;
-    uint32_t *hist = e->a_hist.as<uint32_t>();
-    MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, hist, hist, (int)nbins, e->stream));
-    if ((rc = e->a_tmp.reserve(tmp))) return rc;
-    stage_begin(e, 2);
-    MSFL_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, e->stream));
-    k_transform_keys<true><<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                                       n_surf_total, d_poses, e->a_xq.as<float4>(),
-                                                                       e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist);
-    MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(e->a_tmp.p, tmp, hist, hist, (int)nbins, e->stream));
-    k_scatter_perm<<<(total + 255) / 256, 256, 0, e->stream>>>(e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist, total,
-                                                               e->a_vals_alt.as<uint32_t>());
-    stage_end(e);
-    e->a_perm = e->a_vals_alt.as<uint32_t>();
-    e->launches += 3;  // + the cub scan kernels
-  } else {
-    cub::DoubleBuffer<uint32_t> dk(e->a_keys.as<uint32_t>(), e->a_keys_alt.as<uint32_t>()),
-        dv(e->a_vals.as<uint32_t>(), e->a_vals_alt.as<uint32_t>());
-    size_t tmp = 0;
-    MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
-    if ((rc = e->a_tmp.reserve(tmp))) return rc;
-    stage_begin(e, 2);
-    k_transform_keys<false><<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                                        n_surf_total, d_poses, e->a_xq.as<float4>(), dk.Current(),
-                                                                        dv.Current(), nullptr);
-    MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
-    stage_end(e);
-    e->a_perm = dv.Current();
-    e->launches += 3;
+  DevBuf &ib = (outer & 1) ? e->a_inv2 : e->a_inv;
+  if ((rc = ib.reserve((size_t)total * 4))) return rc;
+  // an outer iteration > 0 may keep the previous cell order (MSFL_RESORT_OUTER=0): the order is only a locality hint
+  const bool keep_order = seeded && !e->resort_outer && e->a_perm != nullptr && prev_inv != nullptr;
+  if (!keep_order) {
+    const long long ncell = (long long)gc.nx * gc.ny * gc.nz + (long long)gs.nx * gs.ny * gs.nz + 2;
+    int cell_bits = 1;
+    while ((1ll << cell_bits) < ncell) ++cell_bits;
+    // sub-cell refinement of the key: 4x4x4 when the 32-bit key has room, 2x2x2 or none for far-spread submaps
+    const int sub_log2 = cell_bits + 6 <= 32 ? 2 : (cell_bits + 3 <= 32 ? 1 : 0);
+    const int end_bit = cell_bits + 3 * sub_log2;
+    if (end_bit > 32) { set_error("submap grid too large for the sorted association path"); return MSFL_ERR_GRID; }  // ncell <= 2^27 + 2: unreachable
+    const long long nbins = ncell << (3 * sub_log2);
+    if (nbins <= e->count_sort_max_bins) {
+      // counting sort: one atomic per query into a bin table that lives in L2, a scan of the bins, one scatter
+      size_t tmp = 0;
+      if ((rc = e->a_hist.reserve((size_t)nbins * 4))) return rc;
+      uint32_t *hist = e->a_hist.as<uint32_t>();
+      MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, hist, hist, (int)nbins, e->stream));
+      if ((rc = e->a_tmp.reserve(tmp))) return rc;
+      stage_begin(e, 2);
+      MSFL_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, e->stream));
+      k_transform_keys<true><<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                         n_surf_total, d_poses, e->a_xq.as<float4>(),
+                                                                         e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist, sub_log2);
+      MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(e->a_tmp.p, tmp, hist, hist, (int)nbins, e->stream));
+      k_scatter_perm<<<(total + 255) / 256, 256, 0, e->stream>>>(e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist, total,
+                                                                 e->a_vals_alt.as<uint32_t>(), ib.as<uint32_t>());
+      stage_end(e);
+      e->a_perm = e->a_vals_alt.as<uint32_t>();
+      e->launches += 3;  // + the cub scan kernels
+    } else {
+      cub::DoubleBuffer<uint32_t> dk(e->a_keys.as<uint32_t>(), e->a_keys_alt.as<uint32_t>()),
+          dv(e->a_vals.as<uint32_t>(), e->a_vals_alt.as<uint32_t>());
+      size_t tmp = 0;
+      MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
+      if ((rc = e->a_tmp.reserve(tmp))) return rc;
+      stage_begin(e, 2);
+      k_transform_keys<false><<<(total + 255) / 256, 256, 0, e->stream>>>(gc, gs, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                          n_surf_total, d_poses, e->a_xq.as<float4>(), dk.Current(),
+                                                                          dv.Current(), nullptr, sub_log2);
+      MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
+      k_invert_perm<<<(total + 255) / 256, 256, 0, e->stream>>>(dv.Current(), total, ib.as<uint32_t>());
+      stage_end(e);
+      e->a_perm = dv.Current();
+      e->launches += 4;
+    }
   }
+  const uint32_t *cur_inv = keep_order ? prev_inv : ib.as<uint32_t>();
   // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
   const bool by_slot = own_knn;
+  const unsigned grid = (total + tb - 1) / tb;
   stage_begin(e, 0);
-  if (by_slot && mode == 3)  // measured on B200 (VLP-16, 2048 scans): 0.523 ms staged vs 0.507 ms direct -- the search is
-                             // instruction-issue-bound (78 % of issue slots), not latency-bound, so staging is opt-in
-    k_knn5_tiled<<<(total + tb - 1) / tb, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, e->a_xq.as<float4>(), e->a_perm, d_knn);
+  if (keep_order)
+    k_knn5<true, false, false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                      n_surf_total, d_poses, nullptr, e->a_perm, d_knn, nt, nullptr,
+                                                                      prev_knn, prev_inv);
+  else if (by_slot && mode == 3)  // measured on B200 (VLP-16, 2048 scans): 0.523 ms staged vs 0.507 ms direct -- the search is
+                                  // instruction-issue-bound (78 % of issue slots), not latency-bound, so staging is opt-in
+    k_knn5_tiled<<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, e->a_xq.as<float4>(), e->a_perm, d_knn);
+  else if (by_slot && seeded)
+    k_knn5<true, true, false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                     n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn, nt,
+                                                                     nullptr, prev_knn, prev_inv);
   else if (by_slot)
-    k_knn5<true, true, false, true><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
-        DeskewTable{}, nullptr);
+    k_knn5<true, true, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                               n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn, nt, nullptr);
   else
-    k_knn5<true, true, false, false><<<(total + tb - 1) / tb, tb, 0, e->stream>>>(
-        gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off, n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn,
-        DeskewTable{}, nullptr);
+    k_knn5<true, true, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn, nt, nullptr);
   stage_end(e);
   stage_begin(e, 3);
   {
-    const unsigned grid = (total + tb - 1) / tb;
-    const DeskewTable nt{};
     if (by_slot && compact) {
       const unsigned grid_c = (n_corner_total + tb - 1) / tb, grid_s = (n_surf_total + tb - 1) / tb;
-      if (grid_c) k_fit<false, true, true, 0><<<grid_c, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
-      if (grid_s) k_fit<false, true, true, 1><<<grid_s, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
-      e->launches += 1;
+      if (grid_c) k_fit<false, true, true, 0><<<grid_c, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+      if (grid_s) {
+        k_fit<false, true, true, 1><<<grid_s, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+        k_fit_qr_list<false, true, true><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+      }
+      e->launches += 2;
     } else if (by_slot) {
-      k_fit<false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm);
+      k_fit<false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+      k_fit_qr_list<false, false, true><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+      e->launches += 1;
     } else {
-      if (compact) k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);
-      else k_fit<false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr);
+      if (compact) {
+        k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+        k_fit_qr_list<false, true, false><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+      } else {
+        k_fit<false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+        k_fit_qr_list<false, false, false><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
+      }
+      e->launches += 1;
     }
   }
   stage_end(e);
   e->launches += 3;
   MSFL_CUDA_OK(cudaGetLastError());
+  e->assoc_prev_knn = by_slot ? d_knn : nullptr;
+  e->assoc_prev_inv = cur_inv;
+  e->assoc_prev_total = total;
   return MSFL_OK;
 }
 
@@ -676,9 +855,14 @@ int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_
   k_knn5<false, false, true, false><<<(total + 127) / 128, 128, 0, e->stream>>>(
       e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_knn, tb,
       d_dsk);
-  k_fit<true, false, false><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk, nullptr);
+  int rcf;
+  if ((rcf = e->a_fb.reserve(((size_t)ns + 2) * 4))) return rcf;
+  uint32_t *fb_count = e->a_fb.as<uint32_t>(), *fb_list = fb_count + 1;
+  MSFL_CUDA_OK(cudaMemsetAsync(fb_count, 0, 4, e->stream));
+  k_fit<true, false, false><<<(total + 127) / 128, 128, 0, e->stream>>>(e->map_corner.view, e->map_surf.view, e->kp, nc, total, d_knn, d_corr, tb, d_dsk, nullptr, fb_list, fb_count);
+  k_fit_qr_list<true, false, false><<<qr_list_grid(e, ns), 128, 0, e->stream>>>(e->map_surf.view, e->kp, nc, d_knn, d_corr, tb, d_dsk, nullptr, fb_list, fb_count);
   stage_end(e);
-  e->launches += 2;
+  e->launches += 3;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }

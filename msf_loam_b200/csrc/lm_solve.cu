@@ -220,9 +220,8 @@ struct TileSrc {
 // Warp-private streaming (the throughput configuration).  Every warp owns a double-buffered ring of
 // tiles and its own mbarriers, issues its own bulk copies (lane 0) and consumes them after a
 // __syncwarp: there is no block-wide barrier inside a sweep, so a warp never waits for the slowest
-// warp of its CTA.  Warp w of W owns the w-th of W equal contiguous shares of each class (edge entries, then plane
-// entries; the shares differ by at most one entry, so the four warps reach the block reduction together -- with
-// round-robin tiles warp 0 carried the odd tile of both classes and the others waited ~20 % of every sweep).  While a
+// warp of its CTA.  Warp w of W streams tiles w, w + W, w + 2W, ... of each class (edge entries,
+// then plane entries), i.e. the CTA as a whole still walks the scan's arrays front to back.  While a
 // warp works on the last tile of a sweep it already fetches the first tile of the next sweep (the
 // data does not depend on the pose), so the copy latency also hides behind the block reduction and
 // the thread-0 LM step.  All shared-memory traffic uses 32-bit shared-space addresses (ld.shared /
@@ -275,7 +274,6 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
 
 // per-warp pipeline state, kept in registers across the sweeps of one solve
 struct WarpPipe {
-  uint32_t e_lo, e_hi, p_lo, p_hi;  // this warp's share of the edge / plane entries of the CTA's arrays
   uint32_t ring;     // shared-space address of this warp's ring (n_stages x SB bytes)
   uint32_t bars;     // shared-space address of this warp's mbarriers (8 B each)
   uint32_t it;       // streaming: tiles consumed so far (stage = it & 1, phase parity = (it >> 1) & 1)
@@ -288,46 +286,42 @@ struct WarpPipe {
 struct TileIt { uint32_t cls, base; };
 
 template <int PB, int PC>
-__device__ __forceinline__ TileIt tile_first(const WarpPipe &wp) {
-  TileIt t{0u, wp.e_lo};
-  if (t.base >= wp.e_hi) {
+__device__ __forceinline__ TileIt tile_first(const TileSrc &ts, uint32_t warp) {
+  TileIt t{0u, warp * WarpTile<PB, PC>::TE};
+  if (t.base >= ts.n_e) {
     t.cls = 1u;
-    t.base = wp.p_lo;
-    if (t.base >= wp.p_hi) t.cls = 2u;
+    t.base = warp * WarpTile<PB, PC>::TP;
+    if (t.base >= ts.n_p) t.cls = 2u;
   }
   return t;
 }
 template <int PB, int PC>
-__device__ __forceinline__ TileIt tile_next(const WarpPipe &wp, TileIt t) {
+__device__ __forceinline__ TileIt tile_next(const TileSrc &ts, uint32_t warp, TileIt t) {
   if (t.cls == 0u) {
-    t.base += WarpTile<PB, PC>::TE;
-    if (t.base >= wp.e_hi) {
+    t.base += kLmWarps * WarpTile<PB, PC>::TE;
+    if (t.base >= ts.n_e) {
       t.cls = 1u;
-      t.base = wp.p_lo;
-      if (t.base >= wp.p_hi) t.cls = 2u;
+      t.base = warp * WarpTile<PB, PC>::TP;
+      if (t.base >= ts.n_p) t.cls = 2u;
     }
   } else {
-    t.base += WarpTile<PB, PC>::TP;
-    if (t.base >= wp.p_hi) t.cls = 2u;
+    t.base += kLmWarps * WarpTile<PB, PC>::TP;
+    if (t.base >= ts.n_p) t.cls = 2u;
   }
   return t;
-}
-// entries of tile t (the last tile of a share is short)
-template <int PB, int PC>
-__device__ __forceinline__ uint32_t tile_count(const WarpPipe &wp, TileIt t) {
-  return t.cls == 0u ? min(WarpTile<PB, PC>::TE, wp.e_hi - t.base) : min(WarpTile<PB, PC>::TP, wp.p_hi - t.base);
 }
 
 // lane 0: two bulk copies (points, constants) of tile t into the stage at shared address dst
 template <int PB, int PC>
-__device__ __forceinline__ void issue_warp_tile(const TileSrc &ts, const WarpPipe &wp, TileIt t, uint32_t dst, uint32_t bar) {
+__device__ __forceinline__ void issue_warp_tile(const TileSrc &ts, TileIt t, uint32_t dst, uint32_t bar) {
   using WT = WarpTile<PB, PC>;
-  const uint32_t cnt = tile_count<PB, PC>(wp, t);
   if (t.cls == 0u) {
+    const uint32_t cnt = min(WT::TE, ts.n_e - t.base);
     mbar_expect_tx_s(bar, cnt * (uint32_t)(PB + 48));
     tma_load_1d_s(dst, ts.pe + (size_t)t.base * PB, cnt * (uint32_t)PB, bar);
     tma_load_1d_s(dst + WT::TE * PB, (const unsigned char *)ts.ce + (size_t)t.base * 48, cnt * 48u, bar);
   } else {
+    const uint32_t cnt = min(WT::TP, ts.n_p - t.base);
     mbar_expect_tx_s(bar, cnt * (uint32_t)(PB + PC));
     tma_load_1d_s(dst, ts.pp + (size_t)t.base * PB, cnt * (uint32_t)PB, bar);
     tma_load_1d_s(dst + WT::TP * PB, (const unsigned char *)ts.cp + (size_t)t.base * PC, cnt * (uint32_t)PC, bar);
@@ -352,11 +346,11 @@ __device__ __forceinline__ void load_point_s(uint32_t a, double &p0, double &p1,
 
 // all entries of one tile that sits in shared memory at `buf`
 template <int PB, int PC>
-__device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx &cx, const WarpPipe &wp, TileIt t, uint32_t buf,
+__device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx &cx, const TileSrc &ts, TileIt t, uint32_t buf,
                                              uint32_t lane, int &cnt_edge, int &cnt_plane) {
   using WT = WarpTile<PB, PC>;
-  const uint32_t cnt = tile_count<PB, PC>(wp, t);
   if (t.cls == 0u) {
+    const uint32_t cnt = min(WT::TE, ts.n_e - t.base);
     uint32_t pa = buf + lane * PB, ca = buf + WT::TE * PB + lane * 48;
 #pragma unroll 1
     for (uint32_t ent = lane; ent < cnt; ent += 32, pa += 32 * PB, ca += 32 * 48) {
@@ -371,6 +365,7 @@ __device__ __forceinline__ void consume_tile(double (&acc)[kAcc], const SweepCtx
       }
     }
   } else {
+    const uint32_t cnt = min(WT::TP, ts.n_p - t.base);
     uint32_t pa = buf + lane * PB, ca = buf + WT::TP * PB + lane * PC;
     // 32 B entries: lanes 4..7 (mod 8) fetch the upper half first so that a quarter-warp's eight 16 B reads
     // cover all 32 banks
@@ -401,7 +396,7 @@ template <int PB, int PC>
 __device__ __forceinline__ void sweep_warp(double (&acc)[kAcc], const TileSrc &ts, WarpPipe &wp, const double *pose, double huber_a,
                                            double sqrt_huber_a, int &cnt_edge, int &cnt_plane) {
   using WT = WarpTile<PB, PC>;
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
   SweepCtx cx;
@@ -410,32 +405,32 @@ __device__ __forceinline__ void sweep_warp(double (&acc)[kAcc], const TileSrc &t
   cx.huber_a = Huber{huber_a, huber_a * huber_a, sqrt_huber_a};
   cnt_edge = 0;
   cnt_plane = 0;
-  TileIt cur = tile_first<PB, PC>(wp);
-  if (cur.cls == 2u) return;  // fewer entries than warps: nothing for this warp
+  TileIt cur = tile_first<PB, PC>(ts, warp);
+  if (cur.cls == 2u) return;  // fewer tiles than warps: nothing for this warp
   if (wp.resident) {
     if (!wp.loaded && lane == 0) {
       uint32_t k = 0;
-      for (TileIt t = cur; t.cls != 2u; t = tile_next<PB, PC>(wp, t), ++k)
-        issue_warp_tile<PB, PC>(ts, wp, t, wp.ring + k * WT::SB, wp.bars + k * 8u);
+      for (TileIt t = cur; t.cls != 2u; t = tile_next<PB, PC>(ts, warp, t), ++k)
+        issue_warp_tile<PB, PC>(ts, t, wp.ring + k * WT::SB, wp.bars + k * 8u);
     }
     uint32_t k = 0;
-    for (; cur.cls != 2u; cur = tile_next<PB, PC>(wp, cur), ++k) {
+    for (; cur.cls != 2u; cur = tile_next<PB, PC>(ts, warp, cur), ++k) {
       if (!wp.loaded) mbar_wait_s(wp.bars + k * 8u, 0u);
-      consume_tile<PB, PC>(acc, cx, wp, cur, wp.ring + k * WT::SB, lane, cnt_edge, cnt_plane);
+      consume_tile<PB, PC>(acc, cx, ts, cur, wp.ring + k * WT::SB, lane, cnt_edge, cnt_plane);
     }
     wp.loaded = true;
     return;
   }
-  if (!wp.loaded && lane == 0) issue_warp_tile<PB, PC>(ts, wp, cur, wp.ring + (wp.it & 1u) * WT::SB, wp.bars + (wp.it & 1u) * 8u);
+  if (!wp.loaded && lane == 0) issue_warp_tile<PB, PC>(ts, cur, wp.ring + (wp.it & 1u) * WT::SB, wp.bars + (wp.it & 1u) * 8u);
   for (;;) {
-    TileIt nxt = tile_next<PB, PC>(wp, cur);
+    TileIt nxt = tile_next<PB, PC>(ts, warp, cur);
     const bool last = nxt.cls == 2u;
-    if (last) nxt = tile_first<PB, PC>(wp);  // prefetch across the sweep boundary
+    if (last) nxt = tile_first<PB, PC>(ts, warp);  // prefetch across the sweep boundary
     const uint32_t s = wp.it & 1u;
     // the other stage held the previous tile: every lane left it at the __syncwarp below
-    if (lane == 0) issue_warp_tile<PB, PC>(ts, wp, nxt, wp.ring + (s ^ 1u) * WT::SB, wp.bars + (s ^ 1u) * 8u);
+    if (lane == 0) issue_warp_tile<PB, PC>(ts, nxt, wp.ring + (s ^ 1u) * WT::SB, wp.bars + (s ^ 1u) * 8u);
     mbar_wait_s(wp.bars + s * 8u, (wp.it >> 1) & 1u);
-    consume_tile<PB, PC>(acc, cx, wp, cur, wp.ring + s * WT::SB, lane, cnt_edge, cnt_plane);
+    consume_tile<PB, PC>(acc, cx, ts, cur, wp.ring + s * WT::SB, lane, cnt_edge, cnt_plane);
     __syncwarp();
     ++wp.it;
     if (last) break;
@@ -457,11 +452,8 @@ __device__ __forceinline__ WarpPipe warp_pipe_init(const TileSrc &ts, unsigned c
   wp.ring = smem_u32(ring_cta) + warp * n_stages * WT::SB;
   wp.bars = smem_u32(bars_cta) + warp * kMaxWarpStages * 8u;
   wp.it = 0;
-  wp.e_lo = (uint32_t)(((uint64_t)ts.n_e * warp) / kLmWarps);
-  wp.e_hi = (uint32_t)(((uint64_t)ts.n_e * (warp + 1)) / kLmWarps);
-  wp.p_lo = (uint32_t)(((uint64_t)ts.n_p * warp) / kLmWarps);
-  wp.p_hi = (uint32_t)(((uint64_t)ts.n_p * (warp + 1)) / kLmWarps);
-  wp.my_tiles = (wp.e_hi - wp.e_lo + WT::TE - 1) / WT::TE + (wp.p_hi - wp.p_lo + WT::TP - 1) / WT::TP;
+  const uint32_t tt_e = (ts.n_e + WT::TE - 1) / WT::TE, tt_p = (ts.n_p + WT::TP - 1) / WT::TP;
+  wp.my_tiles = (tt_e > warp ? (tt_e - warp + kLmWarps - 1) / kLmWarps : 0u) + (tt_p > warp ? (tt_p - warp + kLmWarps - 1) / kLmWarps : 0u);
   wp.resident = n_stages > (uint32_t)kWarpStages && wp.my_tiles <= n_stages;
   wp.loaded = false;
   return wp;

@@ -257,6 +257,8 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   e->sm_count = prop.multiProcessorCount;
   fill_kparams(e);
   if (const char *v = getenv("MSFL_COUNT_SORT_MAX_BINS")) e->count_sort_max_bins = atoll(v);  // tests: force the radix path
+  if (const char *v = getenv("MSFL_SEED_KNN")) e->seed_knn = atoi(v) != 0;
+  if (const char *v = getenv("MSFL_RESORT_OUTER")) e->resort_outer = atoi(v) != 0;
   if (stream) {
     e->stream = (cudaStream_t)stream;
     e->own_stream = false;
@@ -291,7 +293,7 @@ void msfl_destroy(msfl_engine *e) {
                    &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
                    &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc,
                    &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp, &e->a_hist,
-                   &e->k_table, &e->k_dsk, &e->k_pprime};
+                   &e->k_table, &e->k_dsk, &e->k_pprime, &e->d_knn2, &e->a_inv, &e->a_inv2, &e->a_fb};
   for (DevBuf *b : dbs) b->release();
   for (auto &sl : e->slots) {
     sl.d_in.release(); sl.d_stats.release(); sl.h_stage.release(); sl.h_out.release(); sl.h_stats.release();
@@ -378,7 +380,7 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
     const bool compact = true;  // plane constants as 32 B {n, n.c}
     // the cell order is rebuilt for every outer iteration: the first solve moves points by up to ~0.3 m, and
     // re-ordering (0.26 ms) is cheaper than searching with a stale order
-    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr, compact)))
+    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr, compact, outer)))
       return rc;
     stage_begin(e, 1);
     rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
@@ -533,6 +535,10 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
   if ((rc = e->d_corr.reserve((max_total + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   if ((rc = e->d_knn.reserve(max_total * 20))) return rc;
+  if ((rc = e->d_knn2.reserve(max_total * 20))) return rc;
+  if ((rc = e->a_inv.reserve(max_total * 4))) return rc;
+  if ((rc = e->a_inv2.reserve(max_total * 4))) return rc;
+  if ((rc = e->a_fb.reserve((max_total + 2) * 4))) return rc;
   if ((rc = e->a_xq.reserve(max_total * 16))) return rc;
   if ((rc = e->a_keys.reserve(max_total * 4))) return rc;
   if ((rc = e->a_keys_alt.reserve(max_total * 4))) return rc;
