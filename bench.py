@@ -4,12 +4,14 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
   python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
 
-One "step" = one pass of MatchScan2Map over a batch of independent synthetic scans against one
-shared submap (BASELINE config 2 shape at N=1: VLP-16 scan vs 5-scan corner/surf submap, 2 outer
-iterations x 5 LM attempts; config 4 at N>1: scans sharded over GPUs, submap broadcast with NCCL).
-Inputs are produced by the product path itself (ray-cast -> CUDA feature extraction -> CUDA
-VoxelGrid); the CPU oracle is only executed for `cpu_baseline`, the pose check, and `--impl reference`.
-Prints ONE JSON line (rank 0).
+One "step" = one pass of MatchScan2Map over a batch of independent synthetic scans against one shared submap.
+The headline line is BASELINE config 2 (VLP-16 scan vs 5-scan corner/surf submap, 2 outer iterations x 5 LM
+attempts); at N>1 the scans are sharded over the GPUs and every step the owner rank re-indexes the submap and
+broadcasts it WITH its cell index through the C ABI (msfl_bcast_submap, NCCL), the other ranks adopt it (config 4).
+The same JSON line carries a `workloads` record with BASELINE configs 3 (HDL-64E), 4 (one scan per GPU, broadcast
++ adoption + solve latency) and 5 (OS1-128 vs a ~1 M-point 50-scan submap, batch 1 / 8 / 64 per GPU).
+Inputs are produced by the product path itself (ray-cast -> CUDA feature extraction -> CUDA VoxelGrid); the CPU
+oracle is only executed for `cpu_baseline`, the pose checks, and `--impl reference`.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -28,29 +30,34 @@ sys.path.insert(0, ROOT)
 
 from msf_loam_b200 import synth as S  # noqa: E402
 
+# name: sensor, scene, submap scans, trajectory (step m, yaw deg, jitter deg, start), description
 WORKLOADS = {
-    # name: (sensor, scene, description)
-    "vlp16": ("vlp16", "room40", "VLP-16 scan-to-map: 29k-pt scan vs 5-scan corner/surf submap, 10 LM iters"),
-    "hdl64": ("hdl64", "room80", "HDL-64E-shape scan (~130k pts) scan-to-map vs 5-scan submap, 10 LM iters"),
-    "os1-128": ("os1-128", "room80", "OS1-128-shape scan (~260k pts) scan-to-map vs 5-scan submap, 10 LM iters"),
+    "vlp16": dict(sensor="vlp16", scene="room40", map_scans=5, traj=dict(step=0.5, yaw_deg=1.0), seed0=100,
+                  desc="VLP-16 scan-to-map: 29k-pt scan vs 5-scan corner/surf submap, 10 LM iters"),
+    "hdl64": dict(sensor="hdl64", scene="room80", map_scans=5, traj=dict(step=0.5, yaw_deg=1.0), seed0=200,
+                  desc="HDL-64E KITTI-shape scan (~130k pts, 64 rings) scan-to-map vs 5-scan submap, 10 LM iters"),
+    "os1-128": dict(sensor="os1-128", scene="hall300", map_scans=50, seed0=400,
+                    traj=dict(step=5.0, yaw_deg=0.0, jitter_deg=0.05, start=(-140.0, -3.0, 1.5)),
+                    desc="OS1-128-shape 260k-pt scan vs ~1M-pt (50-scan) submap, 10 LM iters"),
 }
-N_MAP_SCANS = 5
 SIGMA = 0.01
 K_OUTER, L_ATTEMPTS = 2, 5  # "10 LM iters" = 2 outer x 5 attempts, fixed count
+OVER = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vlp16", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=2048, help="scans per GPU per step")
+    ap.add_argument("--workload", default="vlp16", choices=sorted(WORKLOADS), help="headline workload")
+    ap.add_argument("--batch", type=int, default=2048, help="scans per GPU per step (headline workload)")
     ap.add_argument("--distinct", type=int, default=32, help="distinct query scans (replicated to fill the batch)")
     ap.add_argument("--cpu-sample", type=int, default=1536, help="scans timed on the CPU oracle for cpu_baseline")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
-    ap.add_argument("--map-scans", type=int, default=N_MAP_SCANS, help="scans merged into the submap (config 5: 50)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / pose-check legs (development)")
+    ap.add_argument("--no-workloads", action="store_true", help="headline workload only (development, profiling)")
+    ap.add_argument("--only-device", action="store_true", help="device-resident leg only (profiling under ncu)")
     return ap.parse_args()
 
 
@@ -61,49 +68,40 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # workload generation
 # ------------------------------------------------------------------------------------------------
-def raw_scans(workload, n_distinct, n_map=N_MAP_SCANS):
-    sensor, scene_kind, _ = WORKLOADS[workload]
-    scene = S.make_scene(scene_kind)
-    # long maps: shorter steps so the trajectory stays inside the room
-    traj = S.trajectory(n_map + n_distinct, step=0.5 if n_map <= 8 else 0.25, yaw_deg=1.0 if n_map <= 8 else 0.5)
-    scans = [S.raycast_scan(scene, sensor, traj[k], seed=100 + k, sigma=SIGMA) for k in range(len(traj))]
+def _raycast_job(a):
+    workload, k, pose = a
+    w = WORKLOADS[workload]
+    return S.raycast_scan(S.make_scene(w["scene"]), w["sensor"], pose, seed=w["seed0"] + k, sigma=SIGMA)
+
+
+def raw_scans(workload, n_distinct, n_workers=1):
+    """Trajectory + raw ray-cast scans (numpy; done before any CUDA context exists so a fork pool is safe)."""
+    w = WORKLOADS[workload]
+    traj = S.trajectory(w["map_scans"] + n_distinct, **w["traj"])
+    jobs = [(workload, k, traj[k]) for k in range(len(traj))]
+    if n_workers > 1 and len(jobs) > 8:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(n_workers, len(jobs))) as pool:
+            scans = pool.map(_raycast_job, jobs, chunksize=1)
+    else:
+        scans = [_raycast_job(j) for j in jobs]
     return traj, scans
 
 
-def build_case_gpu(eng, workload, n_distinct, n_map=N_MAP_SCANS):
-    """submap + query features through the product path (CUDA extraction + CUDA VoxelGrid)."""
-    traj, scans = raw_scans(workload, n_distinct, n_map)
+def build_case(extract, voxel, workload, traj, scans):
+    """submap + query features; `extract` / `voxel` are the engine's (product path) or the oracle's (reference arm)."""
+    n_map = WORKLOADS[workload]["map_scans"]
     mc, ms, queries, n_pts = [], [], [], []
     for k, (xyzi, ring) in enumerate(scans):
-        f = eng.extract_features(xyzi, ring, None)
+        f = extract(xyzi, ring)
         n_pts.append(f["full"].shape[0])
         corner, surf = f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]]
         if k < n_map:
             mc.append(S.transform_cloud(traj[k], corner))
             ms.append(S.transform_cloud(traj[k], surf))
         else:
-            queries.append((eng.voxel_grid(corner, 0.2), eng.voxel_grid(surf, 0.4), traj[k]))
-    map_corner = eng.voxel_grid(np.concatenate(mc), 0.2)
-    map_surf = eng.voxel_grid(np.concatenate(ms), 0.4)
-    return map_corner, map_surf, queries, int(np.mean(n_pts))
-
-
-def build_case_cpu(workload, n_distinct, n_map=N_MAP_SCANS):
-    """same case through the oracle (the reference arm must not touch our kernels)."""
-    import oracle as O
-    P = O.default_params()
-    traj, scans = raw_scans(workload, n_distinct, n_map)
-    mc, ms, queries, n_pts = [], [], [], []
-    for k, (xyzi, ring) in enumerate(scans):
-        f = O.extract_features(P, xyzi, ring, None)
-        n_pts.append(f["full"].shape[0])
-        corner, surf = f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]]
-        if k < n_map:
-            mc.append(S.transform_cloud(traj[k], corner))
-            ms.append(S.transform_cloud(traj[k], surf))
-        else:
-            queries.append((O.voxel_grid(corner, 0.2), O.voxel_grid(surf, 0.4), traj[k]))
-    return O.voxel_grid(np.concatenate(mc), 0.2), O.voxel_grid(np.concatenate(ms), 0.4), queries, int(np.mean(n_pts))
+            queries.append((voxel(corner, 0.2), voxel(surf, 0.4), traj[k]))
+    return voxel(np.concatenate(mc), 0.2), voxel(np.concatenate(ms), 0.4), queries, int(np.mean(n_pts))
 
 
 def assemble_batch(queries, B, seed):
@@ -123,6 +121,15 @@ def algorithmic_bytes(N, M, K=K_OUTER, L=L_ATTEMPTS):
     assoc = 16 * M + 48 * N            # queries + submap once + correspondences written
     solve = 48 * (1 + L) * N           # one fused residual/Jacobian/cost sweep per evaluation point
     return K * (assoc + solve), assoc, solve
+
+
+def workload_config(workload, B, queries, n_full, n_q, Mc, Ms):
+    """The workload description shared VERBATIM by the CUDA arm and the reference arm (the driver compares it)."""
+    return {"workload": WORKLOADS[workload]["desc"], "sensor": workload, "scans_per_gpu_per_step": B,
+            "distinct_scans": len(queries), "points_per_scan": n_full, "queries_per_scan": round(n_q / B, 1),
+            "submap_points": {"corner": Mc, "surf": Ms}, "submap_scans": WORKLOADS[workload]["map_scans"],
+            "outer_iterations": K_OUTER, "lm_attempts_per_outer": L_ATTEMPTS, "early_exit": False,
+            "range_noise_sigma_m": SIGMA, "initial_guess_error": "0.10 m, 1.0 deg (seeded)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -178,7 +185,8 @@ class ClockSampler:
             pw = np.array(power)
             load = pw >= (pw.min() + 0.5 * (pw.max() - pw.min())) if pw.max() > pw.min() else np.ones_like(pw, bool)
             out.update(sm_mhz=float(np.median(np.array(sm)[load])), sm_max_mhz=float(max(smax)),
-                       reasons=sorted(reasons), samples=len(sm), power_w_max=float(pw.max()))
+                       reasons=sorted(reasons), samples=len(sm), samples_under_load=int(load.sum()),
+                       power_w_max=float(pw.max()))
         return out
 
 
@@ -191,62 +199,115 @@ def measured_peak():
 
 
 def ncu_traffic(workload, batch):
-    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    """dram read+write bytes per launch of the stage kernels from the committed ncu capture of this command
+    (profiles/roofline_traffic.json; ncu cannot run inside the timed process)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            t = json.load(f)
-        e = t.get(f"{workload}:{batch}")
-        return (float(e["bytes_per_launch"]), e.get("kernel")) if e else (None, None)
+            return json.load(f).get(f"{workload}:{batch}")
     except Exception:
-        return None, None
+        return None
+
+
+def numa_bind(local_rank):
+    """Binds this rank to the NUMA node of its GPU when the box exposes more than one node (pinned buffers are then
+    allocated node-local by first touch).  Returns a description for the JSON record."""
+    try:
+        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except OSError:
+        nodes = []
+    info = {"numa_nodes_visible": len(nodes), "cpus": len(os.sched_getaffinity(0)), "bound": None}
+    if len(nodes) < 2:
+        return info
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id  # type: ignore[attr-defined]
+    except Exception:
+        bdf = None
+    try:
+        q = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True).stdout.strip().lower()
+        if q.startswith("00000000:"):
+            q = "0000:" + q[9:]
+        with open(f"/sys/bus/pci/devices/{q}/numa_node") as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"] = {"node": node, "cpus": len(cpus)}
+    except Exception as ex:  # topology not readable inside the container: stay unbound
+        info["error"] = str(ex)[:80]
+    return info
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+STAGE_NAMES = {0: "k_knn5_fit (5-NN search over the submap cell index + plane fit)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
+               2: "k_transform_keys + counting sort of the cell keys", 3: "k_fit (fp64 line fit, Householder fallback)"}
+
+
+class Ctx:
+    pass
+
+
+def run_workload(cx, workload, B, n_distinct, steps, warmup, full, lm_cluster=0, sampler=True, e2e=True, cpu_scans=0,
+                 bcast=True, remap=False):
+    """One workload on every rank: device-resident leg (`value`), host-buffer legs (`e2e`), roofline, pose check."""
     import torch
     import torch.distributed as dist
-    from msf_loam_b200 import Engine, default_params
+    from msf_loam_b200 import Engine, default_params, to_pcl
 
-    rank, local_rank, world = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    over = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
-    if os.environ.get("MSFL_BENCH_LM_CLUSTER"):  # development: thread-block cluster size of the LM kernel
-        over["lm_cluster"] = int(os.environ["MSFL_BENCH_LM_CLUSTER"])
+    args, rank, world, dev = cx.args, cx.rank, cx.world, cx.dev
+    over = dict(OVER)
+    if lm_cluster:
+        over["lm_cluster"] = lm_cluster
     stream = torch.cuda.Stream(device=dev)
+    rec = {}
     with torch.cuda.stream(stream):
-        eng = Engine(default_params(**over), device=local_rank, stream=stream.cuda_stream)
-        # ---- inputs (product path) -------------------------------------------------------------
-        map_corner, map_surf, queries, n_full = build_case_gpu(eng, args.workload, args.distinct, args.map_scans)
+        eng = Engine(default_params(**over), device=cx.local_rank, stream=stream.cuda_stream)
+        traj, scans = cx.raw[workload]
+        map_corner, map_surf, queries, n_full = build_case(lambda x, r: eng.extract_features(x, r, None), eng.voxel_grid,
+                                                           workload, traj, scans)
+        queries = queries[:n_distinct]
+        if B < len(queries):  # fewer scans than distinct ones (config 4): every rank takes its own
+            r = (rank * B) % len(queries)
+            queries = queries[r:] + queries[:r]
         qc, c_off, qs, s_off, inits = assemble_batch(queries, B, seed=1000 + rank)
         Mc, Ms = map_corner.shape[0], map_surf.shape[0]
         n_q = int(c_off[-1] + s_off[-1])
-        # submap: owned by rank 0, broadcast over NCCL (config 4), indexed on every rank
-        if world > 1:
+        # the submap is owned by rank 0; every step rank 0 indexes a new map version and broadcasts it with its index
+        # (C ABI, NCCL), the other ranks adopt it without building anything
+        t_mc, t_ms = torch.from_numpy(map_corner).to(dev), torch.from_numpy(map_surf).to(dev)
+        comm = None
+        if world > 1 and bcast:
             from msf_loam_b200 import sharding
-            t_mc, t_ms = sharding.broadcast_submap(map_corner if rank == 0 else None, map_surf if rank == 0 else None,
-                                                   src=0, device=dev)
-        else:
-            t_mc, t_ms = torch.from_numpy(map_corner).to(dev), torch.from_numpy(map_surf).to(dev)
-        stream.synchronize()
-        eng.set_submap_device(t_mc.data_ptr(), Mc, t_ms.data_ptr(), Ms)
-        # device-resident batch
+            comm = sharding.make_submap_comm(eng, device=dev)
+        if rank == 0 or comm is None:
+            eng.set_submap_device(t_mc.data_ptr(), Mc, t_ms.data_ptr(), Ms)
+        if comm is not None:
+            eng.bcast_submap(comm, 0)
         d_qc, d_qs = torch.from_numpy(qc).to(dev), torch.from_numpy(qs).to(dev)
         d_co, d_so = torch.from_numpy(c_off).to(dev), torch.from_numpy(s_off).to(dev)
         d_p0 = torch.from_numpy(inits).to(dev)
         d_p = d_p0.clone()
 
+        def new_map_version():
+            if comm is None:
+                if remap:  # single GPU: the new map version is indexed in place
+                    eng.set_submap_device(t_mc.data_ptr(), Mc, t_ms.data_ptr(), Ms)
+                return
+            if rank == 0:
+                eng.set_submap_device(t_mc.data_ptr(), Mc, t_ms.data_ptr(), Ms)
+            eng.bcast_submap(comm, 0)
+
         def step_device():
-            if world > 1:  # the shared submap travels once per batch (config 4)
-                dist.broadcast(t_mc, 0)
-                dist.broadcast(t_ms, 0)
+            new_map_version()
             d_p.copy_(d_p0)
             eng.scan2map_batch_device(B, d_qc.data_ptr(), d_co.data_ptr(), int(c_off[-1]), d_qs.data_ptr(),
                                       d_so.data_ptr(), int(s_off[-1]), d_p.data_ptr())
@@ -256,8 +317,8 @@ def run_ours(args):
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
-        sampler = ClockSampler(local_rank)
-        for _ in range(max(args.warmup, 3)):
+        smp = ClockSampler(cx.local_rank) if sampler else None
+        for _ in range(max(warmup, 3)):
             step_device()
         barrier()
         eng.get_profile()
@@ -266,7 +327,7 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_device()
         ev1.record(stream)
         barrier()
@@ -275,135 +336,221 @@ def run_ours(args):
         stage_ms, stage_cnt = eng.get_profile()
         eng.set_profiling(False)
         poses_dev = d_p.cpu().numpy()
+        rec["clocks"] = smp.stop() if smp else None
 
-        # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -----------
-        h_qc = torch.from_numpy(qc).pin_memory()
-        h_qs = torch.from_numpy(qs).pin_memory()
-        hc, hs = h_qc.numpy(), h_qs.numpy()
-        prepared = eng.prepare_batch([hc[c_off[i]:c_off[i + 1]] for i in range(B)],
-                                     [hs[s_off[i]:s_off[i + 1]] for i in range(B)])
-        h_p = inits.copy()
-        for _ in range(2):
+        e2e_ms = e2e_pcl_ms = e2e_sync_ms = None
+        if e2e and not args.only_device:
+            # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ---------------------
+            h_qc, h_qs = torch.from_numpy(qc).pin_memory(), torch.from_numpy(qs).pin_memory()
+            hc, hs = h_qc.numpy(), h_qs.numpy()
+            packed = eng.prepare_batch([hc[c_off[i]:c_off[i + 1]] for i in range(B)],
+                                       [hs[s_off[i]:s_off[i + 1]] for i in range(B)])
+            # the layout the reference's adapter passes: one pcl::PointCloud<pcl::PointXYZI> per cloud (32 B points,
+            # pageable memory, separate allocations); the library repacks them into its pinned slot on host threads
+            D = len(queries)  # every scan of the batch gets its own arrays, as B independent clouds would have
+            pcl = eng.prepare_batch([to_pcl(queries[i % D][0]) for i in range(B)], [to_pcl(queries[i % D][1]) for i in range(B)])
+            h_p = inits.copy()
+            eng.scan2map_prepared(packed, h_p)  # synchronous call (the ROS drop-in form)
+            assert np.array_equal(h_p, poses_dev), "host-buffer and device-resident paths disagree"
             h_p[:] = inits
-            eng.scan2map_prepared(prepared, h_p)  # synchronous call (the ROS drop-in form)
-        assert np.array_equal(h_p, poses_dev), "host-buffer and device-resident paths disagree"
-        # timed: a stream of batches through msfl_scan2map_batch_submit / _wait, two in flight, so the upload
-        # of step k+1 overlaps the kernels of step k; every step's inputs come from pinned host memory and
-        # every step's poses are read back to the host inside the timed region
-        h_out = [np.zeros_like(inits), np.zeros_like(inits)]
-        tk = eng.scan2map_submit(prepared, inits)
-        eng.scan2map_wait(tk, h_out[0])
-        e2e_runs = []
-        for _ in range(3):  # K steps each; the median run is reported (host-side timing of a ~40 ms region is noisy)
-            barrier()
-            t0 = time.perf_counter()
-            tk = eng.scan2map_submit(prepared, inits)
-            for i in range(1, args.steps):
-                tk2 = eng.scan2map_submit(prepared, inits)
-                eng.scan2map_wait(tk, h_out[(i - 1) & 1])
-                tk = tk2
-            eng.scan2map_wait(tk, h_out[(args.steps - 1) & 1])
-            torch.cuda.synchronize(dev)
-            e2e_runs.append(time.perf_counter() - t0)
-        e2e_s = sorted(e2e_runs)[1]
-        # the synchronous single-call form, for the record (exposes the first chunk's upload every step)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            h_p[:] = inits
-            eng.scan2map_prepared(prepared, h_p)
-        e2e_sync_s = time.perf_counter() - t0
-        clocks = sampler.stop()
-        # BASELINE config 2 as the ROS node runs it: ONE scan per call through the synchronous C ABI (pageable host
-        # buffers, stream sync per call); lm_cluster = 8 spreads the solve over an 8-CTA thread-block cluster
-        single = None
-        if rank == 0:
-            single = {}
-            c0, s0 = qc[c_off[0]:c_off[1]], qs[s_off[0]:s_off[1]]
-            for G in (1, 8):
-                e1 = Engine(default_params(lm_cluster=G, **over), device=local_rank)
-                e1.set_submap(map_corner, map_surf)
-                for _ in range(5):
-                    e1.scan2map(c0, s0, inits[0], want_stats=False)
-                t0 = time.perf_counter()
-                for _ in range(40):
-                    e1.scan2map(c0, s0, inits[0], want_stats=False)
-                single[f"lm_cluster_{G}_us_per_scan"] = round((time.perf_counter() - t0) / 40 * 1e6, 1)
-                e1.close()
-    assert np.array_equal(h_out[0], poses_dev) and (args.steps < 2 or np.array_equal(h_out[1], poses_dev)), \
-        "pipelined host-buffer path and device-resident path disagree"
+            eng.scan2map_prepared(pcl, h_p)
+            assert np.array_equal(h_p, poses_dev), "PCL-layout host path and device-resident path disagree"
+            h_out = [np.zeros_like(inits), np.zeros_like(inits)]
+
+            def pipelined(prepared):
+                """K steps through msfl_scan2map_batch_submit / _wait, two in flight: the upload of step k+1 overlaps
+                the kernels of step k; every step's inputs come from host memory, every step's poses return to it."""
+                new_map_version()
+                tk = eng.scan2map_submit(prepared, inits)
+                for i in range(1, steps):
+                    new_map_version()
+                    tk2 = eng.scan2map_submit(prepared, inits)
+                    eng.scan2map_wait(tk, h_out[(i - 1) & 1])
+                    tk = tk2
+                eng.scan2map_wait(tk, h_out[(steps - 1) & 1])
+                torch.cuda.synchronize(dev)
+
+            def timed(fn, reps=3):
+                runs = []
+                for _ in range(reps):  # the median run is reported (host-side timing of a short region is noisy)
+                    barrier()
+                    t0 = time.perf_counter()
+                    fn()
+                    runs.append(time.perf_counter() - t0)
+                return sorted(runs)[len(runs) // 2] * 1e3
+
+            pipelined(packed)
+            e2e_ms = timed(lambda: pipelined(packed))
+            assert np.array_equal(h_out[0], poses_dev) and (steps < 2 or np.array_equal(h_out[1], poses_dev)), \
+                "pipelined host-buffer path and device-resident path disagree"
+            pipelined(pcl)
+            e2e_pcl_ms = timed(lambda: pipelined(pcl))
+            assert np.array_equal(h_out[0], poses_dev), "pipelined PCL-layout path and device-resident path disagree"
+
+            def sync_calls():  # the synchronous single-call form, for the record
+                for _ in range(steps):
+                    new_map_version()
+                    h_p[:] = inits
+                    eng.scan2map_prepared(packed, h_p)
+            e2e_sync_ms = timed(sync_calls, reps=1)
+        if comm is not None:
+            eng.sync()
+            eng.nccl_comm_destroy(comm)
+        eng.close()
 
     # max over ranks
-    t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
+    vals = [ms_total, e2e_ms or 0.0, e2e_pcl_ms or 0.0, e2e_sync_ms or 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
-    ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total * 1e-3)
-    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    ms_total, e2e_ms, e2e_pcl_ms, e2e_sync_ms = (float(v) for v in t)
+    ms_per_step = ms_total / steps
+    rate = lambda ms: round(world * B * steps / (ms * 1e-3), 1) if ms else None  # noqa: E731
+    rec.update(value=rate(ms_total), ms_per_step=round(ms_per_step, 4), gpu_launches=int(launches))
+    if rank != 0:
+        return rec
+    peak, peak_src = measured_peak()
+    total_bytes, assoc_bytes, solve_bytes = algorithmic_bytes(n_q, Mc + Ms)
+    per_launch_ms = {s: stage_ms[s] / stage_cnt[s] for s in range(len(stage_ms)) if stage_cnt[s]}
+    dom = max(per_launch_ms, key=lambda s: stage_ms[s])  # dominant kernel = the stage with the largest share of the step
+    dom_bytes = assoc_bytes if dom in (0, 2, 3) else solve_bytes
+    achieved = dom_bytes / (per_launch_ms[dom] * 1e-3) / 1e9
+    tr = ncu_traffic(workload, B) or {}
+    rec["roofline"] = {
+        "bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 5), "traffic": tr.get(str(dom)), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": round(per_launch_ms[dom], 4),
+        "stage_ms_per_step": {STAGE_NAMES[s]: round(stage_ms[s] / steps, 4) for s in per_launch_ms},
+        "stage_share": {STAGE_NAMES[s]: round(stage_ms[s] / sum(stage_ms), 3) for s in per_launch_ms},
+        "whole_step_GBps": round(total_bytes / (ms_per_step * 1e-3) / 1e9, 2),
+        "whole_step_frac": round(total_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+        "traffic_source": tr.get("source"),
+        "note": "achieved = SURVEY 8d algorithmic bytes of that pass / CUDA-event time of the stage; DESIGN.md section 4"}
+    rec["config"] = workload_config(workload, B, queries, n_full, n_q, Mc, Ms)
+    rec["impl_notes"] = {
+        "parallelism": f"scan-sharded x{world}" + (", per step: rank 0 re-indexes the submap, msfl_bcast_submap "
+                                                    "(NCCL, points + cell index), other ranks adopt" if world > 1 and bcast else ""),
+        "lm_cluster": lm_cluster or 1,
+        "l2": "per-step inputs + correspondences (%.0f MB) vs the 126 MB L2" % ((n_q * 16 + n_q * 48) / 1e6)}
+    if e2e_ms:
+        h2d = int(n_q * 16 + (2 * (B + 1)) * 4 + B * 56)
+        rec["e2e"] = {"value": rate(e2e_ms), "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(B * 56),
+                      "api": "msfl_scan2map_batch_submit/_wait, 2 batches in flight, packed float4 clouds in pinned host "
+                             "memory; median of 3 runs of K steps",
+                      "h2d_GBps_per_rank": round(h2d * steps / (e2e_ms * 1e-3) / 1e9, 2),
+                      "pcl_layout_value": rate(e2e_pcl_ms),
+                      "pcl_layout": "same calls fed one pcl::PointXYZI-layout array per cloud (32 B points, pageable, "
+                                    "separate allocations): repacked into the pinned slot by %s host threads" %
+                                    os.environ.get("MSFL_PACK_THREADS", "up to 16"),
+                      "synchronous_call_value": rate(e2e_sync_ms)}
+    if cpu_scans and not args.no_cpu:
+        rec["cpu_baseline"], rec["pose_err_vs_oracle"] = cpu_baseline(map_corner, map_surf, qc, c_off, qs, s_off, inits,
+                                                                        poses_dev, min(cpu_scans, B), over)
+    return rec
 
-    out = None
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        M = Mc + Ms
-        total_bytes, assoc_bytes, solve_bytes = algorithmic_bytes(n_q, M)
-        # dominant kernel = the stage with the larger share of the step
-        names = {0: "k_knn5 (5-NN search over the submap cell index)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
-                 2: "k_transform_keys + counting sort of the cell keys", 3: "k_fit (fp64 line/plane fit)"}
-        per_launch_ms = {s: stage_ms[s] / stage_cnt[s] for s in range(len(stage_ms)) if stage_cnt[s]}
-        dom = max(per_launch_ms, key=lambda s: stage_ms[s])
-        dom_bytes = assoc_bytes if dom in (0, 2, 3) else solve_bytes  # the association pass of SURVEY 8d
-        achieved = dom_bytes / (per_launch_ms[dom] * 1e-3) / 1e9
-        traffic, traffic_kernel = ncu_traffic(args.workload, B)
-        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak,
-                    "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                    "avg_launch_ms": round(per_launch_ms[dom], 4),
-                    "stage_share": {names[s]: round(stage_ms[s] / sum(stage_ms), 3) for s in per_launch_ms},
-                    "whole_step_GBps": round(total_bytes / (ms_per_step * 1e-3) / 1e9, 2),
-                    "note": "achieved = SURVEY 8d algorithmic bytes of that pass / CUDA-event time; see DESIGN.md section 4"}
-        cpu = None
-        pose_err = None
-        if not args.no_cpu and world >= 1:
-            cpu, pose_err = cpu_baseline(map_corner, map_surf, qc, c_off, qs, s_off, inits, poses_dev,
-                                         min(args.cpu_sample, B), over)
-        out = {
-            "metric": "scans/sec scan-to-map", "value": round(value, 1), "unit": "scans/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload][2], "sensor": args.workload,
-                       "scans_per_gpu_per_step": B, "distinct_scans": len(queries),
-                       "points_per_scan": n_full, "queries_per_scan": round(n_q / B, 1),
-                       "submap_points": {"corner": Mc, "surf": Ms}, "submap_scans": args.map_scans, "outer_iterations": K_OUTER,
-                       "lm_attempts_per_outer": L_ATTEMPTS, "early_exit": False,
-                       "range_noise_sigma_m": SIGMA, "parallelism": f"scan-sharded x{world}" + (
-                           ", NCCL submap broadcast per step" if world > 1 else ""),
-                       "l2": "per-step inputs + correspondences (%.0f MB) exceed the 126 MB L2" % (
-                           (n_q * 16 + n_q * 48) / 1e6)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "scans/s",
-                    "h2d_bytes_per_step": int(n_q * 16 + (2 * (B + 1)) * 4 + B * 56),
-                    "d2h_bytes_per_step": int(B * 56),
-                    "api": "msfl_scan2map_batch_submit/_wait, 2 batches in flight, pinned host buffers; median of 3 runs of K steps",
-                    "synchronous_call_value": round(world * B * args.steps / (e2e_sync_ms * 1e-3), 1)},
-            "gpu_launches": int(launches),
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "pose_err_vs_oracle": pose_err,
-            "single_scan_latency": single,
-            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                       "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
-        }
-    eng.close()
+
+def single_scan_latency(cx, workload="vlp16"):
+    """BASELINE config 2 as the ROS node runs it: ONE scan per call through the synchronous C ABI (pageable host buffers,
+    stream sync per call); lm_cluster = 8 spreads the solve over an 8-CTA thread-block cluster."""
+    from msf_loam_b200 import Engine, default_params
+    traj, scans = cx.raw[workload]
+    out = {}
+    e0 = Engine(default_params(**OVER), device=cx.local_rank)
+    mc, ms, queries, _ = build_case(lambda x, r: e0.extract_features(x, r, None), e0.voxel_grid, workload, traj, scans[:WORKLOADS[workload]["map_scans"] + 1])
+    e0.close()
+    c0, s0, gt = queries[0]
+    init = S.perturb_pose(gt, np.random.default_rng(1))
+    for G in (1, 8):
+        e1 = Engine(default_params(lm_cluster=G, **OVER), device=cx.local_rank)
+        e1.set_submap(mc, ms)
+        for _ in range(5):
+            e1.scan2map(c0, s0, init, want_stats=False)
+        t0 = time.perf_counter()
+        for _ in range(40):
+            e1.scan2map(c0, s0, init, want_stats=False)
+        out[f"lm_cluster_{G}_us_per_scan"] = round((time.perf_counter() - t0) / 40 * 1e6, 1)
+        t0 = time.perf_counter()
+        for _ in range(20):  # the reference rebuilds the kd-trees every frame (mapping_scan_matcher.cc:66-72)
+            e1.set_submap(mc, ms)
+            e1.scan2map(c0, s0, init, want_stats=False)
+        out[f"lm_cluster_{G}_us_per_scan_with_submap_build"] = round((time.perf_counter() - t0) / 20 * 1e6, 1)
+        e1.close()
+    return out
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    cx = Ctx()
+    cx.args, cx.rank, cx.local_rank, cx.world = args, rank, local_rank, world
+    extra = not args.no_workloads and not args.only_device
+    # raw scans first: numpy ray-casting in a fork pool, before this process owns a CUDA context
+    n_workers = max(1, (os.cpu_count() or 1) // world)
+    os.environ.setdefault("MSFL_PACK_THREADS", str(max(1, min(16, n_workers))))
+    t_gen = time.perf_counter()
+    cx.raw = {args.workload: raw_scans(args.workload, args.distinct, n_workers)}
+    if extra:
+        for wl, nd in (("hdl64", 8), ("os1-128", 4), ("vlp16", 8)):
+            if wl not in cx.raw:
+                cx.raw[wl] = raw_scans(wl, nd, n_workers)
+    t_gen = time.perf_counter() - t_gen
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    cx.dev = torch.device("cuda", local_rank)
+    numa = numa_bind(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=cx.dev)
+
+    # the CPU legs run on rank 0 at N = 1 only (at N > 1 the other ranks would idle in a barrier meanwhile)
+    main = run_workload(cx, args.workload, args.batch, args.distinct, args.steps, args.warmup, full=True,
+                        cpu_scans=args.cpu_sample if world == 1 else 64)
+    workloads = None
+    if extra:
+        workloads = {}
+        st = max(args.steps, 20)
+        # config 3: HDL-64E
+        workloads["config3_hdl64"] = run_workload(cx, "hdl64", 512, 8, st, 3, full=False, sampler=False, cpu_scans=8)
+        # config 5: OS1-128 vs the ~1 M-point submap, batch sweep per GPU (large scans in small batches: the solve is
+        # spread over thread-block clusters so that the LM kernel fills the chip)
+        for b, g in ((64, 4), (8, 8), (1, 8)):
+            workloads[f"config5_os1-128_batch{b}"] = run_workload(cx, "os1-128", b, 4, st, 3, full=False, lm_cluster=g,
+                                                                 sampler=False, e2e=(b == 64), cpu_scans=4 if b == 64 else 0)
+        # config 4 as worded: one VLP-16 scan per GPU; every step = new map version indexed on rank 0, broadcast,
+        # adopted, one scan solved per rank; ms_per_step is the latency of that whole exchange
+        workloads["config4_one_scan_per_gpu"] = run_workload(cx, "vlp16", 1, 8, st * 5, 5, full=False, lm_cluster=8,
+                                                             sampler=False, e2e=False, cpu_scans=0, remap=True)
+    single = single_scan_latency(cx) if (rank == 0 and not args.only_device) else None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return None
+    clocks = main.pop("clocks") or {}
+    out = {
+        "metric": "scans/sec scan-to-map", "value": main["value"], "unit": "scans/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": main["config"], "impl_notes": main["impl_notes"], "e2e": main.get("e2e"),
+        "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
+        "cpu_baseline": main.get("cpu_baseline"), "pose_err_vs_oracle": main.get("pose_err_vs_oracle"),
+        "single_scan_latency": single,
+        "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "samples_under_load", "power_w_max")},
+        "host": {"numa": numa, "input_generation_s": round(t_gen, 1)},
+    }
+    if workloads is not None:
+        for w in workloads.values():
+            w.pop("clocks", None)
+        out["workloads"] = workloads
     return out
 
 
 def cpu_baseline(map_corner, map_surf, qc, c_off, qs, s_off, inits, poses_gpu, n_sample, over):
     """Oracle (kind "port"), one thread, on a bounded sample of the same batch; also the pose check."""
     import oracle as O
-    P = O.default_params(**{k: v for k, v in over.items()})
+    P = O.default_params(**{k: v for k, v in over.items() if k != "lm_cluster"})
     n = n_sample
     co, so = c_off[: n + 1], s_off[: n + 1]
     t0 = time.perf_counter()
@@ -427,29 +574,34 @@ def run_reference(args):
         return None
     import oracle as O
     threads = os.cpu_count() or 1
-    over = {"early_exit": 0, "max_num_iterations": L_ATTEMPTS, "num_outer": K_OUTER}
-    P = O.default_params(**over)
-    map_corner, map_surf, queries, n_full = build_case_cpu(args.workload, min(args.distinct, 16), args.map_scans)
-    n = max(threads * 2, 8)  # bounded sample per step
-    qc, c_off, qs, s_off, inits = assemble_batch(queries, n, seed=1000)
+    P = O.default_params(**OVER)
+    # the same workload as the CUDA arm: same scans, same submap, same batch assembly (the oracle's extraction and
+    # VoxelGrid are bit-identical to the CUDA ones, so `config` is equal key by key)
+    traj, scans = raw_scans(args.workload, args.distinct, threads)
+    map_corner, map_surf, queries, n_full = build_case(lambda x, r: O.extract_features(P, x, r, None), O.voxel_grid,
+                                                       args.workload, traj, scans)
+    B = args.batch
+    qc, c_off, qs, s_off, inits = assemble_batch(queries, B, seed=1000)
+    n_q = int(c_off[-1] + s_off[-1])
+    n = min(B, max(threads * 2, 8))  # bounded sample per step: the first n scans of the batch
+    co, so = c_off[: n + 1], s_off[: n + 1]
+    sample = (qc[: co[-1]], co, qs[: so[-1]], so, inits[:n])
     for _ in range(max(1, min(args.warmup, 2))):
-        O.scan2map_batch(P, map_corner, map_surf, qc, c_off, qs, s_off, inits, n_threads=threads)
+        O.scan2map_batch(P, map_corner, map_surf, *sample, n_threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.scan2map_batch(P, map_corner, map_surf, qc, c_off, qs, s_off, inits, n_threads=threads)
+        O.scan2map_batch(P, map_corner, map_surf, *sample, n_threads=threads)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     return {
         "impl": "reference", "metric": "scans/sec scan-to-map", "value": round(value, 2), "unit": "scans/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][2], "sensor": args.workload,
-                   "scans_per_step": n, "points_per_scan": n_full, "queries_per_scan": round(int(c_off[-1] + s_off[-1]) / n, 1),
-                   "submap_points": {"corner": int(map_corner.shape[0]), "surf": int(map_surf.shape[0])},
-                   "outer_iterations": K_OUTER, "lm_attempts_per_outer": L_ATTEMPTS, "early_exit": False},
+        "config": workload_config(args.workload, B, queries, n_full, n_q, int(map_corner.shape[0]), int(map_surf.shape[0])),
         "cpu_baseline": {"value": round(value, 2), "unit": "scans/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} scans per step x {args.steps} steps, pthreads over independent scans; "
-                                   "CPU restatement of the reference PCL+Ceres path (libraries not installable offline)"},
+                         "sample": f"first {n} scans of the {B}-scan batch per step x {args.steps} steps, pthreads over "
+                                   "independent scans, kd-trees built once per step; CPU restatement of the reference "
+                                   "PCL+Ceres path (libraries not installable offline)"},
         "e2e": {"value": round(value, 2), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 

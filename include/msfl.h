@@ -179,6 +179,21 @@ int msfl_set_submap_device(msfl_engine *e, const float *d_corner_xyzi, size_t n_
 int msfl_get_submap_device(msfl_engine *e, const float **d_corner_xyzi, size_t *n_corner,
                            const float **d_surf_xyzi, size_t *n_surf);
 
+/* ---- multi-GPU: independent scans are sharded over ranks, one process per GPU; the ONE collective
+ *      is the broadcast of the submap from the rank that owns the map, once per map version.  The payload carries
+ *      the cell index (points in caller order, cell-sorted copy, cell table), so the other ranks adopt it instead of
+ *      repeating the build of mapping_scan_matcher.cc:66-72.  `nccl_comm` is an ncclComm_t (any communicator whose
+ *      ranks each own one engine: the host's own, or one made by msfl_nccl_comm_init); the broadcast runs on the
+ *      engine stream.  Collective: every rank of the communicator must call it.  NCCL is bound at run time
+ *      (libnccl.so.2), MSFL_ERR_CUDA when it is not installed. ------------------------------------------------- */
+int msfl_bcast_submap(msfl_engine *e, void *nccl_comm, int root);
+/* Convenience for hosts without a communicator of their own (ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy):
+ * rank 0 makes the id, the host ships its 128 bytes to the other ranks by any means, every rank calls comm_init. */
+#define MSFL_NCCL_UNIQUE_ID_BYTES 128
+int msfl_nccl_get_unique_id(unsigned char id[MSFL_NCCL_UNIQUE_ID_BYTES]);
+int msfl_nccl_comm_init(msfl_engine *e, const unsigned char id[MSFL_NCCL_UNIQUE_ID_BYTES], int nranks, int rank, void **nccl_comm);
+int msfl_nccl_comm_destroy(void *nccl_comm);
+
 /* One scan vs the resident submap.  pose_tq: in = initial guess (*pose_estimate_map_scan2world),
  * out = estimate.  stats may be NULL. */
 int msfl_scan2map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,

@@ -16,13 +16,15 @@ MSFL_TOO_FEW = 1
 MAX_OUTER = 4
 MAX_ATTEMPTS = 16
 N_STAGES = 4
+NCCL_UNIQUE_ID_BYTES = 128
 NO_FIELD = C.c_size_t(-1).value
 
 # every symbol include/msfl.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "msfl_default_params", "msfl_last_error", "msfl_version", "msfl_abi_check", "msfl_create", "msfl_create_on_stream",
     "msfl_destroy", "msfl_sync", "msfl_stream", "msfl_launch_count", "msfl_set_profiling",
-    "msfl_get_profile", "msfl_set_submap",
+    "msfl_get_profile", "msfl_set_submap", "msfl_bcast_submap", "msfl_nccl_get_unique_id", "msfl_nccl_comm_init",
+    "msfl_nccl_comm_destroy",
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
     "msfl_scan2map_batch_device", "msfl_scan2map_batch_submit", "msfl_scan2map_batch_wait", "msfl_scan2map_deskew", "msfl_associate_map", "msfl_scan2scan", "msfl_associate_scan",
     "msfl_extract_features", "msfl_voxel_grid", "msfl_accumulate", "msfl_map_create", "msfl_map_destroy",

@@ -47,12 +47,10 @@ __device__ __forceinline__ void top5_insert(Top5 &t, float d, int id) {
 // fp32: with 1 m cells the cell boundaries are integers, float subtraction / squaring / addition
 // are monotone, and the bound is accumulated in the same order as the distance itself
 // ((bx^2 + by^2) + bz^2), so  bound > worst  implies  d > worst  for every point of that cell.
-// `seed` (<= thresh) is an upper bound, exclusive, on the 5th-nearest distance when one is known (seed_bound below):
-// the five sentinels start there instead of at the gate, so rows, cells and candidates beyond it are never touched.
-__device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy, float qz, float thresh, float seed, Top5 &t) {
+__device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy, float qz, float thresh, Top5 &t) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    t.d[s] = seed;
+    t.d[s] = thresh;
     t.i[s] = -1;
   }
   const float fxq = floorf(qx * g.inv_edge), fyq = floorf(qy * g.inv_edge), fzq = floorf(qz * g.inv_edge);
@@ -97,23 +95,6 @@ __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy,
     }
   }
   return t.i[4] >= 0;
-}
-
-// Outer iteration >= 1: the five neighbours found at the previous pose are still five distinct map points, so the
-// largest of their (exactly recomputed) distances to the moved query bounds the new 5th-nearest distance from above.
-// Returns the smallest float above that maximum, capped at the gate: every member of the new exact top five is
-// strictly below it, and so beats the sentinels in the (d2, index) order.
-__device__ __forceinline__ float seed_bound(const GridView &g, const int32_t *__restrict__ prev5, float qx, float qy, float qz,
-                                            float thresh) {
-  if (__ldg(prev5 + 4) < 0) return thresh;  // the gate failed last time: no bound
-  float u = 0.f;
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    const float4 m = __ldg(g.pts_orig + __ldg(prev5 + s));
-    const float dx = __fsub_rn(qx, m.x), dy = __fsub_rn(qy, m.y), dz = __fsub_rn(qz, m.z);
-    u = fmaxf(u, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-  }
-  return fminf(__uint_as_float(__float_as_uint(u) + 1u), thresh);
 }
 
 __device__ __forceinline__ void store_corr(double *corr, size_t q, const double a[3], const double n[3]) {
@@ -189,18 +170,10 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
 // counting sort, last pass: slot = first slot of the query's bin + its rank inside the bin
 __global__ void __launch_bounds__(256)
 k_scatter_perm(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ bin_start,
-               uint32_t n, uint32_t *__restrict__ perm, uint32_t *__restrict__ inv) {
+               uint32_t n, uint32_t *__restrict__ perm) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t slot = __ldg(bin_start + __ldg(keys + k)) + __ldg(rank + k);
-  perm[slot] = k;
-  inv[k] = slot;  // where query k's neighbour list will sit: the next outer iteration seeds its search from it
-}
-
-// radix-sort path: the inverse of the sorted permutation
-__global__ void __launch_bounds__(256) k_invert_perm(const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ inv) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot < n) inv[__ldg(perm + slot)] = slot;
+  perm[__ldg(bin_start + __ldg(keys + k)) + __ldg(rank + k)] = k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,16 +264,13 @@ __device__ __forceinline__ float3 deskew_transform(const double pose[7], const D
 // transformed point stored by k_transform_keys instead of transforming here.
 // BY_SLOT: the five indices are stored at the thread's slot (coalesced; k_fit<.., true> then walks the
 // same cell order) instead of at the query's flat index k.
-// SEED: prev_knn holds the neighbour lists of the previous outer iteration (at slot prev_inv[k], or at k when prev_inv
-// is null); they bound the search at the new pose (seed_bound).
-template <bool SORTED, bool STORED_X, bool DESKEW, bool BY_SLOT, bool SEED = false>
+template <bool SORTED, bool STORED_X, bool DESKEW, bool BY_SLOT>
 __global__ void __launch_bounds__(128, 10)
 k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
        const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
        const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
        const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, DeskewTable tb,
-       const double *__restrict__ dsk, const int32_t *__restrict__ prev_knn = nullptr,
-       const uint32_t *__restrict__ prev_inv = nullptr) {
+       const double *__restrict__ dsk) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_corner_total + n_surf_total) return;
   const uint32_t k = SORTED ? __ldg(perm + slot) : slot;
@@ -322,9 +292,7 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
   }
   const GridView &g = is_corner ? gc : gs;
   Top5 t;
-  float seed = kp.knn_max_sq_f;
-  if (SEED) seed = seed_bound(g, prev_knn + (size_t)(prev_inv ? __ldg(prev_inv + k) : k) * 5, x.x, x.y, x.z, kp.knn_max_sq_f);
-  const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, seed, t);  // :125-128 / :195-198
+  const bool gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);  // :125-128 / :195-198
   // 5 neighbour indices per query (-1 when the d5^2 gate fails), consumed by k_fit
   int32_t *o = knn_out + (size_t)(BY_SLOT ? slot : k) * 5;
 #pragma unroll
@@ -476,7 +444,7 @@ k_knn5_tiled(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint
   if (staged && (int)is_corner == anchor[0] && cx == anchor[1] && cy == anchor[2] && cz == anchor[3])
     gate = knn5_tile(tile, rows, g.inv_edge == 1.0f, x.x, x.y, x.z, fxq, fyq, fzq, kp.knn_max_sq_f, t);
   else
-    gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, kp.knn_max_sq_f, t);
+    gate = knn5_grid(g, x.x, x.y, x.z, kp.knn_max_sq_f, t);
   int32_t *o = knn_out + (size_t)slot * 5;
 #pragma unroll
   for (int s = 0; s < 5; ++s) o[s] = gate ? t.i[s] : -1;
@@ -540,15 +508,13 @@ __device__ __forceinline__ bool plane_fit_fast(const float (&mf)[5][3], const do
 // BY_SLOT: slot s holds query perm[s] and the neighbour indices k_knn5 stored at slot s.
 // QR: planes take the pivoted-Householder solve (the fallback kernel); otherwise plane_fit_fast, and a query that
 // needs the Householder path is appended to fb_list instead of being written.
-template <bool DESKEW, bool COMPACT, bool BY_SLOT, bool QR>
-__device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, bool is_corner, uint32_t slot, uint32_t n_corner_total,
-                                          const int32_t *__restrict__ knn, double *__restrict__ corr, const DeskewTable &tb,
-                                          const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
-                                          uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
-  const uint32_t k = BY_SLOT ? __ldg(perm + slot) : slot;
-  int idx[5];
-#pragma unroll
-  for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)slot * 5 + s);
+// fit_from_idx: the neighbour indices are already in registers (the fused search + fit kernel); k = the query's flat
+// index, slot = what a declined plane query is listed under.
+template <bool DESKEW, bool COMPACT, bool QR>
+__device__ __forceinline__ void fit_from_idx(const GridView &g, const KParams &kp, bool is_corner, uint32_t k, uint32_t slot,
+                                             uint32_t n_corner_total, const int (&idx)[5], double *__restrict__ corr,
+                                             const DeskewTable &tb, const double *__restrict__ dsk, uint32_t *__restrict__ fb_list,
+                                             uint32_t *__restrict__ fb_count) {
   double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
   if (idx[4] >= 0) {
     // the five neighbours stay in registers as the fp32 values they are (15 registers, not 30) and are widened
@@ -627,6 +593,71 @@ __device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, 
   }
 }
 
+template <bool DESKEW, bool COMPACT, bool BY_SLOT, bool QR>
+__device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, bool is_corner, uint32_t slot, uint32_t n_corner_total,
+                                          const int32_t *__restrict__ knn, double *__restrict__ corr, const DeskewTable &tb,
+                                          const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
+                                          uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
+  const uint32_t k = BY_SLOT ? __ldg(perm + slot) : slot;
+  int idx[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) idx[s] = __ldg(knn + (size_t)slot * 5 + s);
+  fit_from_idx<DESKEW, COMPACT, QR>(g, kp, is_corner, k, slot, n_corner_total, idx, corr, tb, dsk, fb_list, fb_count);
+}
+
+// Batch path, fused: the search of k_knn5<true, true, false, true> followed, for surf slots, by the closed-form plane
+// fit on the indices still in registers -- the surf neighbour lists (20 B per query written and read back) never
+// touch memory; declined queries store their list and go to the Householder kernel as usual.  Corner slots store
+// their list for k_fit<.., 0> (the Jacobi eigen-solver keeps its own register allocation).
+__global__ void __launch_bounds__(128, 8)
+k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const float4 *__restrict__ xq,
+           const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, double *__restrict__ corr,
+           uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_total) return;
+  const uint32_t k = __ldg(perm + slot);
+  const bool is_corner = slot < n_corner_total;
+  const float4 xs = __ldg(xq + k);
+  const GridView &g = is_corner ? gc : gs;
+  Top5 t;
+  const bool gate = knn5_grid(g, xs.x, xs.y, xs.z, kp.knn_max_sq_f, t);
+  int idx[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) idx[s] = gate ? t.i[s] : -1;
+  if (is_corner) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) knn_out[(size_t)slot * 5 + s] = idx[s];
+    return;
+  }
+  // a declined query is re-fitted by k_fit_qr_list from its stored list
+  float mf[5][3];
+  bool declined = false;
+  if (gate) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const float4 mp = __ldg(g.pts_orig + idx[s]);
+      mf[s][0] = mp.x; mf[s][1] = mp.y; mf[s][2] = mp.z;
+    }
+  }
+  double c[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+  if (gate) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      c[d] = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn((double)mf[0][d], (double)mf[1][d]), (double)mf[2][d]), (double)mf[3][d]), (double)mf[4][d]), 5.0);
+    declined = plane_fit_fast(mf, c, kp.plane_tol, n);
+  }
+  if (declined) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) knn_out[(size_t)slot * 5 + s] = idx[s];
+    fb_list[atomicAdd(fb_count, 1u)] = slot;
+    return;
+  }
+  double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(corr + (size_t)n_corner_total * 6) +
+                                           (size_t)(k - n_corner_total) * 32);
+  o[0] = make_double2(n[0], n[1]);
+  o[1] = make_double2(n[2], __fma_rn(n[2], c[2], __fma_rn(n[1], c[1], __dmul_rn(n[0], c[0]))));
+}
+
 // One thread per query.  Kept apart from the search kernel so that the search runs at 40 registers / 75 %
 // occupancy while the fits do not throttle it.
 // CLS: -1 = one launch over all queries (class decided per thread); 0 / 1 = a launch over the corner / surf queries
@@ -663,28 +694,18 @@ static unsigned qr_list_grid(const msfl_engine *e, uint32_t n_plane_queries) {
   return std::min(want, (unsigned)e->sm_count * 4u);
 }
 
-// outer: outer-iteration index of the calling solve.  For outer > 0 the neighbour lists of the previous call (same
-// queries, same submap, previous pose) seed the search; the caller guarantees that calls with outer > 0 follow the
-// outer - 1 call of the same batch on the same stream.
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool compact, int outer) {
+                         double *d_corr, int32_t *d_knn, bool compact) {
   const uint32_t total = n_corner_total + n_surf_total;
   if (B <= 0 || total == 0) return MSFL_OK;
   const int tb = 128;
   const GridView &gc = e->map_corner.view, &gs = e->map_surf.view;
   const bool own_knn = d_knn == nullptr;
   int rc;
-  // neighbour indices travel from the search kernel to the fit kernel through this scratch; two buffers, so that the
-  // lists of outer iteration o - 1 are still there when iteration o searches
-  const int32_t *prev_knn = nullptr;
-  const uint32_t *prev_inv = nullptr;
-  const bool seeded = own_knn && outer > 0 && e->assoc_prev_total == total && e->assoc_prev_knn != nullptr && e->seed_knn;
-  if (seeded) { prev_knn = e->assoc_prev_knn; prev_inv = e->assoc_prev_inv; }
-  if (own_knn) {
-    DevBuf &kb = (outer & 1) ? e->d_knn2 : e->d_knn;
-    if ((rc = kb.reserve((size_t)total * 5 * 4))) return rc;
-    d_knn = kb.as<int32_t>();
+  if (own_knn) {  // neighbour indices travel from the search kernel to the fit kernel through this scratch
+    if ((rc = e->d_knn.reserve((size_t)total * 5 * 4))) return rc;
+    d_knn = e->d_knn.as<int32_t>();
   }
   if ((rc = e->a_fb.reserve(((size_t)n_surf_total + 2) * 4))) return rc;
   uint32_t *fb_count = e->a_fb.as<uint32_t>(), *fb_list = fb_count + 1;
@@ -695,13 +716,8 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   if (!sorted) {
     stage_begin(e, 0);
     const unsigned grid = (total + tb - 1) / tb;
-    if (seeded)
-      k_knn5<false, false, false, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                                          n_surf_total, d_poses, nullptr, nullptr, d_knn, nt, nullptr,
-                                                                          prev_knn, prev_inv);
-    else
-      k_knn5<false, false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                                    n_surf_total, d_poses, nullptr, nullptr, d_knn, nt, nullptr);
+    k_knn5<false, false, false, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
+                                                                  n_surf_total, d_poses, nullptr, nullptr, d_knn, nt, nullptr);
     if (compact) {
       k_fit<false, true, false><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
       k_fit_qr_list<false, true, false><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, nullptr, fb_list, fb_count);
@@ -712,9 +728,6 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
     stage_end(e);
     e->launches += 3;
     MSFL_CUDA_OK(cudaGetLastError());
-    e->assoc_prev_knn = own_knn ? d_knn : nullptr;
-    e->assoc_prev_inv = nullptr;  // lists sit at the query's own index
-    e->assoc_prev_total = total;
     return MSFL_OK;
   }
   // sorted path: transform + cell keys -> counting / radix sort -> association in cell order
@@ -723,11 +736,12 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   if ((rc = e->a_keys_alt.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_vals.reserve((size_t)total * 4))) return rc;
   if ((rc = e->a_vals_alt.reserve((size_t)total * 4))) return rc;
-  DevBuf &ib = (outer & 1) ? e->a_inv2 : e->a_inv;
-  if ((rc = ib.reserve((size_t)total * 4))) return rc;
-  // an outer iteration > 0 may keep the previous cell order (MSFL_RESORT_OUTER=0): the order is only a locality hint
-  const bool keep_order = seeded && !e->resort_outer && e->a_perm != nullptr && prev_inv != nullptr;
-  if (!keep_order) {
+  // The cell order is rebuilt for every outer iteration.  Measured on B200 (VLP-16, 2048 scans, 0.10 m / 1 deg initial
+  // error: the first solve moves the queries by 0.2 m median, 0.47 m max): keeping the first order costs the second
+  // search 40 % (its lanes stop agreeing on rows and cells), more than the 0.27 ms re-sort; seeding the second search
+  // with the distance bound of the first iteration's neighbours (9 % of the lists survive unchanged, 28 % as sets) gains
+  // nothing either -- the centre row establishes the same bound after ~10 candidates.
+  {
     const long long ncell = (long long)gc.nx * gc.ny * gc.nz + (long long)gs.nx * gs.ny * gs.nz + 2;
     int cell_bits = 1;
     while ((1ll << cell_bits) < ncell) ++cell_bits;
@@ -750,7 +764,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
                                                                          e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist, sub_log2);
       MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(e->a_tmp.p, tmp, hist, hist, (int)nbins, e->stream));
       k_scatter_perm<<<(total + 255) / 256, 256, 0, e->stream>>>(e->a_keys.as<uint32_t>(), e->a_vals.as<uint32_t>(), hist, total,
-                                                                 e->a_vals_alt.as<uint32_t>(), ib.as<uint32_t>());
+                                                                 e->a_vals_alt.as<uint32_t>());
       stage_end(e);
       e->a_perm = e->a_vals_alt.as<uint32_t>();
       e->launches += 3;  // + the cub scan kernels
@@ -765,28 +779,21 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
                                                                           n_surf_total, d_poses, e->a_xq.as<float4>(), dk.Current(),
                                                                           dv.Current(), nullptr, sub_log2);
       MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->a_tmp.p, tmp, dk, dv, (int)total, 0, end_bit, e->stream));
-      k_invert_perm<<<(total + 255) / 256, 256, 0, e->stream>>>(dv.Current(), total, ib.as<uint32_t>());
       stage_end(e);
       e->a_perm = dv.Current();
-      e->launches += 4;
+      e->launches += 3;
     }
   }
-  const uint32_t *cur_inv = keep_order ? prev_inv : ib.as<uint32_t>();
   // neighbour indices stay in cell order between the two kernels unless the caller wants them back (test hook)
   const bool by_slot = own_knn;
   const unsigned grid = (total + tb - 1) / tb;
   stage_begin(e, 0);
-  if (keep_order)
-    k_knn5<true, false, false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                                      n_surf_total, d_poses, nullptr, e->a_perm, d_knn, nt, nullptr,
-                                                                      prev_knn, prev_inv);
+  const bool fused = by_slot && compact && e->fuse_fit && mode != 3;
+  if (fused)
+    k_knn5_fit<<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, e->a_xq.as<float4>(), e->a_perm, d_knn, d_corr, fb_list, fb_count);
   else if (by_slot && mode == 3)  // measured on B200 (VLP-16, 2048 scans): 0.523 ms staged vs 0.507 ms direct -- the search is
                                   // instruction-issue-bound (78 % of issue slots), not latency-bound, so staging is opt-in
     k_knn5_tiled<<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, e->a_xq.as<float4>(), e->a_perm, d_knn);
-  else if (by_slot && seeded)
-    k_knn5<true, true, false, true, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
-                                                                     n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn, nt,
-                                                                     nullptr, prev_knn, prev_inv);
   else if (by_slot)
     k_knn5<true, true, false, true><<<grid, tb, 0, e->stream>>>(gc, gs, e->kp, B, d_qc, d_c_off, n_corner_total, d_qs, d_s_off,
                                                                n_surf_total, d_poses, e->a_xq.as<float4>(), e->a_perm, d_knn, nt, nullptr);
@@ -800,7 +807,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
       const unsigned grid_c = (n_corner_total + tb - 1) / tb, grid_s = (n_surf_total + tb - 1) / tb;
       if (grid_c) k_fit<false, true, true, 0><<<grid_c, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
       if (grid_s) {
-        k_fit<false, true, true, 1><<<grid_s, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+        if (!fused) k_fit<false, true, true, 1><<<grid_s, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
         k_fit_qr_list<false, true, true><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
       }
       e->launches += 2;
@@ -822,9 +829,6 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   stage_end(e);
   e->launches += 3;
   MSFL_CUDA_OK(cudaGetLastError());
-  e->assoc_prev_knn = by_slot ? d_knn : nullptr;
-  e->assoc_prev_inv = cur_inv;
-  e->assoc_prev_total = total;
   return MSFL_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "msfl_internal.h"
@@ -107,10 +108,19 @@ int check_cloud(const msfl_cloud *c, bool need_ring, const char *what) {
 static void pack_cloud_host(const msfl_cloud *c, float *dst4, uint16_t *ring_dst) {
   const size_t n = c->n;
   const char *base = (const char *)c->data;
-  if (c->stride == 16 && c->off_xyz == 0 && (c->off_intensity == 12 || c->off_intensity == MSFL_NO_FIELD)) {
+  const bool has_i = c->off_intensity != MSFL_NO_FIELD;
+  if (c->stride == 16 && c->off_xyz == 0 && (c->off_intensity == 12 || !has_i)) {
     memcpy(dst4, base, n * 16);
+  } else if (((c->stride | c->off_xyz | (has_i ? c->off_intensity : 0) | (size_t)(uintptr_t)base) & 3u) == 0) {
+    // word-aligned points (every PCL type: pcl::PointXYZI is 32 B with intensity at 16): four 32-bit moves per point
+    const size_t sw = c->stride / 4, ox = c->off_xyz / 4, oi = has_i ? c->off_intensity / 4 : 0;
+    const uint32_t *src = (const uint32_t *)base;
+    uint32_t *dst = (uint32_t *)dst4;
+    for (size_t i = 0; i < n; ++i, src += sw, dst += 4) {
+      dst[0] = src[ox]; dst[1] = src[ox + 1]; dst[2] = src[ox + 2];
+      dst[3] = has_i ? src[oi] : 0u;
+    }
   } else {
-    const bool has_i = c->off_intensity != MSFL_NO_FIELD;
     for (size_t i = 0; i < n; ++i) {
       const char *pt = base + i * c->stride;
       memcpy(dst4 + 4 * i, pt + c->off_xyz, 12);
@@ -124,6 +134,43 @@ static void pack_cloud_host(const msfl_cloud *c, float *dst4, uint16_t *ring_dst
     else
       for (size_t i = 0; i < n; ++i) memcpy(ring_dst + i, base + i * c->stride + c->off_ring, 2);
   }
+}
+
+// Packs scans [b0, b1) of a batch into the staging layout [all corner | all surf] (hq: float4 base, corner scan b at
+// c_at[b], surf scan b at nct + s_at[b]).  Large batches (the PCL-layout replay path: 32 B points in pageable memory) are
+// split over host threads -- one memory-bound loop per thread; a 2048-scan VLP-16 batch is 0.3 GB read + 0.16 GB written.
+static void pack_batch_host(msfl_engine *e, int b0, int b1, const msfl_cloud *corner, const msfl_cloud *surf, float *hq,
+                            size_t nct, const size_t *c_at, const size_t *s_at) {
+  size_t pts = 0;
+  for (int b = b0; b < b1; ++b) pts += corner[b].n + surf[b].n;
+  int nt = e->pack_threads;
+  if (nt > b1 - b0) nt = b1 - b0;
+  if (pts < 200000 || nt <= 1) {
+    for (int b = b0; b < b1; ++b) {
+      pack_cloud_host(&corner[b], hq + 4 * c_at[b], nullptr);
+      pack_cloud_host(&surf[b], hq + 4 * (nct + s_at[b]), nullptr);
+    }
+    return;
+  }
+  // contiguous scan ranges with equal point counts
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  int b = b0;
+  size_t done = 0;
+  for (int t = 0; t < nt; ++t) {
+    const size_t goal = pts * (size_t)(t + 1) / (size_t)nt;
+    const int first = b;
+    while (b < b1 && (done < goal || t == nt - 1)) { done += corner[b].n + surf[b].n; ++b; }
+    const int last = b;
+    if (first == last) continue;
+    th.emplace_back([=]() {
+      for (int i = first; i < last; ++i) {
+        pack_cloud_host(&corner[i], hq + 4 * c_at[i], nullptr);
+        pack_cloud_host(&surf[i], hq + 4 * (nct + s_at[i]), nullptr);
+      }
+    });
+  }
+  for (auto &t : th) t.join();
 }
 
 static cudaEvent_t take_event(msfl_engine *e) {
@@ -257,8 +304,12 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   e->sm_count = prop.multiProcessorCount;
   fill_kparams(e);
   if (const char *v = getenv("MSFL_COUNT_SORT_MAX_BINS")) e->count_sort_max_bins = atoll(v);  // tests: force the radix path
-  if (const char *v = getenv("MSFL_SEED_KNN")) e->seed_knn = atoi(v) != 0;
-  if (const char *v = getenv("MSFL_RESORT_OUTER")) e->resort_outer = atoi(v) != 0;
+  {
+    const unsigned hc = std::thread::hardware_concurrency();
+    e->pack_threads = (int)std::min(16u, std::max(1u, hc));
+    if (const char *v = getenv("MSFL_PACK_THREADS")) e->pack_threads = std::max(1, atoi(v));
+  }
+  if (const char *v = getenv("MSFL_FUSE_FIT")) e->fuse_fit = atoi(v) != 0;  // development A/B
   if (stream) {
     e->stream = (cudaStream_t)stream;
     e->own_stream = false;
@@ -293,7 +344,7 @@ void msfl_destroy(msfl_engine *e) {
                    &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
                    &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc,
                    &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp, &e->a_hist,
-                   &e->k_table, &e->k_dsk, &e->k_pprime, &e->d_knn2, &e->a_inv, &e->a_inv2, &e->a_fb};
+                   &e->k_table, &e->k_dsk, &e->k_pprime, &e->a_fb};
   for (DevBuf *b : dbs) b->release();
   for (auto &sl : e->slots) {
     sl.d_in.release(); sl.d_stats.release(); sl.h_stage.release(); sl.h_out.release(); sl.h_stats.release();
@@ -378,9 +429,7 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
     const bool compact = true;  // plane constants as 32 B {n, n.c}
-    // the cell order is rebuilt for every outer iteration: the first solve moves points by up to ~0.3 m, and
-    // re-ordering (0.26 ms) is cheaper than searching with a stale order
-    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr, compact, outer)))
+    if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr, compact)))
       return rc;
     stage_begin(e, 1);
     rc = launch_lm_solve(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, e->d_corr.as<double>(), d_poses,
@@ -438,18 +487,17 @@ static int upload_batch(msfl_engine *e, int B, const msfl_cloud *corner, const m
     }
   }
   size_t ci = 0, si = 0;
+  std::vector<size_t> c_at(B), s_at(B);
   for (int b = 0; b < B; ++b) {
     hoff[b] = (int32_t)ci;
     hoff[B + 1 + b] = (int32_t)si;
-    if (!contiguous) {
-      pack_cloud_host(&corner[b], hq + 4 * ci, nullptr);
-      pack_cloud_host(&surf[b], hq + 4 * (nct + si), nullptr);
-    }
+    c_at[b] = ci; s_at[b] = si;
     ci += corner[b].n;
     si += surf[b].n;
   }
   hoff[B] = (int32_t)ci;
   hoff[2 * B + 1] = (int32_t)si;
+  if (!contiguous) pack_batch_host(e, 0, B, corner, surf, hq, nct, c_at.data(), s_at.data());
   memcpy(hpose, poses, pose_bytes);
   if (contiguous) {
     char *d = e->d_queries.as<char>();
@@ -504,6 +552,7 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
   // chunk tables: per chunk two rebased offset tables (Bc+1 each), stored back to back
   struct Chunk { int b0, b1; size_t ci0, ci1, si0, si1; size_t off_pos; };
   std::vector<Chunk> ch(n_chunks);
+  std::vector<size_t> c_at(B), s_at(B);
   {
     size_t ci = 0, si = 0, pos = 0;
     for (int c = 0; c < n_chunks; ++c) {
@@ -519,6 +568,7 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
       for (int b = k.b0; b < k.b1; ++b) {
         co[b - k.b0] = (int32_t)(ci - k.ci0);
         so[b - k.b0] = (int32_t)(si - k.si0);
+        c_at[b] = ci; s_at[b] = si;
         ci += corner[b].n;
         si += surf[b].n;
       }
@@ -535,9 +585,6 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
   if ((rc = e->d_corr.reserve((max_total + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
   if ((rc = e->d_knn.reserve(max_total * 20))) return rc;
-  if ((rc = e->d_knn2.reserve(max_total * 20))) return rc;
-  if ((rc = e->a_inv.reserve(max_total * 4))) return rc;
-  if ((rc = e->a_inv2.reserve(max_total * 4))) return rc;
   if ((rc = e->a_fb.reserve((max_total + 2) * 4))) return rc;
   if ((rc = e->a_xq.reserve(max_total * 16))) return rc;
   if ((rc = e->a_keys.reserve(max_total * 4))) return rc;
@@ -565,13 +612,7 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
       if (ncc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qc + k.ci0, (const char *)corner[0].data + k.ci0 * 16, ncc * 16, cudaMemcpyHostToDevice, cs));
       if (nsc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qs + k.si0, (const char *)surf[0].data + k.si0 * 16, nsc * 16, cudaMemcpyHostToDevice, cs));
     } else {
-      size_t ci = k.ci0, si = k.si0;
-      for (int b = k.b0; b < k.b1; ++b) {
-        pack_cloud_host(&corner[b], hq + 4 * ci, nullptr);
-        pack_cloud_host(&surf[b], hq + 4 * (nct + si), nullptr);
-        ci += corner[b].n;
-        si += surf[b].n;
-      }
+      pack_batch_host(e, k.b0, k.b1, corner, surf, hq, nct, c_at.data(), s_at.data());
       if (ncc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qc + k.ci0, hq + 4 * k.ci0, ncc * 16, cudaMemcpyHostToDevice, cs));
       if (nsc) MSFL_CUDA_OK(cudaMemcpyAsync(d_qs + k.si0, hq + 4 * (nct + k.si0), nsc * 16, cudaMemcpyHostToDevice, cs));
     }
@@ -671,18 +712,17 @@ int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *corner, 
   char *h_tab = h + (contiguous ? 0 : q_pad);
   int32_t *hoff = (int32_t *)h_tab;
   size_t ci = 0, si = 0;
+  std::vector<size_t> c_at(B), s_at(B);
   for (int b = 0; b < B; ++b) {
     hoff[b] = (int32_t)ci;
     hoff[B + 1 + b] = (int32_t)si;
-    if (!contiguous) {
-      pack_cloud_host(&corner[b], (float *)h + 4 * ci, nullptr);
-      pack_cloud_host(&surf[b], (float *)h + 4 * (nct + si), nullptr);
-    }
+    c_at[b] = ci; s_at[b] = si;
     ci += corner[b].n;
     si += surf[b].n;
   }
   hoff[B] = (int32_t)ci;
   hoff[2 * B + 1] = (int32_t)si;
+  if (!contiguous) pack_batch_host(e, 0, B, corner, surf, (float *)h, nct, c_at.data(), s_at.data());
   memcpy(h_tab + off_pad, poses_in, pose_bytes);
   cudaStream_t cs = e->copy_stream;
   if (contiguous) {

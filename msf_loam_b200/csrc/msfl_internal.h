@@ -87,6 +87,7 @@ struct msfl_engine {
   // enough to live in L2; larger (sparse, far-spread) submaps fall back to a radix sort of the keys
   long long count_sort_max_bins = 16ll << 20;
   int sm_count = 148;
+  int pack_threads = 1;  // host threads that repack strided AoS clouds of a large batch into the pinned staging slot
 
   // per-stage CUDA-event timing (msfl_set_profiling)
   bool profiling = false;
@@ -115,13 +116,8 @@ struct msfl_engine {
   msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
   // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp, a_hist;
-  msfl::DevBuf d_knn2, a_inv, a_inv2, a_fb;  // second neighbour-list buffer, inverse permutations, Householder fallback list
-  // neighbour lists of the previous outer iteration of the batch in flight (seed of the next search)
-  const int32_t *assoc_prev_knn = nullptr;
-  const uint32_t *assoc_prev_inv = nullptr;
-  uint32_t assoc_prev_total = 0;
-  bool seed_knn = true;      // MSFL_SEED_KNN=0 (development): search every outer iteration from scratch
-  bool resort_outer = true;  // MSFL_RESORT_OUTER=0 (development): outer iterations > 0 keep the first cell order
+  bool fuse_fit = true;  // batch path: plane fit inside the search kernel (MSFL_FUSE_FIT=0: separate k_fit launch)
+  msfl::DevBuf a_fb;  // plane queries handed to the Householder fallback kernel: [count | slots]
   msfl::DevBuf k_table, k_dsk, k_pprime;  // deskew branch: preintegration table, per-query (dq, dp, dt), p'
   const uint32_t *a_perm = nullptr;  // cell-order permutation of the batch being associated
 
@@ -151,7 +147,7 @@ void submap_release(Submap &m);
 // same flat order.
 int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t n_corner_total,
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
-                         double *d_corr, int32_t *d_knn, bool compact = false, int outer = 0);
+                         double *d_corr, int32_t *d_knn, bool compact = false);
 
 int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
                           const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,

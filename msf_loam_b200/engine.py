@@ -142,6 +142,22 @@ class Engine:
         self._check(self.lib.msfl_get_submap_device(self.h, C.byref(pc), C.byref(nc), C.byref(ps), C.byref(ns)))
         return pc.value, nc.value, ps.value, ns.value
 
+    # ---------------------------------------------------------------- multi-GPU: submap broadcast (NCCL, C ABI)
+    def nccl_comm_init(self, unique_id: bytes, nranks: int, rank: int) -> int:
+        """msfl_nccl_comm_init: returns the ncclComm_t as an int handle (every rank passes rank 0's id)."""
+        assert len(unique_id) == _lib.NCCL_UNIQUE_ID_BYTES
+        buf = (C.c_ubyte * _lib.NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        comm = C.c_void_p()
+        self._check(self.lib.msfl_nccl_comm_init(self.h, buf, C.c_int(nranks), C.c_int(rank), C.byref(comm)))
+        return comm.value
+
+    def nccl_comm_destroy(self, comm: int):
+        self._check(self.lib.msfl_nccl_comm_destroy(C.c_void_p(comm)))
+
+    def bcast_submap(self, comm: int, root: int = 0):
+        """msfl_bcast_submap: collective; afterwards every rank holds root's submap AND its cell index."""
+        self._check(self.lib.msfl_bcast_submap(self.h, C.c_void_p(comm), C.c_int(root)))
+
     # ---------------------------------------------------------------- scan-to-map
     def scan2map(self, scan_corner, scan_surf, pose, want_stats=True):
         vc, vs = _View(scan_corner), _View(scan_surf)

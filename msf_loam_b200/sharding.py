@@ -50,3 +50,23 @@ def gather_poses(local_poses, n_scans: int, device=None) -> np.ndarray:
         idx = shard_indices(n_scans, r, world)
         poses[idx] = out[r][: len(idx)].cpu().numpy()
     return poses
+
+
+def nccl_unique_id(engine) -> bytes:
+    """Rank 0: ncclGetUniqueId through the C ABI (msfl_nccl_get_unique_id)."""
+    import ctypes as C
+    buf = (C.c_ubyte * 128)()
+    engine._check(engine.lib.msfl_nccl_get_unique_id(buf))
+    return bytes(buf)
+
+
+def make_submap_comm(engine, device=None) -> int:
+    """An NCCL communicator for msfl_bcast_submap with the ranks of the default torch.distributed group: rank 0's
+    unique id travels over the existing process group (any backend), then every rank calls msfl_nccl_comm_init.
+    This is what a C++ host does with its own out-of-band channel."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        ident = torch.frombuffer(bytearray(nccl_unique_id(engine)), dtype=torch.uint8).to(ident.device)
+    dist.broadcast(ident, 0)
+    return engine.nccl_comm_init(bytes(ident.cpu().numpy().tobytes()), world, rank)

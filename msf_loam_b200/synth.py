@@ -103,19 +103,24 @@ def make_scene(kind="room40", seed=7):
     elif kind == "room80":
         half = np.array([40.0, 30.0])
         height = 8.0
+    elif kind == "hall300":  # BASELINE config 5: a 50-scan drive whose submap reaches ~1 M points
+        half = np.array([150.0, 60.0])
+        height = 12.0
     else:
         raise ValueError(kind)
+    n_poles, n_boxes = (12, 8) if kind != "hall300" else (60, 40)
+    box_max = 3.0 if kind != "hall300" else 8.0
     poles = []
-    while len(poles) < 12:
+    while len(poles) < n_poles:
         c = rng.uniform(-half + 2.0, half - 2.0)
-        if np.linalg.norm(c - np.array([-8.0, -3.0])) < 3.0:
+        if np.linalg.norm(c - np.array([-8.0, -3.0])) < 3.0 or (kind == "hall300" and abs(c[1] + 3.0) < 2.0):
             continue
         poles.append((c[0], c[1], 0.1))
     boxes = []
-    while len(boxes) < 8:
-        size = rng.uniform(1.0, 3.0, size=3)
+    while len(boxes) < n_boxes:
+        size = rng.uniform(1.0, box_max, size=3)
         c = rng.uniform(-half + 3.0, half - 3.0)
-        if abs(c[1] + 3.0) < 3.5 and c[0] > -12:  # keep the sensor corridor clear
+        if abs(c[1] + 3.0) < 3.5 + (box_max - 3.0) / 2 and c[0] > -half[0] + 8:  # keep the sensor corridor clear
             continue
         boxes.append((c[0] - size[0] / 2, c[1] - size[1] / 2, 0.0,
                       c[0] + size[0] / 2, c[1] + size[1] / 2, size[2]))

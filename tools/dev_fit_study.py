@@ -8,8 +8,9 @@ from msf_loam_b200 import synth as S
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "vlp16"
 nd = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-mc, ms, queries, _ = bench.build_case_cpu(wl, nd)
 P = O.default_params()
+traj, scans = bench.raw_scans(wl, nd)
+mc, ms, queries, _ = bench.build_case(lambda x, r: O.extract_features(P, x, r, None), O.voxel_grid, wl, traj, scans)
 rng = np.random.default_rng(5)
 tot = 0; worst = 0; nfall = 0; flips = 0
 devs = []
