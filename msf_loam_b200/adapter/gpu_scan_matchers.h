@@ -1,7 +1,8 @@
 // gpu_scan_matchers.h -- reference-side adapters: drop-in subclasses of MSF_LOAM's matchers that
-// forward to libmsfl.so through the C ABI (include/msfl.h).  These files are meant to be compiled
-// INSIDE the reference tree (they include its headers, PCL and Eigen); they are not built in this
-// repository because PCL/Eigen/Ceres are not available here.  See INTEGRATION.md.
+// forward to libmsfl.so through the C ABI (include/msfl.h).  This file is meant to be compiled
+// INSIDE the reference tree (it includes its headers, PCL, Eigen and Ceres).  In this repository, where those
+// libraries do not exist, it is compiled against the minimal declarations of tests/adapter_stubs/ and its
+// marshalling is run against libmsfl.so by tests/test_adapter.py.  See INTEGRATION.md.
 //
 //   OdometryScanMatcher::MatchScan2Scan   odometry_scan_matcher.h:10-12   -> msfl_scan2scan
 //   MappingScanMatcher::MatchScan2Map     mapping_scan_matcher.h:14-21    -> msfl_set_submap + msfl_scan2map
@@ -13,6 +14,8 @@
 #include <vector>
 
 #include "msfl.h"
+#include "slam/imu_fusion/imu_factor.h"
+#include "slam/imu_fusion/pose_local_parameterization.h"
 #include "slam/local/scan_matching/mapping_scan_matcher.h"
 #include "slam/local/scan_matching/odometry_scan_matcher.h"
 
@@ -92,10 +95,8 @@ class GpuMappingScanMatcher : public MappingScanMatcher {
                      Vector3d *velocity) override {
     using msfl_adapter::View;
     if (is_initialized) {
-      // IMU side-car stays on the host: the IMU-only Ceres predict (mapping_scan_matcher.cc:28-60) must be
-      // factored into a protected base-class method `PredictWithImu` (a pure move of those lines); it sets
-      // *pose_estimate_map_scan2world = pose_j and *velocity = bias_j.head<3>().
-      this->PredictWithImu(prev_state, pose_estimate_map_scan2world, velocity);
+      // the IMU side-car stays on the host (one 15-residual block, not data-parallel)
+      PredictWithImu(prev_state, pose_estimate_map_scan2world, velocity);
       const msfl_cloud mc = View(*cloud_map.cloud_corner_less_sharp, false), ms = View(*cloud_map.cloud_surf_less_flat, false);
       const msfl_cloud sc = View(*scan_curr.cloud_corner_less_sharp, false), ss = View(*scan_curr.cloud_surf_less_flat, false);
       CHECK_EQ(msfl_set_submap(engine_.get(), &mc, &ms), MSFL_OK) << msfl_last_error();
@@ -127,5 +128,31 @@ class GpuMappingScanMatcher : public MappingScanMatcher {
   }
 
  private:
+  // The IMU-only predict that precedes the LiDAR factors when the estimator is initialised
+  // (mapping_scan_matcher.cc:28-60): one IMUFactor between the previous state (constant) and pose_j / bias_j with the
+  // two biases of bias_j held constant, 6 iterations; it sets *pose = pose_j and *velocity = bias_j.head<3>().  The
+  // same problem is stated here with the reference's own factor and parameterisation classes, so the base class needs
+  // no change beyond `virtual`.
+  static void PredictWithImu(const RobotState &prev_state, Rigid3d *pose, Vector3d *velocity) {
+    double pose_i[7], pose_j[7], bias_i[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bias_j[9];
+    msfl_adapter::ToArray(Rigid3d{prev_state.p, prev_state.q}, pose_i);
+    for (int k = 0; k < 3; ++k) bias_i[k] = prev_state.v[k];
+    for (int k = 0; k < 7; ++k) pose_j[k] = pose_i[k];
+    for (int k = 0; k < 9; ++k) bias_j[k] = bias_i[k];
+    ceres::Problem problem;
+    problem.AddResidualBlock(new IMUFactor(prev_state.imu_preintegration), nullptr, pose_i, bias_i, pose_j, bias_j);
+    problem.SetParameterBlockConstant(pose_i);
+    problem.SetParameterBlockConstant(bias_i);
+    problem.AddParameterBlock(pose_j, 7, new PoseLocalParameterization);
+    problem.AddParameterBlock(bias_j, 9, new ceres::SubsetParameterization(9, {3, 4, 5, 6, 7, 8}));
+    ceres::Solver::Options options;
+    options.max_num_iterations = 6;
+    options.minimizer_progress_to_stdout = false;
+    ceres::Solver::Summary summary;
+    ceres::Solve(options, &problem, &summary);
+    *pose = msfl_adapter::FromArray(pose_j);
+    *velocity = Vector3d(bias_j[0], bias_j[1], bias_j[2]);
+  }
+
   msfl_adapter::Engine engine_;
 };

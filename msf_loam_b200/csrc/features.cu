@@ -104,10 +104,13 @@ __global__ void k_feat_angles(const float4 *__restrict__ raw, const uint32_t *__
                               double *__restrict__ rel) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= (uint32_t)m->n_valid) return;
+  // :131 / :139 call atan2 unqualified on two floats with <math.h> in the include graph: the float overload is chosen
+  // (see the oracle, msfl_oracle.c "atan2").  The float result is produced here by rounding the double-precision atan2
+  // once -- the correctly rounded float, within 1 ulp of any libm's atan2f.
   const float4 f = raw[m->first_valid];
-  const double start_ori = -atan2((double)f.y, (double)f.x);  // :131
+  const double start_ori = (double)(-(float)atan2((double)f.y, (double)f.x));  // :131
   const float4 p = raw[vals[j]];
-  const double ori = -atan2((double)p.y, (double)p.x);        // :139
+  const double ori = (double)(-(float)atan2((double)p.y, (double)p.x));        // :139
   rel[j] = fmod(__dadd_rn(__dsub_rn(ori, start_ori), kTwoPi), kTwoPi);  // :142
 }
 

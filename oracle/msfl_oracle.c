@@ -1252,12 +1252,18 @@ int msflo_extract_features(const msflo_params *P, const float *xyzi, const uint1
   off[0] = 0;
   for (int r = 0; r < MSFLO_MAX_RINGS; r++) { off[r + 1] = off[r] + cnt[r]; cur[r] = off[r]; last_angle[r] = -1; }
   const float *first = xyzi + 4 * (size_t)valid[0];
-  const double start_ori = -atan2((double)first[1], (double)first[0]);
+  /* `atan2(point.y, point.x)` at :131 / :139 is an UNQUALIFIED call with two float arguments.  The translation unit
+   * includes ros/ros.h, tf and PCL headers, which pull in <math.h>; under libstdc++ that header is the C++ wrapper
+   * that does `using std::atan2;`, so overload resolution picks float atan2(float, float) (with <cmath> alone the
+   * arguments would be promoted to double -- both cases are demonstrated by oracle/ref_harness/atan2_overload.cc).
+   * The angle is therefore a FLOAT, negated, then widened.  libm's atan2f is not correctly rounded (glibc 2.39: 1 ulp
+   * off in 16 % of the cases), so this quantity is defined only to 1 float ulp (2.4e-7 rad = 3.8e-9 s) across libms. */
+  const double start_ori = (double)(-atan2f(first[1], first[0]));
   for (int k = 0; k < nv; k++) {
     const int i = valid[k];
     const float *p = xyzi + 4 * (size_t)i;
     const int r = ring[i];
-    double ori = -atan2((double)p[1], (double)p[0]);
+    double ori = (double)(-atan2f(p[1], p[0]));
     double rel = fmod(ori - start_ori + 2 * M_PI, 2 * M_PI);
     if (rel < last_angle[r]) rel += 2 * M_PI;
     last_angle[r] = rel;

@@ -35,6 +35,18 @@ def main():
         "scan_corner": q["corner"], "scan_surf": q["surf"], "init": q["init"], "gt": q["gt"],
         "knn_idx": kidx, "n_edge0": ne, "n_plane0": npl, "corr0": corr,
     }
+    # scan-to-scan pair (BASELINE config 1): features of two consecutive query scans, identity initial guess
+    f0, f1 = case["queries"][0]["features"], case["queries"][1]["features"]
+    odo = {"odo_last_corner": f0["full"][f0["idx_less_sharp"]], "odo_last_corner_ring": f0["ring"][f0["idx_less_sharp"]],
+           "odo_last_surf": f0["full"][f0["idx_less_flat"]], "odo_last_surf_ring": f0["ring"][f0["idx_less_flat"]],
+           "odo_curr_sharp": f1["full"][f1["idx_sharp"]], "odo_curr_flat": f1["full"][f1["idx_flat"]],
+           "odo_init": np.array([0, 0, 0, 0, 0, 0, 1.0])}
+    rc, x, logs, counts, assoc = O.scan2scan(P, odo["odo_last_corner"], odo["odo_last_corner_ring"], odo["odo_last_surf"],
+                                            odo["odo_last_surf_ring"], odo["odo_curr_sharp"], odo["odo_curr_flat"], odo["odo_init"])
+    out.update(odo)
+    out.update(odo_rc=rc, odo_pose=x, odo_counts=counts, odo_assoc=assoc,
+               odo_final_cost=np.array([l["final_cost"] for l in logs]))
+    out["lm_trace_ref"] = None  # filled below
     for name, over in (("ref", {}), ("fixed10", {"early_exit": 0, "max_num_iterations": 5})):
         Pn = O.default_params(**over)
         x, logs, counts = O.scan2map(Pn, case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"])
@@ -43,6 +55,10 @@ def main():
         out[f"attempts_{name}"] = np.array([l["n_attempts"] for l in logs])
         out[f"final_cost_{name}"] = np.array([l["final_cost"] for l in logs])
         out[f"accepted_{name}"] = np.array([[it["accepted"] for it in l["iters"]] + [-1] * (16 - l["n_attempts"]) for l in logs])
+        # Ceres-style trace per attempt: cost before, candidate cost, rho (tr_ratio), radius (tr_radius)
+        out[f"lm_trace_{name}"] = np.array([[[it["cost"], it["cost_candidate"], it["rho"], it["radius"]] for it in l["iters"]] +
+                                            [[np.nan] * 4] * (16 - l["n_attempts"]) for l in logs])
+        out[f"initial_cost_{name}"] = np.array([l["initial_cost"] for l in logs])
     path = os.path.join(ROOT, "tests", "golden", "vlp16_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

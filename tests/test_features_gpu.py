@@ -1,9 +1,10 @@
 """Parity of the CUDA feature extraction / VoxelGrid / scan-to-scan path against the CPU oracle.
 
 Bit-exact: ring-major order, rings, curvature (fp32), labels, the four index lists, voxel-grid
-centroids, odometry associations.  Relative time (stored in `intensity`): the double-precision
-atan2 of glibc and of CUDA's libm may differ in the last bit, which can flip the final float
-rounding -> compared to 1 float ulp (~4e-9 s).  Poses: <= 1e-4 m / 1e-4 rad (north_star).
+centroids, odometry associations.  Relative time (stored in `intensity`): the reference's azimuth is a
+FLOAT atan2 (msf_loam_node.cc:131,139 resolve to the float overload, see oracle/ref_harness/atan2_overload.cc);
+libm's atan2f is only defined to 1 ulp (2.4e-7 rad = 3.8e-9 s of scan time), and the result is rounded to float
+once more -> compared to 1.6e-8 s (two float ulps at the end of the scan).  Poses: <= 1e-4 m / 1e-4 rad (north_star).
 """
 import numpy as np
 import pytest
@@ -28,7 +29,7 @@ def _check_features(f, g, check_time=True):
     assert np.array_equal(f["ring"], g["ring"])
     assert np.array_equal(f["full"][:, :3], g["full"][:, :3])
     if check_time:
-        assert np.abs(f["full"][:, 3] - g["full"][:, 3]).max() <= 8e-9
+        assert np.abs(f["full"][:, 3] - g["full"][:, 3]).max() <= 1.6e-8
     assert np.array_equal(f["curvature"], g["curvature"])
     assert np.array_equal(f["label"], g["label"])
     for k in ("idx_sharp", "idx_less_sharp", "idx_flat", "idx_less_flat"):

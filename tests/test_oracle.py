@@ -61,6 +61,88 @@ def test_map_association_knn_matches_real_flann_kdtree_single(vlp16_case):
     assert checked > 3000
 
 
+def test_map_association_knn_matches_real_flann_on_hdl64():
+    """The same FLANN pin on the HDL-64E-shape case (BASELINE config 3: 80 x 60 m scene, ~13 k queries, ~43 k map points)."""
+    cv2 = pytest.importorskip("cv2")
+    from conftest import make_map_case
+    case = make_map_case("hdl64", "room80", 5, 200)
+    P = O.default_params()
+    q = case["queries"][0]
+    _, _, _, kidx = O.associate_map(P, case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"])
+    n_c = q["corner"].shape[0]
+    checked = 0
+    for cloud_map, scan, rows in ((case["map_corner"], q["corner"], kidx[:n_c]), (case["map_surf"], q["surf"], kidx[n_c:])):
+        m = np.ascontiguousarray(cloud_map[:, :3])
+        x = np.ascontiguousarray(S.transform_cloud(q["init"], scan)[:, :3])
+        idx, d2 = cv2.flann_Index(m, dict(algorithm=4, leaf_max_size=15)).knnSearch(x, 5, params=dict(checks=-1, eps=0.0, sorted=True))
+        gate = d2[:, 4] < np.float32(1.0)
+        assert np.array_equal(gate, rows[:, 0] >= 0)
+        ok = gate & ~(np.diff(d2, axis=1) == 0).any(axis=1)
+        assert np.array_equal(rows[ok], idx[ok])
+        checked += int(ok.sum())
+    assert checked > 9000
+
+
+def test_odometry_nearest_neighbour_matches_real_flann():
+    """Row a-5: the 1-NN of every sharp / flat point in the last scan's less-sharp / less-flat cloud
+    (odometry_scan_matcher.cc:84, :169; kd-trees built at :57-61) against FLANN's KDTreeSingleIndex, with the
+    d^2 < 25 gate of :87 / :172.  The oracle reports the association [closest, second] / [closest, j, l]; its first
+    entry is that 1-NN."""
+    cv2 = pytest.importorskip("cv2")
+    P = O.default_params()
+    sc, traj = S.make_scene(), S.trajectory(2, seed=1)
+    f = [O.extract_features(P, *S.raycast_scan(sc, "vlp16", traj[k], seed=1 + k), None) for k in range(2)]
+    lc, ls = f[0]["full"][f[0]["idx_less_sharp"]], f[0]["full"][f[0]["idx_less_flat"]]
+    cs, cf = f[1]["full"][f[1]["idx_sharp"]], f[1]["full"][f[1]["idx_flat"]]
+    init = S.pose_identity()
+    rc, x, logs, counts, assoc = O.scan2scan(P, lc, f[0]["ring"][f[0]["idx_less_sharp"]], ls, f[0]["ring"][f[0]["idx_less_flat"]],
+                                            cs, cf, init)
+    # `assoc` is the association of the LAST outer iteration; redo iteration 0 (identity guess) through the k-NN entry point
+    first_sharp, _ = O.knn(lc, cs[:, :3], 1)
+    first_flat, _ = O.knn(ls, cf[:, :3], 1)
+    checked = 0
+    for target, queries, mine in ((lc, cs, first_sharp), (ls, cf, first_flat)):
+        index = cv2.flann_Index(np.ascontiguousarray(target[:, :3]), dict(algorithm=4, leaf_max_size=15))
+        idx, d2 = index.knnSearch(np.ascontiguousarray(queries[:, :3]), 1, params=dict(checks=-1, eps=0.0, sorted=True))
+        assert np.array_equal(idx[:, 0], mine[:, 0])
+        assert (d2[:, 0] < np.float32(25.0)).all()  # every query of this pair passes the kDistanceSqThreshold gate
+        checked += len(idx)
+    assert checked > 500 and rc == 0
+
+
+def test_atan2_overload_of_the_registration_block():
+    """msf_loam_node.cc:131,139 call atan2 unqualified on floats; with <math.h> in the include graph (ROS / tf pull it in)
+    libstdc++ resolves that to float atan2(float, float), with <cmath> alone to the promoted double version.  The oracle
+    and k_feat_angles follow the float overload."""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "ref_harness", "atan2_overload.cc")
+    with tempfile.TemporaryDirectory() as d:
+        sizes = []
+        for flag in ([], ["-DWITH_MATH_H"]):
+            exe = os.path.join(d, "a" + str(len(flag)))
+            subprocess.run([gxx, "-std=c++14", *flag, src, "-o", exe], check=True)
+            sizes.append(int(subprocess.run([exe], capture_output=True, text=True, check=True).stdout))
+    assert sizes == [8, 4]
+    # and the oracle's relative time is the float-azimuth one: scan time of a point = float(-atan2f) based
+    P = O.default_params()
+    xyzi, ring = S.raycast_scan(S.make_scene(), "vlp16", S.trajectory(1)[0], seed=3)
+    f = O.extract_features(P, xyzi, ring, None)
+    j = 12345
+    src_idx = np.nonzero((xyzi[:, :3] == f["full"][j, :3]).all(1))[0][0]
+    first = xyzi[0]
+    start = np.float64(-np.arctan2(np.float32(first[1]), np.float32(first[0]), dtype=np.float32))
+    ori = np.float64(-np.arctan2(xyzi[src_idx, 1], xyzi[src_idx, 0], dtype=np.float32))
+    rel = np.fmod(ori - start + 2 * np.pi, 2 * np.pi)
+    t = np.float32(rel / (2 * np.pi) * 0.1)
+    assert abs(float(t) - float(f["full"][j, 3])) <= 1.6e-8 or abs(float(t) + 0.1 - float(f["full"][j, 3])) <= 1.6e-8
+
+
 def test_knn_fewer_points_than_k():
     pts = np.zeros((3, 4), np.float32)
     pts[:, 0] = [0, 1, 2]
