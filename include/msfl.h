@@ -83,10 +83,12 @@ typedef struct msfl_params {
   int32_t early_exit;          /* 1 = Ceres termination tests; 0 = fixed attempt count
                                   (throughput schedule)                 */
   /* engine */
-  int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan in the LM kernel: 0 / 1 = one
-                                  CTA per scan (a scan's pose is then bit-identical alone and in any
-                                  batch), 2/4/8 = partial sums meet over distributed shared memory:
-                                  lower latency for single scans and for small batches of large scans */
+  int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan: 0 / 1 = one CTA per scan (a scan's
+                                  pose is then bit-identical alone and in any batch), 2/4/8/16 = partial sums meet
+                                  over distributed shared memory: small batches of large scans fill the chip, and
+                                  a SINGLE scan (msfl_scan2map, the ROS call pattern) runs as one fused launch --
+                                  association into shared memory + solve, scan2map_fused.cu; 16 needs a GPC with
+                                  16 free SMs and falls back to 8 */
   int32_t assoc_sorted;        /* scan-to-map association order: 0 = auto (order the batch's queries
                                   by submap cell when it holds >= 65536 queries), 1 = never, 2 = always,
                                   3 = always + search against TMA-staged shared-memory tiles of the

@@ -427,6 +427,12 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   int rc;
   if ((rc = e->d_corr.reserve(((size_t)nct + nst + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
+  if (B == 1) {  // the ROS node's call pattern: one cluster owns the scan for the whole call, one launch
+    stage_begin(e, 1);
+    rc = launch_scan2map_fused(e, d_qc, nct, d_qs, nst, d_poses, e->d_status.as<int32_t>(), d_stats);
+    stage_end(e);
+    if (rc <= 0) return rc;
+  }
   for (int outer = 0; outer < e->params.num_outer; ++outer) {  // mapping_scan_matcher.cc:75
     const bool compact = true;  // plane constants as 32 B {n, n.c}
     if ((rc = launch_associate_map(e, B, d_qc, d_c_off, nct, d_qs, d_s_off, nst, d_poses, e->d_corr.as<double>(), nullptr, compact)))

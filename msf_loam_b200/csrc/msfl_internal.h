@@ -82,6 +82,8 @@ struct msfl_engine {
   std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
   bool lm_attr_set[8] = {false, false, false, false, false, false, false, false};
+  bool fused_attr_set = false;  // k_scan2map_fused: dynamic smem + non-portable cluster size attributes
+  int fused_max16 = -1;         // cudaOccupancyMaxActiveClusters of the 16-CTA configuration (-1: not asked yet)
   bool pick_attr_set = false;  // k_feat_pick's dynamic shared-memory attribute (per device, so kept per engine)
   // the cell keys of a batch are counting-sorted while the bin table (64 sub-cell bins per submap cell) stays small
   // enough to live in L2; larger (sparse, far-spread) submaps fall back to a radix sort of the keys
@@ -167,6 +169,10 @@ int launch_lm_solve_pd(msfl_engine *e, int B, const double *d_qe, const int32_t 
                        msfl_stats *d_stats, int outer, int min_corr);
 int launch_accumulate(msfl_engine *e, const float4 *d_p, const double *d_corr, int n_edge, int n_plane,
                       const double *d_pose, double *d_out28);
+
+// ---- scan2map_fused.cu: one scan, one launch (MSFL_OK = enqueued, 1 = does not qualify, < 0 error)
+int launch_scan2map_fused(msfl_engine *e, const float4 *d_qc, uint32_t nc, const float4 *d_qs, uint32_t ns, double *d_pose,
+                          int32_t *d_status, msfl_stats *d_stats);
 
 // ---- scan2scan.cu
 int launch_associate_scan(msfl_engine *e, const float4 *d_last_corner, const uint16_t *d_last_corner_ring, uint32_t n_lc,

@@ -96,3 +96,39 @@ def test_tiny_and_degenerate_maps(vlp16_case):
     with pytest.raises(MsflError):
         e.set_submap(line, bad)
     e.close()
+
+
+def test_far_spread_submap_large_batch_uses_reduced_subcell_keys(vlp16_case):
+    """A submap whose two classes span > 2^26 cells in total (two sites 3.6 km apart): the cell-ordered association used
+    to refuse it (cell id + 6 sub-cell bits > 32 bits) once a batch reached 65536 queries, although single scans worked.
+    It now drops to 2x2x2 sub-cells (radix-sorted keys): same neighbours as the flat path, and a >= 65536-query batch runs."""
+    far = np.array([2990.0, 1990.0, 0.0, 0.0], np.float32)
+    mc = np.concatenate([vlp16_case["map_corner"], vlp16_case["map_corner"] + far])
+    ms = np.concatenate([vlp16_case["map_surf"], vlp16_case["map_surf"] + far])
+    qs = vlp16_case["queries"]
+    P = O.default_params()
+    e = Engine(default_params())  # auto mode
+    e.set_submap(mc, ms)
+    q = qs[0]
+    flat = Engine(default_params(assoc_sorted=1))
+    flat.set_submap(mc, ms)
+    knn_flat, corr_flat = flat.associate_map(q["corner"], q["surf"], q["init"])
+    srt = Engine(default_params(assoc_sorted=2))
+    srt.set_submap(mc, ms)
+    knn_sorted, corr_sorted = srt.associate_map(q["corner"], q["surf"], q["init"])
+    assert np.array_equal(knn_flat, knn_sorted) and np.array_equal(corr_flat, corr_sorted)
+    _, _, _, kidx = O.associate_map(P, mc, ms, q["corner"], q["surf"], q["init"])
+    assert np.array_equal(knn_sorted, kidx)
+    B = 16  # 16 x ~4.7 k queries >= 65536
+    n_q = sum(qs[i % 3]["corner"].shape[0] + qs[i % 3]["surf"].shape[0] for i in range(B))
+    assert n_q >= 65536
+    rc, xs, _ = e.scan2map_batch([qs[i % 3]["corner"] for i in range(B)], [qs[i % 3]["surf"] for i in range(B)],
+                                 [qs[i % 3]["init"] for i in range(B)])
+    assert rc == 0
+    for i in range(3):
+        x_ref, _, _ = O.scan2map(P, mc, ms, qs[i]["corner"], qs[i]["surf"], qs[i]["init"])
+        dt, dr = S.pose_error(xs[i], x_ref)
+        assert dt < 1e-7 and dr < 1e-9
+        assert np.array_equal(xs[i], xs[i + 3])
+    for x in (e, flat, srt):
+        x.close()

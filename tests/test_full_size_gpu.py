@@ -101,3 +101,56 @@ def test_full_batch_2048_replicas_bitwise_near_gt_and_idempotent(vlp16_case):
         dt, dr = S.pose_error(xs2[i], xs[i])
         assert dt < 2e-3 and dr < 2e-4
     e.close()
+
+
+@pytest.mark.parametrize("G", [8, 16])
+def test_hdl64_cluster_paths_match_oracle(G):
+    """HDL-64E-shape scans through the clustered paths: the fused one-launch kernel (single scan) and the clustered LM
+    kernel (small batch), against the oracle."""
+    case = make_map_case("hdl64", "room80", 5, 200)
+    P = O.default_params()
+    e = Engine(default_params(lm_cluster=G))
+    e.set_submap(case["map_corner"], case["map_surf"])
+    qs = case["queries"]
+    refs = [O.scan2map(P, case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"]) for q in qs]
+    for q, (x_ref, logs, counts) in zip(qs, refs):
+        rc, x, st = e.scan2map(q["corner"], q["surf"], q["init"])
+        dt, dr = S.pose_error(x, x_ref)
+        assert rc == 0 and dt < 1e-7 and dr < 1e-8
+        assert st["n_edge"] == list(counts[:, 0]) and st["n_plane"] == list(counts[:, 1])
+        assert [l["n_attempts"] for l in st["lm"]] == [l["n_attempts"] for l in logs]
+    rc, xs, _ = e.scan2map_batch([q["corner"] for q in qs], [q["surf"] for q in qs], [q["init"] for q in qs])
+    for x, (x_ref, _, _) in zip(xs, refs):
+        dt, dr = S.pose_error(x, x_ref)
+        assert rc == 0 and dt < 1e-7 and dr < 1e-8
+    e.close()
+
+
+def test_os1_128_against_million_point_submap_matches_oracle():
+    """BASELINE config 5 at real size: OS1-128-shape scans (~60 k queries each) against the ~1 M-point submap of a
+    50-scan drive through the 300 x 120 m hall (bench.py's workload, built here with the oracle's extraction): pose
+    parity with the oracle for the single-scan paths (one CTA, cluster of 8) and for a cell-ordered batch."""
+    import os
+    import bench
+    traj, scans = bench.raw_scans("os1-128", 2, n_workers=os.cpu_count() or 1)
+    P = O.default_params()
+    mc, ms, queries, _ = bench.build_case(lambda x, r: O.extract_features(P, x, r, None), O.voxel_grid, "os1-128", traj, scans)
+    assert mc.shape[0] + ms.shape[0] > 900_000
+    rng = np.random.default_rng(17)
+    inits = [S.perturb_pose(q[2], rng) for q in queries]
+    refs = [O.scan2map(P, mc, ms, q[0], q[1], x0) for q, x0 in zip(queries, inits)]
+    for G in (0, 8):
+        e = Engine(default_params(lm_cluster=G))
+        e.set_submap(mc, ms)
+        for q, x0, (x_ref, logs, counts) in zip(queries, inits, refs):
+            rc, x, st = e.scan2map(q[0], q[1], x0)
+            dt, dr = S.pose_error(x, x_ref)
+            assert rc == 0 and dt <= 1e-4 and dr <= 1e-4  # north_star tolerance
+            assert dt < 1e-6 and dr < 1e-7                # what the fp64 path achieves at 100 m ranges
+            assert st["n_edge"] == list(counts[:, 0]) and st["n_plane"] == list(counts[:, 1])
+        if G == 8:  # 2 x 60 k queries >= 65536: the cell-ordered batch association, clustered LM
+            rc, xs, _ = e.scan2map_batch([q[0] for q in queries], [q[1] for q in queries], inits)
+            for x, (x_ref, _, _) in zip(xs, refs):
+                dt, dr = S.pose_error(x, x_ref)
+                assert rc == 0 and dt < 1e-6 and dr < 1e-7
+        e.close()

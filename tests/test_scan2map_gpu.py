@@ -152,10 +152,11 @@ def test_large_host_batch_pipelined_path_bitwise(eng, vlp16_case):
     assert st[B - 1]["n_plane"] == st[(B - 1) % 3]["n_plane"] and st[B - 1]["lm"][1]["n_attempts"] > 0
 
 
-@pytest.mark.parametrize("G", [2, 4, 8])
+@pytest.mark.parametrize("G", [2, 4, 8, 16])
 def test_cluster_lm_matches_oracle(vlp16_case, G):
-    """lm_cluster = G: one thread-block cluster of G CTAs per scan, partial sums combined over DSMEM.
-    The summation grouping differs from G = 1, so parity is to rounding (1e-8), not bitwise."""
+    """lm_cluster = G: one thread-block cluster of G CTAs per scan, partial sums combined over DSMEM.  A single scan
+    (e.scan2map) takes the fused one-launch kernel (scan2map_fused.cu: association into shared memory + solve), a batch
+    the clustered LM kernel.  The summation grouping differs from G = 1, so parity is to rounding (1e-8), not bitwise."""
     P = O.default_params()
     e = Engine(default_params(lm_cluster=G))
     e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
@@ -174,6 +175,20 @@ def test_cluster_lm_matches_oracle(vlp16_case, G):
                                   [qs[0]["init"], qs[1]["init"], far], want_stats=True)
     assert rc == 0 and np.array_equal(xs[1], qs[1]["init"]) and np.array_equal(xs[2], far)
     assert S.pose_error(xs[0], qs[0]["gt"])[0] < 0.03
+    # fused kernel: no correspondence at all -> pose untouched, zero counts; and both LM schedules
+    rc, x, st = e.scan2map(qs[0]["corner"], qs[0]["surf"], far)
+    assert rc == 0 and np.array_equal(x, far) and st["n_edge"] == [0, 0] and st["n_plane"] == [0, 0]
+    e.close()
+    e = Engine(default_params(lm_cluster=G, early_exit=0, max_num_iterations=5))
+    e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+    Pf = O.default_params(early_exit=0, max_num_iterations=5)
+    x_ref, logs, _ = O.scan2map(Pf, vlp16_case["map_corner"], vlp16_case["map_surf"], qs[2]["corner"], qs[2]["surf"], qs[2]["init"])
+    rc, x, st = e.scan2map(qs[2]["corner"], qs[2]["surf"], qs[2]["init"])
+    dt, dr = S.pose_error(x, x_ref)
+    assert rc == 0 and dt < 1e-8 and dr < 1e-8
+    for l, lr in zip(st["lm"], logs):
+        assert [it["accepted"] for it in l["iters"]] == [it["accepted"] for it in lr["iters"]]
+        assert abs(l["final_cost"] - lr["final_cost"]) <= 1e-9 * lr["final_cost"]
     e.close()
 
 
