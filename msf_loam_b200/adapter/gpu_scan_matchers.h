@@ -49,9 +49,10 @@ class Engine {
   explicit Engine(int device = 0) {
     msfl_params p;
     msfl_default_params(&p);
-    // the ROS node matches one scan at a time: spread each solve over a thread-block cluster of 8 CTAs
-    // (0.23 ms instead of 0.33 ms per VLP-16 scan-to-map; batches keep the default of one CTA per scan)
-    p.lm_cluster = 8;
+    // the ROS node matches one scan at a time: a thread-block cluster of 16 CTAs (8 where a GPC cannot host 16) owns
+    // the scan for the whole call -- association into shared memory + solve in ONE launch (scan2map_fused.cu);
+    // batches keep the default of one CTA per scan
+    p.lm_cluster = 16;
     if (msfl_create(&p, device, &e_) != MSFL_OK) throw std::runtime_error(std::string("msfl_create: ") + msfl_last_error());
   }
   ~Engine() { msfl_destroy(e_); }

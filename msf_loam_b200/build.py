@@ -93,7 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists(tmp):
             os.unlink(tmp)
         raise RuntimeError("nvcc failed linking libmsfl.so")
-    os.replace(tmp, LIB)
+    os.replace(tmp, os.environ.get("MSFL_LIB_OUT", LIB))  # development: build a variant next to the tree's library
     if verbose:
         sys.stderr.write("".join(log))
     return LIB

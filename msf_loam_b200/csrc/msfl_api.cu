@@ -351,7 +351,8 @@ void msfl_destroy(msfl_engine *e) {
     if (sl.uploaded) cudaEventDestroy(sl.uploaded);
     if (sl.done) cudaEventDestroy(sl.done);
   }
-  PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc};
+  PinBuf *pbs[] = {&e->h_stage, &e->h_poses, &e->h_stats, &e->h_misc, &e->h_map_stage};
+  if (e->map_uploaded) cudaEventDestroy(e->map_uploaded);
   for (PinBuf *b : pbs) b->release();
   for (auto &s : e->stage_events) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
@@ -390,6 +391,27 @@ int msfl_set_submap_device(msfl_engine *e, const float *d_corner, size_t n_corne
   return MSFL_OK;
 }
 
+// cell bounding box of a packed cloud for the given cell edge, computed with the kernels' own arithmetic
+// (floorf(x * inv_edge) in fp32); false when a point is non-finite or beyond 1e6 m (the device build refuses those too)
+static bool host_cell_bounds(const float *xyzw, size_t n, float inv_edge, int lo[3], int hi[3]) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool ok = true;
+  for (size_t i = 0; i < n; ++i) {
+    for (int d = 0; d < 3; ++d) {
+      const float v = xyzw[4 * i + d];
+      if (!(fabsf(v) <= 1e6f)) ok = false;  // also catches NaN
+      mn[d] = v < mn[d] ? v : mn[d];
+      mx[d] = v > mx[d] ? v : mx[d];
+    }
+  }
+  if (!ok) return false;
+  for (int d = 0; d < 3; ++d) {  // x -> floorf(x * inv_edge) is monotone, so the extreme points give the extreme cells
+    lo[d] = (int)floorf(mn[d] * inv_edge);
+    hi[d] = (int)floorf(mx[d] * inv_edge);
+  }
+  return true;
+}
+
 int msfl_set_submap(msfl_engine *e, const msfl_cloud *map_corner, const msfl_cloud *map_surf) {
   if (!e) { set_error("msfl_set_submap: null engine"); return MSFL_ERR_ARG; }
   int rc;
@@ -398,15 +420,33 @@ int msfl_set_submap(msfl_engine *e, const msfl_cloud *map_corner, const msfl_clo
   if (map_corner->n == 0 || map_surf->n == 0) { set_error("msfl_set_submap: empty submap class"); return MSFL_ERR_ARG; }
   MSFL_CUDA_OK(cudaSetDevice(e->device));
   const size_t nc = map_corner->n, ns = map_surf->n;
-  if ((rc = e->h_stage.reserve((nc + ns) * 16))) return rc;
-  float *h = e->h_stage.as<float>();
+  // own staging buffer (the batch calls repack into h_stage while this upload may still be in flight); the previous
+  // map upload must have left it
+  if (e->map_uploaded) MSFL_CUDA_OK(cudaEventSynchronize(e->map_uploaded));
+  else MSFL_CUDA_OK(cudaEventCreateWithFlags(&e->map_uploaded, cudaEventDisableTiming));
+  if ((rc = e->h_map_stage.reserve((nc + ns) * 16))) return rc;
+  float *h = e->h_map_stage.as<float>();
   pack_cloud_host(map_corner, h, nullptr);
   pack_cloud_host(map_surf, h + 4 * nc, nullptr);
   if ((rc = e->map_corner.orig.reserve(nc * 16))) return rc;
   if ((rc = e->map_surf.orig.reserve(ns * 16))) return rc;
+  e->has_submap = false;
   MSFL_CUDA_OK(cudaMemcpyAsync(e->map_corner.orig.p, h, nc * 16, cudaMemcpyHostToDevice, e->stream));
   MSFL_CUDA_OK(cudaMemcpyAsync(e->map_surf.orig.p, h + 4 * nc, ns * 16, cudaMemcpyHostToDevice, e->stream));
-  return msfl_set_submap_device(e, e->map_corner.orig.as<float>(), nc, e->map_surf.orig.as<float>(), ns);
+  MSFL_CUDA_OK(cudaEventRecord(e->map_uploaded, e->stream));
+  // The points pass through the host anyway: take the cell bounding box here, so the index build needs no device
+  // round trip (the reference rebuilds its kd-trees every frame, mapping_scan_matcher.cc:66-72 -- this call is on the
+  // latency path of the drop-in).  Counting sort of the cells: no library sort, no synchronisation.
+  const float edge = cell_edge(e), inv_edge = 1.0f / edge;
+  int lo_c[3], hi_c[3], lo_s[3], hi_s[3];
+  if (!host_cell_bounds(h, nc, inv_edge, lo_c, hi_c) || !host_cell_bounds(h + 4 * nc, ns, inv_edge, lo_s, hi_s)) {
+    set_error("submap contains non-finite or out-of-range (>1e6 m) points");
+    return MSFL_ERR_ARG;
+  }
+  if ((rc = submap_build_host_bounds(e, e->map_corner, nc, edge, lo_c, hi_c))) return rc;
+  if ((rc = submap_build_host_bounds(e, e->map_surf, ns, edge, lo_s, hi_s))) return rc;
+  e->has_submap = true;
+  return MSFL_OK;
 }
 
 int msfl_get_submap_device(msfl_engine *e, const float **d_corner, size_t *n_corner, const float **d_surf, size_t *n_surf) {

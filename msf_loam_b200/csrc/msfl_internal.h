@@ -115,7 +115,8 @@ struct msfl_engine {
 
   // batch scratch
   msfl::DevBuf d_queries, d_corr, d_poses, d_status, d_stats, d_knn, d_off, d_misc;
-  msfl::PinBuf h_stage, h_poses, h_stats, h_misc;
+  msfl::PinBuf h_stage, h_poses, h_stats, h_misc, h_map_stage;
+  cudaEvent_t map_uploaded = nullptr;  // the last msfl_set_submap upload has left h_map_stage
   // sorted association scratch: transformed queries, cell keys / permutation (double-buffered), cub temp
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp, a_hist;
   bool fuse_fit = true;  // batch path: plane fit inside the search kernel (MSFL_FUSE_FIT=0: separate k_fit launch)
@@ -141,6 +142,7 @@ void stage_end(msfl_engine *e);
 
 // ---- submap_index.cu
 int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge);
+int submap_build_host_bounds(msfl_engine *e, Submap &m, size_t n, float edge, const int lo[3], const int hi[3]);
 void submap_release(Submap &m);
 
 // ---- associate_map.cu

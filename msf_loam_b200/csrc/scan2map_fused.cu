@@ -23,7 +23,10 @@ namespace cg = cooperative_groups;
 
 namespace msfl {
 
-constexpr int kFusedThreads = 256;
+#ifndef MSFL_FUSED_THREADS
+#define MSFL_FUSED_THREADS 512
+#endif
+constexpr int kFusedThreads = MSFL_FUSED_THREADS;
 using FusedShared = LmSharedT<kFusedThreads / 32>;
 
 // this thread's entries out of shared memory: edge entries {a, n} (6 doubles), plane entries {n, n.c} (4 doubles)

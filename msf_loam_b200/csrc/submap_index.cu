@@ -6,6 +6,7 @@
 // linear cell id, original index in .w), cell_start uint32[ncell+1].  Cell edge = search radius
 // (sqrt(knn_max_sq) = 1 m), so the d5^2 < 1 gate makes a 3x3x3 neighbourhood search exact.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <limits.h>
 
@@ -86,6 +87,72 @@ __global__ void k_cell_start(const uint32_t *__restrict__ keys_sorted, uint32_t 
     else hi = mid;
   }
   cell_start[c] = lo;
+}
+
+// ---- counting-sort build (host-known grid: no device round trip) --------------------------------------------------
+// one atomic per point returns its rank inside its cell; after an exclusive scan of the cell counts one scatter puts the
+// point at cell_start[cell] + rank.  The order inside a cell follows the atomics, which the 5-NN does not see: its
+// candidates are ordered by (distance, original index), whatever order they arrive in.
+__global__ void k_cell_count(const float4 *__restrict__ pts, uint32_t n, float inv_edge, int ox, int oy, int oz, int nx, int ny,
+                             uint32_t *__restrict__ count, uint32_t *__restrict__ keys, uint32_t *__restrict__ rank) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const int cx = (int)floorf(p.x * inv_edge) - ox, cy = (int)floorf(p.y * inv_edge) - oy, cz = (int)floorf(p.z * inv_edge) - oz;
+  const uint32_t key = (uint32_t)((cz * ny + cy) * nx + cx);
+  keys[i] = key;
+  rank[i] = atomicAdd(count + key, 1u);
+}
+
+__global__ void k_cell_scatter(const float4 *__restrict__ pts, uint32_t n, const uint32_t *__restrict__ keys,
+                               const uint32_t *__restrict__ rank, const uint32_t *__restrict__ cell_start, float4 *__restrict__ sorted) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  p.w = __int_as_float((int)i);
+  sorted[__ldg(cell_start + __ldg(keys + i)) + __ldg(rank + i)] = p;
+}
+
+// Cell index over points already in m.orig, with the cell bounding box known on the host (msfl_set_submap computes it
+// while it repacks the caller's cloud): five stream operations, no synchronisation, no library sort.
+int submap_build_host_bounds(msfl_engine *e, Submap &m, size_t n, float edge, const int lo[3], const int hi[3]) {
+  cudaStream_t st = e->stream;
+  if (n == 0 || n > 0x7fffffffull) { set_error("submap class is empty or too large (n=%zu)", n); return MSFL_ERR_ARG; }
+  const uint32_t N = (uint32_t)n;
+  const float inv_edge = 1.0f / edge;
+  const long long nx = (long long)hi[0] - lo[0] + 5, ny = (long long)hi[1] - lo[1] + 5, nz = (long long)hi[2] - lo[2] + 5;
+  const long long ncell = nx * ny * nz;
+  if (ncell > (1ll << 26)) {
+    set_error("submap bounding box needs %lld cells (> 2^26); dense cell index refused", ncell);
+    return MSFL_ERR_GRID;
+  }
+  int rc;
+  if ((rc = m.sorted.reserve(n * sizeof(float4)))) return rc;
+  if ((rc = m.keys.reserve(n * 4))) return rc;
+  if ((rc = m.vals.reserve(n * 4))) return rc;
+  if ((rc = m.cell_start.reserve((size_t)(ncell + 1) * 4))) return rc;
+  size_t tmp_bytes = 0;
+  uint32_t *cs = m.cell_start.as<uint32_t>();
+  MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cs, cs, (int)(ncell + 1), st));
+  if ((rc = m.cub_tmp.reserve(tmp_bytes))) return rc;
+  const int ox = lo[0] - 2, oy = lo[1] - 2, oz = lo[2] - 2;
+  const int tb = 256;
+  const float4 *pts = m.orig.as<float4>();
+  MSFL_CUDA_OK(cudaMemsetAsync(cs, 0, (size_t)(ncell + 1) * 4, st));
+  k_cell_count<<<(N + tb - 1) / tb, tb, 0, st>>>(pts, N, inv_edge, ox, oy, oz, (int)nx, (int)ny, cs, m.keys.as<uint32_t>(), m.vals.as<uint32_t>());
+  MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(m.cub_tmp.p, tmp_bytes, cs, cs, (int)(ncell + 1), st));
+  k_cell_scatter<<<(N + tb - 1) / tb, tb, 0, st>>>(pts, N, m.keys.as<uint32_t>(), m.vals.as<uint32_t>(), cs, m.sorted.as<float4>());
+  e->launches += 2 + 2;
+  MSFL_CUDA_OK(cudaGetLastError());
+  m.n = n;
+  m.view.pts_sorted = m.sorted.as<float4>();
+  m.view.pts_orig = pts;
+  m.view.cell_start = cs;
+  m.view.nx = (int)nx; m.view.ny = (int)ny; m.view.nz = (int)nz;
+  m.view.ox = ox; m.view.oy = oy; m.view.oz = oz;
+  m.view.inv_edge = inv_edge;
+  m.view.n = N;
+  return MSFL_OK;
 }
 
 void submap_release(Submap &m) {

@@ -2,6 +2,7 @@
 // adapters the way LaserOdometry / LaserMapping do (laser_odometry.cc:75, laser_mapping.cc:304-311): the clouds are
 // read from a flat binary case file (tests/test_adapter.py writes it), filled into pcl::PointCloud stand-ins, and
 // the poses that come back are printed for comparison with the Python binding's.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -48,6 +49,32 @@ int main(int argc, char **argv) {
   double out[7];
   msfl_adapter::ToArray(pose, out);
   std::printf("MAP %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)ok_map, out[0], out[1], out[2], out[3], out[4], out[5], out[6]);
+
+  if (argc > 2 && !std::strcmp(argv[2], "bench")) {  // latency of the drop-in call, no Python in the loop
+    const int reps = 200;
+    for (int w = 0; w < 10; ++w) { pose = msfl_adapter::FromArray(init_map); mbase->MatchScan2Map(map, scan, false, nullptr, Vector3d(0, 0, -9.8), RobotState{}, &pose, &velocity); }
+    auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) {
+      pose = msfl_adapter::FromArray(init_map);
+      mbase->MatchScan2Map(map, scan, false, nullptr, Vector3d(0, 0, -9.8), RobotState{}, &pose, &velocity);
+    }
+    const double us_full = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+    // the same without the per-frame submap upload + index build (a caller that keeps the map resident)
+    msfl_adapter::Engine eng;
+    const msfl_cloud mc = msfl_adapter::View(*map.cloud_corner_less_sharp, false), ms = msfl_adapter::View(*map.cloud_surf_less_flat, false);
+    const msfl_cloud sc = msfl_adapter::View(*scan.cloud_corner_less_sharp, false), ss = msfl_adapter::View(*scan.cloud_surf_less_flat, false);
+    msfl_set_submap(eng.get(), &mc, &ms);
+    double p7[7];
+    for (int w = 0; w < 10; ++w) { std::memcpy(p7, init_map, sizeof p7); msfl_scan2map(eng.get(), &sc, &ss, p7, nullptr); }
+    t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) { std::memcpy(p7, init_map, sizeof p7); msfl_scan2map(eng.get(), &sc, &ss, p7, nullptr); }
+    const double us_solve = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+    t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) msfl_set_submap(eng.get(), &mc, &ms);
+    const double us_map = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+    std::printf("BENCH MatchScan2Map_us %.1f scan2map_us %.1f set_submap_us %.1f\n", us_full, us_solve, us_map);
+    return 0;
+  }
 
   // ---- LaserOdometry::AddLaserScan -> MatchScan2Scan
   TimestampedPointCloud<PointTypeOriginal> last, curr;

@@ -61,7 +61,7 @@ def test_adapter_poses_equal_the_python_binding(tmp_path, vlp16_case):
     r = subprocess.run([exe, path], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stdout + r.stderr
     got = {l.split()[0]: np.array(l.split()[1:], dtype=np.float64) for l in r.stdout.splitlines() if l[:3] in ("MAP", "ODO", "DSK")}
-    eng = Engine(default_params(lm_cluster=8))  # the adapter's engine configuration
+    eng = Engine(default_params(lm_cluster=16))  # the adapter's engine configuration
     eng.set_submap(case["map_corner"], case["map_surf"])
     _, pose_map, _ = eng.scan2map(to_pcl(q["corner"]), to_pcl(q["surf"]), q["init"])
     rc, pose_odo, _ = eng.scan2scan(to_pcl(lc, rlc), to_pcl(ls, rls), to_pcl(cs, np.zeros(len(cs))), to_pcl(cf, np.zeros(len(cf))),

@@ -99,10 +99,10 @@ def test_tiny_and_degenerate_maps(vlp16_case):
 
 
 def test_far_spread_submap_large_batch_uses_reduced_subcell_keys(vlp16_case):
-    """A submap whose two classes span > 2^26 cells in total (two sites 3.6 km apart): the cell-ordered association used
+    """A submap whose two classes span > 2^26 cells in total (two sites 3.2 km apart): the cell-ordered association used
     to refuse it (cell id + 6 sub-cell bits > 32 bits) once a batch reached 65536 queries, although single scans worked.
     It now drops to 2x2x2 sub-cells (radix-sorted keys): same neighbours as the flat path, and a >= 65536-query batch runs."""
-    far = np.array([2990.0, 1990.0, 0.0, 0.0], np.float32)
+    far = np.array([2500.0, 1990.0, 0.0, 0.0], np.float32)
     mc = np.concatenate([vlp16_case["map_corner"], vlp16_case["map_corner"] + far])
     ms = np.concatenate([vlp16_case["map_surf"], vlp16_case["map_surf"] + far])
     qs = vlp16_case["queries"]
