@@ -271,6 +271,25 @@ int msfl_associate_scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp
 int msfl_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T_lidar2imu[7],
                           msfl_features *out);
 
+/* The same for B independent scans in one launch sequence (replay of a log: every kernel runs with grid.y = scan, one
+ * stable sort orders the whole batch by (scan, ring)); outs[b] receives scan b's results, bit-identical to B single calls. */
+int msfl_extract_features_batch(msfl_engine *e, int B, const msfl_cloud *raw, const double T_lidar2imu[7],
+                                msfl_features *outs);
+
+/* ---- raw clouds -> poses for B independent scans against the resident submap (replay of a log, re-localisation):
+ *      scan registration (msf_loam_node.cc:160-371), the caller's VoxelGrid of the less-sharp / less-flat features
+ *      (laser_mapping.cc:264-270; leaf 0.2 / 0.4 = mapping_line_resolution / mapping_plane_resolution) and
+ *      MatchScan2Map (mapping_scan_matcher.cc:63-278), every stage once for the whole batch; intermediate clouds stay in
+ *      HBM.  poses_tq: B x 7, in = initial guesses, out = estimates; counts / stats: B entries or NULL.  Results are
+ *      bit-identical to msfl_extract_features -> msfl_voxel_grid x 2 -> msfl_scan2map_batch on the same scans. */
+typedef struct msfl_chain_counts {
+  int32_t n_full, n_sharp, n_less_sharp, n_flat, n_less_flat;  /* registration output sizes            */
+  int32_t n_corner_queries, n_surf_queries;                     /* after the VoxelGrid: the matcher's queries */
+} msfl_chain_counts;
+int msfl_register_and_match_batch(msfl_engine *e, int B, const msfl_cloud *raw, const double T_lidar2imu[7],
+                                  float leaf_corner, float leaf_surf, double *poses_tq, msfl_chain_counts *counts,
+                                  msfl_stats *stats);
+
 /* ---- GPU-resident STGM submap producer: HybridGrid of hybrid_grid.h:32-35,
  *      hybrid_grid.cc:403-521, one map per feature class (laser_mapping.h hybrid_grid_map_corner_ /
  *      _surf_, resolution 3 m; leaf = mapping_line_resolution 0.2 / mapping_plane_resolution 0.4).

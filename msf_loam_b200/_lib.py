@@ -27,7 +27,7 @@ EXPORTS = [
     "msfl_nccl_comm_destroy",
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
     "msfl_scan2map_batch_device", "msfl_scan2map_batch_submit", "msfl_scan2map_batch_wait", "msfl_scan2map_deskew", "msfl_associate_map", "msfl_scan2scan", "msfl_associate_scan",
-    "msfl_extract_features", "msfl_voxel_grid", "msfl_accumulate", "msfl_map_create", "msfl_map_destroy",
+    "msfl_extract_features", "msfl_extract_features_batch", "msfl_register_and_match_batch", "msfl_voxel_grid", "msfl_accumulate", "msfl_map_create", "msfl_map_destroy",
     "msfl_cloud_from_pointcloud2", "msfl_map_insert", "msfl_map_surround", "msfl_map_size", "msfl_map_download", "msfl_set_submap_from_maps",
 ]
 
@@ -96,6 +96,11 @@ class Deskew(C.Structure):
     _fields_ = [("sum_dt", C.POINTER(C.c_double)), ("delta_q", C.POINTER(C.c_double)),
                 ("delta_p", C.POINTER(C.c_double)), ("n", C.c_int32), ("_pad", C.c_int32),
                 ("velocity", C.c_double * 3), ("gravity", C.c_double * 3)]
+
+
+class ChainCounts(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("n_full", "n_sharp", "n_less_sharp", "n_flat", "n_less_flat",
+                                          "n_corner_queries", "n_surf_queries")]
 
 
 class Pc2Field(C.Structure):

@@ -12,6 +12,10 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
@@ -30,7 +34,17 @@ struct FeatMeta {
   int tot[4];
 };
 
-__global__ void k_feat_init(FeatMeta *m) {
+// Batched form: B scans live back to back in every per-point array; soff (B + 1 entries, device) gives each scan's
+// first point.  Per-point kernels run with grid.y = scan, per-ring kernels with grid = (ring, scan); inside a kernel
+// every array is shifted to the scan's own base, so the bodies read like the single-scan code they were.
+struct ScanView { uint32_t b, base, n; };
+__device__ __forceinline__ ScanView scan_view(const uint32_t *__restrict__ soff, uint32_t b) {
+  const uint32_t base = __ldg(soff + b);
+  return ScanView{b, base, __ldg(soff + b + 1) - base};
+}
+
+__global__ void k_feat_init(FeatMeta *metas) {
+  FeatMeta *m = metas + blockIdx.x;
   const int t = threadIdx.x;
   if (t == 0) { m->first_valid = INT_MAX; m->bad_ring = 0; m->n_valid = 0; m->sector_overflow = 0; }
   if (t < MSFL_MAX_RINGS) {
@@ -68,10 +82,13 @@ __global__ void k_unpack_aos(const unsigned char *__restrict__ raw, uint32_t n, 
 }
 
 // RemoveInvalidPointsFromCloud (:96-103): float norm vs double min_range, non-finite dropped.
-__global__ void k_feat_keys(const float4 *__restrict__ raw, const uint16_t *__restrict__ ring, uint32_t n, double min_range,
-                            uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, FeatMeta *m) {
+__global__ void k_feat_keys(const float4 *__restrict__ raw, const uint16_t *__restrict__ ring, const uint32_t *__restrict__ soff,
+                            double min_range, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, FeatMeta *metas) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= sv.n) return;
+  raw += sv.base; ring += sv.base; keys += sv.base; vals += sv.base;
+  FeatMeta *m = metas + sv.b;
   const float4 p = raw[i];
   const float nr = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)), __fmul_rn(p.z, p.z)));
   const bool valid = !((double)nr < min_range || !isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z));
@@ -82,17 +99,21 @@ __global__ void k_feat_keys(const float4 *__restrict__ raw, const uint16_t *__re
     else key = r;
     atomicMin(&m->first_valid, (int)i);
   }
-  keys[i] = key;
+  keys[i] = (sv.b << 8) | key;  // scan-major, ring-minor: one stable sort orders every scan of the batch
   vals[i] = i;
 }
 
-__global__ void k_feat_ring_start(const uint32_t *__restrict__ keys_sorted, uint32_t n, FeatMeta *m) {
+__global__ void k_feat_ring_start(const uint32_t *__restrict__ keys_sorted, const uint32_t *__restrict__ soff, FeatMeta *metas) {
+  const ScanView sv = scan_view(soff, blockIdx.x);
+  keys_sorted += sv.base;
+  FeatMeta *m = metas + sv.b;
+  const uint32_t n = sv.n;
   const uint32_t r = threadIdx.x;
   if (r > MSFL_MAX_RINGS) return;
   uint32_t lo = 0, hi = n;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (keys_sorted[mid] < r) lo = mid + 1;
+    if ((keys_sorted[mid] & 255u) < r) lo = mid + 1;
     else hi = mid;
   }
   m->ring_start[r] = lo;
@@ -100,8 +121,11 @@ __global__ void k_feat_ring_start(const uint32_t *__restrict__ keys_sorted, uint
 }
 
 // ComputeRelaTimeForEachPoint (:131-151), first half: the raw relative angle of every point.
-__global__ void k_feat_angles(const float4 *__restrict__ raw, const uint32_t *__restrict__ vals, const FeatMeta *__restrict__ m,
-                              double *__restrict__ rel) {
+__global__ void k_feat_angles(const float4 *__restrict__ raw, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ soff,
+                              const FeatMeta *__restrict__ metas, double *__restrict__ rel) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  const FeatMeta *m = metas + sv.b;
+  raw += sv.base; vals += sv.base; rel += sv.base;
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= (uint32_t)m->n_valid) return;
   // :131 / :139 call atan2 unqualified on two floats with <math.h> in the include graph: the float overload is chosen
@@ -117,19 +141,27 @@ __global__ void k_feat_angles(const float4 *__restrict__ raw, const uint32_t *__
 // "if (relative_angle < last_relative_angles[ring]) += 2 pi" (:145-149): once a point of a ring is
 // bumped every later point of that ring is bumped too, so the recurrence collapses to "j >= first
 // position whose raw angle is below its predecessor's".
-__global__ void k_feat_first_dec(const uint32_t *__restrict__ keys_sorted, const double *__restrict__ rel, FeatMeta *m) {
+__global__ void k_feat_first_dec(const uint32_t *__restrict__ keys_sorted, const double *__restrict__ rel,
+                                 const uint32_t *__restrict__ soff, FeatMeta *metas) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  FeatMeta *m = metas + sv.b;
+  keys_sorted += sv.base; rel += sv.base;
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0 || j >= (uint32_t)m->n_valid) return;
-  const uint32_t r = keys_sorted[j];
-  if (keys_sorted[j - 1] == r && rel[j] < rel[j - 1]) atomicMin(&m->first_dec[r], (int)j);
+  const uint32_t r = keys_sorted[j] & 255u;
+  if ((keys_sorted[j - 1] & 255u) == r && rel[j] < rel[j - 1]) atomicMin(&m->first_dec[r], (int)j);
 }
 
 __global__ void k_feat_full(const float4 *__restrict__ raw, const uint32_t *__restrict__ keys_sorted,
-                            const uint32_t *__restrict__ vals, const double *__restrict__ rel, const FeatMeta *__restrict__ m,
-                            double scan_period, float4 *__restrict__ full, uint16_t *__restrict__ ring_out) {
+                            const uint32_t *__restrict__ vals, const double *__restrict__ rel, const uint32_t *__restrict__ soff,
+                            const FeatMeta *__restrict__ metas, double scan_period, float4 *__restrict__ full,
+                            uint16_t *__restrict__ ring_out) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  const FeatMeta *m = metas + sv.b;
+  raw += sv.base; keys_sorted += sv.base; vals += sv.base; rel += sv.base; full += sv.base; ring_out += sv.base;
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= (uint32_t)m->n_valid) return;
-  const uint32_t r = keys_sorted[j];
+  const uint32_t r = keys_sorted[j] & 255u;
   double a = rel[j];
   if ((int)j >= m->first_dec[r]) a = __dadd_rn(a, kTwoPi);
   const double t = __dmul_rn(__ddiv_rn(a, kTwoPi), scan_period);  // :151
@@ -139,8 +171,11 @@ __global__ void k_feat_full(const float4 *__restrict__ raw, const uint32_t *__re
 }
 
 // a-2 curvature (:213-240)
-__global__ void k_feat_curv(const float4 *__restrict__ full, const FeatMeta *__restrict__ m, float *__restrict__ curv,
-                            int32_t *__restrict__ label, uint8_t *__restrict__ picked) {
+__global__ void k_feat_curv(const float4 *__restrict__ full, const uint32_t *__restrict__ soff, const FeatMeta *__restrict__ metas,
+                            float *__restrict__ curv, int32_t *__restrict__ label, uint8_t *__restrict__ picked) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  const FeatMeta *m = metas + sv.b;
+  full += sv.base; curv += sv.base; label += sv.base; picked += sv.base;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = m->n_valid;
   if (i >= N) return;
@@ -190,9 +225,15 @@ constexpr size_t kPickSmem = (size_t)kKeysCap * 8 + (size_t)kRingCap * (16 + 4 +
 
 __global__ void __launch_bounds__(kPickThreads)
 k_feat_pick(const float4 *__restrict__ full, const float *__restrict__ curv, int32_t *__restrict__ label,
-            uint8_t *__restrict__ picked, FeatMeta *m, double curv_thr, double gap_thr, int n_sectors, int n_sharp,
-            int n_less, int n_flat, int32_t *__restrict__ slot_sharp, int32_t *__restrict__ slot_less,
+            uint8_t *__restrict__ picked, const uint32_t *__restrict__ soff, FeatMeta *metas, double curv_thr, double gap_thr,
+            int n_sectors, int n_sharp, int n_less, int n_flat, int32_t *__restrict__ slot_sharp, int32_t *__restrict__ slot_less,
             int32_t *__restrict__ slot_flat, int32_t *__restrict__ lessflat_tmp) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  FeatMeta *m = metas + sv.b;
+  full += sv.base; curv += sv.base; label += sv.base; picked += sv.base; lessflat_tmp += sv.base;
+  slot_sharp += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_sharp;
+  slot_less += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_less;
+  slot_flat += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_flat;
   extern __shared__ __align__(16) unsigned char pick_smem[];
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(pick_smem);
   float4 *s_full = reinterpret_cast<float4 *>(pick_smem + (size_t)kKeysCap * 8);
@@ -365,11 +406,17 @@ k_feat_pick(const float4 *__restrict__ full, const float *__restrict__ curv, int
 // ring-major concatenation of the per-ring lists (the push_back order of :279-283, :314, :350): one CTA per ring,
 // its four output offsets are the exclusive prefix sums of the per-ring counts (warp w scans list w)
 __global__ void __launch_bounds__(128)
-k_feat_compact(FeatMeta *m, int n_sectors, int n_sharp, int n_less, int n_flat,
+k_feat_compact(const uint32_t *__restrict__ soff, FeatMeta *metas, int n_sectors, int n_sharp, int n_less, int n_flat,
                const int32_t *__restrict__ slot_sharp, const int32_t *__restrict__ slot_less,
                const int32_t *__restrict__ slot_flat, const int32_t *__restrict__ lessflat_tmp,
                int32_t *__restrict__ out_sharp, int32_t *__restrict__ out_less,
                int32_t *__restrict__ out_flat, int32_t *__restrict__ out_lf) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  FeatMeta *m = metas + sv.b;
+  lessflat_tmp += sv.base; out_sharp += sv.base; out_less += sv.base; out_flat += sv.base; out_lf += sv.base;
+  slot_sharp += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_sharp;
+  slot_less += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_less;
+  slot_flat += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_flat;
   __shared__ int off[4], cnt[4];
   const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
@@ -398,7 +445,11 @@ k_feat_compact(FeatMeta *m, int n_sectors, int n_sharp, int n_less, int n_flat,
 
 // a-4 TransformPointCloudInPlace (:367-371; rigid_transform.h:140-145)
 struct Pose7 { double v[7]; };
-__global__ void k_feat_extrinsic(const float4 *__restrict__ in, const FeatMeta *__restrict__ m, Pose7 T, float4 *__restrict__ out) {
+__global__ void k_feat_extrinsic(const float4 *__restrict__ in, const uint32_t *__restrict__ soff, const FeatMeta *__restrict__ metas,
+                                 Pose7 T, float4 *__restrict__ out) {
+  const ScanView sv = scan_view(soff, blockIdx.y);
+  const FeatMeta *m = metas + sv.b;
+  in += sv.base; out += sv.base;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m->n_valid) return;
   const float4 p = in[i];
@@ -406,49 +457,56 @@ __global__ void k_feat_extrinsic(const float4 *__restrict__ in, const FeatMeta *
   out[i] = make_float4(x.x, x.y, x.z, p.w);
 }
 
-int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7], msfl_features *out) {
-  cudaStream_t st = e->stream;
-  const size_t n = raw->n;
-  const uint32_t N = (uint32_t)n;
+// scratch for a batch of N points in B scans; the packed input (float4 xyz+i, then uint16 rings) goes to f_raw
+static int feat_reserve(msfl_engine *e, size_t N, int B) {
   const msfl_params &P = e->params;
+  const size_t slots = (size_t)B * MSFL_MAX_RINGS * P.n_sectors * (P.n_sharp + P.n_less_sharp + P.n_flat);
   int rc;
-  // raw AoS bytes -> device, unpacked there (no per-point host loop)
-  const size_t raw_bytes = n * raw->stride;
+  if ((rc = e->f_raw.reserve(N * 16 + N * 2 + 64))) return rc;
+  if ((rc = e->f_keys.reserve(N * 4))) return rc;
+  if ((rc = e->f_keys_alt.reserve(N * 4))) return rc;
+  if ((rc = e->f_vals.reserve(N * 4))) return rc;
+  if ((rc = e->f_vals_alt.reserve(N * 4))) return rc;
+  if ((rc = e->f_angle.reserve(N * 8))) return rc;
+  if ((rc = e->f_full.reserve(2 * N * 16))) return rc;  // pre- and post-extrinsic
+  if ((rc = e->f_ring.reserve(N * 2 + 64))) return rc;
+  if ((rc = e->f_curv.reserve(N * 4))) return rc;
+  if ((rc = e->f_label.reserve(N * 4 + N))) return rc;  // labels + picked flags
+  if ((rc = e->f_idx.reserve((5 * N + slots) * 4))) return rc;
+  if ((rc = e->f_cnt.reserve((size_t)B * sizeof(FeatMeta)))) return rc;
+  if ((rc = e->f_soff.reserve((size_t)(B + 1) * 4))) return rc;
+  return MSFL_OK;
+}
+
+// Enqueues the whole registration block for B scans whose packed points / rings are in f_raw and whose offsets are in
+// f_soff (device) / h_off (host).  No synchronisation; results stay on the device (FeatDev).
+static int extract_enqueue(msfl_engine *e, int B, const uint32_t *h_off, const double T[7], FeatDevice *fd) {
+  cudaStream_t st = e->stream;
+  const msfl_params &P = e->params;
+  const size_t n = h_off[B];
+  const uint32_t N = (uint32_t)n;
+  uint32_t max_n = 0;
+  for (int b = 0; b < B; ++b) max_n = std::max(max_n, h_off[b + 1] - h_off[b]);
   const int S = P.n_sectors;
-  const size_t slots = (size_t)MSFL_MAX_RINGS * S * (P.n_sharp + P.n_less_sharp + P.n_flat);
-  if ((rc = e->f_raw.reserve(n * 16 + n * 2 + 64))) return rc;
-  if ((rc = e->f_misc.reserve(raw_bytes + 64))) return rc;
-  if ((rc = e->f_keys.reserve(n * 4))) return rc;
-  if ((rc = e->f_keys_alt.reserve(n * 4))) return rc;
-  if ((rc = e->f_vals.reserve(n * 4))) return rc;
-  if ((rc = e->f_vals_alt.reserve(n * 4))) return rc;
-  if ((rc = e->f_angle.reserve(n * 8))) return rc;
-  if ((rc = e->f_full.reserve(2 * n * 16))) return rc;  // pre- and post-extrinsic
-  if ((rc = e->f_ring.reserve(n * 2 + 64))) return rc;
-  if ((rc = e->f_curv.reserve(n * 4))) return rc;
-  if ((rc = e->f_label.reserve(n * 4 + n))) return rc;  // labels + picked flags
-  if ((rc = e->f_idx.reserve((5 * n + slots) * 4))) return rc;
-  if ((rc = e->f_cnt.reserve(sizeof(FeatMeta)))) return rc;
-  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_misc.p, raw->data, raw_bytes, cudaMemcpyHostToDevice, st));
+  int rc;
   const float4 *d_raw = e->f_raw.as<float4>();
   const uint16_t *d_ring_in = (const uint16_t *)(e->f_raw.as<char>() + n * 16);
-  k_unpack_aos<<<(N + 255) / 256, 256, 0, st>>>(e->f_misc.as<unsigned char>(), N, (uint32_t)raw->stride, (uint32_t)raw->off_xyz,
-                                               raw->off_intensity == MSFL_NO_FIELD ? 0u : (uint32_t)raw->off_intensity,
-                                               (uint32_t)raw->off_ring, raw->off_intensity != MSFL_NO_FIELD,
-                                               e->f_raw.as<float4>(), (uint16_t *)(e->f_raw.as<char>() + n * 16));
+  const uint32_t *soff = e->f_soff.as<uint32_t>();
   FeatMeta *meta = e->f_cnt.as<FeatMeta>();
   uint32_t *keys = e->f_keys.as<uint32_t>(), *vals = e->f_vals.as<uint32_t>();
   const int tb = 256;
-  const unsigned gb = (N + tb - 1) / tb;
-  k_feat_init<<<1, 128, 0, st>>>(meta);
-  k_feat_keys<<<gb, tb, 0, st>>>(d_raw, d_ring_in, N, P.min_range, keys, vals, meta);
+  const dim3 gp((max_n + tb - 1) / tb, (unsigned)B);  // per-point kernels: grid.y = scan
+  k_feat_init<<<B, 128, 0, st>>>(meta);
+  k_feat_keys<<<gp, tb, 0, st>>>(d_raw, d_ring_in, soff, P.min_range, keys, vals, meta);
+  int bits = 8;
+  while ((1 << (bits - 8)) < B) ++bits;  // key = scan << 8 | ring (255 = invalid point)
   cub::DoubleBuffer<uint32_t> dk(keys, e->f_keys_alt.as<uint32_t>()), dv(vals, e->f_vals_alt.as<uint32_t>());
   size_t tmp = 0;
-  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)N, 0, 8, st));
+  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)N, 0, bits, st));
   if ((rc = e->f_tmp.reserve(tmp))) return rc;
-  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->f_tmp.p, tmp, dk, dv, (int)N, 0, 8, st));
+  MSFL_CUDA_OK(cub::DeviceRadixSort::SortPairs(e->f_tmp.p, tmp, dk, dv, (int)N, 0, bits, st));
   const uint32_t *ks = dk.Current(), *vs = dv.Current();
-  k_feat_ring_start<<<1, 160, 0, st>>>(ks, N, meta);
+  k_feat_ring_start<<<B, 160, 0, st>>>(ks, soff, meta);
   double *rel = e->f_angle.as<double>();
   float4 *full_pre = e->f_full.as<float4>(), *full_post = full_pre + n;
   uint16_t *d_ring = e->f_ring.as<uint16_t>();
@@ -456,47 +514,143 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
   int32_t *label = e->f_label.as<int32_t>();
   uint8_t *picked = (uint8_t *)(label + n);
   int32_t *o_sharp = e->f_idx.as<int32_t>(), *o_less = o_sharp + n, *o_flat = o_less + n, *o_lf = o_flat + n,
-          *lf_tmp = o_lf + n, *slot_sharp = lf_tmp + n, *slot_less = slot_sharp + (size_t)MSFL_MAX_RINGS * S * P.n_sharp,
-          *slot_flat = slot_less + (size_t)MSFL_MAX_RINGS * S * P.n_less_sharp;
-  k_feat_angles<<<gb, tb, 0, st>>>(d_raw, vs, meta, rel);
-  k_feat_first_dec<<<gb, tb, 0, st>>>(ks, rel, meta);
-  k_feat_full<<<gb, tb, 0, st>>>(d_raw, ks, vs, rel, meta, P.scan_period, full_pre, d_ring);
-  k_feat_curv<<<gb, tb, 0, st>>>(full_pre, meta, curv, label, picked);
+          *lf_tmp = o_lf + n, *slot_sharp = lf_tmp + n, *slot_less = slot_sharp + (size_t)B * MSFL_MAX_RINGS * S * P.n_sharp,
+          *slot_flat = slot_less + (size_t)B * MSFL_MAX_RINGS * S * P.n_less_sharp;
+  k_feat_angles<<<gp, tb, 0, st>>>(d_raw, vs, soff, meta, rel);
+  k_feat_first_dec<<<gp, tb, 0, st>>>(ks, rel, soff, meta);
+  k_feat_full<<<gp, tb, 0, st>>>(d_raw, ks, vs, rel, soff, meta, P.scan_period, full_pre, d_ring);
+  k_feat_curv<<<gp, tb, 0, st>>>(full_pre, soff, meta, curv, label, picked);
   if (!e->pick_attr_set) {
     MSFL_CUDA_OK(cudaFuncSetAttribute(k_feat_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPickSmem));
     e->pick_attr_set = true;
   }
-  k_feat_pick<<<MSFL_MAX_RINGS, kPickThreads, kPickSmem, st>>>(full_pre, curv, label, picked, meta, P.curvature_thresh,
-                                                       P.neighbor_gap_sq, S, P.n_sharp, P.n_less_sharp, P.n_flat,
-                                                       slot_sharp, slot_less, slot_flat, lf_tmp);
-  k_feat_compact<<<MSFL_MAX_RINGS, 128, 0, st>>>(meta, S, P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat,
-                                    lf_tmp, o_sharp, o_less, o_flat, o_lf);
+  const dim3 gr(MSFL_MAX_RINGS, (unsigned)B);  // per-ring kernels: grid = (ring, scan)
+  k_feat_pick<<<gr, kPickThreads, kPickSmem, st>>>(full_pre, curv, label, picked, soff, meta, P.curvature_thresh, P.neighbor_gap_sq, S,
+                                                   P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat, lf_tmp);
+  k_feat_compact<<<gr, 128, 0, st>>>(soff, meta, S, P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat, lf_tmp, o_sharp,
+                                     o_less, o_flat, o_lf);
   Pose7 T7;
   for (int i = 0; i < 7; ++i) T7.v[i] = T ? T[i] : (i == 6 ? 1.0 : 0.0);
-  k_feat_extrinsic<<<gb, tb, 0, st>>>(full_pre, meta, T7, full_post);
+  k_feat_extrinsic<<<gp, tb, 0, st>>>(full_pre, soff, meta, T7, full_post);
   e->launches += 11 + 3;
   MSFL_CUDA_OK(cudaGetLastError());
-  FeatMeta hm;
-  MSFL_CUDA_OK(cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, st));
-  MSFL_CUDA_OK(cudaStreamSynchronize(st));
-  if (hm.bad_ring) { set_error("extract_features: ring >= %d (kMaxScanNum)", MSFL_MAX_RINGS); return MSFL_ERR_RING; }
-  if (hm.n_valid <= 0) { set_error("extract_features: no valid points"); return MSFL_ERR_EMPTY; }
-  if (hm.sector_overflow) { set_error("extract_features: a ring sector holds more than %d points", kMaxSectorPts); return MSFL_ERR_ARG; }
+  fd->full_post = full_post; fd->ring = d_ring; fd->curv = curv; fd->label = label;
+  fd->o_sharp = o_sharp; fd->o_less = o_less; fd->o_flat = o_flat; fd->o_lf = o_lf;
+  fd->metas = meta; fd->soff = soff;
+  return MSFL_OK;
+}
+
+static int check_feat_meta(const FeatMeta &hm, int b) {
+  if (hm.bad_ring) { set_error("extract_features: ring >= %d (kMaxScanNum) in scan %d", MSFL_MAX_RINGS, b); return MSFL_ERR_RING; }
+  if (hm.n_valid <= 0) { set_error("extract_features: no valid points in scan %d", b); return MSFL_ERR_EMPTY; }
+  if (hm.sector_overflow) { set_error("extract_features: a ring sector of scan %d holds more than %d points", b, kMaxSectorPts); return MSFL_ERR_ARG; }
+  return MSFL_OK;
+}
+
+// copies one scan's results to the caller's arrays (async; the caller synchronises)
+static int download_features(msfl_engine *e, const FeatDevice &fd, uint32_t base, const FeatMeta &hm, msfl_features *out) {
+  cudaStream_t st = e->stream;
   const size_t nv = (size_t)hm.n_valid;
   out->n_full = hm.n_valid;
   out->n_sharp = hm.tot[0];
   out->n_less_sharp = hm.tot[1];
   out->n_flat = hm.tot[2];
   out->n_less_flat = hm.tot[3];
-  if (out->full_xyzi) MSFL_CUDA_OK(cudaMemcpyAsync(out->full_xyzi, full_post, nv * 16, cudaMemcpyDeviceToHost, st));
-  if (out->full_ring) MSFL_CUDA_OK(cudaMemcpyAsync(out->full_ring, d_ring, nv * 2, cudaMemcpyDeviceToHost, st));
-  if (out->curvature) MSFL_CUDA_OK(cudaMemcpyAsync(out->curvature, curv, nv * 4, cudaMemcpyDeviceToHost, st));
-  if (out->label) MSFL_CUDA_OK(cudaMemcpyAsync(out->label, label, nv * 4, cudaMemcpyDeviceToHost, st));
-  if (out->idx_sharp) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_sharp, o_sharp, (size_t)hm.tot[0] * 4, cudaMemcpyDeviceToHost, st));
-  if (out->idx_less_sharp) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_less_sharp, o_less, (size_t)hm.tot[1] * 4, cudaMemcpyDeviceToHost, st));
-  if (out->idx_flat) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_flat, o_flat, (size_t)hm.tot[2] * 4, cudaMemcpyDeviceToHost, st));
-  if (out->idx_less_flat) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_less_flat, o_lf, (size_t)hm.tot[3] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->full_xyzi) MSFL_CUDA_OK(cudaMemcpyAsync(out->full_xyzi, fd.full_post + base, nv * 16, cudaMemcpyDeviceToHost, st));
+  if (out->full_ring) MSFL_CUDA_OK(cudaMemcpyAsync(out->full_ring, fd.ring + base, nv * 2, cudaMemcpyDeviceToHost, st));
+  if (out->curvature) MSFL_CUDA_OK(cudaMemcpyAsync(out->curvature, fd.curv + base, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (out->label) MSFL_CUDA_OK(cudaMemcpyAsync(out->label, fd.label + base, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_sharp) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_sharp, fd.o_sharp + base, (size_t)hm.tot[0] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_less_sharp) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_less_sharp, fd.o_less + base, (size_t)hm.tot[1] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_flat) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_flat, fd.o_flat + base, (size_t)hm.tot[2] * 4, cudaMemcpyDeviceToHost, st));
+  if (out->idx_less_flat) MSFL_CUDA_OK(cudaMemcpyAsync(out->idx_less_flat, fd.o_lf + base, (size_t)hm.tot[3] * 4, cudaMemcpyDeviceToHost, st));
+  return MSFL_OK;
+}
+
+int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7], msfl_features *out) {
+  cudaStream_t st = e->stream;
+  const size_t n = raw->n;
+  const uint32_t N = (uint32_t)n;
+  int rc;
+  // raw AoS bytes -> device, unpacked there (no per-point host loop)
+  const size_t raw_bytes = n * raw->stride;
+  if ((rc = feat_reserve(e, n, 1))) return rc;
+  if ((rc = e->f_misc.reserve(raw_bytes + 64))) return rc;
+  const uint32_t h_off[2] = {0u, N};
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_soff.p, h_off, sizeof h_off, cudaMemcpyHostToDevice, st));
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_misc.p, raw->data, raw_bytes, cudaMemcpyHostToDevice, st));
+  k_unpack_aos<<<(N + 255) / 256, 256, 0, st>>>(e->f_misc.as<unsigned char>(), N, (uint32_t)raw->stride, (uint32_t)raw->off_xyz,
+                                               raw->off_intensity == MSFL_NO_FIELD ? 0u : (uint32_t)raw->off_intensity,
+                                               (uint32_t)raw->off_ring, raw->off_intensity != MSFL_NO_FIELD,
+                                               e->f_raw.as<float4>(), (uint16_t *)(e->f_raw.as<char>() + n * 16));
+  FeatDevice fd;
+  if ((rc = extract_enqueue(e, 1, h_off, T, &fd))) return rc;
+  FeatMeta hm;
+  MSFL_CUDA_OK(cudaMemcpyAsync(&hm, fd.metas, sizeof hm, cudaMemcpyDeviceToHost, st));
   MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  if ((rc = check_feat_meta(hm, 0))) return rc;
+  if ((rc = download_features(e, fd, 0, hm, out))) return rc;
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  return MSFL_OK;
+}
+
+// B raw clouds -> packed float4 + rings in pinned staging (host threads), one upload, one launch sequence for the batch
+static int upload_raw_batch(msfl_engine *e, int B, const msfl_cloud *raw, std::vector<uint32_t> &h_off) {
+  h_off.assign(B + 1, 0);
+  size_t N = 0;
+  for (int b = 0; b < B; ++b) {
+    h_off[b] = (uint32_t)N;
+    N += raw[b].n;
+  }
+  if (N > 0x3fffffffull) { set_error("extract_features_batch: batch too large"); return MSFL_ERR_ARG; }
+  h_off[B] = (uint32_t)N;
+  int rc;
+  if ((rc = feat_reserve(e, N, B))) return rc;
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));  // the staging buffer may still feed an earlier upload
+  if ((rc = e->h_stage.reserve(N * 18 + (size_t)(B + 1) * 4 + 64))) return rc;
+  float *h4 = e->h_stage.as<float>();
+  uint16_t *hr = (uint16_t *)(e->h_stage.as<char>() + N * 16);
+  uint32_t *ho = (uint32_t *)(e->h_stage.as<char>() + ((N * 18 + 15) & ~(size_t)15));
+  memcpy(ho, h_off.data(), (size_t)(B + 1) * 4);
+  pack_clouds_parallel(e, B, raw, h4, hr, h_off.data());
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_raw.p, h4, N * 18, cudaMemcpyHostToDevice, e->stream));
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_soff.p, ho, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+  return MSFL_OK;
+}
+
+// upload + extraction of a batch, results left on the device; h_counts receives B x 5 ints (n_valid, sharp, less_sharp,
+// flat, less_flat).  One synchronisation (the counts size everything downstream).
+int extract_batch_to_device(msfl_engine *e, int B, const msfl_cloud *raw, const double T[7], FeatDevice *fd,
+                            std::vector<uint32_t> &h_off, std::vector<int32_t> &h_counts) {
+  int rc;
+  if ((rc = upload_raw_batch(e, B, raw, h_off))) return rc;
+  if ((rc = extract_enqueue(e, B, h_off.data(), T, fd))) return rc;
+  std::vector<FeatMeta> hm(B);
+  MSFL_CUDA_OK(cudaMemcpyAsync(hm.data(), fd->metas, (size_t)B * sizeof(FeatMeta), cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  h_counts.resize((size_t)B * 5);
+  for (int b = 0; b < B; ++b) {
+    if ((rc = check_feat_meta(hm[b], b))) return rc;
+    h_counts[5 * b] = hm[b].n_valid;
+    for (int k = 0; k < 4; ++k) h_counts[5 * b + 1 + k] = hm[b].tot[k];
+  }
+  return MSFL_OK;
+}
+
+int run_extract_features_batch(msfl_engine *e, int B, const msfl_cloud *raw, const double T[7], msfl_features *outs) {
+  std::vector<uint32_t> h_off;
+  int rc;
+  if ((rc = upload_raw_batch(e, B, raw, h_off))) return rc;
+  FeatDevice fd;
+  if ((rc = extract_enqueue(e, B, h_off.data(), T, &fd))) return rc;
+  std::vector<FeatMeta> hm(B);
+  MSFL_CUDA_OK(cudaMemcpyAsync(hm.data(), fd.metas, (size_t)B * sizeof(FeatMeta), cudaMemcpyDeviceToHost, e->stream));
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  for (int b = 0; b < B; ++b) {
+    if ((rc = check_feat_meta(hm[b], b))) return rc;
+    if ((rc = download_features(e, fd, h_off[b], hm[b], &outs[b]))) return rc;
+  }
+  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
   return MSFL_OK;
 }
 
@@ -516,4 +670,17 @@ extern "C" int msfl_extract_features(msfl_engine *e, const msfl_cloud *raw, cons
   }
   MSFL_CUDA_OK(cudaSetDevice(e->device));
   return run_extract_features(e, raw, T_lidar2imu, out);
+}
+
+extern "C" int msfl_extract_features_batch(msfl_engine *e, int B, const msfl_cloud *raw, const double T_lidar2imu[7],
+                                           msfl_features *outs) {
+  if (!e || !raw || !outs || B <= 0) { set_error("msfl_extract_features_batch: bad argument"); return MSFL_ERR_ARG; }
+  for (int b = 0; b < B; ++b) {
+    outs[b].n_full = outs[b].n_sharp = outs[b].n_less_sharp = outs[b].n_flat = outs[b].n_less_flat = 0;
+    int rc;
+    if ((rc = check_cloud(&raw[b], true, "extract_features_batch"))) return rc;
+    if (raw[b].n == 0) { set_error("extract_features_batch: scan %d is empty", b); return MSFL_ERR_EMPTY; }
+  }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  return run_extract_features_batch(e, B, raw, T_lidar2imu, outs);
 }

@@ -173,6 +173,31 @@ static void pack_batch_host(msfl_engine *e, int b0, int b1, const msfl_cloud *co
   for (auto &t : th) t.join();
 }
 
+void pack_clouds_parallel(msfl_engine *e, int B, const msfl_cloud *clouds, float *dst4, uint16_t *ring_dst, const uint32_t *off) {
+  size_t pts = 0;
+  for (int b = 0; b < B; ++b) pts += clouds[b].n;
+  int nt = std::min(e->pack_threads, B);
+  if (pts < 200000 || nt <= 1) {
+    for (int b = 0; b < B; ++b) pack_cloud_host(&clouds[b], dst4 + 4 * (size_t)off[b], ring_dst ? ring_dst + off[b] : nullptr);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  int b = 0;
+  size_t done = 0;
+  for (int t = 0; t < nt; ++t) {
+    const size_t goal = pts * (size_t)(t + 1) / (size_t)nt;
+    const int first = b;
+    while (b < B && (done < goal || t == nt - 1)) { done += clouds[b].n; ++b; }
+    const int last = b;
+    if (first == last) continue;
+    th.emplace_back([=]() {
+      for (int i = first; i < last; ++i) pack_cloud_host(&clouds[i], dst4 + 4 * (size_t)off[i], ring_dst ? ring_dst + off[i] : nullptr);
+    });
+  }
+  for (auto &t : th) t.join();
+}
+
 static cudaEvent_t take_event(msfl_engine *e) {
   if (!e->event_pool.empty()) {
     cudaEvent_t ev = e->event_pool.back();
@@ -341,8 +366,9 @@ void msfl_destroy(msfl_engine *e) {
   DevBuf *dbs[] = {&e->d_queries, &e->d_corr, &e->d_poses, &e->d_status, &e->d_stats, &e->d_knn, &e->d_off, &e->d_misc,
                    &e->d_last_corner, &e->d_last_surf, &e->d_last_corner_ring, &e->d_last_surf_ring, &e->d_ring_tab,
                    &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,
-                   &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->v_in,
-                   &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc,
+                   &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->f_soff, &e->v_in,
+                   &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc, &e->vb_keys, &e->vb_keys_alt, &e->vb_vals, &e->vb_vals_alt, &e->vb_tmp, &e->vb_misc,
+                   &e->c_in, &e->c_off, &e->c_q,
                    &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp, &e->a_hist,
                    &e->k_table, &e->k_dsk, &e->k_pprime, &e->a_fb};
   for (DevBuf *b : dbs) b->release();
@@ -461,9 +487,9 @@ int msfl_get_submap_device(msfl_engine *e, const float **d_corner, size_t *n_cor
 // ------------------------------------------------------------------------------------------------
 // scan-to-map
 // ------------------------------------------------------------------------------------------------
-static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t nct,
-                            const float4 *d_qs, const int32_t *d_s_off, uint32_t nst, double *d_poses,
-                            msfl_stats *d_stats) {
+}  // extern "C"
+int msfl::scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t nct, const float4 *d_qs,
+                           const int32_t *d_s_off, uint32_t nst, double *d_poses, msfl_stats *d_stats) {
   int rc;
   if ((rc = e->d_corr.reserve(((size_t)nct + nst + 1) * 6 * sizeof(double)))) return rc;
   if ((rc = e->d_status.reserve((size_t)B * 4))) return rc;
@@ -485,6 +511,8 @@ static int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int
   }
   return MSFL_OK;
 }
+
+extern "C" {
 
 int msfl_scan2map_batch_device(msfl_engine *e, int B, const float *d_corner, const int32_t *d_corner_off,
                                size_t n_corner_total, const float *d_surf, const int32_t *d_surf_off,

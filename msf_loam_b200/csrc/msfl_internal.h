@@ -129,9 +129,11 @@ struct msfl_engine {
 
   // feature extraction scratch
   msfl::DevBuf f_raw, f_keys, f_keys_alt, f_vals, f_vals_alt, f_tmp, f_full, f_ring, f_curv, f_label,
-      f_idx, f_cnt, f_angle, f_misc;
+      f_idx, f_cnt, f_angle, f_misc, f_soff;
   // voxel grid scratch
   msfl::DevBuf v_in, v_keys, v_keys_alt, v_vals, v_vals_alt, v_tmp, v_out, v_misc;
+  msfl::DevBuf vb_keys, vb_keys_alt, vb_vals, vb_vals_alt, vb_tmp, vb_misc;  // batched VoxelGrid scratch
+  msfl::DevBuf c_in, c_off, c_q;                                              // chain: gathered feature clouds, offset tables, queries
 };
 
 namespace msfl {
@@ -185,12 +187,36 @@ int launch_associate_scan(msfl_engine *e, const float4 *d_last_corner, const uin
 
 // ---- features.cu
 int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7], msfl_features *out);
+// device-side results of one extraction batch (views into the engine's scratch; valid until the next extraction)
+struct FeatMeta;
+struct FeatDevice {
+  float4 *full_post;   // [N] extrinsic applied, intensity = relative time; scan b at soff[b], n_valid[b] points
+  uint16_t *ring;
+  float *curv;
+  int32_t *label;
+  int32_t *o_sharp, *o_less, *o_flat, *o_lf;  // per scan at soff[b]: indices into the scan's own full cloud
+  FeatMeta *metas;       // [B]
+  const uint32_t *soff;  // [B + 1] device
+};
+int extract_batch_to_device(msfl_engine *e, int B, const msfl_cloud *raw, const double T[7], FeatDevice *fd,
+                            std::vector<uint32_t> &h_off, std::vector<int32_t> &h_counts);
+// ---- msfl_api.cu: the launch sequence of a scan-to-map batch whose inputs are in HBM
+int scan2map_enqueue(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t nct, const float4 *d_qs,
+                     const int32_t *d_s_off, uint32_t nst, double *d_poses, msfl_stats *d_stats);
 
 // ---- voxel_grid.cu
 int run_voxel_grid(msfl_engine *e, const float4 *d_in, size_t n, float leaf, float4 *d_out, size_t *n_out);
+// B clouds back to back in d_in (scan b at d_in_off[b], device offsets): centroids back to back in d_out, d_out_off
+// (B + 1 int32, device) receives where each scan's centroids start.  No synchronisation.  vb = 0 / 1 selects one of two
+// scratch sets so that two batches (corner, surf) can be in flight.
+int run_voxel_grid_batch(msfl_engine *e, int B, const float4 *d_in, const uint32_t *d_in_off, size_t n_total, uint32_t max_n,
+                         float leaf, float4 *d_out, int32_t *d_out_off, int vb);
 
 // ---- cloud-view validation and repack (msfl_api.cu)
 int check_cloud(const msfl_cloud *c, bool need_ring, const char *what);
+// B strided AoS clouds -> packed float4 (dst4 + 4 off[b]) and, when ring_dst is given, uint16 rings (ring_dst + off[b]),
+// split over the engine's pack threads
+void pack_clouds_parallel(msfl_engine *e, int B, const msfl_cloud *clouds, float *dst4, uint16_t *ring_dst, const uint32_t *off);
 int upload_cloud_packed(msfl_engine *e, const msfl_cloud *c, float4 *d_dst, uint16_t *d_ring_dst);
 
 }  // namespace msfl

@@ -308,6 +308,57 @@ class Engine:
             "idx_flat": idx[2][: f.n_flat], "idx_less_flat": idx[3][: f.n_less_flat],
         }
 
+    def extract_features_batch(self, raws, rings, T_lidar2imu=None):
+        """msfl_extract_features_batch: B raw scans through one launch sequence; returns a list of dicts like
+        extract_features."""
+        B = len(raws)
+        views = [_View(r, g) for r, g in zip(raws, rings)]
+        carr = (Cloud * B)(*[v.cloud for v in views])
+        feats = (Features * B)()
+        bufs = []
+        for b, v in enumerate(views):
+            n = v.n
+            full, fring, curv, label = np.zeros((n, 4), np.float32), np.zeros(n, np.uint16), np.zeros(n, np.float32), np.zeros(n, np.int32)
+            idx = [np.zeros(n, np.int32) for _ in range(4)]
+            f = feats[b]
+            f.full_xyzi = full.ctypes.data_as(C.POINTER(C.c_float))
+            f.full_ring = fring.ctypes.data_as(C.POINTER(C.c_uint16))
+            f.curvature = curv.ctypes.data_as(C.POINTER(C.c_float))
+            f.label = label.ctypes.data_as(C.POINTER(C.c_int32))
+            f.idx_sharp, f.idx_less_sharp, f.idx_flat, f.idx_less_flat = [a.ctypes.data_as(C.POINTER(C.c_int32)) for a in idx]
+            bufs.append((full, fring, curv, label, idx))
+        T = _pose(T_lidar2imu) if T_lidar2imu is not None else None
+        self._check(self.lib.msfl_extract_features_batch(
+            self.h, C.c_int(B), carr, T.ctypes.data_as(C.POINTER(C.c_double)) if T is not None else None, feats))
+        out = []
+        for b, (full, fring, curv, label, idx) in enumerate(bufs):
+            f = feats[b]
+            nf = f.n_full
+            out.append({"full": full[:nf], "ring": fring[:nf], "curvature": curv[:nf], "label": label[:nf],
+                        "idx_sharp": idx[0][: f.n_sharp], "idx_less_sharp": idx[1][: f.n_less_sharp],
+                        "idx_flat": idx[2][: f.n_flat], "idx_less_flat": idx[3][: f.n_less_flat]})
+        return out
+
+    def prepare_raw_batch(self, raws, rings):
+        """msfl_cloud table of B raw scans in the reference's PointXYZIRT layout (built once, reused by timed loops)."""
+        views = [_View(r, g) for r, g in zip(raws, rings)]
+        return {"B": len(views), "views": views, "arr": (Cloud * len(views))(*[v.cloud for v in views])}
+
+    def register_and_match_batch(self, raw_batch, poses, T_lidar2imu=None, leaf_corner=0.2, leaf_surf=0.4, want_counts=False):
+        """msfl_register_and_match_batch: raw scans -> poses (registration, VoxelGrid, scan-to-map on the GPU)."""
+        if not isinstance(raw_batch, dict):
+            raw_batch = self.prepare_raw_batch(*raw_batch)
+        B = raw_batch["B"]
+        x = np.ascontiguousarray(poses, dtype=np.float64).reshape(B, 7).copy()
+        T = _pose(T_lidar2imu) if T_lidar2imu is not None else None
+        cnt = (_lib.ChainCounts * B)() if want_counts else None
+        self._check(self.lib.msfl_register_and_match_batch(
+            self.h, C.c_int(B), raw_batch["arr"], T.ctypes.data_as(C.POINTER(C.c_double)) if T is not None else None,
+            C.c_float(leaf_corner), C.c_float(leaf_surf), x.ctypes.data_as(C.POINTER(C.c_double)), cnt, None))
+        if want_counts:
+            return x, [{k: getattr(c, k) for k, _ in _lib.ChainCounts._fields_} for c in cnt]
+        return x
+
     def voxel_grid(self, xyzi, leaf):
         v = _View(xyzi)
         out = np.zeros((max(v.n, 1), 4), np.float32)

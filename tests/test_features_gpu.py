@@ -210,3 +210,46 @@ def test_registration_to_mapping_pipeline(eng):
     gt = S.pose_mul(S.pose_inv(traj[0]), traj[1])
     dt, dr = S.pose_error(pose, gt)
     assert ok and dt < 0.05 and dr < 0.01
+
+
+def test_batched_extraction_is_bitwise_the_single_scan_extraction(eng):
+    """msfl_extract_features_batch: scans of different sensors and sizes in ONE launch sequence (grid.y = scan, one sort
+    over (scan, ring)) give exactly what B single calls give -- and what the oracle gives."""
+    scene40, scene80 = S.make_scene("room40"), S.make_scene("room80")
+    traj = S.trajectory(4)
+    raws = [S.raycast_scan(scene40, "vlp16", traj[0], seed=900), S.raycast_scan(scene80, "hdl64", traj[1], seed=901),
+            S.raycast_scan(scene40, "vlp16", traj[2], seed=902), S.raycast_scan(scene80, "os1-128", traj[3], seed=903),
+            S.raycast_scan(scene40, "vlp16", traj[1], seed=904)]
+    T = np.array([0.1, -0.2, 0.3, 0.0, 0.0, np.sin(0.05), np.cos(0.05)])
+    batch = eng.extract_features_batch([r[0] for r in raws], [r[1] for r in raws], T)
+    P = O.default_params()
+    for (xyzi, ring), fb in zip(raws, batch):
+        fs = eng.extract_features(xyzi, ring, T)
+        for k in ("full", "ring", "curvature", "label", "idx_sharp", "idx_less_sharp", "idx_flat", "idx_less_flat"):
+            assert np.array_equal(fb[k], fs[k]), k
+        _check_features(fb, O.extract_features(P, xyzi, ring, T))
+
+
+def test_raw_to_pose_chain_equals_the_stage_by_stage_calls(eng, vlp16_case):
+    """msfl_register_and_match_batch (registration + VoxelGrid x 2 + scan-to-map, everything batched on the GPU) against
+    the same stages called one by one through the C ABI: bit-identical poses, same query counts; and against the oracle."""
+    case = vlp16_case
+    eng.set_submap(case["map_corner"], case["map_surf"])
+    raws = [q["raw"] for q in case["queries"]] * 2   # 6 scans
+    inits = [q["init"] for q in case["queries"]] * 2
+    poses, counts = eng.register_and_match_batch(([r[0] for r in raws], [r[1] for r in raws]), inits, want_counts=True)
+    corners, surfs = [], []
+    for (xyzi, ring), c in zip(raws, counts):
+        f = eng.extract_features(xyzi, ring, None)
+        corners.append(eng.voxel_grid(f["full"][f["idx_less_sharp"]], 0.2))
+        surfs.append(eng.voxel_grid(f["full"][f["idx_less_flat"]], 0.4))
+        assert c["n_full"] == f["full"].shape[0] and c["n_less_sharp"] == len(f["idx_less_sharp"]) and c["n_less_flat"] == len(f["idx_less_flat"])
+        assert c["n_corner_queries"] == corners[-1].shape[0] and c["n_surf_queries"] == surfs[-1].shape[0]
+    rc, ref, _ = eng.scan2map_batch(corners, surfs, inits)
+    assert rc == 0 and np.array_equal(poses, ref)
+    P = O.default_params()
+    for i, q in enumerate(case["queries"]):
+        x_ref, _, _ = O.scan2map(P, case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"])
+        dt, dr = S.pose_error(poses[i], x_ref)
+        # the oracle's queries carry the oracle's relative times in `intensity` (1-ulp atan2f difference); xyz are equal
+        assert dt < 1e-8 and dr < 1e-8
