@@ -477,6 +477,9 @@ static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int3
   // double-buffered streaming (4 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
   // occupancy is irrelevant) a deep ring so that a warp's tiles stay resident in smem across the sweeps
   const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)kWarpStages;
+  // (capping the resident CTAs so that the factor arrays in flight fit the 126 MB L2 -- 3 per SM: 444 x 222 KB = 99 MB
+  // -- was measured on B200: 0.706 -> 0.772 ms per launch at 3 CTAs/SM, 0.976 ms at 2; the sweep needs the warps more
+  // than it needs the L2 hits)
   const int smem = (int)n_stages * sb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * G);
