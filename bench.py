@@ -336,7 +336,6 @@ def run_workload(cx, workload, B, n_distinct, steps, warmup, full, lm_cluster=0,
         stage_ms, stage_cnt = eng.get_profile()
         eng.set_profiling(False)
         poses_dev = d_p.cpu().numpy()
-        rec["clocks"] = smp.stop() if smp else None
 
         e2e_ms = e2e_pcl_ms = e2e_sync_ms = None
         if e2e and not args.only_device:
@@ -393,6 +392,8 @@ def run_workload(cx, workload, B, n_distinct, steps, warmup, full, lm_cluster=0,
                     h_p[:] = inits
                     eng.scan2map_prepared(packed, h_p)
             e2e_sync_ms = timed(sync_calls, reps=1)
+        # the clock sampler spans the device-timed steps AND the host-buffer legs (the same kernels under the same load)
+        rec["clocks"] = smp.stop() if smp else None
         if comm is not None:
             eng.sync()
             eng.nccl_comm_destroy(comm)
