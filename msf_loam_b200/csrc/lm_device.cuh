@@ -214,41 +214,44 @@ __device__ void lm_prepare_step(SH &sh, const KParams &kp, msfl_lm_log *log) {
     msfl_lm_iter *L = log ? &log->it[sh.iteration - 1] : nullptr;
     if (log) log->n_attempts = sh.iteration;
     if (L) { L->cost = sh.cost; L->cost_candidate = sh.cost; L->model_change = 0; L->rho = 0; L->radius = sh.radius; L->valid = 0; L->accepted = 0; }
-    // everything below lives in registers: packed upper triangles (tri6), every loop unrolled
-    double Hs[21], gs[6], A[21], nb[6], y[6], S[6];
+    // everything below lives in registers: one packed upper triangle (tri6) factored in place, every loop unrolled
+    double A[21], nb[6], y[6], S[6];
 #pragma unroll
     for (int u = 0; u < 6; ++u) S[u] = sh.S[u];
 #pragma unroll
     for (int u = 0; u < 6; ++u) {
-      gs[u] = S[u] * sh.g[u];
+      nb[u] = -(S[u] * sh.g[u]);
 #pragma unroll
-      for (int v = u; v < 6; ++v) Hs[tri6(u, v)] = S[u] * sh.H[tri6(u, v)] * S[v];
+      for (int v = u; v < 6; ++v) A[tri6(u, v)] = S[u] * sh.H[tri6(u, v)] * S[v];  // H' = S H S
     }
     if (!sh.reuse) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) sh.diag[k] = fmin(fmax(Hs[tri6(k, k)], kp.min_diag), kp.max_diag);
+      for (int k = 0; k < 6; ++k) sh.diag[k] = fmin(fmax(A[tri6(k, k)], kp.min_diag), kp.max_diag);
     }
-#pragma unroll
-    for (int i = 0; i < 21; ++i) A[i] = Hs[i];
     {
       const double radius = sh.radius;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { A[tri6(k, k)] += sh.diag[k] / radius; nb[k] = -gs[k]; }
+      for (int k = 0; k < 6; ++k) A[tri6(k, k)] += sh.diag[k] / radius;
     }
     const bool ok = chol_solve6_packed(A, nb, y);
     sh.reuse = 1;  // LevenbergMarquardtStrategy::ComputeStep
     double model = 0;
+    double delta[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) delta[k] = y[k] * S[k];
     if (ok) {
-      double yg = 0, yHy = 0;
+      // model_cost_change = -(y.g' + y^T H' y / 2) with g' = S g, H' = S H S and delta = S y  ==  -(delta.g + delta^T H delta / 2):
+      // evaluated on the unscaled H, g still in shared memory, so no second copy of the matrix is kept in registers
+      double dg = 0, dHd = 0;
 #pragma unroll
       for (int u = 0; u < 6; ++u) {
-        yg += y[u] * gs[u];
+        dg += delta[u] * sh.g[u];
         double t = 0;
 #pragma unroll
-        for (int v = 0; v < 6; ++v) t += Hs[u <= v ? tri6(u, v) : tri6(v, u)] * y[v];
-        yHy += y[u] * t;
+        for (int v = 0; v < 6; ++v) t += sh.H[u <= v ? tri6(u, v) : tri6(v, u)] * delta[v];
+        dHd += delta[u] * t;
       }
-      model = -(yg + 0.5 * yHy);
+      model = -(dg + 0.5 * dHd);
     }
     sh.step_successful = 0;
     if (!ok || !(model > 0.0)) {  // HandleInvalidStep
@@ -260,9 +263,7 @@ __device__ void lm_prepare_step(SH &sh, const KParams &kp, msfl_lm_log *log) {
     }
     sh.n_invalid = 0;
     sh.model = model;
-    double delta[6], x0[7], xc[7];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) delta[k] = y[k] * S[k];
+    double x0[7], xc[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) x0[k] = sh.x[k];
     pose_plus(x0, delta, xc);

@@ -217,31 +217,32 @@ __device__ __forceinline__ void lstsq_5x3(double (&A)[5][3], double (&b)[5], dou
 // index of the (u,v) entry, u <= v, in the packed upper triangle of a 6x6 (row-major)
 __host__ __device__ __forceinline__ constexpr int tri6(int u, int v) { return u * 6 - (u * (u - 1)) / 2 + (v - u); }
 
-// 6x6 SPD solve by Cholesky (the LM normal equations) on the packed upper triangle: A[tri6(j, i)] = A_ij for j <= i.
+// 6x6 SPD solve by Cholesky (the LM normal equations) on the packed upper triangle, IN PLACE: A[tri6(j, i)] = A_ij for
+// j <= i comes in and L_ij goes out in the same slot (column j only reads the finished columns k < j and itself).
 // Returns false when not positive definite / non-finite (Ceres LINEAR_SOLVER_FAILURE -> invalid step).  Every index is
-// a compile-time constant, so A, L and the right-hand sides live in registers; one reciprocal square root per pivot
-// replaces the sqrt + divisions of the textbook form (this runs on a single thread between two sweeps: its latency is
-// exposed).
-__device__ __forceinline__ bool chol_solve6_packed(const double (&A)[21], const double (&b)[6], double (&y)[6]) {
-  double L[21], inv[6];  // L[tri6(j, i)] = L_ij, i >= j
+// a compile-time constant, so the 21 + 18 values live in registers -- with a separate L the serial LM step spilled --
+// and one reciprocal square root per pivot replaces the sqrt + divisions of the textbook form (this runs on a single
+// thread between two sweeps: its latency is exposed).
+__device__ __forceinline__ bool chol_solve6_packed(double (&A)[21], const double (&b)[6], double (&y)[6]) {
+  double inv[6];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = A[tri6(j, j)];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
-      if (k < j) d -= L[tri6(k, j)] * L[tri6(k, j)];
+      if (k < j) d -= A[tri6(k, j)] * A[tri6(k, j)];
     if (!(d > 0) || !isfinite(d)) ok = false;
     inv[j] = rsqrt(d);
-    L[tri6(j, j)] = d * inv[j];
+    A[tri6(j, j)] = d * inv[j];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       if (i > j) {
         double s = A[tri6(j, i)];
 #pragma unroll
         for (int k = 0; k < 6; ++k)
-          if (k < j) s -= L[tri6(k, i)] * L[tri6(k, j)];
-        L[tri6(j, i)] = s * inv[j];
+          if (k < j) s -= A[tri6(k, i)] * A[tri6(k, j)];
+        A[tri6(j, i)] = s * inv[j];
       }
     }
   }
@@ -252,7 +253,7 @@ __device__ __forceinline__ bool chol_solve6_packed(const double (&A)[21], const 
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
-      if (k < i) s -= L[tri6(k, i)] * z[k];
+      if (k < i) s -= A[tri6(k, i)] * z[k];
     z[i] = s * inv[i];
   }
 #pragma unroll
@@ -260,7 +261,7 @@ __device__ __forceinline__ bool chol_solve6_packed(const double (&A)[21], const 
     double s = z[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
-      if (k > i) s -= L[tri6(i, k)] * y[k];
+      if (k > i) s -= A[tri6(i, k)] * y[k];
     y[i] = s * inv[i];
   }
 #pragma unroll
