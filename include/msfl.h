@@ -216,11 +216,13 @@ int msfl_scan2map_batch_device(msfl_engine *e, int B,
  * and returns a ticket without waiting; wait blocks until that batch is done and writes its B x 7
  * poses (and B stats entries when want_stats was set; stats may be NULL otherwise).  Up to
  * MSFL_MAX_INFLIGHT batches may be in flight, so the upload of batch k+1 overlaps the kernels of
- * batch k; batches complete in submission order and give bit-identical poses to the synchronous
+ * batch k (and, for clouds that need the host repack, the repack of batch k+2 overlaps both); batches complete in submission order and give bit-identical poses to the synchronous
  * call.  The clouds must stay valid and unchanged until the matching wait returns (packed,
- * page-locked clouds are DMA'd straight from the caller's memory).  Submitting while
+ * page-locked clouds are DMA'd straight from the caller's memory: float4 points, stride 16, or xyz-only points, stride 12
+ * with off_intensity = MSFL_NO_FIELD -- the LiDAR-only matcher never reads a query's intensity, and 12 B points put a
+ * quarter less on the PCIe link; any other layout is repacked into a pinned slot by host threads).  Submitting while
  * MSFL_MAX_INFLIGHT tickets are outstanding returns MSFL_ERR_ARG. */
-#define MSFL_MAX_INFLIGHT 2
+#define MSFL_MAX_INFLIGHT 3
 int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *scan_corner,
                                const msfl_cloud *scan_surf, const double *poses_tq_in, int want_stats,
                                int *ticket);

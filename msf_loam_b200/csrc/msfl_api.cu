@@ -1,5 +1,6 @@
 // msfl_api.cu -- the C ABI of libmsfl.so (include/msfl.h): engine lifetime, host<->device
 // marshalling of AoS cloud views, and the launch sequences of the scan-matching path.
+#include <emmintrin.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -111,6 +112,24 @@ static void pack_cloud_host(const msfl_cloud *c, float *dst4, uint16_t *ring_dst
   const bool has_i = c->off_intensity != MSFL_NO_FIELD;
   if (c->stride == 16 && c->off_xyz == 0 && (c->off_intensity == 12 || !has_i)) {
     memcpy(dst4, base, n * 16);
+  } else if (((c->stride | c->off_xyz | (has_i ? c->off_intensity : 0) | (size_t)(uintptr_t)base) & 3u) == 0 &&
+             c->off_xyz + 16 <= c->stride && (((uintptr_t)dst4) & 15u) == 0) {
+    // word-aligned points with 16 readable bytes at xyz (every PCL type: pcl::PointXYZI is x y z pad | intensity ...):
+    // one 16-byte load, the intensity dropped into lane 3, one NON-TEMPORAL 16-byte store -- the staging slot is
+    // written once and read by the DMA engine, so it should not be pulled into the cache first (write-allocate would
+    // add a third of the traffic of this memory-bound loop)
+    const size_t st = c->stride;
+    const char *px = base + c->off_xyz, *pi = has_i ? base + c->off_intensity : nullptr;
+    const __m128i keep_xyz = _mm_set_epi32(0, -1, -1, -1);
+    for (size_t i = 0; i < n; ++i, px += st) {
+      __m128i v = _mm_and_si128(_mm_loadu_si128((const __m128i *)px), keep_xyz);
+      if (has_i) {
+        v = _mm_or_si128(v, _mm_slli_si128(_mm_cvtsi32_si128(*(const int *)pi), 12));
+        pi += st;
+      }
+      _mm_stream_si128((__m128i *)(dst4 + 4 * i), v);
+    }
+    _mm_sfence();
   } else if (((c->stride | c->off_xyz | (has_i ? c->off_intensity : 0) | (size_t)(uintptr_t)base) & 3u) == 0) {
     // word-aligned points (every PCL type: pcl::PointXYZI is 32 B with intensity at 16): four 32-bit moves per point
     const size_t sw = c->stride / 4, ox = c->off_xyz / 4, oi = has_i ? c->off_intensity / 4 : 0;
@@ -196,6 +215,14 @@ void pack_clouds_parallel(msfl_engine *e, int B, const msfl_cloud *clouds, float
     });
   }
   for (auto &t : th) t.join();
+}
+
+// xyz-only uploads (12 B per point: the LiDAR-only matcher never reads a query's intensity) are widened to the kernels'
+// float4 layout on the device; the PCIe link carries a quarter less
+__global__ void k_expand_xyz(const float *__restrict__ xyz, uint32_t n, float4 *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 0.f);
 }
 
 static cudaEvent_t take_event(msfl_engine *e) {
@@ -373,7 +400,7 @@ void msfl_destroy(msfl_engine *e) {
                    &e->k_table, &e->k_dsk, &e->k_pprime, &e->a_fb};
   for (DevBuf *b : dbs) b->release();
   for (auto &sl : e->slots) {
-    sl.d_in.release(); sl.d_stats.release(); sl.h_stage.release(); sl.h_out.release(); sl.h_stats.release();
+    sl.d_in.release(); sl.d_in3.release(); sl.d_stats.release(); sl.h_stage.release(); sl.h_out.release(); sl.h_stats.release();
     if (sl.uploaded) cudaEventDestroy(sl.uploaded);
     if (sl.done) cudaEventDestroy(sl.done);
   }
@@ -758,7 +785,8 @@ int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *corner, 
   if (sl.busy) { set_error("msfl_scan2map_batch_submit: %d batches already in flight", MSFL_MAX_INFLIGHT); return MSFL_ERR_ARG; }
   int rc;
   size_t nct = 0, nst = 0;
-  bool contiguous = true;
+  bool contiguous = true;  // packed float4 clouds back to back: DMA straight from the caller's memory
+  bool packed3 = true;     // packed xyz-only clouds (12 B points) back to back: DMA + widening on the device
   for (int b = 0; b < B; ++b) {
     if ((rc = check_cloud(&corner[b], false, "scan_corner"))) return rc;
     if ((rc = check_cloud(&surf[b], false, "scan_surf"))) return rc;
@@ -767,6 +795,8 @@ int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *corner, 
     for (int c = 0; c < 2; ++c) {
       if (cl[c]->stride != 16 || cl[c]->off_xyz != 0) contiguous = false;
       if (nx[c] && (const char *)nx[c]->data != (const char *)cl[c]->data + cl[c]->n * 16) contiguous = false;
+      if (cl[c]->stride != 12 || cl[c]->off_xyz != 0 || cl[c]->off_intensity != MSFL_NO_FIELD) packed3 = false;
+      if (nx[c] && (const char *)nx[c]->data != (const char *)cl[c]->data + cl[c]->n * 12) packed3 = false;
     }
     nct += corner[b].n;
     nst += surf[b].n;
@@ -779,11 +809,13 @@ int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *corner, 
   const size_t q_bytes = (nct + nst) * 16, q_pad = (q_bytes + 15) & ~(size_t)15;
   const size_t off_bytes = (size_t)2 * (B + 1) * 4, off_pad = (off_bytes + 15) & ~(size_t)15;
   const size_t pose_bytes = (size_t)B * 7 * 8;
-  if ((rc = sl.h_stage.reserve((contiguous ? 0 : q_pad) + off_pad + pose_bytes))) return rc;
+  const bool direct = contiguous || packed3;
+  if ((rc = sl.h_stage.reserve((direct ? 0 : q_pad) + off_pad + pose_bytes))) return rc;
   if ((rc = sl.d_in.reserve(q_pad + off_pad + pose_bytes))) return rc;
+  if (packed3 && (rc = sl.d_in3.reserve((nct + nst) * 12 + 16))) return rc;
   if ((rc = sl.h_out.reserve(pose_bytes))) return rc;
   char *h = sl.h_stage.as<char>(), *d = sl.d_in.as<char>();
-  char *h_tab = h + (contiguous ? 0 : q_pad);
+  char *h_tab = h + (direct ? 0 : q_pad);
   int32_t *hoff = (int32_t *)h_tab;
   size_t ci = 0, si = 0;
   std::vector<size_t> c_at(B), s_at(B);
@@ -796,18 +828,27 @@ int msfl_scan2map_batch_submit(msfl_engine *e, int B, const msfl_cloud *corner, 
   }
   hoff[B] = (int32_t)ci;
   hoff[2 * B + 1] = (int32_t)si;
-  if (!contiguous) pack_batch_host(e, 0, B, corner, surf, (float *)h, nct, c_at.data(), s_at.data());
+  if (!direct) pack_batch_host(e, 0, B, corner, surf, (float *)h, nct, c_at.data(), s_at.data());
   memcpy(h_tab + off_pad, poses_in, pose_bytes);
   cudaStream_t cs = e->copy_stream;
   if (contiguous) {
     if (nct) MSFL_CUDA_OK(cudaMemcpyAsync(d, corner[0].data, nct * 16, cudaMemcpyHostToDevice, cs));
     if (nst) MSFL_CUDA_OK(cudaMemcpyAsync(d + nct * 16, surf[0].data, nst * 16, cudaMemcpyHostToDevice, cs));
+  } else if (packed3) {
+    char *d3 = sl.d_in3.as<char>();
+    if (nct) MSFL_CUDA_OK(cudaMemcpyAsync(d3, corner[0].data, nct * 12, cudaMemcpyHostToDevice, cs));
+    if (nst) MSFL_CUDA_OK(cudaMemcpyAsync(d3 + nct * 12, surf[0].data, nst * 12, cudaMemcpyHostToDevice, cs));
   } else if (q_bytes) {
     MSFL_CUDA_OK(cudaMemcpyAsync(d, h, q_bytes, cudaMemcpyHostToDevice, cs));
   }
   MSFL_CUDA_OK(cudaMemcpyAsync(d + q_pad, h_tab, off_pad + pose_bytes, cudaMemcpyHostToDevice, cs));
   MSFL_CUDA_OK(cudaEventRecord(sl.uploaded, cs));
   MSFL_CUDA_OK(cudaStreamWaitEvent(e->stream, sl.uploaded, 0));
+  if (packed3 && nct + nst) {
+    const uint32_t n = (uint32_t)(nct + nst);
+    k_expand_xyz<<<(n + 255) / 256, 256, 0, e->stream>>>(sl.d_in3.as<float>(), n, (float4 *)d);
+    e->launches += 1;
+  }
   msfl_stats *d_stats = nullptr;
   if (want_stats) {
     if ((rc = sl.d_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;

@@ -104,7 +104,7 @@ struct msfl_engine {
   // asynchronous batches (msfl_scan2map_batch_submit / _wait): per-slot input / output buffers; the
   // association / LM scratch below is shared because the kernels of all batches run in order on `stream`
   struct BatchSlot {
-    msfl::DevBuf d_in, d_stats;
+    msfl::DevBuf d_in, d_in3, d_stats;
     msfl::PinBuf h_stage, h_out, h_stats;
     cudaEvent_t uploaded = nullptr, done = nullptr;
     bool busy = false, want_stats = false;

@@ -63,6 +63,10 @@ class _View:
             offs = {n: self.buf.dtype.fields[n][1] for n in self.buf.dtype.names}
             self.cloud = Cloud(self.buf.ctypes.data, self.buf.shape[0], self.buf.dtype.itemsize,
                                offs["x"], offs["intensity"], offs["ring"])
+        elif a.ndim == 2 and a.shape[1] == 3:  # xyz only (12 B points): enough for the LiDAR-only matcher's queries
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            self.buf = a
+            self.cloud = Cloud(a.ctypes.data, a.shape[0], 12, 0, NO_FIELD, NO_FIELD)
         else:
             a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 4)
             self.buf = a
@@ -214,7 +218,7 @@ class Engine:
 
     def scan2map_submit(self, batch, poses_in: np.ndarray) -> int:
         """msfl_scan2map_batch_submit on a prepared batch: enqueues upload + kernels + pose download and
-        returns a ticket; up to 2 batches may be in flight (the upload of one overlaps the kernels of the other)."""
+        returns a ticket; up to 3 batches may be in flight (repack of k+2, upload of k+1, kernels of k)."""
         assert poses_in.dtype == np.float64 and poses_in.flags.c_contiguous
         t = C.c_int(-1)
         self._check(self.lib.msfl_scan2map_batch_submit(

@@ -1,4 +1,4 @@
-"""msfl_scan2map_batch_submit / _wait (two batches in flight: upload of batch k+1 overlaps the kernels of
+"""msfl_scan2map_batch_submit / _wait (up to three batches in flight: upload of batch k+1 overlaps the kernels of
 batch k) must give bit-identical poses to the synchronous msfl_scan2map_batch and stay within tolerance of the oracle."""
 import numpy as np
 import pytest
@@ -54,18 +54,51 @@ def test_third_submit_without_wait_is_refused_and_bad_ticket(vlp16_case):
     pb = e.prepare_batch(c, s)
     t0 = e.scan2map_submit(pb, x0)
     t1 = e.scan2map_submit(pb, x0)
+    tm = e.scan2map_submit(pb, x0)  # MSFL_MAX_INFLIGHT = 3
     with pytest.raises(MsflError):
         e.scan2map_submit(pb, x0)
     out = np.zeros_like(x0)
     with pytest.raises(MsflError):
-        e.scan2map_wait(t1 + 5, out)
+        e.scan2map_wait(tm + 5, out)
     e.scan2map_wait(t0, out)
     a = out.copy()
     e.scan2map_wait(t1, out)
+    assert np.array_equal(a, out)
+    e.scan2map_wait(tm, out)
     assert np.array_equal(a, out)
     with pytest.raises(MsflError):
         e.scan2map_wait(t1, out)  # already collected
     t2 = e.scan2map_submit(pb, x0)  # slots are free again
     e.scan2map_wait(t2, out)
     assert np.array_equal(a, out)
+    e.close()
+
+
+def test_xyz_only_and_pcl_layout_uploads_equal_the_float4_upload(vlp16_case):
+    """The three host layouts of a batch -- packed float4 (DMA in place), packed xyz-only (12 B points, DMA in place +
+    widening on the device), one 32-byte pcl::PointXYZI array per cloud (threaded host repack) -- give the same bits,
+    through the asynchronous and the synchronous entry points."""
+    from msf_loam_b200 import to_pcl
+    e = Engine(default_params())
+    e.set_submap(vlp16_case["map_corner"], vlp16_case["map_surf"])
+    (c, s, x0), = _batches(vlp16_case, 1, 48)
+    cat_c, cat_s = np.concatenate(c), np.concatenate(s)
+    co = np.concatenate([[0], np.cumsum([a.shape[0] for a in c])])
+    so = np.concatenate([[0], np.cumsum([a.shape[0] for a in s])])
+    c3, s3 = np.ascontiguousarray(cat_c[:, :3]), np.ascontiguousarray(cat_s[:, :3])
+    layouts = {
+        "float4": e.prepare_batch([cat_c[co[i]:co[i + 1]] for i in range(48)], [cat_s[so[i]:so[i + 1]] for i in range(48)]),
+        "xyz": e.prepare_batch([c3[co[i]:co[i + 1]] for i in range(48)], [s3[so[i]:so[i + 1]] for i in range(48)]),
+        "pcl": e.prepare_batch([to_pcl(a) for a in c], [to_pcl(a) for a in s]),
+    }
+    ref = None
+    for name, pb in layouts.items():
+        out = np.zeros_like(x0)
+        e.scan2map_wait(e.scan2map_submit(pb, x0), out)
+        x = x0.copy()
+        e.scan2map_prepared(pb, x)
+        assert np.array_equal(out, x), name
+        if ref is None:
+            ref = out
+        assert np.array_equal(out, ref), name
     e.close()
