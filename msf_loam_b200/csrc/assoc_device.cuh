@@ -12,8 +12,14 @@ struct Top5 {
   int i[5];
 };
 
+// (d, id) < (bd, bi) in the exact candidate order (distance, then original index).  Squared distances are >= +0, so
+// the order of the floats is the order of their bit patterns and the pair compares as ONE 64-bit unsigned integer
+// (two ISETP instead of two FSETP + ISETP + predicate logic; this comparison is 15 % of the search's instructions).
+// Callers filter NaN distances with a float compare first.  Indices are non-negative.
 __device__ __forceinline__ bool cand_less(float d, int id, float bd, int bi) {
-  return d < bd || (d == bd && id < bi);
+  const unsigned long long a = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)id;
+  const unsigned long long b = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned)bi;
+  return a < b;
 }
 
 // Sorted insertion without branches and in place: l_s = "entry s stays ahead of the candidate"; every slot is
@@ -38,10 +44,12 @@ __device__ __forceinline__ void top5_insert(Top5 &t, float d, int id) {
 // are monotone, and the bound is accumulated in the same order as the distance itself
 // ((bx^2 + by^2) + bz^2), so  bound > worst  implies  d > worst  for every point of that cell.
 __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy, float qz, float thresh, Top5 &t) {
+  // sentinels (thresh, 0): no real candidate compares below them at d == thresh, and a real entry always has
+  // d < thresh, so "five neighbours inside the gate" <=> t.d[4] < thresh
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     t.d[s] = thresh;
-    t.i[s] = -1;
+    t.i[s] = 0;
   }
   const float fxq = floorf(qx * g.inv_edge), fyq = floorf(qy * g.inv_edge), fzq = floorf(qz * g.inv_edge);
   const int cx = (int)fxq - g.ox, cy = (int)fyq - g.oy, cz = (int)fzq - g.oz;
@@ -58,8 +66,11 @@ __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy,
   //      (dy,dz): (0,0) (-1,0) (1,0) (0,-1) (0,1) (-1,-1) (-1,1) (1,-1) (1,1)
   constexpr uint32_t kDyPacked = 1u | (0u << 2) | (2u << 4) | (1u << 6) | (1u << 8) | (0u << 10) | (0u << 12) | (2u << 14) | (2u << 16);
   constexpr uint32_t kDzPacked = 1u | (1u << 2) | (1u << 4) | (0u << 6) | (2u << 8) | (0u << 10) | (2u << 12) | (0u << 14) | (2u << 16);
+  // only the rows that hold a point at all (k_row_mask; all nine when the table was not built)
+  uint32_t rows = g.row_mask ? (uint32_t)__ldg(g.row_mask + ((size_t)cz * g.ny + cy) * g.nx + cx) : 0x1ffu;
 #pragma unroll 1
-  for (int r = 0; r < 9; ++r) {
+  for (; rows; rows &= rows - 1u) {
+    const int r = __ffs(rows) - 1;
     const int dy = (int)((kDyPacked >> (2 * r)) & 3u) - 1, dz = (int)((kDzPacked >> (2 * r)) & 3u) - 1;
     const float by = dy == 0 ? 0.f : (dy < 0 ? loy : hiy), bz = dz == 0 ? 0.f : (dz < 0 ? loz : hiz);
     const float by2 = __fmul_rn(by, by), bz2 = __fmul_rn(bz, bz);
@@ -84,7 +95,7 @@ __device__ __forceinline__ bool knn5_grid(const GridView &g, float qx, float qy,
       }
     }
   }
-  return t.i[4] >= 0;
+  return t.d[4] < thresh;
 }
 
 // ---------------------------------------------------------------------------------------------

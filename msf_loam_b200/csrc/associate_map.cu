@@ -242,7 +242,7 @@ __device__ __forceinline__ bool knn5_tile(const float4 *__restrict__ tile, const
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     t.d[s] = thresh;
-    t.i[s] = -1;
+    t.i[s] = 0;
   }
   const float lox = exact_cells ? __fsub_rn(qx, fxq) : 0.f, hix = exact_cells ? __fsub_rn(fxq + 1.0f, qx) : 0.f;
   const float loy = exact_cells ? __fsub_rn(qy, fyq) : 0.f, hiy = exact_cells ? __fsub_rn(fyq + 1.0f, qy) : 0.f;
@@ -274,7 +274,7 @@ __device__ __forceinline__ bool knn5_tile(const float4 *__restrict__ tile, const
       }
     }
   }
-  return t.i[4] >= 0;
+  return t.d[4] < thresh;
 }
 
 __global__ void __launch_bounds__(128, 10)

@@ -46,6 +46,8 @@ struct GridView {
   const float4 *pts_sorted;   // xyz + original index (int bits in w)
   const float4 *pts_orig;     // original order (xyz, *), for gathering the k neighbours
   const uint32_t *cell_start; // ncell + 1
+  const uint16_t *row_mask;   // per cell: bit r set <=> row r (nearest-first order of knn5_grid) of its 3x3x3
+                              // neighbourhood holds a point; nullptr = not built (every row is visited)
   int nx, ny, nz;
   int ox, oy, oz;             // cell coordinate (floor(x * inv_edge)) of grid cell (0,0,0)
   float inv_edge;
@@ -53,7 +55,7 @@ struct GridView {
 };
 
 struct Submap {
-  DevBuf orig, sorted, cell_start, keys, keys_alt, vals, vals_alt, cub_tmp, bounds;
+  DevBuf orig, sorted, cell_start, keys, keys_alt, vals, vals_alt, cub_tmp, bounds, row_mask;
   GridView view{};
   size_t n = 0;
 };
@@ -143,7 +145,8 @@ void stage_begin(msfl_engine *e, int stage);
 void stage_end(msfl_engine *e);
 
 // ---- submap_index.cu
-int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge);
+int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge, bool want_row_mask = true);
+int submap_row_mask(msfl_engine *e, Submap &m);  // (re)builds m.view.row_mask from the cell table; no-op for huge grids
 int submap_build_host_bounds(msfl_engine *e, Submap &m, size_t n, float edge, const int lo[3], const int hi[3]);
 void submap_release(Submap &m);
 

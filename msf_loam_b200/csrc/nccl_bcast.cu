@@ -180,6 +180,7 @@ int msfl_bcast_submap(msfl_engine *e, void *nccl_comm, int root) {
       m.view.ox = h->dims[c][3]; m.view.oy = h->dims[c][4]; m.view.oz = h->dims[c][5];
       m.view.inv_edge = h->inv_edge[c];
       m.view.n = (uint32_t)m.n;
+      if ((rc = submap_row_mask(e, m))) return rc;  // derived from the adopted cell table (one small kernel)
     }
     e->has_submap = true;
   }

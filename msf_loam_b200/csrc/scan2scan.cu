@@ -327,8 +327,8 @@ static int scan2scan_impl(msfl_engine *e, const msfl_cloud *lc, const msfl_cloud
   }
   // cell indices over the last scan's feature clouds (the two kd-tree builds, :57-61)
   Submap &g_corner = e->last_corner_grid, &g_surf = e->last_surf_grid;  // rebuilt every call, like the reference
-  if ((rc = submap_build(e, g_corner, e->d_last_corner.as<float4>(), lc->n, 1.0f))) return rc;
-  if ((rc = submap_build(e, g_surf, e->d_last_surf.as<float4>(), ls->n, 1.0f))) return rc;
+  if ((rc = submap_build(e, g_corner, e->d_last_corner.as<float4>(), lc->n, 1.0f, false))) return rc;
+  if ((rc = submap_build(e, g_surf, e->d_last_surf.as<float4>(), ls->n, 1.0f, false))) return rc;
   ScanGrid gc{g_corner.view, e->d_last_corner_ring.as<uint16_t>(), (uint32_t)lc->n};
   ScanGrid gs{g_surf.view, e->d_last_surf_ring.as<uint16_t>(), (uint32_t)ls->n};
   if ((rc = e->d_ring_tab.reserve((lc->n + ls->n) * 2 + 64))) return rc;

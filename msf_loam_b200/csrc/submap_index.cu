@@ -155,13 +155,49 @@ int submap_build_host_bounds(msfl_engine *e, Submap &m, size_t n, float edge, co
   return MSFL_OK;
 }
 
+// Row occupancy of every cell's 3x3x3 neighbourhood: most of the nine (dy, dz) rows around a query are EMPTY in a map
+// of surfaces (a floor patch fills three rows of nine), and an empty row still costs the search its four cell-table
+// loads and bounds.  Bit r follows knn5_grid's nearest-first row order.
+__global__ void k_row_mask(const uint32_t *__restrict__ cell_start, int nx, int ny, int nz, uint16_t *__restrict__ mask) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ncell = (long long)nx * ny * nz;
+  if (c >= ncell) return;
+  const int cx = (int)(c % nx), cy = (int)((c / nx) % ny), cz = (int)(c / ((long long)nx * ny));
+  uint32_t m = 0;
+  if (cx >= 1 && cy >= 1 && cz >= 1 && cx <= nx - 2 && cy <= ny - 2 && cz <= nz - 2) {
+    constexpr uint32_t kDyPacked = 1u | (0u << 2) | (2u << 4) | (1u << 6) | (1u << 8) | (0u << 10) | (0u << 12) | (2u << 14) | (2u << 16);
+    constexpr uint32_t kDzPacked = 1u | (1u << 2) | (1u << 4) | (0u << 6) | (2u << 8) | (0u << 10) | (2u << 12) | (0u << 14) | (2u << 16);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int dy = (int)((kDyPacked >> (2 * r)) & 3u) - 1, dz = (int)((kDzPacked >> (2 * r)) & 3u) - 1;
+      const long long row = ((long long)(cz + dz) * ny + (cy + dy)) * nx + cx;
+      if (__ldg(cell_start + row + 2) > __ldg(cell_start + row - 1)) m |= 1u << r;
+    }
+  }
+  mask[c] = (uint16_t)m;
+}
+
+int submap_row_mask(msfl_engine *e, Submap &m) {
+  m.view.row_mask = nullptr;
+  const long long ncell = (long long)m.view.nx * m.view.ny * m.view.nz;
+  if (ncell > (1ll << 24)) return MSFL_OK;  // far-spread grid: the table would cost more than it saves
+  int rc;
+  if ((rc = m.row_mask.reserve((size_t)ncell * 2))) return rc;
+  k_row_mask<<<(unsigned)((ncell + 255) / 256), 256, 0, e->stream>>>(m.view.cell_start, m.view.nx, m.view.ny, m.view.nz,
+                                                                    m.row_mask.as<uint16_t>());
+  e->launches += 1;
+  MSFL_CUDA_OK(cudaGetLastError());
+  m.view.row_mask = m.row_mask.as<uint16_t>();
+  return MSFL_OK;
+}
+
 void submap_release(Submap &m) {
   m.orig.release(); m.sorted.release(); m.cell_start.release(); m.keys.release(); m.keys_alt.release();
-  m.vals.release(); m.vals_alt.release(); m.cub_tmp.release(); m.bounds.release();
+  m.vals.release(); m.vals_alt.release(); m.cub_tmp.release(); m.bounds.release(); m.row_mask.release();
   m.n = 0;
 }
 
-int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge) {
+int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float edge, bool want_row_mask) {
   cudaStream_t st = e->stream;
   if (n == 0 || n > 0x7fffffffull) { set_error("submap class is empty or too large (n=%zu)", n); return MSFL_ERR_ARG; }
   const uint32_t N = (uint32_t)n;
@@ -219,7 +255,8 @@ int submap_build(msfl_engine *e, Submap &m, const float4 *d_pts, size_t n, float
   m.view.ox = ox; m.view.oy = oy; m.view.oz = oz;
   m.view.inv_edge = inv_edge;
   m.view.n = N;
-  return MSFL_OK;
+  m.view.row_mask = nullptr;
+  return want_row_mask ? submap_row_mask(e, m) : MSFL_OK;
 }
 
 }  // namespace msfl

@@ -61,21 +61,25 @@ int main(void) {
   int async_ok = 1;
   {
     msfl_cloud bc[3] = {qc, qc, qc}, bs[3] = {qs, qs, qs};
-    double init[21], out0[21], out1[21];
+    double init[21], out0[21], out1[21], out2[21];
     for (int b = 0; b < 3; ++b)
       for (int k = 0; k < 7; ++k) init[7 * b + k] = k == 6 ? 1.0 : 0.0;
-    int t0 = -1, t1 = -1, t2 = -1;
-    if (msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t0) != MSFL_OK || msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t1) != MSFL_OK) {
+    int t0 = -1, t1 = -1, t2 = -1, t3 = -1;
+    if (msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t0) != MSFL_OK || msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t1) != MSFL_OK ||
+        msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t2) != MSFL_OK) {
       fprintf(stderr, "submit: %s\n", msfl_last_error());
       return 5;
     }
-    if (msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t2) == MSFL_OK) async_ok = 0; /* a third ticket must be refused */
-    if (msfl_scan2map_batch_wait(e, t0, out0, NULL) != MSFL_OK || msfl_scan2map_batch_wait(e, t1, out1, NULL) != MSFL_OK) {
+    if (msfl_scan2map_batch_submit(e, 3, bc, bs, init, 0, &t3) == MSFL_OK) async_ok = 0; /* MSFL_MAX_INFLIGHT = 3: a fourth ticket must be refused */
+    if (msfl_scan2map_batch_wait(e, t0, out0, NULL) != MSFL_OK || msfl_scan2map_batch_wait(e, t1, out1, NULL) != MSFL_OK ||
+        msfl_scan2map_batch_wait(e, t2, out2, NULL) != MSFL_OK) {
       fprintf(stderr, "wait: %s\n", msfl_last_error());
       return 6;
     }
     for (int b = 0; b < 3; ++b)
-      if (memcmp(out0 + 7 * b, pose, sizeof pose) != 0 || memcmp(out1 + 7 * b, pose, sizeof pose) != 0) async_ok = 0;
+      if (memcmp(out0 + 7 * b, pose, sizeof pose) != 0 || memcmp(out1 + 7 * b, pose, sizeof pose) != 0 ||
+          memcmp(out2 + 7 * b, pose, sizeof pose) != 0)
+        async_ok = 0;
     printf("async batches %s\n", async_ok ? "match the synchronous pose bit for bit" : "MISMATCH");
   }
   msfl_destroy(e);
