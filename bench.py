@@ -248,8 +248,8 @@ def numa_bind(local_rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-STAGE_NAMES = {0: "k_knn5_fit (5-NN search over the submap cell index + plane fit)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
-               2: "k_transform_keys + counting sort of the cell keys", 3: "k_fit (fp64 line fit, Householder fallback)"}
+STAGE_NAMES = {0: "k_knn5_fit (5-NN search over the submap cell index + line / plane fit)", 1: "k_lm_solve (residual/Jacobian/6x6 LM)",
+               2: "k_transform_keys + counting sort of the cell keys", 3: "k_fit_qr_list (Householder fallback of declined plane fits)"}
 
 
 class Ctx:

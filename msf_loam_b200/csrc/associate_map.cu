@@ -443,10 +443,11 @@ __device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, 
   fit_from_idx<DESKEW, COMPACT, QR>(g, kp, is_corner, k, slot, n_corner_total, idx, corr, tb, dsk, fb_list, fb_count);
 }
 
-// Batch path, fused: the search of k_knn5<true, true, false, true> followed, for surf slots, by the closed-form plane
-// fit on the indices still in registers -- the surf neighbour lists (20 B per query written and read back) never
-// touch memory; declined queries store their list and go to the Householder kernel as usual.  Corner slots store
-// their list for k_fit<.., 0> (the Jacobi eigen-solver keeps its own register allocation).
+// Batch path, fused: the search of k_knn5<true, true, false, true> followed by the fit on the indices still in
+// registers -- closed-form plane fit for surf slots, closed-form eigen line test for corner slots -- so the neighbour
+// lists (20 B per query written and read back) never touch memory and the whole association of an outer iteration is
+// ONE kernel after the sort; only the plane queries the closed form declines store their list and go to the
+// Householder kernel.
 __global__ void __launch_bounds__(128, 8)
 k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const float4 *__restrict__ xq,
            const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, double *__restrict__ corr,
@@ -462,14 +463,7 @@ k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32
   int idx[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) idx[s] = gate ? t.i[s] : -1;
-  if (is_corner) {
-#pragma unroll
-    for (int s = 0; s < 5; ++s) knn_out[(size_t)slot * 5 + s] = idx[s];
-    return;
-  }
-  // a declined query is re-fitted by k_fit_qr_list from its stored list
   float mf[5][3];
-  bool declined = false;
   if (gate) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
@@ -478,10 +472,16 @@ k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32
     }
   }
   double c[3] = {0, 0, 0}, n[3] = {0, 0, 0};
-  if (gate) {
-    centroid5(mf, c);
-    declined = plane_fit_fast(mf, c, kp.plane_tol, n);
+  if (gate) centroid5(mf, c);
+  if (is_corner) {  // line test + direction (closed-form eigen-solver): the edge entry {a, n}, 48 B
+    double a[3] = {0, 0, 0};
+    if (gate) line_fit(mf, c, kp, a, n);
+    store_corr(corr, k, a, n);
+    return;
   }
+  // a declined plane query is re-fitted by k_fit_qr_list from its stored list
+  bool declined = false;
+  if (gate) declined = plane_fit_fast(mf, c, kp.plane_tol, n);
   if (declined) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) knn_out[(size_t)slot * 5 + s] = idx[s];
@@ -641,7 +641,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   {
     if (by_slot && compact) {
       const unsigned grid_c = (n_corner_total + tb - 1) / tb, grid_s = (n_surf_total + tb - 1) / tb;
-      if (grid_c) k_fit<false, true, true, 0><<<grid_c, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
+      if (grid_c && !fused) k_fit<false, true, true, 0><<<grid_c, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
       if (grid_s) {
         if (!fused) k_fit<false, true, true, 1><<<grid_s, tb, 0, e->stream>>>(gc, gs, e->kp, n_corner_total, total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);
         k_fit_qr_list<false, true, true><<<qr_list_grid(e, n_surf_total), tb, 0, e->stream>>>(gs, e->kp, n_corner_total, d_knn, d_corr, nt, nullptr, e->a_perm, fb_list, fb_count);

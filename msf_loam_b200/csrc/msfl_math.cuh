@@ -81,60 +81,71 @@ __host__ __device__ inline void pose_plus(const double x[7], const double d[6], 
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3x3 symmetric eigen-decomposition (stands in for Eigen::SelfAdjointEigenSolver<Matrix3d>,
-// mapping_scan_matcher.cc:141).  Cyclic Jacobi on the upper triangle; returns the largest and
-// middle eigenvalues and the unit eigenvector of the largest.
+// Largest eigenpair + middle eigenvalue of a 3x3 symmetric positive semi-definite matrix (stands in for
+// Eigen::SelfAdjointEigenSolver<Matrix3d> at mapping_scan_matcher.cc:141, whose only use is the line test
+// lambda_max > 3 lambda_mid and the direction of the largest eigenvector, :147-151).
+//
+// Branch-free and iteration-free, ~200 fp64 instructions instead of ~1200 for cyclic Jacobi:
+//   1. M = S / tr(S), squared five times: M^32 = sum (lambda_i / tr)^32 u_i u_i^T.  Whenever the line test can pass
+//      (lambda_mid < lambda_max / 3) the other two terms are below 3^-32 = 5e-16 of the first, so any column of M^32 IS
+//      the largest eigenvector to round-off; the column with the largest diagonal entry is used.
+//   2. lambda_max = u^T S u (Rayleigh quotient: second-order accurate in u).
+//   3. lambda_mid = the larger eigenvalue of S compressed to the plane orthogonal to u, from the cancellation-free
+//      formula (m00 + m11) / 2 + sqrt(((m00 - m11) / 2)^2 + m01^2).
+// When lambda_max is NOT isolated u is meaningless, but then u^T S u <= lambda_max and (Cauchy interlacing) the
+// compressed eigenvalue >= lambda_mid, so the computed ratio can only be smaller than the true one: the test fails as it
+// must.  The eigenvector's sign is implementation-defined upstream (it falls out of Eigen's QL iteration) and the factor
+// is invariant to it; it is fixed by the rule "largest-magnitude component positive" here and in the oracle.
 // ---------------------------------------------------------------------------------------------
-__device__ inline void sym_eig3_top(double a00, double a01, double a02, double a11, double a12, double a22,
-                                    double &lam_max, double &lam_mid, double u[3]) {
-  double A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
-  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
-    const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
-    if (off <= 1e-32 * dg || off == 0.0) break;
+__device__ __forceinline__ void sym_eig3_top(double a00, double a01, double a02, double a11, double a12, double a22,
+                                             double &lam_max, double &lam_mid, double u[3]) {
+  const double tr = a00 + a11 + a22;
+  u[0] = 1.0; u[1] = 0.0; u[2] = 0.0;
+  lam_max = 0.0; lam_mid = 0.0;
+  if (!(tr > 0.0) || !isfinite(tr)) return;  // zero scatter (five coincident points): 0 > 3 * 0 is false, no line
+  const double it = 1.0 / tr;
+  double m00 = a00 * it, m01 = a01 * it, m02 = a02 * it, m11 = a11 * it, m12 = a12 * it, m22 = a22 * it;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-#pragma unroll
-      for (int q = p + 1; q < 3; ++q) {
-        const double apq = A[p][q];
-        if (apq == 0.0) continue;
-        const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
-        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double akp = A[k][p], akq = A[k][q];
-          A[k][p] = c * akp - s * akq;
-          A[k][q] = s * akp + c * akq;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = c * apk - s * aqk;
-          A[q][k] = s * apk + c * aqk;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = c * vkp - s * vkq;
-          V[k][q] = s * vkp + c * vkq;
-        }
-      }
-    }
+  for (int k = 0; k < 5; ++k) {  // M <- M M (symmetric): eigenvalues in [0, 1], the largest >= 1/3, so 3^-32 never underflows
+    const double n00 = m00 * m00 + m01 * m01 + m02 * m02, n01 = m00 * m01 + m01 * m11 + m02 * m12,
+                 n02 = m00 * m02 + m01 * m12 + m02 * m22, n11 = m01 * m01 + m11 * m11 + m12 * m12,
+                 n12 = m01 * m02 + m11 * m12 + m12 * m22, n22 = m02 * m02 + m12 * m12 + m22 * m22;
+    m00 = n00; m01 = n01; m02 = n02; m11 = n11; m12 = n12; m22 = n22;
   }
-  const double e0 = A[0][0], e1 = A[1][1], e2 = A[2][2];
-  // ascending order with the oracle's tie rule (stable bubble: first index wins the lower slot)
-  int i0 = 0, i1 = 1, i2 = 2;
-  double f0 = e0, f1 = e1, f2 = e2;
-  if (f0 > f1) { double t = f0; f0 = f1; f1 = t; int ti = i0; i0 = i1; i1 = ti; }
-  if (f1 > f2) { double t = f1; f1 = f2; f2 = t; int ti = i1; i1 = i2; i2 = ti; }
-  if (f0 > f1) { double t = f0; f0 = f1; f1 = t; int ti = i0; i0 = i1; i1 = ti; }
-  lam_max = f2;
-  lam_mid = f1;
-  u[0] = (i2 == 0) ? V[0][0] : (i2 == 1 ? V[0][1] : V[0][2]);
-  u[1] = (i2 == 0) ? V[1][0] : (i2 == 1 ? V[1][1] : V[1][2]);
-  u[2] = (i2 == 0) ? V[2][0] : (i2 == 1 ? V[2][1] : V[2][2]);
+  // the column with the largest diagonal entry (= largest u_j^2)
+  double v0 = m00, v1 = m01, v2 = m02, best = m00;
+  if (m11 > best) { best = m11; v0 = m01; v1 = m11; v2 = m12; }
+  if (m22 > best) { best = m22; v0 = m02; v1 = m12; v2 = m22; }
+  const double vn = v0 * v0 + v1 * v1 + v2 * v2;
+  if (!(vn > 0.0)) return;
+  const double iv = rsqrt(vn);
+  double x = v0 * iv, y = v1 * iv, z = v2 * iv;
+  // sign rule: the largest-magnitude component is positive (first one on ties)
+  {
+    const double ax = fabs(x), ay = fabs(y), az = fabs(z);
+    const double lead = (ax >= ay && ax >= az) ? x : (ay >= az ? y : z);
+    if (lead < 0.0) { x = -x; y = -y; z = -z; }
+  }
+  // Rayleigh quotient on the unscaled matrix
+  const double s0 = a00 * x + a01 * y + a02 * z, s1 = a01 * x + a11 * y + a12 * z, s2 = a02 * x + a12 * y + a22 * z;
+  lam_max = x * s0 + y * s1 + z * s2;
+  // orthonormal basis (p, q) of the plane orthogonal to u: p = e_k x u for the axis k along which u is smallest
+  double p0, p1, p2;
+  {
+    const double ax = fabs(x), ay = fabs(y), az = fabs(z);
+    if (ax <= ay && ax <= az) { p0 = 0.0; p1 = -z; p2 = y; }       // e_x x u
+    else if (ay <= az) { p0 = z; p1 = 0.0; p2 = -x; }              // e_y x u
+    else { p0 = -y; p1 = x; p2 = 0.0; }                            // e_z x u
+    const double ip = rsqrt(p0 * p0 + p1 * p1 + p2 * p2);
+    p0 *= ip; p1 *= ip; p2 *= ip;
+  }
+  const double q0 = y * p2 - z * p1, q1 = z * p0 - x * p2, q2 = x * p1 - y * p0;  // u x p
+  const double sp0 = a00 * p0 + a01 * p1 + a02 * p2, sp1 = a01 * p0 + a11 * p1 + a12 * p2, sp2 = a02 * p0 + a12 * p1 + a22 * p2;
+  const double sq0 = a00 * q0 + a01 * q1 + a02 * q2, sq1 = a01 * q0 + a11 * q1 + a12 * q2, sq2 = a02 * q0 + a12 * q1 + a22 * q2;
+  const double c00 = p0 * sp0 + p1 * sp1 + p2 * sp2, c01 = q0 * sp0 + q1 * sp1 + q2 * sp2, c11 = q0 * sq0 + q1 * sq1 + q2 * sq2;
+  const double h = 0.5 * (c00 - c11);
+  lam_mid = 0.5 * (c00 + c11) + sqrt(h * h + c01 * c01);
+  u[0] = x; u[1] = y; u[2] = z;
 }
 
 // ---------------------------------------------------------------------------------------------

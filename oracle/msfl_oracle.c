@@ -632,6 +632,14 @@ void msflo_sym_eig3(const double Ain[9], double evals[3], double V[9]) {
   for (int c = 0; c < 3; c++) {
     evals[c] = e[ord[c]];
     for (int r = 0; r < 3; r++) Vs[r * 3 + c] = V[r * 3 + ord[c]];
+    /* The SIGN of an eigenvector is implementation-defined upstream (it falls out of Eigen's tridiagonal QL iteration)
+     * and the edge factor is invariant to it (n and a = c + 0.1 n flip together: r, J^T J and J^T r keep their values,
+     * SURVEY.md Appendix A).  Resolved by a rule, like the std::sort ties: the largest-magnitude component is positive
+     * (the first one on ties).  The CUDA eigen-solver follows the same rule. */
+    double ax = fabs(Vs[0 * 3 + c]), ay = fabs(Vs[1 * 3 + c]), az = fabs(Vs[2 * 3 + c]);
+    double lead = (ax >= ay && ax >= az) ? Vs[0 * 3 + c] : (ay >= az ? Vs[1 * 3 + c] : Vs[2 * 3 + c]);
+    if (lead < 0.0)
+      for (int r = 0; r < 3; r++) Vs[r * 3 + c] = -Vs[r * 3 + c];
   }
   memcpy(V, Vs, sizeof Vs);
 }
