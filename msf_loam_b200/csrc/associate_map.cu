@@ -448,7 +448,10 @@ __device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, 
 // lists (20 B per query written and read back) never touch memory and the whole association of an outer iteration is
 // ONE kernel after the sort; only the plane queries the closed form declines store their list and go to the
 // Householder kernel.
-__global__ void __launch_bounds__(128, 8)
+#ifndef MSFL_KNNFIT_MINB
+#define MSFL_KNNFIT_MINB 10
+#endif
+__global__ void __launch_bounds__(128, MSFL_KNNFIT_MINB)
 k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const float4 *__restrict__ xq,
            const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, double *__restrict__ corr,
            uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
