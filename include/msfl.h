@@ -261,6 +261,15 @@ int msfl_scan2map_deskew(msfl_engine *e, const msfl_cloud *scan_corner, const ms
 int msfl_scan2scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp,
                    const msfl_cloud *last_surf_less_flat, const msfl_cloud *curr_corner_sharp,
                    const msfl_cloud *curr_surf_flat, double pose_tq[7], msfl_stats *stats);
+
+/* B independent MatchScan2Scan problems in one call (replay of a log: pair b = scans b and b + 1, laser_odometry.cc:75).
+ * Arrays of B clouds each; poses_tq 7 B doubles in-out (the B initial guesses / estimates of pose_curr2last);
+ * status: B entries (MSFL_OK / MSFL_TOO_FEW per pair, pose of a MSFL_TOO_FEW pair as in the single call) or NULL;
+ * stats: B entries or NULL.  Every pair gets its own 1 m cell index over its last-scan clouds (built for all pairs at
+ * once); results are those of B msfl_scan2scan calls.  Returns MSFL_OK or the first error (no pose written). */
+int msfl_scan2scan_batch(msfl_engine *e, int B, const msfl_cloud *last_corner_less_sharp,
+                         const msfl_cloud *last_surf_less_flat, const msfl_cloud *curr_corner_sharp,
+                         const msfl_cloud *curr_surf_flat, double *poses_tq, int32_t *status, msfl_stats *stats);
 /* outer-iteration-0 association only (parity tests): assoc = n_sharp x 2 then n_flat x 3 ints */
 int msfl_associate_scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp,
                         const msfl_cloud *last_surf_less_flat, const msfl_cloud *curr_corner_sharp,
@@ -291,6 +300,20 @@ typedef struct msfl_chain_counts {
 int msfl_register_and_match_batch(msfl_engine *e, int B, const msfl_cloud *raw, const double T_lidar2imu[7],
                                   float leaf_corner, float leaf_surf, double *poses_tq, msfl_chain_counts *counts,
                                   msfl_stats *stats);
+
+/* Replay of B CONSECUTIVE raw scans: msfl_register_and_match_batch plus the odometry between them, all from one
+ * registration pass whose features stay in HBM.  Pair b (b >= 1) is OdometryScanMatcher::MatchScan2Scan(last = scan
+ * b - 1, curr = scan b) (laser_odometry.cc:75), all B - 1 pairs in one launch sequence (msfl_scan2scan_batch's):
+ *   odom_tq      7 B doubles; entry b >= 1 in-out = pose_curr2last of scan b (initial guess in, estimate out; the
+ *                reference feeds the previous frame's estimate, a batch takes the caller's); entry 0 is not read
+ *   odom_status  B entries or NULL (MSFL_OK / MSFL_TOO_FEW; [0] = MSFL_OK)
+ *   compose      != 0: the map matcher's initial guesses are dead-reckoned from poses_tq[0]:
+ *                poses_tq[b] = poses_tq[b - 1] * odom_tq[b] (pose_scan2world_ * pose_curr2last_, laser_odometry.cc:79);
+ *                == 0: poses_tq holds the B guesses as in msfl_register_and_match_batch
+ * then VoxelGrid + scan-to-map of all B scans against the current submap; poses_tq returns the B estimates. */
+int msfl_replay_batch(msfl_engine *e, int B, const msfl_cloud *raw, const double T_lidar2imu[7], float leaf_corner,
+                      float leaf_surf, double *odom_tq, int32_t *odom_status, int compose, double *poses_tq,
+                      msfl_chain_counts *counts, msfl_stats *stats);
 
 /* ---- GPU-resident STGM submap producer: HybridGrid of hybrid_grid.h:32-35,
  *      hybrid_grid.cc:403-521, one map per feature class (laser_mapping.h hybrid_grid_map_corner_ /

@@ -58,10 +58,23 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
                  uint32_t n_surf_total, const double *__restrict__ poses, float4 *__restrict__ xq,
                  uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ hist, int sub_log2) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_corner_total + n_surf_total) return;
+  const uint32_t n_total = n_corner_total + n_surf_total;
   const bool is_corner = k < n_corner_total;
   const uint32_t kk = is_corner ? k : k - n_corner_total;
-  const int scan = find_scan(is_corner ? c_off : s_off, B, kk);
+  const int32_t *off = is_corner ? c_off : s_off;
+  // scan id: the 32 queries of a warp are consecutive, so ONE binary search (lane 0) and a forward walk that almost
+  // never takes a step replace 32 chains of log2(B) dependent loads; a warp that straddles the corner / surf boundary
+  // searches per lane
+  const bool class0 = __shfl_sync(0xffffffffu, is_corner, 0);
+  int scan = 0;
+  if ((threadIdx.x & 31) == 0 && k < n_total) scan = find_scan(off, B, kk);
+  scan = __shfl_sync(0xffffffffu, scan, 0);
+  if (k >= n_total) return;
+  if (is_corner == class0) {
+    while ((uint32_t)__ldg(off + scan + 1) <= kk) ++scan;
+  } else {
+    scan = find_scan(off, B, kk);
+  }
   double pose[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) pose[i] = __ldg(poses + (size_t)scan * 7 + i);

@@ -356,6 +356,7 @@ int msfl_create_on_stream(const msfl_params *params, int device, void *stream, m
   e->sm_count = prop.multiProcessorCount;
   fill_kparams(e);
   if (const char *v = getenv("MSFL_COUNT_SORT_MAX_BINS")) e->count_sort_max_bins = atoll(v);  // tests: force the radix path
+  if (const char *v = getenv("MSFL_PAIR_CELL_BUDGET")) e->pair_cell_budget = std::max(1ll, atoll(v));  // tests: force chunks
   {
     const unsigned hc = std::thread::hardware_concurrency();
     e->pack_threads = (int)std::min(16u, std::max(1u, hc));
@@ -395,7 +396,8 @@ void msfl_destroy(msfl_engine *e) {
                    &e->d_assoc, &e->f_raw, &e->f_keys, &e->f_keys_alt, &e->f_vals, &e->f_vals_alt, &e->f_tmp, &e->f_full,
                    &e->f_ring, &e->f_curv, &e->f_label, &e->f_idx, &e->f_cnt, &e->f_angle, &e->f_misc, &e->f_soff, &e->v_in,
                    &e->v_keys, &e->v_keys_alt, &e->v_vals, &e->v_vals_alt, &e->v_tmp, &e->v_out, &e->v_misc, &e->vb_keys, &e->vb_keys_alt, &e->vb_vals, &e->vb_vals_alt, &e->vb_tmp, &e->vb_misc,
-                   &e->c_in, &e->c_off, &e->c_q,
+                   &e->c_in, &e->c_off, &e->c_q, &e->ob_in, &e->ob_bounds, &e->ob_hdr, &e->ob_sorted, &e->ob_ring_sorted, &e->ob_cells,
+                   &e->ob_keys, &e->ob_rank, &e->ob_tmp,
                    &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp, &e->a_hist,
                    &e->k_table, &e->k_dsk, &e->k_pprime, &e->a_fb};
   for (DevBuf *b : dbs) b->release();

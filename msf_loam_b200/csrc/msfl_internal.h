@@ -90,6 +90,7 @@ struct msfl_engine {
   // the cell keys of a batch are counting-sorted while the bin table (64 sub-cell bins per submap cell) stays small
   // enough to live in L2; larger (sparse, far-spread) submaps fall back to a radix sort of the keys
   long long count_sort_max_bins = 16ll << 20;
+  long long pair_cell_budget = 1ll << 27;  // batched scan-to-scan: cells (uint32) of the pair grids indexed at once
   int sm_count = 148;
   int pack_threads = 1;  // host threads that repack strided AoS clouds of a large batch into the pinned staging slot
 
@@ -128,6 +129,8 @@ struct msfl_engine {
 
   // odometry scratch
   msfl::DevBuf d_last_corner, d_last_surf, d_last_corner_ring, d_last_surf_ring, d_ring_tab, d_assoc;
+  // batched odometry scratch: inputs, per-grid bounds / headers, cell-ordered points + rings, cell table, sort scratch
+  msfl::DevBuf ob_in, ob_bounds, ob_hdr, ob_sorted, ob_ring_sorted, ob_cells, ob_keys, ob_rank, ob_tmp;
 
   // feature extraction scratch
   msfl::DevBuf f_raw, f_keys, f_keys_alt, f_vals, f_vals_alt, f_tmp, f_full, f_ring, f_curv, f_label,
@@ -187,6 +190,11 @@ int launch_associate_scan(msfl_engine *e, const float4 *d_last_corner, const uin
                           const uint32_t *d_ring_start_corner, const uint32_t *d_ring_start_surf,
                           const float4 *d_queries, uint32_t n_sharp, uint32_t n_flat, const double *d_pose,
                           double *d_corr, int32_t *d_assoc);
+
+int scan2scan_batch_device(msfl_engine *e, int B, const float4 *last_pts, const uint16_t *last_ring, const uint32_t *d_goff,
+                           const uint32_t *h_goff, const float4 *q_sharp, const int32_t *d_e_off, const int32_t *h_e_off,
+                           const float4 *q_flat, const int32_t *d_p_off, const int32_t *h_p_off, double *d_poses,
+                           int32_t *d_status, msfl_stats *d_stats);
 
 // ---- features.cu
 int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7], msfl_features *out);

@@ -9,6 +9,14 @@
 // ring filter", evaluated here on the 1 m cell index by expanding Chebyshev shells (one warp per query) until the
 // best candidate is provably nearest or the 5 m radius is exhausted.  Ties (equal fp32 distance) follow
 // the reference's visiting order: forward indices ascending, then backward indices descending.
+#include <cub/device/device_scan.cuh>
+
+#include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
 
@@ -168,23 +176,13 @@ __device__ __forceinline__ void warp_shell_search(const ScanGrid &sg, const uint
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_associate_scan(ScanGrid gc, ScanGrid gs, const uint16_t *__restrict__ ring_sorted_c, const uint16_t *__restrict__ ring_sorted_s,
-                 KParams kp, const float4 *__restrict__ q_sharp, uint32_t n_sharp, const float4 *__restrict__ q_flat,
-                 uint32_t n_flat, const double *__restrict__ pose_g, double *__restrict__ corr, int32_t *__restrict__ assoc) {
-  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per query
-  const uint32_t lane = threadIdx.x & 31;
-  if (k >= n_sharp + n_flat) return;
-  double pose[7];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) pose[i] = pose_g[i];
-  const bool is_sharp = k < n_sharp;
-  const float4 p = is_sharp ? q_sharp[k] : q_flat[k - n_sharp];
+// One query (the whole warp): the searches of a sharp / flat point against the last scan's cloud `sg` and the factor
+// constants [a(3), n(3)] (n = 0: no factor).  nn / b2 / b3 return the association indices.
+__device__ __forceinline__ void associate_scan_query(const ScanGrid &sg, const uint16_t *__restrict__ ring_sorted, const KParams &kp,
+                                                     const double pose[7], const float4 p, bool is_sharp, double a[3], double n[3],
+                                                     Best &nn, Best &b2, Best &b3) {
   const float3 x = transform_point_f(pose, p.x, p.y, p.z);  // TransformToStart, s = 1 (:21-33)
-  const ScanGrid &sg = is_sharp ? gc : gs;
-  const uint16_t *ring_sorted = is_sharp ? ring_sorted_c : ring_sorted_s;
-  double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
-  Best nn, b2, b3;
+  a[0] = a[1] = a[2] = 0; n[0] = n[1] = n[2] = 0;
   b2.idx = b3.idx = -1;
   warp_shell_search<0, false>(sg, ring_sorted, x.x, x.y, x.z, kp.dist_sq_thresh_f, -1, 0, 0.0, nn, b2, b3);  // :84-87 / :169-173
   if (nn.idx >= 0) {
@@ -218,6 +216,23 @@ k_associate_scan(ScanGrid gc, ScanGrid gs, const uint16_t *__restrict__ ring_sor
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(128)
+k_associate_scan(ScanGrid gc, ScanGrid gs, const uint16_t *__restrict__ ring_sorted_c, const uint16_t *__restrict__ ring_sorted_s,
+                 KParams kp, const float4 *__restrict__ q_sharp, uint32_t n_sharp, const float4 *__restrict__ q_flat,
+                 uint32_t n_flat, const double *__restrict__ pose_g, double *__restrict__ corr, int32_t *__restrict__ assoc) {
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per query
+  const uint32_t lane = threadIdx.x & 31;
+  if (k >= n_sharp + n_flat) return;
+  double pose[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) pose[i] = pose_g[i];
+  const bool is_sharp = k < n_sharp;
+  const float4 p = is_sharp ? q_sharp[k] : q_flat[k - n_sharp];
+  double a[3], n[3];
+  Best nn, b2, b3;
+  associate_scan_query(is_sharp ? gc : gs, is_sharp ? ring_sorted_c : ring_sorted_s, kp, pose, p, is_sharp, a, n, nn, b2, b3);
   if (lane != 0) return;
   store6(corr, k, a, n);
   if (assoc) {
@@ -372,6 +387,368 @@ static int scan2scan_impl(msfl_engine *e, const msfl_cloud *lc, const msfl_cloud
     MSFL_CUDA_OK(cudaMemcpyAsync(assoc_out, e->d_assoc.p, (2 * (size_t)n_sharp + 3 * (size_t)n_flat) * 4, cudaMemcpyDeviceToHost, st));
   MSFL_CUDA_OK(cudaStreamSynchronize(st));
   return h_status;
+}
+
+// =============================================================================================================
+// Batched form: B independent MatchScan2Scan problems (replay of a log: pair b = scans b, b + 1) in one launch sequence.
+// The 2B last-scan clouds (grid g = 2 b + class, class 0 = less-sharp, 1 = less-flat) lie back to back in HBM; every
+// grid gets its own dense 1 m cell table inside ONE cell array (header table: origin, dims, first cell, first point),
+// built for all grids at once by a counting sort: one atomic per point (rank inside its cell), ONE exclusive scan over
+// the cells of all grids, one scatter.  The search then runs one warp per query of the whole batch and the LM kernel
+// one CTA (or cluster) per pair, exactly as in the batched scan-to-map.  Pairs are processed in chunks whose cell
+// tables fit the engine's pair_cell_budget (2^27 cells = 0.5 GB).
+// =============================================================================================================
+namespace msfl {
+
+struct PairGridHdr {
+  int ox, oy, oz, nx, ny, nz;
+  uint32_t cell_base;  // first entry of this grid in the chunk's cell array (ncell + 1 entries)
+  uint32_t pt_base;    // first point of this grid in the concatenated last-scan arrays
+  uint32_t n, chunk_pt_base;  // points in this grid; first point of the grid's chunk
+};
+
+__global__ void k_pair_bounds_init(int *bounds, uint32_t G) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * 8) return;
+  const uint32_t f = i & 7u;
+  bounds[i] = f < 3 ? INT_MAX : (f < 6 ? INT_MIN : 0);
+}
+
+// occupied cell range of every grid (blockIdx.y = grid); bounds[g] = {lo[3], hi[3], bad, -}
+__global__ void k_pair_bounds(const float4 *__restrict__ pts, const uint32_t *__restrict__ goff, float inv_edge, int *bounds) {
+  const uint32_t g = blockIdx.y, base = goff[g], n = goff[g + 1] - base;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  int bad = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[base + i];
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) || fabsf(p.x) > 1e6f || fabsf(p.y) > 1e6f || fabsf(p.z) > 1e6f) {
+      bad = 1;
+      continue;
+    }
+    const int c[3] = {(int)floorf(p.x * inv_edge), (int)floorf(p.y * inv_edge), (int)floorf(p.z * inv_edge)};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { lo[d] = min(lo[d], c[d]); hi[d] = max(hi[d], c[d]); }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    int *b = bounds + 8 * g;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (lo[d] != INT_MAX) atomicMin(&b[d], lo[d]);
+      if (hi[d] != INT_MIN) atomicMax(&b[3 + d], hi[d]);
+    }
+    if (bad) atomicOr(&b[6], 1);
+  }
+}
+
+// counting sort, pass 1 (blockIdx.y = grid of the chunk): cell key + rank inside the cell
+__global__ void k_pair_cell_count(const float4 *__restrict__ pts, const PairGridHdr *__restrict__ hdr, uint32_t g0, float inv_edge,
+                                  uint32_t *__restrict__ cells, uint32_t *__restrict__ keys, uint32_t *__restrict__ rank) {
+  const PairGridHdr h = hdr[g0 + blockIdx.y];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h.n) return;
+  const float4 p = pts[h.pt_base + i];
+  const int cx = (int)floorf(p.x * inv_edge) - h.ox, cy = (int)floorf(p.y * inv_edge) - h.oy, cz = (int)floorf(p.z * inv_edge) - h.oz;
+  const uint32_t key = h.cell_base + (uint32_t)((cz * h.ny + cy) * h.nx + cx);
+  keys[h.pt_base + i] = key;
+  rank[h.pt_base + i] = atomicAdd(cells + key, 1u);
+}
+
+// pass 2: the point (index inside its own cloud in .w) and its ring go to cell order
+__global__ void k_pair_cell_scatter(const float4 *__restrict__ pts, const uint16_t *__restrict__ ring,
+                                    const PairGridHdr *__restrict__ hdr, uint32_t g0, const uint32_t *__restrict__ cells,
+                                    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
+                                    float4 *__restrict__ sorted, uint16_t *__restrict__ ring_sorted) {
+  const PairGridHdr h = hdr[g0 + blockIdx.y];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h.n) return;
+  const uint32_t src = h.pt_base + i;
+  float4 p = pts[src];
+  p.w = __int_as_float((int)i);
+  const uint32_t dst = h.chunk_pt_base + __ldg(cells + __ldg(keys + src)) + __ldg(rank + src);
+  sorted[dst] = p;
+  ring_sorted[dst] = ring[src];
+}
+
+struct PairArrays {
+  const float4 *pts;         // last-scan clouds, caller order
+  const uint16_t *ring;
+  const float4 *sorted;      // cell order (chunk-relative positions in `cells`)
+  const uint16_t *ring_sorted;
+  const uint32_t *cells;
+  const PairGridHdr *hdr;
+  float inv_edge;
+};
+
+// one warp per query of pairs [b0, b1): the chunk's sharp queries first, then its flat queries
+__global__ void __launch_bounds__(128)
+k_associate_scan_batch(PairArrays pa, KParams kp, int B, int b0, int b1, const float4 *__restrict__ q_sharp,
+                       const int32_t *__restrict__ e_off, uint32_t n_sharp_total, const float4 *__restrict__ q_flat,
+                       const int32_t *__restrict__ p_off, const double *__restrict__ poses, const int32_t *__restrict__ status,
+                       int outer, double *__restrict__ corr) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t s0 = (uint32_t)e_off[b0], ns = (uint32_t)e_off[b1] - s0, f0 = (uint32_t)p_off[b0], nf = (uint32_t)p_off[b1] - f0;
+  if (w >= ns + nf) return;
+  const bool is_sharp = w < ns;
+  const uint32_t kk = is_sharp ? s0 + w : f0 + (w - ns);  // index inside the class
+  int lo = b0, hi = b1;                                   // pair: largest b with off[b] <= kk
+  const int32_t *off = is_sharp ? e_off : p_off;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((uint32_t)__ldg(off + mid) <= kk) lo = mid;
+    else hi = mid;
+  }
+  const int b = lo;
+  if (outer > 0 && status[b] != MSFL_OK) return;  // this pair bailed out in an earlier outer iteration (:262-267)
+  const PairGridHdr h = pa.hdr[2 * b + (is_sharp ? 0 : 1)];
+  ScanGrid sg;
+  sg.g.pts_sorted = pa.sorted + h.chunk_pt_base;
+  sg.g.pts_orig = pa.pts + h.pt_base;
+  sg.g.cell_start = pa.cells + h.cell_base;
+  sg.g.row_mask = nullptr;
+  sg.g.nx = h.nx; sg.g.ny = h.ny; sg.g.nz = h.nz;
+  sg.g.ox = h.ox; sg.g.oy = h.oy; sg.g.oz = h.oz;
+  sg.g.inv_edge = pa.inv_edge;
+  sg.g.n = h.n;
+  sg.ring = pa.ring + h.pt_base;
+  sg.n = h.n;
+  double pose[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) pose[i] = poses[(size_t)b * 7 + i];
+  const float4 p = is_sharp ? q_sharp[kk] : q_flat[kk];
+  double a[3], n[3];
+  Best nn, b2, b3;
+  associate_scan_query(sg, pa.ring_sorted + h.chunk_pt_base, kp, pose, p, is_sharp, a, n, nn, b2, b3);
+  if (lane == 0) store6(corr, is_sharp ? kk : n_sharp_total + kk, a, n);
+}
+
+// Inputs in HBM: last_pts / last_ring = the 2B last-scan clouds back to back (h_goff[2B + 1] host copy of d_goff);
+// q_sharp / q_flat = the queries of all pairs with offset tables d_e_off / d_p_off [B + 1] (host copies h_*); d_poses 7B
+// in-out; d_status B; d_stats B or null.  One host synchronisation (the grid bounds).
+int scan2scan_batch_device(msfl_engine *e, int B, const float4 *last_pts, const uint16_t *last_ring, const uint32_t *d_goff,
+                           const uint32_t *h_goff, const float4 *q_sharp, const int32_t *d_e_off, const int32_t *h_e_off,
+                           const float4 *q_flat, const int32_t *d_p_off, const int32_t *h_p_off, double *d_poses,
+                           int32_t *d_status, msfl_stats *d_stats) {
+  cudaStream_t st = e->stream;
+  const uint32_t G = 2u * (uint32_t)B;
+  const float inv_edge = 1.0f;
+  const size_t n_last = h_goff[G];
+  const uint32_t n_sharp_total = (uint32_t)h_e_off[B], n_flat_total = (uint32_t)h_p_off[B];
+  int rc;
+  uint32_t max_n = 0;
+  for (uint32_t g = 0; g < G; ++g) max_n = std::max(max_n, h_goff[g + 1] - h_goff[g]);
+  // 1. occupied cell range of every grid
+  if ((rc = e->ob_bounds.reserve((size_t)G * 32))) return rc;
+  int *d_bounds = e->ob_bounds.as<int>();
+  k_pair_bounds_init<<<(G * 8 + 255) / 256, 256, 0, st>>>(d_bounds, G);
+  if (max_n > 0) k_pair_bounds<<<dim3(std::min((max_n + 255u) / 256u, 32u), G), 256, 0, st>>>(last_pts, d_goff, inv_edge, d_bounds);
+  e->launches += 2;
+  std::vector<int> hb((size_t)G * 8);
+  MSFL_CUDA_OK(cudaMemcpyAsync(hb.data(), d_bounds, (size_t)G * 32, cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  // 2. headers and chunks of pairs
+  std::vector<PairGridHdr> hdr(G);
+  std::vector<int> chunk_first;  // first pair of every chunk (+ B at the end)
+  std::vector<long long> chunk_cells;
+  long long cells_here = 0, max_chunk_cells = 0;
+  for (int b = 0; b < B; ++b) {
+    long long pair_cells = 0;
+    for (uint32_t g = 2u * b; g < 2u * b + 2; ++g) {
+      PairGridHdr &h = hdr[g];
+      const int *bb = &hb[(size_t)g * 8];
+      h.pt_base = h_goff[g];
+      h.n = h_goff[g + 1] - h_goff[g];
+      if (bb[6]) { set_error("scan2scan batch: pair %d holds non-finite or out-of-range (>1e6 m) points", b); return MSFL_ERR_ARG; }
+      if (h.n == 0) { h.ox = h.oy = h.oz = 0; h.nx = h.ny = h.nz = 1; }
+      else {
+        const long long nx = (long long)bb[3] - bb[0] + 5, ny = (long long)bb[4] - bb[1] + 5, nz = (long long)bb[5] - bb[2] + 5;
+        if (nx * ny * nz > (1ll << 26)) {
+          set_error("scan2scan batch: pair %d needs %lld cells (> 2^26); dense cell index refused", b, nx * ny * nz);
+          return MSFL_ERR_GRID;
+        }
+        h.ox = bb[0] - 2; h.oy = bb[1] - 2; h.oz = bb[2] - 2;
+        h.nx = (int)nx; h.ny = (int)ny; h.nz = (int)nz;
+      }
+      pair_cells += (long long)h.nx * h.ny * h.nz + 1;
+    }
+    if (chunk_first.empty() || cells_here + pair_cells > e->pair_cell_budget) {
+      if (!chunk_first.empty()) chunk_cells.push_back(cells_here);
+      chunk_first.push_back(b);
+      cells_here = 0;
+    }
+    for (uint32_t g = 2u * b; g < 2u * b + 2; ++g) {
+      hdr[g].cell_base = (uint32_t)cells_here;
+      hdr[g].chunk_pt_base = h_goff[2 * chunk_first.back()];
+      cells_here += (long long)hdr[g].nx * hdr[g].ny * hdr[g].nz + 1;
+    }
+  }
+  chunk_cells.push_back(cells_here);
+  chunk_first.push_back(B);
+  for (long long c : chunk_cells) max_chunk_cells = std::max(max_chunk_cells, c);
+  // 3. scratch
+  if ((rc = e->ob_hdr.reserve((size_t)G * sizeof(PairGridHdr)))) return rc;
+  if ((rc = e->ob_sorted.reserve(n_last * 16 + 16))) return rc;
+  if ((rc = e->ob_ring_sorted.reserve(n_last * 2 + 16))) return rc;
+  if ((rc = e->ob_keys.reserve(n_last * 4 + 16))) return rc;
+  if ((rc = e->ob_rank.reserve(n_last * 4 + 16))) return rc;
+  if ((rc = e->ob_cells.reserve((size_t)max_chunk_cells * 4 + 16))) return rc;
+  if ((rc = e->d_corr.reserve(((size_t)n_sharp_total + n_flat_total + 1) * 48))) return rc;
+  size_t tmp_bytes = 0;
+  uint32_t *cells = e->ob_cells.as<uint32_t>();
+  MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cells, cells, (int)max_chunk_cells, st));
+  if ((rc = e->ob_tmp.reserve(tmp_bytes))) return rc;
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->ob_hdr.p, hdr.data(), (size_t)G * sizeof(PairGridHdr), cudaMemcpyHostToDevice, st));
+  PairArrays pa{last_pts, last_ring, e->ob_sorted.as<float4>(), e->ob_ring_sorted.as<uint16_t>(), cells,
+                e->ob_hdr.as<PairGridHdr>(), inv_edge};
+  // 4. per chunk: index build, then the reference's outer loop (:64) for every pair of the chunk at once
+  for (size_t c = 0; c + 1 < chunk_first.size(); ++c) {
+    const int b0 = chunk_first[c], b1 = chunk_first[c + 1];
+    const uint32_t g0 = 2u * b0, ng = 2u * (uint32_t)(b1 - b0);
+    uint32_t cmax = 0;
+    for (uint32_t g = g0; g < g0 + ng; ++g) cmax = std::max(cmax, hdr[g].n);
+    const long long ncell = chunk_cells[c];
+    MSFL_CUDA_OK(cudaMemsetAsync(cells, 0, (size_t)ncell * 4, st));
+    if (cmax > 0) {
+      k_pair_cell_count<<<dim3((cmax + 255) / 256, ng), 256, 0, st>>>(last_pts, pa.hdr, g0, inv_edge, cells, e->ob_keys.as<uint32_t>(),
+                                                                     e->ob_rank.as<uint32_t>());
+      MSFL_CUDA_OK(cub::DeviceScan::ExclusiveSum(e->ob_tmp.p, tmp_bytes, cells, cells, (int)ncell, st));
+      k_pair_cell_scatter<<<dim3((cmax + 255) / 256, ng), 256, 0, st>>>(last_pts, last_ring, pa.hdr, g0, cells, e->ob_keys.as<uint32_t>(),
+                                                                       e->ob_rank.as<uint32_t>(), e->ob_sorted.as<float4>(),
+                                                                       e->ob_ring_sorted.as<uint16_t>());
+      e->launches += 2 + 2;
+    }
+    const uint32_t nq = (uint32_t)(h_e_off[b1] - h_e_off[b0]) + (uint32_t)(h_p_off[b1] - h_p_off[b0]);
+    for (int outer = 0; outer < e->params.num_outer; ++outer) {
+      if (nq > 0) {
+        k_associate_scan_batch<<<(unsigned)(((size_t)nq * 32 + 127) / 128), 128, 0, st>>>(
+            pa, e->kp, B, b0, b1, q_sharp, d_e_off, n_sharp_total, q_flat, d_p_off, d_poses, d_status, outer, e->d_corr.as<double>());
+        e->launches += 1;
+      }
+      MSFL_CUDA_OK(cudaGetLastError());
+      if ((rc = launch_lm_solve(e, b1 - b0, q_sharp, d_e_off + b0, n_sharp_total, q_flat, d_p_off + b0, e->d_corr.as<double>(),
+                                d_poses + (size_t)7 * b0, d_status + b0, d_stats ? d_stats + b0 : nullptr, outer,
+                                e->params.min_correspondences)))
+        return rc;
+    }
+  }
+  return MSFL_OK;
+}
+
+}  // namespace msfl
+
+extern "C" int msfl_scan2scan_batch(msfl_engine *e, int B, const msfl_cloud *last_corner_less_sharp,
+                                    const msfl_cloud *last_surf_less_flat, const msfl_cloud *curr_corner_sharp,
+                                    const msfl_cloud *curr_surf_flat, double *poses_tq, int32_t *status, msfl_stats *stats) {
+  if (!e || B <= 0 || !last_corner_less_sharp || !last_surf_less_flat || !curr_corner_sharp || !curr_surf_flat || !poses_tq) {
+    set_error("msfl_scan2scan_batch: bad argument");
+    return MSFL_ERR_ARG;
+  }
+  int rc;
+  size_t n_last = 0, n_sharp = 0, n_flat = 0;
+  for (int b = 0; b < B; ++b) {
+    if ((rc = check_cloud(&last_corner_less_sharp[b], true, "scan2scan_batch last_corner_less_sharp"))) return rc;
+    if ((rc = check_cloud(&last_surf_less_flat[b], true, "scan2scan_batch last_surf_less_flat"))) return rc;
+    if ((rc = check_cloud(&curr_corner_sharp[b], false, "scan2scan_batch curr_corner_sharp"))) return rc;
+    if ((rc = check_cloud(&curr_surf_flat[b], false, "scan2scan_batch curr_surf_flat"))) return rc;
+    n_last += last_corner_less_sharp[b].n + last_surf_less_flat[b].n;
+    n_sharp += curr_corner_sharp[b].n;
+    n_flat += curr_surf_flat[b].n;
+  }
+  if (n_last > 0x7fffffffull || n_sharp + n_flat > 0x7fffffffull) { set_error("msfl_scan2scan_batch: batch too large"); return MSFL_ERR_ARG; }
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  // pinned staging: [last pts float4 | sharp float4 | flat float4 | rings u16 | goff | e_off | p_off | poses]
+  const size_t nq = n_sharp + n_flat;
+  auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t at_ring = (n_last + nq) * 16, at_goff = al16(at_ring + n_last * 2);
+  const size_t at_eoff = at_goff + al16(((size_t)2 * B + 1) * 4), at_poff = at_eoff + al16(((size_t)B + 1) * 4);
+  const size_t at_pose = at_poff + al16(((size_t)B + 1) * 4), total = at_pose + (size_t)B * 56;
+  if ((rc = e->h_stage.reserve(total))) return rc;
+  if ((rc = e->ob_in.reserve(total))) return rc;
+  char *h = e->h_stage.as<char>();
+  float *hl = (float *)h, *hs = hl + 4 * n_last, *hf = hs + 4 * n_sharp;
+  uint16_t *hr = (uint16_t *)(h + at_ring);
+  uint32_t *goff = (uint32_t *)(h + at_goff);
+  int32_t *e_off = (int32_t *)(h + at_eoff), *p_off = (int32_t *)(h + at_poff);
+  size_t wl = 0, ws = 0, wf = 0;
+  for (int b = 0; b < B; ++b) {
+    const msfl_cloud *lc[2] = {&last_corner_less_sharp[b], &last_surf_less_flat[b]};
+    for (int c = 0; c < 2; ++c) {
+      goff[2 * b + c] = (uint32_t)wl;
+      const char *base = (const char *)lc[c]->data;
+      const bool has_i = lc[c]->off_intensity != MSFL_NO_FIELD;
+      uint16_t prev = 0;
+      for (size_t i = 0; i < lc[c]->n; ++i, ++wl) {
+        const char *pt = base + i * lc[c]->stride;
+        memcpy(hl + 4 * wl, pt + lc[c]->off_xyz, 12);
+        float w = 0.f;
+        if (has_i) memcpy(&w, pt + lc[c]->off_intensity, 4);
+        hl[4 * wl + 3] = w;
+        uint16_t r;
+        memcpy(&r, pt + lc[c]->off_ring, 2);
+        if (r < prev) { set_error("scan2scan batch: last-scan cloud of pair %d is not ring-sorted at point %zu", b, i); return MSFL_ERR_RING; }
+        if (r >= MSFL_MAX_RINGS) { set_error("scan2scan batch: ring %u >= %d", (unsigned)r, MSFL_MAX_RINGS); return MSFL_ERR_RING; }
+        prev = r;
+        hr[wl] = r;
+      }
+    }
+    e_off[b] = (int32_t)ws;
+    p_off[b] = (int32_t)wf;
+    const msfl_cloud *qc[2] = {&curr_corner_sharp[b], &curr_surf_flat[b]};
+    // nothing to search in (or with): the pair keeps no queries and comes back MSFL_TOO_FEW with its pose untouched,
+    // like the single call
+    const bool dead = lc[0]->n == 0 || lc[1]->n == 0 || qc[0]->n + qc[1]->n == 0;
+    for (int c = 0; c < 2 && !dead; ++c) {
+      const char *base = (const char *)qc[c]->data;
+      float *dst = c ? hf : hs;
+      size_t &w = c ? wf : ws;
+      for (size_t i = 0; i < qc[c]->n; ++i, ++w) {
+        memcpy(dst + 4 * w, base + i * qc[c]->stride + qc[c]->off_xyz, 12);
+        dst[4 * w + 3] = 0.f;
+      }
+    }
+  }
+  goff[2 * B] = (uint32_t)wl;
+  e_off[B] = (int32_t)ws;
+  p_off[B] = (int32_t)wf;
+  memcpy(h + at_pose, poses_tq, (size_t)B * 56);
+  char *d = e->ob_in.as<char>();
+  MSFL_CUDA_OK(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
+  if ((rc = e->d_status.reserve((size_t)B * 4 + 16))) return rc;
+  MSFL_CUDA_OK(cudaMemsetAsync(e->d_status.p, 0, (size_t)B * 4, st));
+  msfl_stats *d_stats = nullptr;
+  if (stats) {
+    if ((rc = e->d_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    d_stats = e->d_stats.as<msfl_stats>();
+    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, (size_t)B * sizeof(msfl_stats), st));
+  }
+  const float4 *d_last = (const float4 *)d, *d_sharp = d_last + n_last, *d_flat = d_sharp + n_sharp;
+  double *d_poses = (double *)(d + at_pose);
+  // the host copies of the offset tables stay valid: h_stage is not touched again before the final synchronisation
+  if ((rc = scan2scan_batch_device(e, B, d_last, (const uint16_t *)(d + at_ring), (const uint32_t *)(d + at_goff), goff, d_sharp,
+                                   (const int32_t *)(d + at_eoff), e_off, d_flat, (const int32_t *)(d + at_poff), p_off, d_poses,
+                                   e->d_status.as<int32_t>(), d_stats)))
+    return rc;
+  if ((rc = e->h_poses.reserve((size_t)B * 60))) return rc;
+  char *ho = e->h_poses.as<char>();
+  MSFL_CUDA_OK(cudaMemcpyAsync(ho, d_poses, (size_t)B * 56, cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaMemcpyAsync(ho + (size_t)B * 56, e->d_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (stats) {
+    if ((rc = e->h_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    MSFL_CUDA_OK(cudaMemcpyAsync(e->h_stats.p, d_stats, (size_t)B * sizeof(msfl_stats), cudaMemcpyDeviceToHost, st));
+  }
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  memcpy(poses_tq, ho, (size_t)B * 56);
+  if (status) memcpy(status, ho + (size_t)B * 56, (size_t)B * 4);
+  if (stats) memcpy(stats, e->h_stats.p, (size_t)B * sizeof(msfl_stats));
+  return MSFL_OK;
 }
 
 extern "C" int msfl_scan2scan(msfl_engine *e, const msfl_cloud *last_corner_less_sharp, const msfl_cloud *last_surf_less_flat,

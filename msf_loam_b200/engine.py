@@ -276,6 +276,18 @@ class Engine:
                                                  C.byref(st) if st is not None else None))
         return rc, x, (st.as_dict() if st is not None else None)
 
+    def scan2scan_batch(self, last_corners, last_surfs, curr_sharps, curr_flats, poses, want_stats=False):
+        """B independent MatchScan2Scan problems in one call; returns (status[B], poses[B,7], stats list or None)."""
+        B = len(last_corners)
+        views = [[_View(a) for a in lst] for lst in (last_corners, last_surfs, curr_sharps, curr_flats)]
+        arrs = [(Cloud * B)(*[v.cloud for v in vs]) for vs in views]
+        x = np.ascontiguousarray(poses, dtype=np.float64).reshape(B, 7).copy()
+        status = np.zeros(B, np.int32)
+        st = (Stats * B)() if want_stats else None
+        self._check(self.lib.msfl_scan2scan_batch(self.h, C.c_int(B), *arrs, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                                  status.ctypes.data_as(C.POINTER(C.c_int32)), st))
+        return status, x, ([s.as_dict() for s in st] if st is not None else None)
+
     def associate_scan(self, last_corner, last_surf, curr_sharp, curr_flat, pose):
         views = [_View(a) for a in (last_corner, last_surf, curr_sharp, curr_flat)]
         x = _pose(pose)
@@ -362,6 +374,23 @@ class Engine:
         if want_counts:
             return x, [{k: getattr(c, k) for k, _ in _lib.ChainCounts._fields_} for c in cnt]
         return x
+
+    def replay_batch(self, raw_batch, odom, poses, compose=True, T_lidar2imu=None, leaf_corner=0.2, leaf_surf=0.4):
+        """msfl_replay_batch: B consecutive raw scans -> odometry of the B - 1 pairs + scan-to-map poses.
+        odom (B,7): entry b >= 1 = initial guess of pose_curr2last of scan b.  Returns (odom, odom_status, poses)."""
+        if not isinstance(raw_batch, dict):
+            raw_batch = self.prepare_raw_batch(*raw_batch)
+        B = raw_batch["B"]
+        od = np.ascontiguousarray(odom, dtype=np.float64).reshape(B, 7).copy()
+        x = np.ascontiguousarray(poses, dtype=np.float64).reshape(B, 7).copy()
+        status = np.zeros(B, np.int32)
+        T = _pose(T_lidar2imu) if T_lidar2imu is not None else None
+        self._check(self.lib.msfl_replay_batch(
+            self.h, C.c_int(B), raw_batch["arr"], T.ctypes.data_as(C.POINTER(C.c_double)) if T is not None else None,
+            C.c_float(leaf_corner), C.c_float(leaf_surf), od.ctypes.data_as(C.POINTER(C.c_double)),
+            status.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(1 if compose else 0),
+            x.ctypes.data_as(C.POINTER(C.c_double)), None, None))
+        return od, status, x
 
     def voxel_grid(self, xyzi, leaf):
         v = _View(xyzi)

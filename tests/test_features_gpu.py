@@ -190,6 +190,61 @@ def test_scan2scan_too_few_correspondences(eng):
     assert ok is False and np.array_equal(pose, init)
 
 
+def _pair_batch():
+    P, f0, f1, gt = _scan_pair()
+    lc, lcr = f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]]
+    ls, lsr = f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]]
+    cs, cf = f1["full"][f1["idx_sharp"]], f1["full"][f1["idx_flat"]]
+    lc1, lcr1 = f1["full"][f1["idx_less_sharp"]], f1["ring"][f1["idx_less_sharp"]]
+    ls1, lsr1 = f1["full"][f1["idx_less_flat"]], f1["ring"][f1["idx_less_flat"]]
+    cs0, cf0 = f0["full"][f0["idx_sharp"]], f0["full"][f0["idx_flat"]]
+    empty = np.zeros((0, 4), np.float32)
+    shifted = lc.copy()
+    shifted[:, :3] += np.float32([40.0, -25.0, 3.0])  # another grid origin / extent for this pair
+    sls = ls.copy()
+    sls[:, :3] += np.float32([40.0, -25.0, 3.0])
+    scs, scf = cs.copy(), cf.copy()
+    scs[:, :3] += np.float32([40.0, -25.0, 3.0])
+    scf[:, :3] += np.float32([40.0, -25.0, 3.0])
+    pairs = [  # (last corner, rings, last surf, rings, sharp, flat, initial guess)
+        (lc, lcr, ls, lsr, cs, cf, S.pose_identity()),
+        (lc, lcr, ls, lsr, cs, cf, gt),
+        (lc1, lcr1, ls1, lsr1, cs0, cf0, S.pose_inv(gt)),                            # the pair backwards
+        (lc, lcr, ls, lsr, cs[:3], cf[:4], np.array([0.01, 0.02, 0.0, 0, 0, 0, 1.0])),  # too few
+        (empty, np.zeros(0, np.uint16), ls, lsr, cs, cf, S.pose_identity()),            # nothing to search in
+        (shifted, lcr, sls, lsr, scs, scf, S.pose_identity()),
+        (lc, lcr, ls, lsr, empty, empty, gt),                                           # no queries
+    ]
+    return pairs
+
+
+@pytest.mark.parametrize("budget", [None, 1])
+def test_scan2scan_batch_equals_single_calls(budget, monkeypatch):
+    """msfl_scan2scan_batch = B msfl_scan2scan calls (poses, statuses, correspondence counts, LM traces), with all
+    pair grids indexed at once (budget None) and one pair per chunk (budget 1 cell -> every pair is its own chunk)."""
+    if budget is not None:
+        monkeypatch.setenv("MSFL_PAIR_CELL_BUDGET", str(budget))
+    e = Engine()
+    pairs = _pair_batch()
+    single = [e.scan2scan(to_pcl(p[0], p[1]), to_pcl(p[2], p[3]), p[4], p[5], p[6]) for p in pairs]
+    status, poses, st = e.scan2scan_batch([to_pcl(p[0], p[1]) for p in pairs], [to_pcl(p[2], p[3]) for p in pairs],
+                                          [p[4] for p in pairs], [p[5] for p in pairs], np.stack([p[6] for p in pairs]),
+                                          want_stats=True)
+    assert list(status) == [s[0] for s in single] == [0, 0, 0, 1, 1, 0, 1]
+    for b, (rc, x, s1) in enumerate(single):
+        assert np.array_equal(poses[b], x), b
+        assert st[b]["status"] == s1["status"] and st[b]["n_outer"] == s1["n_outer"], b
+        assert st[b]["n_edge"] == s1["n_edge"] and st[b]["n_plane"] == s1["n_plane"], b
+        for la, lb in zip(st[b]["lm"], s1["lm"]):
+            assert la["n_attempts"] == lb["n_attempts"] and la["termination"] == lb["termination"]
+    # and against the oracle for the first pair
+    P = O.default_params()
+    p = pairs[0]
+    rc_ref, x_ref, _, _, _ = O.scan2scan(P, p[0], p[1], p[2], p[3], p[4], p[5], p[6])
+    dt, dr = S.pose_error(poses[0], x_ref)
+    assert rc_ref == 0 and dt < 1e-8 and dr < 1e-8
+
+
 def test_scan2scan_rejects_unsorted_rings(eng):
     P, f0, f1, gt = _scan_pair()
     lc, lcr = f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]].copy()
@@ -253,3 +308,38 @@ def test_raw_to_pose_chain_equals_the_stage_by_stage_calls(eng, vlp16_case):
         dt, dr = S.pose_error(poses[i], x_ref)
         # the oracle's queries carry the oracle's relative times in `intensity` (1-ulp atan2f difference); xyz are equal
         assert dt < 1e-8 and dr < 1e-8
+
+
+def test_replay_batch_odometry_and_map_matching_from_one_registration_pass(eng, vlp16_case):
+    """msfl_replay_batch on three consecutive raw scans: the odometry of the two pairs is bit-identical to
+    msfl_scan2scan on the separately extracted features; with compose the map matcher starts from the dead-reckoned
+    guesses pose[b-1] * odom[b] (laser_odometry.cc:79); without, it is msfl_register_and_match_batch."""
+    case = vlp16_case
+    eng.set_submap(case["map_corner"], case["map_surf"])
+    qs = case["queries"]
+    raws = ([q["raw"][0] for q in qs], [q["raw"][1] for q in qs])
+    B = len(qs)
+    ident = np.tile(S.pose_identity(), (B, 1))
+    inits = np.stack([q["init"] for q in qs])
+    od, status, poses = eng.replay_batch(raws, ident, inits, compose=True)
+    feats = [eng.extract_features(x, r, None) for x, r in zip(*raws)]
+    assert list(status) == [0] * B and np.array_equal(od[0], S.pose_identity())
+    for b in range(1, B):
+        f0, f1 = feats[b - 1], feats[b]
+        rc, x, _ = eng.scan2scan(to_pcl(f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]]),
+                                 to_pcl(f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]]),
+                                 f1["full"][f1["idx_sharp"]], f1["full"][f1["idx_flat"]], S.pose_identity())
+        assert rc == 0 and np.array_equal(od[b], x), b
+        dt, dr = S.pose_error(od[b], S.pose_mul(S.pose_inv(qs[b - 1]["gt"]), qs[b]["gt"]))
+        assert dt < 0.05 and dr < 0.01
+    guesses = [inits[0]]
+    for b in range(1, B):
+        guesses.append(S.pose_mul(guesses[-1], od[b]))
+    ref = eng.register_and_match_batch(raws, np.stack(guesses))
+    for b in range(B):
+        dt, dr = S.pose_error(poses[b], ref[b])
+        assert dt < 1e-9 and dr < 1e-9, b
+        dt, dr = S.pose_error(poses[b], qs[b]["gt"])
+        assert dt < 0.05 and dr < 0.01, b
+    od2, status2, poses2 = eng.replay_batch(raws, ident, inits, compose=False)
+    assert np.array_equal(od2, od) and np.array_equal(poses2, eng.register_and_match_batch(raws, inits))
