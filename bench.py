@@ -521,6 +521,27 @@ def chain_raw_to_pose(cx, workload="vlp16", B=256, steps=5):
     for _ in range(steps):
         eng.register_and_match_batch(batch, inits)
     dt = time.perf_counter() - t0
+    # the same replay WITH the odometry of the B - 1 consecutive pairs (msfl_replay_batch): the scans run forwards and
+    # backwards along the trajectory so that every pair of the batch is a pair of neighbouring scans
+    tri = [(i % (2 * D - 2)) if D > 1 else 0 for i in range(B)]
+    tri = [t if t < D else 2 * D - 2 - t for t in tri]
+    raws_o = [scans[n_map + t] for t in tri]
+    batch_o = eng.prepare_raw_batch([r[0].copy() for r in raws_o], [r[1].copy() for r in raws_o])
+    inits_o = np.stack([S.perturb_pose(queries[t][2], rng) for t in tri])
+    ident = np.tile(S.pose_identity(), (B, 1))
+    od, od_status, poses_o = eng.replay_batch(batch_o, ident, inits_o, compose=False)
+    eng.replay_batch(batch_o, ident, inits_o, compose=False)
+    torch.cuda.synchronize(cx.dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.replay_batch(batch_o, ident, inits_o, compose=False)
+    dt_o = time.perf_counter() - t0
+    od_gt = [S.pose_error(od[b], S.pose_mul(S.pose_inv(queries[tri[b - 1]][2]), queries[tri[b]][2])) for b in range(1, B)]
+    with_odo = {"value": round(B * steps / dt_o, 1), "unit": "scans/s", "ms_per_step": round(dt_o / steps * 1e3, 3),
+                "pairs_per_step": B - 1, "pairs_ok": int((od_status[1:] == 0).sum()),
+                "odometry_err_vs_ground_truth": {"max_trans_m": float(max(e[0] for e in od_gt)), "max_rot_rad": float(max(e[1] for e in od_gt))},
+                "api": "msfl_replay_batch: the call above plus OdometryScanMatcher::MatchScan2Scan of the B - 1 consecutive pairs "
+                       "(identity initial guesses) from the same registration pass; one synchronous call per step"}
     eng.close()
     rec = {"value": round(B * steps / dt, 1), "unit": "scans/s", "ms_per_step": round(dt / steps * 1e3, 3), "scans_per_step": B,
            "points_per_scan": n_full, "queries_per_scan": round(float(np.mean([c["n_corner_queries"] + c["n_surf_queries"] for c in counts])), 1),
@@ -538,6 +559,18 @@ def chain_raw_to_pose(cx, workload="vlp16", B=256, steps=5):
             errs.append(S.pose_error(poses[i], x))
         rec["pose_err_vs_oracle"] = {"max_trans_m": float(max(e[0] for e in errs)), "max_rot_rad": float(max(e[1] for e in errs)),
                                      "scans_checked": len(errs), "tolerance": "1e-4 m / 1e-4 rad"}
+        errs = []
+        fo = [O.extract_features(P, raws_o[i][0], raws_o[i][1], None) for i in range(min(3, B))]
+        for b in range(1, len(fo)):
+            f0, f1 = fo[b - 1], fo[b]
+            _, x, _, _, _ = O.scan2scan(P, f0["full"][f0["idx_less_sharp"]], f0["ring"][f0["idx_less_sharp"]],
+                                        f0["full"][f0["idx_less_flat"]], f0["ring"][f0["idx_less_flat"]],
+                                        f1["full"][f1["idx_sharp"]], f1["full"][f1["idx_flat"]], S.pose_identity())
+            errs.append(S.pose_error(od[b], x))
+        if errs:
+            with_odo["odometry_err_vs_oracle"] = {"max_trans_m": float(max(e[0] for e in errs)), "max_rot_rad": float(max(e[1] for e in errs)),
+                                                  "pairs_checked": len(errs), "tolerance": "1e-4 m / 1e-4 rad"}
+    rec["with_odometry"] = with_odo
     return rec
 
 

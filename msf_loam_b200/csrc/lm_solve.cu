@@ -14,6 +14,8 @@
 #include <cooperative_groups.h>
 
 #include "lm_device.cuh"
+#include <algorithm>
+
 #include "msfl_internal.h"
 #include "msfl_math.cuh"
 
@@ -21,15 +23,17 @@ namespace cg = cooperative_groups;
 
 namespace msfl {
 
-// 96 threads = 3 warps per CTA, 5 CTAs per SM (128 registers): 15 warps per SM like 4 x 4, but 740 resident scans instead
-// of 592 (2048 scans = 2.8 waves instead of 3.5) and one warp fewer at every CTA barrier.  Measured on B200 (VLP-16 x
-// 2048): 64 / 96 / 128 threads -> 0.684 / 0.666 / 0.698 ms per launch.  One configuration for every launch size, so a
-// scan's pose stays bit-identical alone and in any batch.
-#ifndef MSFL_LM_THREADS
-#define MSFL_LM_THREADS 96
-#endif
-constexpr int kLmThreads = MSFL_LM_THREADS;
-using LmShared = LmSharedT<kLmThreads / 32>;
+// Two CTA shapes, picked by launch size (launch_lm_solve_t).  96 threads = 3 warps per CTA, 5 CTAs per SM (128 registers):
+// 15 warps per SM like 4 x 4, but 740 resident scans instead of 592 (2048 scans = 2.8 waves instead of 3.5) and one warp
+// fewer at every CTA barrier -- measured on B200 (VLP-16 x 2048): 64 / 96 / 128 / 160 threads -> 0.684 / 0.666 / 0.698 /
+// 0.725 ms per launch.  A launch that does not fill those 740 slots (HDL-64 x 512, OS1-128 x 64 with clusters of 4, any
+// single scan) gains nothing from a fifth CTA per SM and loses a quarter of its warps: it keeps 128 threads (measured:
+// HDL-64 x 512 222.9 k vs 230.9 k scans/s, OS1-128 x 64 28.4 k vs 31.3 k).  The summation order depends on the warp count,
+// so a scan's pose is bit-identical across launches of the same shape class, and within 1e-14 m across the two.
+constexpr int kLmThreadsBig = 128;  // also the test hook's block size
+constexpr int kLmThreadsSmall = 96;
+constexpr int kLmThreads = kLmThreadsBig;
+using LmShared = LmSharedT<kLmThreadsBig / 32>;
 
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk, 1-D) staging of correspondence tiles.  The per-scan arrays are contiguous, so a
@@ -60,9 +64,6 @@ struct TileSrc {
 // PC = bytes of plane constants per entry: 32 = {n, n.c} written by k_fit for the batch path,
 // 48 = {c, n} (odometry, deskew, test hooks).  A stage holds TE edge entries or TP plane entries.
 // ---------------------------------------------------------------------------------------------
-#ifndef MSFL_LM_MINB
-#define MSFL_LM_MINB (512 / MSFL_LM_THREADS)
-#endif
 #ifndef MSFL_LM_TILE_BYTES
 #define MSFL_LM_TILE_BYTES 6144u
 #endif
@@ -71,7 +72,6 @@ struct TileSrc {
 #endif
 constexpr int kWarpStages = MSFL_LM_STAGES;  // streaming: double buffer per warp
 constexpr int kMaxWarpStages = 9;  // resident configuration (small launches): a warp's tiles stay in smem across sweeps
-constexpr uint32_t kLmWarps = kLmThreads / 32;
 template <int PB, int PC>
 struct WarpTile {
   static constexpr uint32_t SB = PB == 16 ? MSFL_LM_TILE_BYTES : 10240u;  // bytes per stage
@@ -137,14 +137,14 @@ __device__ __forceinline__ TileIt tile_first(const TileSrc &ts, uint32_t warp) {
 template <int PB, int PC>
 __device__ __forceinline__ TileIt tile_next(const TileSrc &ts, uint32_t warp, TileIt t) {
   if (t.cls == 0u) {
-    t.base += kLmWarps * WarpTile<PB, PC>::TE;
+    t.base += (blockDim.x >> 5) * WarpTile<PB, PC>::TE;
     if (t.base >= ts.n_e) {
       t.cls = 1u;
       t.base = warp * WarpTile<PB, PC>::TP;
       if (t.base >= ts.n_p) t.cls = 2u;
     }
   } else {
-    t.base += kLmWarps * WarpTile<PB, PC>::TP;
+    t.base += (blockDim.x >> 5) * WarpTile<PB, PC>::TP;
     if (t.base >= ts.n_p) t.cls = 2u;
   }
   return t;
@@ -292,7 +292,8 @@ __device__ __forceinline__ WarpPipe warp_pipe_init(const TileSrc &ts, unsigned c
   wp.bars = smem_u32(bars_cta) + warp * kMaxWarpStages * 8u;
   wp.it = 0;
   const uint32_t tt_e = (ts.n_e + WT::TE - 1) / WT::TE, tt_p = (ts.n_p + WT::TP - 1) / WT::TP;
-  wp.my_tiles = (tt_e > warp ? (tt_e - warp + kLmWarps - 1) / kLmWarps : 0u) + (tt_p > warp ? (tt_p - warp + kLmWarps - 1) / kLmWarps : 0u);
+  const uint32_t nw = blockDim.x >> 5;
+  wp.my_tiles = (tt_e > warp ? (tt_e - warp + nw - 1) / nw : 0u) + (tt_p > warp ? (tt_p - warp + nw - 1) / nw : 0u);
   wp.resident = n_stages > (uint32_t)kWarpStages && wp.my_tiles <= n_stages;
   wp.loaded = false;
   return wp;
@@ -300,7 +301,8 @@ __device__ __forceinline__ WarpPipe warp_pipe_init(const TileSrc &ts, unsigned c
 
 // ---- cluster-level combine over distributed shared memory (G CTAs per scan) ---------------------
 // rank 0 adds the other CTAs' block sums in rank order (deterministic), then owns the LM step.
-__device__ __forceinline__ void cluster_reduce(cg::cluster_group &cluster, LmShared &sh, uint32_t G, uint32_t rank,
+template <class SH>
+__device__ __forceinline__ void cluster_reduce(cg::cluster_group &cluster, SH &sh, uint32_t G, uint32_t rank,
                                                bool with_counts) {
   cluster.sync();  // every CTA's sh.cand (and counts) are written
   if (rank == 0) {
@@ -322,7 +324,8 @@ __device__ __forceinline__ void cluster_reduce(cg::cluster_group &cluster, LmSha
 }
 
 // rank 0 publishes the candidate pose / done flag; the other CTAs copy them into their own smem
-__device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, LmShared &sh, uint32_t rank) {
+template <class SH>
+__device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, SH &sh, uint32_t rank) {
   cluster.sync();  // rank 0's xc / done are final
   if (rank != 0) {
     if (threadIdx.x < 7) sh.xc[threadIdx.x] = *cluster.map_shared_rank(&sh.xc[threadIdx.x], 0);
@@ -333,13 +336,14 @@ __device__ __forceinline__ void cluster_broadcast(cg::cluster_group &cluster, Lm
 }
 
 // PB: bytes per point (16 float4 / 32 double4), PC: bytes of plane constants per entry (32 / 48)
-template <int PB, int PC>
-__global__ void __launch_bounds__(kLmThreads, MSFL_LM_MINB)
+template <int PB, int PC, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ e_off, uint32_t n_edge_total,
            const void *__restrict__ qp, const int32_t *__restrict__ p_off, const double *__restrict__ corr,
            double *__restrict__ poses, int32_t *__restrict__ status, msfl_stats *__restrict__ stats, int outer,
            int min_corr, uint32_t n_stages) {
-  __shared__ LmShared sh;
+  constexpr uint32_t kLmWarps = NT / 32;
+  __shared__ LmSharedT<NT / 32> sh;
   __shared__ __align__(8) uint64_t bars[kLmWarps * kMaxWarpStages];
   extern __shared__ __align__(128) unsigned char ring[];
   // One thread-block cluster per scan: G CTAs (G = 1, 2, 4 or 8) each sweep 1/G of the scan's
@@ -390,7 +394,7 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   block_reduce(acc, sh);
   if (tid == 0) {
     int ne = 0, np = 0;
-    for (int w = 0; w < kLmThreads / 32; ++w) { ne += sh.cnt[w][0]; np += sh.cnt[w][1]; }
+    for (int w = 0; w < NT / 32; ++w) { ne += sh.cnt[w][0]; np += sh.cnt[w][1]; }
     sh.n_edge = ne;
     sh.n_plane = np;
   }
@@ -473,21 +477,18 @@ k_lm_solve(KParams kp, const void *__restrict__ qe, const int32_t *__restrict__ 
   if (G > 1) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
-template <int PB, int PC>
-static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
-                             const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
-                             int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
-  constexpr int sb = (int)(kLmWarps * WarpTile<PB, PC>::SB);  // smem per ring stage (whole CTA)
+template <int PB, int PC, int NT>
+static int launch_lm_solve_nt(msfl_engine *e, int B, int G, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                              const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
+                              int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
+  constexpr int sb = (int)((NT / 32) * WarpTile<PB, PC>::SB);  // smem per ring stage (whole CTA)
   constexpr int max_stages = kMaxWarpStages * sb <= 227 * 1024 ? kMaxWarpStages : (227 * 1024) / sb;
-  bool &attr_set = e->lm_attr_set[(PB == 16 ? 0 : 1) + (PC == 32 ? 2 : 0)];  // per engine: attributes are per device
+  bool &attr_set = e->lm_attr_set[(PB == 16 ? 0 : 1) + (PC == 32 ? 2 : 0) + (NT == kLmThreadsBig ? 0 : 4)];  // per engine: attributes are per device
   if (!attr_set) {
-    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stages * sb));
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_lm_solve<PB, PC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stages * sb));
     attr_set = true;
   }
-  int G = e->params.lm_cluster;
-  if (G == 16) G = 8;  // 16 is the fused single-scan kernel's non-portable size; this kernel stays portable
-  if (G != 2 && G != 4 && G != 8) G = 1;  // 0 / 1: one CTA per scan (results are then independent of the batch shape)
-  // double-buffered streaming (4 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
+  // double-buffered streaming (4 or 5 CTAs/SM) for throughput batches; for small launches (fewer CTAs than SMs:
   // occupancy is irrelevant) a deep ring so that a warp's tiles stay resident in smem across the sweeps
   const uint32_t n_stages = ((long long)B * G <= (long long)e->sm_count) ? (uint32_t)max_stages : (uint32_t)kWarpStages;
   // (capping the resident CTAs so that the factor arrays in flight fit the 126 MB L2 -- 3 per SM: 444 x 222 KB = 99 MB
@@ -496,7 +497,7 @@ static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int3
   const int smem = (int)n_stages * sb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * G);
-  cfg.blockDim = dim3(kLmThreads);
+  cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = e->stream;
   cudaLaunchAttribute attr[1];
@@ -506,11 +507,26 @@ static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int3
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB, PC>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
+  MSFL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lm_solve<PB, PC, NT>, e->kp, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses,
                                   d_status, d_stats, outer, min_corr, n_stages));
   e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
+}
+
+template <int PB, int PC>
+static int launch_lm_solve_t(msfl_engine *e, int B, const void *d_qe, const int32_t *d_e_off, uint32_t n_edge_total,
+                             const void *d_qp, const int32_t *d_p_off, const double *d_corr, double *d_poses,
+                             int32_t *d_status, msfl_stats *d_stats, int outer, int min_corr) {
+  int G = e->params.lm_cluster;
+  if (G == 16) G = 8;  // 16 is the fused single-scan kernel's non-portable size; this kernel stays portable
+  if (G != 2 && G != 4 && G != 8) G = 1;  // 0 / 1: one CTA per scan
+  // three-warp CTAs once the launch fills five CTAs on every SM, four-warp CTAs below that
+  if ((long long)std::max(B, e->lm_shape_scans) * G >= 5ll * e->sm_count)
+    return launch_lm_solve_nt<PB, PC, kLmThreadsSmall>(e, B, G, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status,
+                                                       d_stats, outer, min_corr);
+  return launch_lm_solve_nt<PB, PC, kLmThreadsBig>(e, B, G, d_qe, d_e_off, n_edge_total, d_qp, d_p_off, d_corr, d_poses, d_status,
+                                                   d_stats, outer, min_corr);
 }
 
 // plane_bytes: 48 = plane constants {c, n} (6 doubles, same layout as the edge entries), 32 = {n, n.c} (k_fit compact)

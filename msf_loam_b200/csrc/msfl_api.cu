@@ -723,9 +723,11 @@ static int scan2map_batch_pipelined(msfl_engine *e, int B, const msfl_cloud *cor
     MSFL_CUDA_OK(cudaStreamWaitEvent(e->stream, e->chunk_events[c], 0));
     const int Bc = k.b1 - k.b0;
     const int32_t *co = d_off + k.off_pos, *so = co + (Bc + 1);
-    if ((rc = scan2map_enqueue(e, Bc, d_qc + k.ci0, co, (uint32_t)ncc, d_qs + k.si0, so, (uint32_t)nsc, d_poses + (size_t)k.b0 * 7,
-                               d_stats ? d_stats + k.b0 : nullptr)))
-      return rc;
+    e->lm_shape_scans = B;  // every chunk solves with the CTA shape of the whole call: poses = the unchunked batch's
+    rc = scan2map_enqueue(e, Bc, d_qc + k.ci0, co, (uint32_t)ncc, d_qs + k.si0, so, (uint32_t)nsc, d_poses + (size_t)k.b0 * 7,
+                          d_stats ? d_stats + k.b0 : nullptr);
+    e->lm_shape_scans = 0;
+    if (rc) return rc;
   }
   MSFL_CUDA_OK(cudaMemcpyAsync(e->h_poses.p, d_poses, pose_bytes, cudaMemcpyDeviceToHost, e->stream));
   if (stats)

@@ -84,6 +84,7 @@ struct msfl_engine {
   std::vector<cudaEvent_t> chunk_events;
   uint64_t launches = 0;
   bool lm_attr_set[8] = {false, false, false, false, false, false, false, false};
+  int lm_shape_scans = 0;  // > 0: the LM launches of a chunked call pick their CTA shape as a launch of this many scans would
   bool fused_attr_set = false;  // k_scan2map_fused: dynamic smem + non-portable cluster size attributes
   int fused_max16 = -1;         // cudaOccupancyMaxActiveClusters of the 16-CTA configuration (-1: not asked yet)
   bool pick_attr_set = false;  // k_feat_pick's dynamic shared-memory attribute (per device, so kept per engine)

@@ -15,3 +15,8 @@ print('same config:', d['config']==r['config'], 'reference', r['value'], r['cpu_
 for k,w in (d.get('workloads') or {}).items():
     print('   ',k, w.get('value'), w.get('ms_per_step'), (w.get('e2e') or {}).get('value'), w.get('pose_err_vs_oracle'))
 PY
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench_n1.json').read().strip().splitlines()[-1])
+print('with_odometry', json.dumps(d['workloads']['chain_raw_to_pose_vlp16'].get('with_odometry'))[:900])
+PY
