@@ -84,7 +84,8 @@ typedef struct msfl_params {
                                   (throughput schedule)                 */
   /* engine */
   int32_t lm_cluster;          /* CTAs (thread-block cluster size) per scan: 0 / 1 = one CTA per scan (a scan's
-                                  pose is then bit-identical alone and in any batch), 2/4/8/16 = partial sums meet
+                                  pose is then bit-identical alone and anywhere in a batch; calls of >= 5 x SM-count
+                                  scans solve with three-warp CTAs: same pose to < 1e-12 m), 2/4/8/16 = partial sums meet
                                   over distributed shared memory: small batches of large scans fill the chip, and
                                   a SINGLE scan (msfl_scan2map, the ROS call pattern) runs as one fused launch --
                                   association into shared memory + solve, scan2map_fused.cu; 16 needs a GPC with

@@ -10,7 +10,8 @@
 // formula in SURVEY.md 8d).  The sweep streams the scan's points and factor constants from HBM with
 // warp-private, double-buffered TMA bulk copies (cp.async.bulk + mbarrier), see sweep_warp.  All
 // factor math is fp64 (the reference's is); sums are combined in a fixed order, so results are
-// bit-reproducible run to run and independent of the batch size.
+// bit-reproducible run to run and independent of the position in the batch (and of its size within a CTA-shape class,
+// see kLmThreadsSmall).
 #include <cooperative_groups.h>
 
 #include "lm_device.cuh"
