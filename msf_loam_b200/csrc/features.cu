@@ -22,8 +22,7 @@
 
 namespace msfl {
 
-constexpr int kMaxSectorPts = 8192;  // = kKeysCap of k_feat_pick
-constexpr int kPickThreads = 1024;
+constexpr int kMaxSectorPts = 8192;  // = the largest k_feat_pick shape's sort-key capacity
 constexpr double kTwoPi = 2 * 3.14159265358979323846;
 
 struct FeatMeta {
@@ -219,11 +218,23 @@ __device__ __forceinline__ float gap_sq(const float4 a, const float4 b) {  // Ve
 // order-dependent sweeps sector by sector: the lanes scan 32 sorted candidates at a time for "above the threshold and
 // not yet picked", the picks of a chunk are taken in order, and the +-5 neighbour suppression of a pick is evaluated
 // by ten lanes at once.  Same decisions, same output order as the sequential loops of :263-350.
-constexpr int kRingCap = 4096;   // ring points staged in shared memory
-constexpr int kKeysCap = 8192;   // sort keys in shared memory (all sectors of a ring, padded to powers of two)
-constexpr size_t kPickSmem = (size_t)kKeysCap * 8 + (size_t)kRingCap * (16 + 4 + 1);
+// Three shapes <threads, ring points staged in shared memory, sort keys in shared memory (all sectors of a ring, padded to
+// powers of two)>.  The order-dependent sweeps run on ONE warp, so what a batch needs is many rings in flight per SM:
+// the shape is the smallest that holds the rings the engine saw in its previous extraction (a sensor does not change
+// between calls) -- VLP-16 / OS1-128 rings (<= 2048 points) run three 74 KB CTAs per SM, HDL-64E rings two 84 KB CTAs,
+// anything else (and the first call) the 148 KB shape.  A ring longer than the staged capacity still works (on the
+// global arrays); a sector that does not fit the keys raises sector_overflow and the host re-runs the larger shape.
+template <int NT, int RING_CAP, int KEYS_CAP>
+struct PickShape {
+  static constexpr int kThreads = NT, kRingCap = RING_CAP, kKeysCap = KEYS_CAP;
+  static constexpr size_t kSmem = (size_t)KEYS_CAP * 8 + (size_t)RING_CAP * (16 + 4 + 1);
+};
+using PickSmall = PickShape<512, 2048, 4096>;
+using PickMid = PickShape<1024, 2560, 4096>;
+using PickBig = PickShape<1024, 4096, kMaxSectorPts>;
 
-__global__ void __launch_bounds__(kPickThreads)
+template <class SHAPE>
+__global__ void __launch_bounds__(SHAPE::kThreads)
 k_feat_pick(const float4 *__restrict__ full, const float *__restrict__ curv, int32_t *__restrict__ label,
             uint8_t *__restrict__ picked, const uint32_t *__restrict__ soff, FeatMeta *metas, double curv_thr, double gap_thr,
             int n_sectors, int n_sharp, int n_less, int n_flat, int32_t *__restrict__ slot_sharp, int32_t *__restrict__ slot_less,
@@ -234,6 +245,7 @@ k_feat_pick(const float4 *__restrict__ full, const float *__restrict__ curv, int
   slot_sharp += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_sharp;
   slot_less += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_less;
   slot_flat += (size_t)sv.b * MSFL_MAX_RINGS * n_sectors * n_flat;
+  constexpr int kPickThreads = SHAPE::kThreads, kRingCap = SHAPE::kRingCap, kKeysCap = SHAPE::kKeysCap;
   extern __shared__ __align__(16) unsigned char pick_smem[];
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(pick_smem);
   float4 *s_full = reinterpret_cast<float4 *>(pick_smem + (size_t)kKeysCap * 8);
@@ -480,7 +492,23 @@ static int feat_reserve(msfl_engine *e, size_t N, int B) {
 
 // Enqueues the whole registration block for B scans whose packed points / rings are in f_raw and whose offsets are in
 // f_soff (device) / h_off (host).  No synchronisation; results stay on the device (FeatDev).
-static int extract_enqueue(msfl_engine *e, int B, const uint32_t *h_off, const double T[7], FeatDevice *fd) {
+template <class SHAPE>
+static int launch_feat_pick(msfl_engine *e, int which, dim3 gr, const float4 *full_pre, const float *curv, int32_t *label, uint8_t *picked,
+                            const uint32_t *soff, FeatMeta *meta, int32_t *slot_sharp, int32_t *slot_less, int32_t *slot_flat,
+                            int32_t *lf_tmp) {
+  const msfl_params &P = e->params;
+  if (!(e->pick_attr_mask & (1 << which))) {  // per engine: attributes are per device
+    MSFL_CUDA_OK(cudaFuncSetAttribute(k_feat_pick<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHAPE::kSmem));
+    e->pick_attr_mask |= 1 << which;
+  }
+  k_feat_pick<SHAPE><<<gr, SHAPE::kThreads, SHAPE::kSmem, e->stream>>>(full_pre, curv, label, picked, soff, meta, P.curvature_thresh,
+                                                                       P.neighbor_gap_sq, P.n_sectors, P.n_sharp, P.n_less_sharp, P.n_flat,
+                                                                       slot_sharp, slot_less, slot_flat, lf_tmp);
+  return MSFL_OK;
+}
+
+// shape: 0 small, 1 mid, 2 big (see PickShape)
+static int extract_enqueue(msfl_engine *e, int B, const uint32_t *h_off, const double T[7], FeatDevice *fd, int shape) {
   cudaStream_t st = e->stream;
   const msfl_params &P = e->params;
   const size_t n = h_off[B];
@@ -520,13 +548,11 @@ static int extract_enqueue(msfl_engine *e, int B, const uint32_t *h_off, const d
   k_feat_first_dec<<<gp, tb, 0, st>>>(ks, rel, soff, meta);
   k_feat_full<<<gp, tb, 0, st>>>(d_raw, ks, vs, rel, soff, meta, P.scan_period, full_pre, d_ring);
   k_feat_curv<<<gp, tb, 0, st>>>(full_pre, soff, meta, curv, label, picked);
-  if (!e->pick_attr_set) {
-    MSFL_CUDA_OK(cudaFuncSetAttribute(k_feat_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPickSmem));
-    e->pick_attr_set = true;
-  }
   const dim3 gr(MSFL_MAX_RINGS, (unsigned)B);  // per-ring kernels: grid = (ring, scan)
-  k_feat_pick<<<gr, kPickThreads, kPickSmem, st>>>(full_pre, curv, label, picked, soff, meta, P.curvature_thresh, P.neighbor_gap_sq, S,
-                                                   P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat, lf_tmp);
+  if (shape == 0) rc = launch_feat_pick<PickSmall>(e, 0, gr, full_pre, curv, label, picked, soff, meta, slot_sharp, slot_less, slot_flat, lf_tmp);
+  else if (shape == 1) rc = launch_feat_pick<PickMid>(e, 1, gr, full_pre, curv, label, picked, soff, meta, slot_sharp, slot_less, slot_flat, lf_tmp);
+  else rc = launch_feat_pick<PickBig>(e, 2, gr, full_pre, curv, label, picked, soff, meta, slot_sharp, slot_less, slot_flat, lf_tmp);
+  if (rc) return rc;
   k_feat_compact<<<gr, 128, 0, st>>>(soff, meta, S, P.n_sharp, P.n_less_sharp, P.n_flat, slot_sharp, slot_less, slot_flat, lf_tmp, o_sharp,
                                      o_less, o_flat, o_lf);
   Pose7 T7;
@@ -544,6 +570,42 @@ static int check_feat_meta(const FeatMeta &hm, int b) {
   if (hm.bad_ring) { set_error("extract_features: ring >= %d (kMaxScanNum) in scan %d", MSFL_MAX_RINGS, b); return MSFL_ERR_RING; }
   if (hm.n_valid <= 0) { set_error("extract_features: no valid points in scan %d", b); return MSFL_ERR_EMPTY; }
   if (hm.sector_overflow) { set_error("extract_features: a ring sector of scan %d holds more than %d points", b, kMaxSectorPts); return MSFL_ERR_ARG; }
+  return MSFL_OK;
+}
+
+// Enqueue + metas to the host + synchronise.  The pick shape follows the rings of the engine's previous extraction; a
+// shape that turns out too small for a sector (sector_overflow) is re-run with the largest one -- f_raw is untouched by
+// the kernels, so the block simply runs again.
+static int extract_run(msfl_engine *e, int B, const uint32_t *h_off, const double T[7], FeatDevice *fd, std::vector<FeatMeta> &hm) {
+  const int S = e->params.n_sectors;
+  int shape = 2;
+  if (e->pick_seen_ring >= 0) {
+    int P = 1;
+    while (P < e->pick_seen_sector) P <<= 1;
+    if (e->pick_seen_ring <= PickSmall::kRingCap && (long long)P * S <= PickSmall::kKeysCap) shape = 0;
+    else if (e->pick_seen_ring <= PickMid::kRingCap && (long long)P * S <= PickMid::kKeysCap) shape = 1;
+  }
+  if (const char *v = getenv("MSFL_PICK_SHAPE")) shape = std::min(2, std::max(0, atoi(v)));  // tests: force a shape
+  hm.resize(B);
+  int rc;
+  for (;;) {
+    if ((rc = extract_enqueue(e, B, h_off, T, fd, shape))) return rc;
+    MSFL_CUDA_OK(cudaMemcpyAsync(hm.data(), fd->metas, (size_t)B * sizeof(FeatMeta), cudaMemcpyDeviceToHost, e->stream));
+    MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+    bool overflow = false;
+    for (int b = 0; b < B; ++b) overflow = overflow || hm[b].sector_overflow;
+    if (!overflow || shape == 2) break;
+    shape = 2;
+  }
+  int ring_max = 0, sector_max = 0;
+  for (int b = 0; b < B; ++b)
+    for (int r = 0; r < MSFL_MAX_RINGS; ++r) {
+      const int len = (int)(hm[b].ring_start[r + 1] - hm[b].ring_start[r]);
+      ring_max = std::max(ring_max, len);
+      sector_max = std::max(sector_max, (len - 11 + S - 1) / S + 1);  // sectors split [start + 5, end - 6]
+    }
+  e->pick_seen_ring = ring_max;
+  e->pick_seen_sector = std::max(sector_max, 1);
   return MSFL_OK;
 }
 
@@ -584,12 +646,10 @@ int run_extract_features(msfl_engine *e, const msfl_cloud *raw, const double T[7
                                                (uint32_t)raw->off_ring, raw->off_intensity != MSFL_NO_FIELD,
                                                e->f_raw.as<float4>(), (uint16_t *)(e->f_raw.as<char>() + n * 16));
   FeatDevice fd;
-  if ((rc = extract_enqueue(e, 1, h_off, T, &fd))) return rc;
-  FeatMeta hm;
-  MSFL_CUDA_OK(cudaMemcpyAsync(&hm, fd.metas, sizeof hm, cudaMemcpyDeviceToHost, st));
-  MSFL_CUDA_OK(cudaStreamSynchronize(st));
-  if ((rc = check_feat_meta(hm, 0))) return rc;
-  if ((rc = download_features(e, fd, 0, hm, out))) return rc;
+  std::vector<FeatMeta> hm;
+  if ((rc = extract_run(e, 1, h_off, T, &fd, hm))) return rc;
+  if ((rc = check_feat_meta(hm[0], 0))) return rc;
+  if ((rc = download_features(e, fd, 0, hm[0], out))) return rc;
   MSFL_CUDA_OK(cudaStreamSynchronize(st));
   return MSFL_OK;
 }
@@ -624,10 +684,8 @@ int extract_batch_to_device(msfl_engine *e, int B, const msfl_cloud *raw, const 
                             std::vector<uint32_t> &h_off, std::vector<int32_t> &h_counts) {
   int rc;
   if ((rc = upload_raw_batch(e, B, raw, h_off))) return rc;
-  if ((rc = extract_enqueue(e, B, h_off.data(), T, fd))) return rc;
-  std::vector<FeatMeta> hm(B);
-  MSFL_CUDA_OK(cudaMemcpyAsync(hm.data(), fd->metas, (size_t)B * sizeof(FeatMeta), cudaMemcpyDeviceToHost, e->stream));
-  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  std::vector<FeatMeta> hm;
+  if ((rc = extract_run(e, B, h_off.data(), T, fd, hm))) return rc;
   h_counts.resize((size_t)B * 5);
   for (int b = 0; b < B; ++b) {
     if ((rc = check_feat_meta(hm[b], b))) return rc;
@@ -642,10 +700,8 @@ int run_extract_features_batch(msfl_engine *e, int B, const msfl_cloud *raw, con
   int rc;
   if ((rc = upload_raw_batch(e, B, raw, h_off))) return rc;
   FeatDevice fd;
-  if ((rc = extract_enqueue(e, B, h_off.data(), T, &fd))) return rc;
-  std::vector<FeatMeta> hm(B);
-  MSFL_CUDA_OK(cudaMemcpyAsync(hm.data(), fd.metas, (size_t)B * sizeof(FeatMeta), cudaMemcpyDeviceToHost, e->stream));
-  MSFL_CUDA_OK(cudaStreamSynchronize(e->stream));
+  std::vector<FeatMeta> hm;
+  if ((rc = extract_run(e, B, h_off.data(), T, &fd, hm))) return rc;
   for (int b = 0; b < B; ++b) {
     if ((rc = check_feat_meta(hm[b], b))) return rc;
     if ((rc = download_features(e, fd, h_off[b], hm[b], &outs[b]))) return rc;

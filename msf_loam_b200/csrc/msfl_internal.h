@@ -87,7 +87,8 @@ struct msfl_engine {
   int lm_shape_scans = 0;  // > 0: the LM launches of a chunked call pick their CTA shape as a launch of this many scans would
   bool fused_attr_set = false;  // k_scan2map_fused: dynamic smem + non-portable cluster size attributes
   int fused_max16 = -1;         // cudaOccupancyMaxActiveClusters of the 16-CTA configuration (-1: not asked yet)
-  bool pick_attr_set = false;  // k_feat_pick's dynamic shared-memory attribute (per device, so kept per engine)
+  int pick_attr_mask = 0;      // k_feat_pick shapes whose dynamic shared-memory attribute is set (per device, so per engine)
+  int pick_seen_ring = -1, pick_seen_sector = -1;  // longest ring / sector of the previous extraction (-1: none yet)
   // the cell keys of a batch are counting-sorted while the bin table (64 sub-cell bins per submap cell) stays small
   // enough to live in L2; larger (sparse, far-spread) submaps fall back to a radix sort of the keys
   long long count_sort_max_bins = 16ll << 20;

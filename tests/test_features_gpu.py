@@ -81,6 +81,32 @@ def test_extract_long_rings_take_the_unstaged_and_batched_sort_paths(eng, n_ring
     _check_features(f, g)
 
 
+@pytest.mark.parametrize("shape", [0, 1, 2])
+def test_extract_pick_shapes_agree(shape, monkeypatch):
+    """k_feat_pick runs in one of three shapes (512 threads / 2048 staged ring points / 4096 sort keys ... 1024 / 4096 /
+    8192), chosen from the rings of the engine's previous extraction; a sector that does not fit the keys re-runs the
+    largest shape.  Every shape gives the oracle's lists: a VLP-16 scan, a batch, and a 30 000-point ring (sectors of
+    4 998 points: overflow of the two smaller shapes -> retry)."""
+    monkeypatch.setenv("MSFL_PICK_SHAPE", str(shape))
+    e = Engine()
+    P = O.default_params()
+    sc = S.make_scene()
+    traj = S.trajectory(2)
+    scans = [S.raycast_scan(sc, "vlp16", traj[k], seed=300 + k) for k in range(2)]
+    for xyzi, ring in scans:
+        _check_features(O.extract_features(P, xyzi, ring, None), e.extract_features(xyzi, ring, None))
+    fb = e.extract_features_batch([x for x, _ in scans], [r for _, r in scans], None)
+    for (xyzi, ring), g in zip(scans, fb):
+        _check_features(O.extract_features(P, xyzi, ring, None), g)
+    rng = np.random.default_rng(5)
+    n = 30000
+    az = -np.linspace(0.0, 2 * np.pi, n, endpoint=False)
+    rr = 8.0 / np.maximum(np.abs(np.cos(az)), np.abs(np.sin(az))) + rng.normal(0, 0.02, n)
+    xyzi = np.stack([rr * np.cos(az), rr * np.sin(az), np.full(n, -0.5), np.zeros(n)], axis=1).astype(np.float32)
+    ring = np.zeros(n, np.uint16)
+    _check_features(O.extract_features(P, xyzi, ring, None), e.extract_features(xyzi, ring, None))
+
+
 def test_extract_ring_major_input_invalid_points_and_ragged_rings(eng):
     """ring-major input, NaN / too-close points removed, rings with < 12 points skipped."""
     P = O.default_params()
