@@ -672,9 +672,22 @@ static int upload_raw_batch(msfl_engine *e, int B, const msfl_cloud *raw, std::v
   uint16_t *hr = (uint16_t *)(e->h_stage.as<char>() + N * 16);
   uint32_t *ho = (uint32_t *)(e->h_stage.as<char>() + ((N * 18 + 15) & ~(size_t)15));
   memcpy(ho, h_off.data(), (size_t)(B + 1) * 4);
-  pack_clouds_parallel(e, B, raw, h4, hr, h_off.data());
-  MSFL_CUDA_OK(cudaMemcpyAsync(e->f_raw.p, h4, N * 18, cudaMemcpyHostToDevice, e->stream));
   MSFL_CUDA_OK(cudaMemcpyAsync(e->f_soff.p, ho, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+  // repack and upload in a few pieces: the DMA of piece k runs while the host threads repack piece k + 1
+  const int n_pieces = N >= 2000000 ? 4 : 1;
+  char *d_raw = e->f_raw.as<char>();
+  int b0 = 0;
+  for (int k = 0; k < n_pieces && b0 < B; ++k) {
+    int b1 = b0;
+    const size_t goal = k == n_pieces - 1 ? N : N * (size_t)(k + 1) / n_pieces;
+    while (b1 < B && (h_off[b1] < goal || k == n_pieces - 1)) ++b1;
+    if (b1 == b0) continue;
+    pack_clouds_parallel(e, b1 - b0, raw + b0, h4, hr, h_off.data() + b0);
+    const size_t p0 = h_off[b0], np = h_off[b1] - p0;
+    MSFL_CUDA_OK(cudaMemcpyAsync(d_raw + p0 * 16, h4 + 4 * p0, np * 16, cudaMemcpyHostToDevice, e->stream));
+    MSFL_CUDA_OK(cudaMemcpyAsync(d_raw + N * 16 + p0 * 2, hr + p0, np * 2, cudaMemcpyHostToDevice, e->stream));
+    b0 = b1;
+  }
   return MSFL_OK;
 }
 
