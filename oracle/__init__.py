@@ -66,6 +66,37 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libmsfl_ref_factors.so")
+REFERENCE_ROOT = os.environ.get("MSFL_REFERENCE_ROOT", "/root/reference")
+
+
+def build_ref(force: bool = False):
+    """Compile the REFERENCE's own lidar_factor.cc / pose_local_parameterization.cc (oracle/Makefile, target ``ref``)
+    from the checkout at REFERENCE_ROOT into oracle/_ref/.  Returns the .so path, or None when there is neither a
+    checkout nor a prebuilt library (the GPU box only ever uses the prebuilt file)."""
+    srcs = [os.path.join(REFERENCE_ROOT, "src/slam/local/scan_matching/lidar_factor.cc"),
+            os.path.join(REFERENCE_ROOT, "src/slam/imu_fusion/pose_local_parameterization.cc")]
+    if not all(os.path.exists(f) for f in srcs):
+        return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
+    cmd = ["make", "-C", _HERE, "REF=" + REFERENCE_ROOT, "ref"] + (["-B"] if force else [])
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return _REF_LIB_PATH
+
+
+_ref_lib = None
+
+
+def ref_lib():
+    """ctypes handle of oracle/_ref/libmsfl_ref_factors.so (the reference's compiled factor code), or None."""
+    global _ref_lib
+    if _ref_lib is None:
+        path = build_ref()
+        if path is None:
+            return None
+        _ref_lib = C.CDLL(path)
+    return _ref_lib
+
+
 _lib = None
 
 

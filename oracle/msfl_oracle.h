@@ -7,7 +7,11 @@
  * bench.py's cpu_baseline / --impl reference legs may load it.  The product (msf_loam_b200/)
  * never links, imports or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference cannot be built in this image (PCL 1.10 / FLANN 1.9, Ceres <= 2.1,
+ * PARITY PINNED FOR THE FACTORS ONLY: rows a-8, the Deskew factors of f-3 and PoseLocalParameterization::Plus of a-9
+ * are checked against the reference's OWN lidar_factor.cc / pose_local_parameterization.cc, compiled unmodified into
+ * oracle/_ref/libmsfl_ref_factors.so (Makefile target `ref`; stand-in Eigen / Ceres interface headers in ref_stubs/):
+ * residuals, Jacobians and Plus are bit-equal on 4000 + 4000 + 3000 random cases (tests/test_ref_factors.py).
+ * PARITY UNPINNED FOR EVERYTHING ELSE: the matchers cannot be built in this image (PCL 1.10 / FLANN 1.9, Ceres <= 2.1,
  * Eigen 3.3, ROS are un-vendored third-party dependencies and absent; no network) and the
  * reference's own tests hold no golden vector for this path (only quaternion identities,
  * src/slam/imu_fusion/utility_test.cc:8-34).  The third-party arithmetic is therefore restated
