@@ -66,16 +66,20 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
-_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libmsfl_ref_factors.so")
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libmsfl_ref.so")
 REFERENCE_ROOT = os.environ.get("MSFL_REFERENCE_ROOT", "/root/reference")
 
 
 def build_ref(force: bool = False):
-    """Compile the REFERENCE's own lidar_factor.cc / pose_local_parameterization.cc (oracle/Makefile, target ``ref``)
-    from the checkout at REFERENCE_ROOT into oracle/_ref/.  Returns the .so path, or None when there is neither a
+    """Compile the REFERENCE's own scan-matching sources (oracle/Makefile, target ``ref``: lidar_factor.cc,
+    odometry_scan_matcher.cc, mapping_scan_matcher.cc, scan_matcher.cc, pose_local_parameterization.cc,
+    scan_undistortion.cc, unmodified, against the stand-in headers of oracle/ref_stubs/) from the checkout at
+    REFERENCE_ROOT into oracle/_ref/.  Returns the .so path, or None when there is neither a
     checkout nor a prebuilt library (the GPU box only ever uses the prebuilt file)."""
-    srcs = [os.path.join(REFERENCE_ROOT, "src/slam/local/scan_matching/lidar_factor.cc"),
-            os.path.join(REFERENCE_ROOT, "src/slam/imu_fusion/pose_local_parameterization.cc")]
+    srcs = [os.path.join(REFERENCE_ROOT, "src/slam/local/scan_matching", f) for f in
+            ("lidar_factor.cc", "odometry_scan_matcher.cc", "mapping_scan_matcher.cc", "scan_matcher.cc")]
+    srcs += [os.path.join(REFERENCE_ROOT, "src/slam/imu_fusion", f) for f in
+             ("pose_local_parameterization.cc", "scan_undistortion.cc")]
     if not all(os.path.exists(f) for f in srcs):
         return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
     cmd = ["make", "-C", _HERE, "REF=" + REFERENCE_ROOT, "ref"] + (["-B"] if force else [])
@@ -87,7 +91,7 @@ _ref_lib = None
 
 
 def ref_lib():
-    """ctypes handle of oracle/_ref/libmsfl_ref_factors.so (the reference's compiled factor code), or None."""
+    """ctypes handle of oracle/_ref/libmsfl_ref.so (the reference's compiled scan-matching code), or None."""
     global _ref_lib
     if _ref_lib is None:
         path = build_ref()

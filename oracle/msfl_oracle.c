@@ -322,6 +322,13 @@ int msflo_lm_solve(const msflo_params *P, const double *corr, int n_corr, double
   return lm_solve_generic(P, eval_plain, &c, n_corr, pose, log);
 }
 
+/* the same loop over a caller-supplied evaluation (oracle/ref_shim.cc: the stand-in ceres::Solve evaluates the REFERENCE's
+ * own cost functions through this) */
+int msflo_lm_solve_cb(const msflo_params *P, msflo_eval_fn eval, const void *ctx, int n_blocks, double pose[7],
+                      msflo_lm_log *log) {
+  return lm_solve_generic(P, eval, ctx, n_blocks, pose, log);
+}
+
 static int lm_solve_generic(const msflo_params *P, lm_eval_fn eval, const void *ctx, int n_corr, double pose[7],
                             msflo_lm_log *log) {
   double x[7], H[36], g[6], S[6], diag[6] = {0, 0, 0, 0, 0, 0};

@@ -121,6 +121,12 @@ void msflo_accumulate(const msflo_params *P, const double *corr, int n_corr, con
 /* ---- a-9: Ceres-semantics LM on one SE(3) block; pose in/out ---- */
 int msflo_lm_solve(const msflo_params *P, const double *corr, int n_corr, double pose[7], msflo_lm_log *log);
 
+/* the same loop over a caller-supplied evaluation: eval fills cost and, when non-NULL, H (6x6 row-major) and g at pose */
+typedef void (*msflo_eval_fn)(const msflo_params *P, const void *ctx, const double pose[7], double *cost, double H[36],
+                              double g[6]);
+int msflo_lm_solve_cb(const msflo_params *P, msflo_eval_fn eval, const void *ctx, int n_blocks, double pose[7],
+                      msflo_lm_log *log);
+
 /* ---- exact k-NN (kd-tree, FLANN L2_Simple<float> semantics) ---- */
 typedef struct msflo_kdtree msflo_kdtree;
 msflo_kdtree *msflo_kdtree_build(const float *xyzi, int n);       /* xyzi: n x 4 float, not copied */

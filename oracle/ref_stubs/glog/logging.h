@@ -1,0 +1,27 @@
+// Stand-in for <glog/logging.h> (TEST INFRASTRUCTURE): log statements are swallowed, a failed CHECK aborts like glog's.
+#ifndef MSFL_GLOG_STANDIN_H
+#define MSFL_GLOG_STANDIN_H
+#include <cstdio>
+#include <cstdlib>
+#include <ostream>
+namespace msfl_glog {
+struct NullStream {
+  template <typename T>
+  NullStream &operator<<(const T &) { return *this; }
+  NullStream &operator<<(std::ostream &(*)(std::ostream &)) { return *this; }
+};
+struct FatalStream {
+  FatalStream(const char *file, int line, const char *what) { std::fprintf(stderr, "%s:%d CHECK failed: %s\n", file, line, what); }
+  [[noreturn]] ~FatalStream() { std::abort(); }
+  template <typename T>
+  FatalStream &operator<<(const T &) { return *this; }
+};
+}  // namespace msfl_glog
+#define LOG(severity) ::msfl_glog::NullStream()
+#define CHECK(c) \
+  if (c) {       \
+  } else         \
+    ::msfl_glog::FatalStream(__FILE__, __LINE__, #c)
+#define CHECK_GE(a, b) CHECK((a) >= (b))
+#define CHECK_EQ(a, b) CHECK((a) == (b))
+#endif
