@@ -71,7 +71,7 @@ REFERENCE_ROOT = os.environ.get("MSFL_REFERENCE_ROOT", "/root/reference")
 
 
 def build_ref(force: bool = False):
-    """Compile the REFERENCE's own scan-matching sources (oracle/Makefile, target ``ref``: lidar_factor.cc,
+    """Compile the REFERENCE's own hot-path sources (oracle/Makefile, target ``ref``: msf_loam_node.cc, lidar_factor.cc,
     odometry_scan_matcher.cc, mapping_scan_matcher.cc, scan_matcher.cc, pose_local_parameterization.cc,
     scan_undistortion.cc, unmodified, against the stand-in headers of oracle/ref_stubs/) from the checkout at
     REFERENCE_ROOT into oracle/_ref/.  Returns the .so path, or None when there is neither a
@@ -80,6 +80,7 @@ def build_ref(force: bool = False):
             ("lidar_factor.cc", "odometry_scan_matcher.cc", "mapping_scan_matcher.cc", "scan_matcher.cc")]
     srcs += [os.path.join(REFERENCE_ROOT, "src/slam/imu_fusion", f) for f in
              ("pose_local_parameterization.cc", "scan_undistortion.cc")]
+    srcs.append(os.path.join(REFERENCE_ROOT, "src/msf_loam_node.cc"))
     if not all(os.path.exists(f) for f in srcs):
         return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
     cmd = ["make", "-C", _HERE, "REF=" + REFERENCE_ROOT, "ref"] + (["-B"] if force else [])

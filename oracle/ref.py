@@ -97,3 +97,25 @@ def scan2scan(last_corner, last_corner_ring, last_surf, last_surf_ring, curr_sha
                                      _ptr(lsr, C.c_uint16), C.c_int(ls.shape[0]), _ptr(cs, C.c_float), C.c_int(cs.shape[0]),
                                      _ptr(cf, C.c_float), C.c_int(cf.shape[0]), _ptr(x, C.c_double))
     return bool(ok), x
+
+
+def extract_features(xyzi, ring, T_ext=None, min_range=0.3):
+    """RealHandleLaserCloudMessage (msf_loam_node.cc:160-378).  Returns the registered full cloud, its rings and the four
+    feature clouds in the reference's push order."""
+    pts = _f32(xyzi, 4)
+    rg = np.ascontiguousarray(ring, dtype=np.uint16)
+    n = pts.shape[0]
+    T = _pose(T_ext if T_ext is not None else [0, 0, 0, 0, 0, 0, 1])
+    names = ("full", "sharp", "less_sharp", "flat", "less_flat")
+    bufs = {k: np.zeros((n, 4), np.float32) for k in names}
+    cnt = {k: C.c_int() for k in names}
+    full_ring = np.zeros(n, np.uint16)
+    rc = ref_lib().msflref_extract_features(
+        _ptr(pts, C.c_float), _ptr(rg, C.c_uint16), C.c_int(n), _ptr(T, C.c_double), C.c_double(min_range),
+        _ptr(bufs["full"], C.c_float), _ptr(full_ring, C.c_uint16), C.byref(cnt["full"]),
+        _ptr(bufs["sharp"], C.c_float), C.byref(cnt["sharp"]), _ptr(bufs["less_sharp"], C.c_float), C.byref(cnt["less_sharp"]),
+        _ptr(bufs["flat"], C.c_float), C.byref(cnt["flat"]), _ptr(bufs["less_flat"], C.c_float), C.byref(cnt["less_flat"]))
+    assert rc == 1
+    out = {k: bufs[k][:cnt[k].value] for k in names}
+    out["ring"] = full_ring[:cnt["full"].value]
+    return out

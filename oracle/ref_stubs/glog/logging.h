@@ -23,5 +23,17 @@ struct FatalStream {
   } else         \
     ::msfl_glog::FatalStream(__FILE__, __LINE__, #c)
 #define CHECK_GE(a, b) CHECK((a) >= (b))
+#define CHECK_GT(a, b) CHECK((a) > (b))
+#define CHECK_LT(a, b) CHECK((a) < (b))
 #define CHECK_EQ(a, b) CHECK((a) == (b))
+#define LOG_IF(severity, condition) ::msfl_glog::NullStream()
+// the gflags slice msf_loam_node.cc uses (glog pulls gflags in upstream)
+#include <string>
+#define DEFINE_bool(name, value, help) bool FLAGS_##name = value
+#define DEFINE_string(name, value, help) std::string FLAGS_##name = value
+static bool FLAGS_alsologtostderr __attribute__((unused)) = false;
+namespace google {
+inline void InitGoogleLogging(const char *) {}
+inline void ParseCommandLineFlags(int *, char ***, bool) {}
+}  // namespace google
 #endif
