@@ -254,6 +254,12 @@ typedef struct msfl_deskew {
 /* MSFL_ERR_ARG when a point time lies outside [sum_dt[0], sum_dt[n-1]] (the reference CHECK-fails). */
 int msfl_scan2map_deskew(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
                          const msfl_deskew *deskew, double pose_tq[7], msfl_stats *stats);
+/* B scans of a replayed log through the same branch in one launch sequence (arrays of B clouds / B tables, every scan
+ * with its own preintegration buffers, velocity and gravity; poses_tq 7 B doubles in-out = the poses after each scan's
+ * IMU-only predict; stats B entries or NULL).  Results are those of B msfl_scan2map_deskew calls.  MSFL_ERR_ARG (no pose
+ * written) when a point time of any scan lies outside that scan's window. */
+int msfl_scan2map_deskew_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                               const msfl_deskew *deskew, double *poses_tq, msfl_stats *stats);
 
 /* ---- scan-to-scan: OdometryScanMatcher::MatchScan2Scan
  *      (odometry_scan_matcher.h:10-12, odometry_scan_matcher.cc:43-285) ----------------------

@@ -118,23 +118,32 @@ k_scatter_perm(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ r
 // and the factor sees p' = dq p + dp (fp64) and the constant offset o = V dt - g dt^2 / 2
 // (lidar_factor.cc:53,81), which is folded into the line point / plane centre (C' = C - o).
 // ---------------------------------------------------------------------------------------------
-struct DeskewTable {
+struct DeskewTable {  // one scan's preintegration table as the prepare kernel sees it
   const double *sum_dt, *delta_q, *delta_p;  // device arrays: [n], [n][4] xyzw, [n][3]
   int n;
-  double V[3], G[3];
 };
 
-// per query: dq(4) dp(3) dt(1) -> dsk[8]; p' -> pprime (double4).  flag |= 1 when dt is out of range.
-__global__ void k_deskew_prepare(DeskewTable tb, const float4 *__restrict__ q, uint32_t n, double *__restrict__ dsk,
-                                 double *__restrict__ pprime, int *__restrict__ flag) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const float4 p = q[k];
+// what the search and fit kernels of the deskew branch need besides dsk: the per-query offset o = V dt - g dt^2 / 2
+// (4 doubles per query), written by k_deskew_prepare with the velocity / gravity of the query's own scan
+struct DeskewOffsets {
+  const double *o4;
+};
+
+// o = Vi dt - 0.5 g dt^2 as the reference evaluates it (mapping_scan_matcher.cc:120, lidar_factor.cc:53)
+__device__ __forceinline__ void deskew_offset_vg(const double V[3], const double G[3], double dt, double o[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = __dsub_rn(__dmul_rn(V[i], dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, G[i]), dt), dt));
+}
+__device__ __forceinline__ void deskew_offset(const DeskewOffsets &tb, size_t k, double o[3]) {
+  const double2 a = *reinterpret_cast<const double2 *>(tb.o4 + k * 4);
+  o[0] = a.x; o[1] = a.y; o[2] = tb.o4[k * 4 + 2];
+}
+
+// per query: dq(4) dp(3) dt(1) -> dsk[8]; p' -> pprime (double4).  Returns false when dt is out of range.
+__device__ __forceinline__ bool deskew_prepare_one(const DeskewTable &tb, const float4 p, double *__restrict__ o,
+                                                   double *__restrict__ pp) {
   const double dt = (double)p.w;  // auto dt = pointOri.intensity  (:114)
-  if (tb.n < 2 || !(dt <= tb.sum_dt[tb.n - 1] && dt >= tb.sum_dt[0])) {  // CHECK scan_undistortion.cc:26
-    atomicOr(flag, 1);
-    return;
-  }
+  if (tb.n < 2 || !(dt <= tb.sum_dt[tb.n - 1] && dt >= tb.sum_dt[0])) return false;  // CHECK scan_undistortion.cc:26
   int lo = 0, hi = tb.n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -160,20 +169,42 @@ __global__ void k_deskew_prepare(DeskewTable tb, const float4 *__restrict__ q, u
   const double *pa = tb.delta_p + 3 * idx, *pb = pa + 3;
 #pragma unroll
   for (int i = 0; i < 3; ++i) dp[i] = __dadd_rn(__dmul_rn(1 - s, pa[i]), __dmul_rn(s, pb[i]));
-  double *o = dsk + (size_t)k * 8;
   o[0] = dq[0]; o[1] = dq[1]; o[2] = dq[2]; o[3] = dq[3]; o[4] = dp[0]; o[5] = dp[1]; o[6] = dp[2]; o[7] = dt;
   double r0, r1, r2;
   quat_rotate_exact(dq, (double)p.x, (double)p.y, (double)p.z, r0, r1, r2);
-  double *pp = pprime + (size_t)k * 4;
   pp[0] = __dadd_rn(r0, dp[0]); pp[1] = __dadd_rn(r1, dp[1]); pp[2] = __dadd_rn(r2, dp[2]); pp[3] = 0.0;
+  return true;
+}
+
+// B scans, every scan with its own table, velocity and gravity: the query's scan comes from the offset tables of the
+// [all corner | all surf] layout; also stores the per-query offset o (DeskewOffsets).  flags[scan] |= 1 when a dt of that
+// scan is out of range.
+__global__ void k_deskew_prepare(const DeskewScan *__restrict__ scans, const double *__restrict__ sum_dt,
+                                       const double *__restrict__ delta_q, const double *__restrict__ delta_p, int B,
+                                       const int32_t *__restrict__ c_off, const int32_t *__restrict__ s_off,
+                                       uint32_t n_corner_total, const float4 *__restrict__ q, uint32_t n_total,
+                                       double *__restrict__ dsk, double *__restrict__ pprime, double *__restrict__ o4,
+                                       int *__restrict__ flags) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_total) return;
+  const bool is_corner = k < n_corner_total;
+  const int scan = find_scan(is_corner ? c_off : s_off, B, is_corner ? k : k - n_corner_total);
+  const DeskewScan sc = scans[scan];
+  const DeskewTable tb{sum_dt + sc.row0, delta_q + (size_t)sc.row0 * 4, delta_p + (size_t)sc.row0 * 3, sc.n};
+  const float4 p = q[k];
+  if (!deskew_prepare_one(tb, p, dsk + (size_t)k * 8, pprime + (size_t)k * 4)) {
+    atomicOr(flags + scan, 1);
+    return;
+  }
+  double o[3];
+  deskew_offset_vg(sc.V, sc.G, (double)p.w, o);
+  o4[(size_t)k * 4] = o[0]; o4[(size_t)k * 4 + 1] = o[1]; o4[(size_t)k * 4 + 2] = o[2]; o4[(size_t)k * 4 + 3] = 0.0;
 }
 
 // the total transform of the deskew branch applied to p, rounded to fp32 like TransformPoint
-__device__ __forceinline__ float3 deskew_transform(const double pose[7], const DeskewTable &tb, const double *dsk8, float px,
-                                                   float py, float pz, double o[3]) {
-  const double dt = dsk8[7];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) o[i] = __dsub_rn(__dmul_rn(tb.V[i], dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, tb.G[i]), dt), dt));
+__device__ __forceinline__ float3 deskew_transform(const double pose[7], const DeskewOffsets &tb, size_t k, const double *dsk8,
+                                                   float px, float py, float pz, double o[3]) {
+  deskew_offset(tb, k, o);
   const double qc[4] = {-pose[3], -pose[4], -pose[5], pose[6]};
   double t0, t1, t2, u0, u1, u2;
   quat_rotate_exact(qc, o[0], o[1], o[2], t0, t1, t2);
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(128, 10)
 k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ qc,
        const int32_t *__restrict__ c_off, uint32_t n_corner_total, const float4 *__restrict__ qs,
        const int32_t *__restrict__ s_off, uint32_t n_surf_total, const double *__restrict__ poses,
-       const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, DeskewTable tb,
+       const float4 *__restrict__ xq, const uint32_t *__restrict__ perm, int32_t *__restrict__ knn_out, DeskewOffsets tb,
        const double *__restrict__ dsk) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_corner_total + n_surf_total) return;
@@ -221,7 +252,7 @@ k_knn5(GridView gc, GridView gs, KParams kp, int B, const float4 *__restrict__ q
 #pragma unroll
     for (int i = 0; i < 7; ++i) pose[i] = __ldg(poses + (size_t)scan * 7 + i);
     const float4 p = __ldg((is_corner ? qc : qs) + kk);
-    if (DESKEW) x = deskew_transform(pose, tb, dsk + (size_t)k * 8, p.x, p.y, p.z, dsk_o);  // :120 / :190
+    if (DESKEW) x = deskew_transform(pose, tb, k, dsk + (size_t)k * 8, p.x, p.y, p.z, dsk_o);  // :120 / :190
     else x = transform_point_f(pose, p.x, p.y, p.z);  // mapping_scan_matcher.cc:123 / :193
   }
   const GridView &g = is_corner ? gc : gs;
@@ -396,7 +427,7 @@ k_knn5_tiled(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint
 template <bool DESKEW, bool COMPACT, bool QR>
 __device__ __forceinline__ void fit_from_idx(const GridView &g, const KParams &kp, bool is_corner, uint32_t k, uint32_t slot,
                                              uint32_t n_corner_total, const int (&idx)[5], double *__restrict__ corr,
-                                             const DeskewTable &tb, const double *__restrict__ dsk, uint32_t *__restrict__ fb_list,
+                                             const DeskewOffsets &tb, const double *__restrict__ dsk, uint32_t *__restrict__ fb_list,
                                              uint32_t *__restrict__ fb_count) {
   double a[3] = {0, 0, 0}, n[3] = {0, 0, 0};
   if (idx[4] >= 0) {
@@ -430,9 +461,10 @@ __device__ __forceinline__ void fit_from_idx(const GridView &g, const KParams &k
     }
   }
   if (DESKEW && (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0)) {  // fold the constant offset: C' = C - o, o = V dt - g dt^2 / 2
-    const double dt = dsk[(size_t)k * 8 + 7];
+    double off[3];
+    deskew_offset(tb, k, off);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) a[d] -= __dsub_rn(__dmul_rn(tb.V[d], dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, tb.G[d]), dt), dt));
+    for (int d = 0; d < 3; ++d) a[d] -= off[d];
   }
   if (COMPACT && !is_corner) {
     double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(corr + (size_t)n_corner_total * 6) +
@@ -446,7 +478,7 @@ __device__ __forceinline__ void fit_from_idx(const GridView &g, const KParams &k
 
 template <bool DESKEW, bool COMPACT, bool BY_SLOT, bool QR>
 __device__ __forceinline__ void fit_query(const GridView &g, const KParams &kp, bool is_corner, uint32_t slot, uint32_t n_corner_total,
-                                          const int32_t *__restrict__ knn, double *__restrict__ corr, const DeskewTable &tb,
+                                          const int32_t *__restrict__ knn, double *__restrict__ corr, const DeskewOffsets &tb,
                                           const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
                                           uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
   const uint32_t k = BY_SLOT ? __ldg(perm + slot) : slot;
@@ -518,7 +550,7 @@ k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32
 template <bool DESKEW, bool COMPACT, bool BY_SLOT, int CLS = -1>
 __global__ void __launch_bounds__(128)
 k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_total, const int32_t *__restrict__ knn,
-      double *__restrict__ corr, DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
+      double *__restrict__ corr, DeskewOffsets tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
       uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (CLS == 1 ? n_corner_total : 0u);
   if (slot >= (CLS == 0 ? n_corner_total : n_total)) return;
@@ -533,7 +565,7 @@ k_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32_t n_
 template <bool DESKEW, bool COMPACT, bool BY_SLOT>
 __global__ void __launch_bounds__(128)
 k_fit_qr_list(GridView gs, KParams kp, uint32_t n_corner_total, const int32_t *__restrict__ knn, double *__restrict__ corr,
-              DeskewTable tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
+              DeskewOffsets tb, const double *__restrict__ dsk, const uint32_t *__restrict__ perm,
               const uint32_t *__restrict__ fb_list, const uint32_t *__restrict__ fb_count) {
   const uint32_t cnt = *fb_count;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
@@ -562,7 +594,7 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   if ((rc = e->a_fb.reserve(((size_t)n_surf_total + 2) * 4))) return rc;
   uint32_t *fb_count = e->a_fb.as<uint32_t>(), *fb_list = fb_count + 1;
   MSFL_CUDA_OK(cudaMemsetAsync(fb_count, 0, 4, e->stream));
-  const DeskewTable nt{};
+  const DeskewOffsets nt{};
   const int mode = e->params.assoc_sorted;  // 0 auto, 1 never, 2 always
   const bool sorted = mode == 2 || mode == 3 || (mode == 0 && total >= 65536u);
   if (!sorted) {
@@ -684,21 +716,21 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
   return MSFL_OK;
 }
 
-// ---- deskew branch launchers (single scan) ------------------------------------------------------
-int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
-                          const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,
-                          double *d_pprime, int *d_flag) {
-  DeskewTable tb{d_sum_dt, d_dq, d_dp, n_tab, {V[0], V[1], V[2]}, {G[0], G[1], G[2]}};
-  k_deskew_prepare<<<(n + 127) / 128, 128, 0, e->stream>>>(tb, d_q, n, d_dsk, d_pprime, d_flag);
+// ---- deskew branch launchers -----------------------------------------------------------------------
+int launch_deskew_prepare(msfl_engine *e, int B, const DeskewScan *d_scans, const double *d_sum_dt, const double *d_dq,
+                          const double *d_dp, const float4 *d_q, const int32_t *d_c_off, const int32_t *d_s_off, uint32_t nc,
+                          uint32_t n, double *d_dsk, double *d_pprime, double *d_o4, int *d_flags) {
+  if (n == 0) return MSFL_OK;
+  k_deskew_prepare<<<(n + 127) / 128, 128, 0, e->stream>>>(d_scans, d_sum_dt, d_dq, d_dp, B, d_c_off, d_s_off, nc, d_q, n, d_dsk,
+                                                           d_pprime, d_o4, d_flags);
   e->launches += 1;
   MSFL_CUDA_OK(cudaGetLastError());
   return MSFL_OK;
 }
 
-int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_t *d_c_off, uint32_t nc, const float4 *d_qs,
-                                const int32_t *d_s_off, uint32_t ns, const double *d_pose, const double *d_sum_dt,
-                                const double *d_dq, const double *d_dp, int n_tab, const double V[3], const double G[3],
-                                const double *d_dsk, double *d_corr, int32_t *d_knn) {
+int launch_associate_map_deskew(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t nc,
+                                const float4 *d_qs, const int32_t *d_s_off, uint32_t ns, const double *d_pose,
+                                const double *d_o4, const double *d_dsk, double *d_corr, int32_t *d_knn) {
   const uint32_t total = nc + ns;
   if (total == 0) return MSFL_OK;
   if (!d_knn) {
@@ -706,10 +738,10 @@ int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_
     if ((rck = e->d_knn.reserve((size_t)total * 5 * 4))) return rck;
     d_knn = e->d_knn.as<int32_t>();
   }
-  DeskewTable tb{d_sum_dt, d_dq, d_dp, n_tab, {V[0], V[1], V[2]}, {G[0], G[1], G[2]}};
+  const DeskewOffsets tb{d_o4};
   stage_begin(e, 0);
   k_knn5<false, false, true, false><<<(total + 127) / 128, 128, 0, e->stream>>>(
-      e->map_corner.view, e->map_surf.view, e->kp, 1, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_knn, tb,
+      e->map_corner.view, e->map_surf.view, e->kp, B, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, nullptr, nullptr, d_knn, tb,
       d_dsk);
   int rcf;
   if ((rcf = e->a_fb.reserve(((size_t)ns + 2) * 4))) return rcf;

@@ -893,73 +893,105 @@ int msfl_scan2map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_clou
   return msfl_scan2map_batch(e, 1, scan_corner, scan_surf, pose_tq, stats);
 }
 
-int msfl_scan2map_deskew(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
-                         const msfl_deskew *dk, double pose_tq[7], msfl_stats *stats) {
-  if (!e || !scan_corner || !scan_surf || !dk || !pose_tq) { set_error("msfl_scan2map_deskew: bad argument"); return MSFL_ERR_ARG; }
+// IMU-initialised branch for B scans: every scan with its own preintegration table, velocity and gravity.
+int msfl_scan2map_deskew_batch(msfl_engine *e, int B, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                               const msfl_deskew *dk, double *poses_tq, msfl_stats *stats) {
+  if (!e || B <= 0 || !scan_corner || !scan_surf || !dk || !poses_tq) { set_error("msfl_scan2map_deskew: bad argument"); return MSFL_ERR_ARG; }
   if (!e->has_submap) { set_error("msfl_scan2map_deskew: no submap set"); return MSFL_ERR_NOSUBMAP; }
-  if (dk->n < 2 || !dk->sum_dt || !dk->delta_q || !dk->delta_p) { set_error("msfl_scan2map_deskew: preintegration table needs >= 2 samples"); return MSFL_ERR_ARG; }
-  if (scan_corner->off_intensity == MSFL_NO_FIELD || scan_surf->off_intensity == MSFL_NO_FIELD) { set_error("msfl_scan2map_deskew: clouds need the intensity (relative time) field"); return MSFL_ERR_ARG; }
+  size_t rows = 0;
+  for (int b = 0; b < B; ++b) {
+    if (dk[b].n < 2 || !dk[b].sum_dt || !dk[b].delta_q || !dk[b].delta_p) { set_error("msfl_scan2map_deskew: preintegration table of scan %d needs >= 2 samples", b); return MSFL_ERR_ARG; }
+    if (scan_corner[b].off_intensity == MSFL_NO_FIELD || scan_surf[b].off_intensity == MSFL_NO_FIELD) { set_error("msfl_scan2map_deskew: clouds need the intensity (relative time) field"); return MSFL_ERR_ARG; }
+    rows += (size_t)dk[b].n;
+  }
+  if (rows > 0x7fffffffull) { set_error("msfl_scan2map_deskew: preintegration tables too large"); return MSFL_ERR_ARG; }
   MSFL_CUDA_OK(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
   int rc;
   uint32_t nc = 0, ns = 0;
-  if ((rc = upload_batch(e, 1, scan_corner, scan_surf, pose_tq, &nc, &ns))) return rc;
+  if ((rc = upload_batch(e, B, scan_corner, scan_surf, poses_tq, &nc, &ns))) return rc;
   const size_t total = (size_t)nc + ns;
-  if (stats) memset(stats, 0, sizeof *stats);
+  if (stats) memset(stats, 0, (size_t)B * sizeof *stats);
   if (total == 0) return MSFL_OK;
-  const size_t q_pad = (total * 16 + 15) & ~(size_t)15, off_pad = ((size_t)2 * 2 * 4 + 15) & ~(size_t)15;
+  const size_t q_pad = (total * 16 + 15) & ~(size_t)15, off_pad = ((size_t)2 * (B + 1) * 4 + 15) & ~(size_t)15;
   char *d = e->d_queries.as<char>();
   const float4 *d_qc = (const float4 *)d, *d_qs = d_qc + nc;
-  const int32_t *d_c_off = (const int32_t *)(d + q_pad), *d_s_off = d_c_off + 2;
-  double *d_pose = (double *)(d + q_pad + off_pad);
-  // preintegration table -> device: [sum_dt n | delta_q 4n | delta_p 3n | flag]
-  const size_t n = (size_t)dk->n;
-  if ((rc = e->k_table.reserve(n * 8 * 8 + 64))) return rc;
-  if ((rc = e->h_misc.reserve(n * 8 * 8 + 64))) return rc;
+  const int32_t *d_c_off = (const int32_t *)(d + q_pad), *d_s_off = d_c_off + (B + 1);
+  double *d_poses = (double *)(d + q_pad + off_pad);
+  // preintegration tables -> device: [sum_dt N | delta_q 4N | delta_p 3N | DeskewScan B | flags B]
+  const size_t tab_bytes = rows * 64, scans_bytes = (size_t)B * sizeof(msfl::DeskewScan), flag_bytes = (size_t)B * 4;
+  if ((rc = e->k_table.reserve(tab_bytes + scans_bytes + flag_bytes))) return rc;
+  if ((rc = e->h_misc.reserve(tab_bytes + scans_bytes + flag_bytes))) return rc;
   double *ht = e->h_misc.as<double>();
-  memcpy(ht, dk->sum_dt, n * 8);
-  memcpy(ht + n, dk->delta_q, n * 32);
-  memcpy(ht + 5 * n, dk->delta_p, n * 24);
-  memset(ht + 8 * n, 0, 8);
-  MSFL_CUDA_OK(cudaMemcpyAsync(e->k_table.p, ht, n * 64 + 8, cudaMemcpyHostToDevice, st));
-  const double *t_dt = e->k_table.as<double>(), *t_dq = t_dt + n, *t_dp = t_dt + 5 * n;
-  int *d_flag = (int *)(e->k_table.as<double>() + 8 * n);
+  msfl::DeskewScan *hs = (msfl::DeskewScan *)(e->h_misc.as<char>() + tab_bytes);
+  size_t row = 0;
+  for (int b = 0; b < B; ++b) {
+    const size_t n = (size_t)dk[b].n;
+    memcpy(ht + row, dk[b].sum_dt, n * 8);
+    memcpy(ht + rows + 4 * row, dk[b].delta_q, n * 32);
+    memcpy(ht + 5 * rows + 3 * row, dk[b].delta_p, n * 24);
+    hs[b].row0 = (uint32_t)row;
+    hs[b].n = dk[b].n;
+    for (int i = 0; i < 3; ++i) hs[b].V[i] = dk[b].velocity[i], hs[b].G[i] = dk[b].gravity[i];
+    row += n;
+  }
+  memset(e->h_misc.as<char>() + tab_bytes + scans_bytes, 0, flag_bytes);
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->k_table.p, ht, tab_bytes + scans_bytes + flag_bytes, cudaMemcpyHostToDevice, st));
+  const double *t_dt = e->k_table.as<double>(), *t_dq = t_dt + rows, *t_dp = t_dt + 5 * rows;
+  const msfl::DeskewScan *d_scans = (const msfl::DeskewScan *)(e->k_table.as<char>() + tab_bytes);
+  int *d_flags = (int *)(e->k_table.as<char>() + tab_bytes + scans_bytes);
   if ((rc = e->k_dsk.reserve(total * 64))) return rc;
   if ((rc = e->k_pprime.reserve(total * 32))) return rc;
+  if ((rc = e->k_o4.reserve(total * 32))) return rc;
   if ((rc = e->d_corr.reserve((total + 1) * 48))) return rc;
-  if ((rc = e->d_status.reserve(16))) return rc;
+  if ((rc = e->d_status.reserve((size_t)B * 4 + 16))) return rc;
   msfl_stats *d_stats = nullptr;
   if (stats) {
-    if ((rc = e->d_stats.reserve(sizeof(msfl_stats)))) return rc;
+    if ((rc = e->d_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
+    if ((rc = e->h_stats.reserve((size_t)B * sizeof(msfl_stats)))) return rc;
     d_stats = e->d_stats.as<msfl_stats>();
-    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(msfl_stats), st));
+    MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, (size_t)B * sizeof(msfl_stats), st));
   }
-  if ((rc = launch_deskew_prepare(e, t_dt, t_dq, t_dp, dk->n, dk->velocity, dk->gravity, d_qc, (uint32_t)total,
-                                  e->k_dsk.as<double>(), e->k_pprime.as<double>(), d_flag)))
+  // a query whose time is outside its scan's table keeps stale (dq, dp, p', o): give them defined contents; the call
+  // fails below and no pose is written, so they never reach a result
+  MSFL_CUDA_OK(cudaMemsetAsync(e->k_dsk.p, 0, total * 64, st));
+  MSFL_CUDA_OK(cudaMemsetAsync(e->k_pprime.p, 0, total * 32, st));
+  MSFL_CUDA_OK(cudaMemsetAsync(e->k_o4.p, 0, total * 32, st));
+  if ((rc = launch_deskew_prepare(e, B, d_scans, t_dt, t_dq, t_dp, d_qc, d_c_off, d_s_off, nc, (uint32_t)total,
+                                  e->k_dsk.as<double>(), e->k_pprime.as<double>(), e->k_o4.as<double>(), d_flags)))
     return rc;
   const double *pp_c = e->k_pprime.as<double>(), *pp_s = pp_c + (size_t)nc * 4;
   for (int outer = 0; outer < e->params.num_outer; ++outer) {
-    if ((rc = launch_associate_map_deskew(e, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_pose, t_dt, t_dq, t_dp, dk->n, dk->velocity,
-                                          dk->gravity, e->k_dsk.as<double>(), e->d_corr.as<double>(), nullptr)))
+    if ((rc = launch_associate_map_deskew(e, B, d_qc, d_c_off, nc, d_qs, d_s_off, ns, d_poses, e->k_o4.as<double>(),
+                                          e->k_dsk.as<double>(), e->d_corr.as<double>(), nullptr)))
       return rc;
     stage_begin(e, 1);
-    rc = launch_lm_solve_pd(e, 1, pp_c, d_c_off, nc, pp_s, d_s_off, e->d_corr.as<double>(), d_pose, e->d_status.as<int32_t>(),
+    rc = launch_lm_solve_pd(e, B, pp_c, d_c_off, nc, pp_s, d_s_off, e->d_corr.as<double>(), d_poses, e->d_status.as<int32_t>(),
                             d_stats, outer, 0);
     stage_end(e);
     if (rc) return rc;
   }
-  int h_flag = 0;
-  MSFL_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
-  double h_pose[7];
-  MSFL_CUDA_OK(cudaMemcpyAsync(h_pose, d_pose, 56, cudaMemcpyDeviceToHost, st));
-  if (stats) MSFL_CUDA_OK(cudaMemcpyAsync(stats, d_stats, sizeof(msfl_stats), cudaMemcpyDeviceToHost, st));
+  if ((rc = e->h_poses.reserve((size_t)B * 7 * 8 + flag_bytes))) return rc;
+  int *h_flags = (int *)(e->h_poses.as<char>() + (size_t)B * 7 * 8);
+  MSFL_CUDA_OK(cudaMemcpyAsync(h_flags, d_flags, flag_bytes, cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaMemcpyAsync(e->h_poses.p, d_poses, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, st));
+  if (stats) MSFL_CUDA_OK(cudaMemcpyAsync(e->h_stats.p, d_stats, (size_t)B * sizeof(msfl_stats), cudaMemcpyDeviceToHost, st));
   MSFL_CUDA_OK(cudaStreamSynchronize(st));
-  if (h_flag) {
-    set_error("msfl_scan2map_deskew: a point time lies outside the preintegration window [%g, %g]", dk->sum_dt[0], dk->sum_dt[n - 1]);
-    return MSFL_ERR_ARG;
-  }
-  memcpy(pose_tq, h_pose, 56);
+  for (int b = 0; b < B; ++b)
+    if (h_flags[b]) {
+      set_error("msfl_scan2map_deskew: a point time of scan %d lies outside its preintegration window [%g, %g]", b,
+                dk[b].sum_dt[0], dk[b].sum_dt[dk[b].n - 1]);
+      if (stats) memset(stats, 0, (size_t)B * sizeof *stats);
+      return MSFL_ERR_ARG;
+    }
+  memcpy(poses_tq, e->h_poses.p, (size_t)B * 7 * 8);
+  if (stats) memcpy(stats, e->h_stats.p, (size_t)B * sizeof(msfl_stats));
   return MSFL_OK;
+}
+
+int msfl_scan2map_deskew(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,
+                         const msfl_deskew *dk, double pose_tq[7], msfl_stats *stats) {
+  return msfl_scan2map_deskew_batch(e, 1, scan_corner, scan_surf, dk, pose_tq, stats);
 }
 
 int msfl_associate_map(msfl_engine *e, const msfl_cloud *scan_corner, const msfl_cloud *scan_surf,

@@ -126,7 +126,7 @@ struct msfl_engine {
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp, a_hist;
   bool fuse_fit = true;  // batch path: plane fit inside the search kernel (MSFL_FUSE_FIT=0: separate k_fit launch)
   msfl::DevBuf a_fb;  // plane queries handed to the Householder fallback kernel: [count | slots]
-  msfl::DevBuf k_table, k_dsk, k_pprime;  // deskew branch: preintegration table, per-query (dq, dp, dt), p'
+  msfl::DevBuf k_table, k_dsk, k_pprime, k_o4;  // deskew branch: preintegration tables, per-query (dq, dp, dt), p', offset o
   const uint32_t *a_perm = nullptr;  // cell-order permutation of the batch being associated
 
   // odometry scratch
@@ -163,13 +163,21 @@ int launch_associate_map(msfl_engine *e, int B, const float4 *d_qc, const int32_
                          const float4 *d_qs, const int32_t *d_s_off, uint32_t n_surf_total, const double *d_poses,
                          double *d_corr, int32_t *d_knn, bool compact = false);
 
-int launch_deskew_prepare(msfl_engine *e, const double *d_sum_dt, const double *d_dq, const double *d_dp, int n_tab,
-                          const double V[3], const double G[3], const float4 *d_q, uint32_t n, double *d_dsk,
-                          double *d_pprime, int *d_flag);
-int launch_associate_map_deskew(msfl_engine *e, const float4 *d_qc, const int32_t *d_c_off, uint32_t nc, const float4 *d_qs,
-                                const int32_t *d_s_off, uint32_t ns, const double *d_pose, const double *d_sum_dt,
-                                const double *d_dq, const double *d_dp, int n_tab, const double V[3], const double G[3],
-                                const double *d_dsk, double *d_corr, int32_t *d_knn);
+// Deskew branch (mapping_scan_matcher.cc with is_initialized == true), B >= 1 scans.  The preintegration tables of all
+// scans are concatenated on the device (sum_dt [N], delta_q [N][4], delta_p [N][3]); scan b's table is rows
+// [row0, row0 + n) and it has its own velocity / gravity.  prepare: per query (dq, dp, dt) -> dsk[8], p' -> pprime[4],
+// o = V dt - g dt^2 / 2 -> o4[4]; flags[b] |= 1 when a point time of scan b is outside its table.
+struct DeskewScan {
+  uint32_t row0;
+  int32_t n;
+  double V[3], G[3];
+};
+int launch_deskew_prepare(msfl_engine *e, int B, const DeskewScan *d_scans, const double *d_sum_dt, const double *d_dq,
+                          const double *d_dp, const float4 *d_q, const int32_t *d_c_off, const int32_t *d_s_off, uint32_t nc,
+                          uint32_t n, double *d_dsk, double *d_pprime, double *d_o4, int *d_flags);
+int launch_associate_map_deskew(msfl_engine *e, int B, const float4 *d_qc, const int32_t *d_c_off, uint32_t nc,
+                                const float4 *d_qs, const int32_t *d_s_off, uint32_t ns, const double *d_pose,
+                                const double *d_o4, const double *d_dsk, double *d_corr, int32_t *d_knn);
 
 // ---- lm_solve.cu
 // outer: outer-iteration index (stats slot); min_corr: 0 for mapping, params.min_correspondences for odometry

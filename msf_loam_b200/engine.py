@@ -201,6 +201,28 @@ class Engine:
                                                        C.byref(st) if st is not None else None))
         return rc, x, (st.as_dict() if st is not None else None)
 
+    def scan2map_deskew_batch(self, scan_corners, scan_surfs, tables, poses, want_stats=True):
+        """msfl_scan2map_deskew_batch: B scans of a replayed log through the IMU-initialised branch in one call.
+        tables[b] = (sum_dt, delta_q, delta_p, velocity, gravity) of scan b; poses (B, 7) = the poses after each scan's
+        IMU-only predict.  Returns (rc, poses (B, 7), list of stats dicts or None)."""
+        B = len(scan_corners)
+        vcs, vss = [_View(a) for a in scan_corners], [_View(a) for a in scan_surfs]
+        keep, dks = [], (Deskew * B)()
+        for b, (sum_dt, delta_q, delta_p, velocity, gravity) in enumerate(tables):
+            t = np.ascontiguousarray(sum_dt, dtype=np.float64)
+            q = np.ascontiguousarray(delta_q, dtype=np.float64).reshape(-1, 4)
+            p = np.ascontiguousarray(delta_p, dtype=np.float64).reshape(-1, 3)
+            keep.append((t, q, p))
+            dks[b] = Deskew(t.ctypes.data_as(C.POINTER(C.c_double)), q.ctypes.data_as(C.POINTER(C.c_double)),
+                            p.ctypes.data_as(C.POINTER(C.c_double)), t.shape[0], 0,
+                            (C.c_double * 3)(*velocity), (C.c_double * 3)(*gravity))
+        x = np.ascontiguousarray(poses, dtype=np.float64).reshape(B, 7).copy()
+        st = (Stats * B)() if want_stats else None
+        rc = self._check(self.lib.msfl_scan2map_deskew_batch(
+            self.h, C.c_int(B), (Cloud * B)(*[v.cloud for v in vcs]), (Cloud * B)(*[v.cloud for v in vss]), dks,
+            x.ctypes.data_as(C.POINTER(C.c_double)), st))
+        return rc, x, ([s.as_dict() for s in st] if st is not None else None)
+
     def prepare_batch(self, scan_corners, scan_surfs):
         """Builds the msfl_cloud tables once so a timed loop only pays the C call."""
         B = len(scan_corners)

@@ -106,3 +106,49 @@ def test_cuda_deskew_branch_matches_oracle(vlp16_case):
     with pytest.raises(MsflError):  # point times outside the preintegration window (CHECK, scan_undistortion.cc:26)
         e.scan2map_deskew(q["corner"], q["surf"], t[:5], dq[:5], dp[:5], VEL, GRAV, q["init"])
     e.close()
+
+
+@pytest.mark.gpu
+def test_cuda_deskew_batch_equals_single_calls(vlp16_case):
+    """msfl_scan2map_deskew_batch = B msfl_scan2map_deskew calls, bit for bit: every scan has its own preintegration
+    table (different lengths, rates and motions), velocity and gravity; a scan whose times leave its window fails the
+    whole call and no pose is written."""
+    from msf_loam_b200 import Engine, MsflError
+    c = vlp16_case
+    tabs = [make_preintegration() + (VEL, GRAV),
+            make_preintegration(rate_hz=200.0, span=0.11, omega=(-0.05, 0.02, -0.3), acc=(-0.3, 0.5, 0.0), v0=(0.0, 0.04, 0.01))
+            + ((-0.2, 0.25, 0.05), (0.0, 0.3, 9.78)),
+            make_preintegration(rate_hz=1000.0, span=0.12, omega=(0.0, 0.0, 0.0), acc=(0.0, 0.0, 0.0), v0=(0.0, 0.0, 0.0))
+            + ((0.0, 0.0, 0.0), (0.0, 0.0, 0.0)),
+            make_preintegration() + (VEL, GRAV)]
+    qs = [c["queries"][i % 3] for i in range(4)]
+    e = Engine()
+    try:
+        e.set_submap(c["map_corner"], c["map_surf"])
+        single = [e.scan2map_deskew(q["corner"], q["surf"], *t, q["init"]) for q, t in zip(qs, tabs)]
+        rc, poses, st = e.scan2map_deskew_batch([q["corner"] for q in qs], [q["surf"] for q in qs], tabs,
+                                                np.stack([q["init"] for q in qs]))
+        assert rc == 0
+        for b, (rc1, x1, st1) in enumerate(single):
+            assert rc1 == 0 and np.array_equal(poses[b], x1), b
+            assert st[b]["n_edge"] == st1["n_edge"] and st[b]["n_plane"] == st1["n_plane"]
+            assert [l["n_attempts"] for l in st[b]["lm"]] == [l["n_attempts"] for l in st1["lm"]]
+        # scans 0 and 3 are the same problem at different batch positions
+        assert np.array_equal(poses[0], poses[3])
+        # identity motion, zero velocity / gravity = the plain branch (scan 2)
+        x_plain = e.scan2map(qs[2]["corner"], qs[2]["surf"], qs[2]["init"])[1]
+        assert S.pose_error(poses[2], x_plain)[0] < 1e-9
+        # against the oracle
+        P = O.default_params()
+        for b in (1, 3):
+            _, x_ref, _, _, _ = O.scan2map_deskew(P, c["map_corner"], c["map_surf"], qs[b]["corner"], qs[b]["surf"], *tabs[b],
+                                                  qs[b]["init"])
+            dt_, dr_ = S.pose_error(poses[b], x_ref)
+            assert dt_ < 1e-7 and dr_ < 1e-7
+        bad = list(tabs)
+        bad[1] = (tabs[1][0][:5], tabs[1][1][:5], tabs[1][2][:5]) + tabs[1][3:]
+        init = np.stack([q["init"] for q in qs])
+        with pytest.raises(MsflError, match="scan 1"):
+            e.scan2map_deskew_batch([q["corner"] for q in qs], [q["surf"] for q in qs], bad, init)
+    finally:
+        e.close()
