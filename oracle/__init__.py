@@ -1,4 +1,5 @@
-"""CPU oracle (TEST INFRASTRUCTURE ONLY -- parity unpinned, see msfl_oracle.h).
+"""CPU oracle (TEST INFRASTRUCTURE ONLY -- pinned to the reference's own compiled code in oracle/_ref, third-party numerics
+restated; see msfl_oracle.h and ref_shim.cc).
 
 ctypes bindings over ``libmsfl_oracle.so`` (plain-C restatement of the reference hot path).
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``

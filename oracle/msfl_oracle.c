@@ -1,6 +1,7 @@
 /*
  * msfl_oracle.c -- CPU ORACLE (test infrastructure; see msfl_oracle.h header comment).
- * PARITY UNPINNED (no reference golden vectors exist; third-party arithmetic restated).
+ * Checked bit for bit against the reference's own compiled sources (oracle/_ref, ref_shim.cc); the third-party arithmetic
+ * underneath (FLANN, Eigen decompositions, the Ceres loop, PCL VoxelGrid) is restated, see msfl_oracle.h.
  *
  * Compile with -ffp-contract=off so that fp32 distance arithmetic matches a generic x86-64
  * build of FLANN/PCL (no FMA contraction).

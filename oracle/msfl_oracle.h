@@ -7,15 +7,17 @@
  * bench.py's cpu_baseline / --impl reference legs may load it.  The product (msf_loam_b200/)
  * never links, imports or calls anything in this directory.
  *
- * PARITY PINNED FOR THE FACTORS ONLY: rows a-8, the Deskew factors of f-3 and PoseLocalParameterization::Plus of a-9
- * are checked against the reference's OWN lidar_factor.cc / pose_local_parameterization.cc, compiled unmodified into
- * oracle/_ref/libmsfl_ref_factors.so (Makefile target `ref`; stand-in Eigen / Ceres interface headers in ref_stubs/):
- * residuals, Jacobians and Plus are bit-equal on 4000 + 4000 + 3000 random cases (tests/test_ref_factors.py).
- * PARITY UNPINNED FOR EVERYTHING ELSE: the matchers cannot be built in this image (PCL 1.10 / FLANN 1.9, Ceres <= 2.1,
- * Eigen 3.3, ROS are un-vendored third-party dependencies and absent; no network) and the
- * reference's own tests hold no golden vector for this path (only quaternion identities,
- * src/slam/imu_fusion/utility_test.cc:8-34).  The third-party arithmetic is therefore restated
- * from the libraries' published algorithms:
+ * PINNED TO THE REFERENCE'S OWN CODE: msf_loam_node.cc (scan registration), odometry_scan_matcher.cc,
+ * mapping_scan_matcher.cc, scan_matcher.cc, lidar_factor.cc, pose_local_parameterization.cc and scan_undistortion.cc are
+ * compiled UNMODIFIED into oracle/_ref/libmsfl_ref.so (Makefile target `ref`; ref_shim.cc / ref_extract_shim.cc) and this
+ * restatement is bit-equal to them: factors, Plus, TransformPoint, GetDeltaQP, the registered clouds and feature lists, the
+ * poses / correspondence counts / iteration traces of MatchScan2Map (both branches) and MatchScan2Scan
+ * (tests/test_ref_factors.py, test_ref_matchers.py, test_ref_extract.py, test_golden.py).
+ * RESTATED, NOT PINNED: the third-party numerics underneath, which those sources get from stand-in headers
+ * (oracle/ref_stubs/) because the libraries (PCL 1.10 / FLANN 1.9, Ceres <= 2.1,
+ * Eigen 3.3, ROS) are un-vendored and absent from the image (no network); the reference's own tests hold
+ * no golden vector for this path (only quaternion identities, src/slam/imu_fusion/utility_test.cc:8-34).
+ * That arithmetic is restated from the libraries' published algorithms:
  *   - pcl::KdTreeFLANN::nearestKSearch  -> exact k-NN, FLANN L2_Simple<float> distance
  *     (fp32, ((dx*dx)+dy*dy)+dz*dz, no FMA), ascending, ties broken on the lower index;
  *   - pcl::VoxelGrid<PointXYZI>::filter -> centroid voxel filter (fp32 sums, output ascending
@@ -29,7 +31,7 @@
  * same neighbours, order, fp32 distances and gate on the VLP-16 case), numpy / scipy (cKDTree, eigh,
  * lstsq), finite-difference Jacobians, an independent numpy LM, scipy's least_squares with Huber
  * loss at convergence, and known-transform recovery.  That pins the k-NN row against third-party
- * code; the other rows stay pinned only by these independent restatements.
+ * code; the Eigen decompositions, the Ceres loop and PCL's VoxelGrid rest on these independent restatements.
  */
 #ifndef MSFL_ORACLE_H
 #define MSFL_ORACLE_H

@@ -4,7 +4,8 @@ oracle/ref_harness/ builds `ref_dump` from the unmodified reference sources on a
 (not this image) and runs MappingScanMatcher::MatchScan2Map / OdometryScanMatcher::MatchScan2Scan on the arrays of
 tests/golden/vlp16_golden.npz.  When its output has been committed as tests/golden/ref_dump_vlp16.txt this test compares
 the oracle's poses and its Levenberg-Marquardt trace (cost, step quality, trust-region radius per iteration) with the
-reference's own; until then parity stays UNPINNED upstream and the test says so."""
+reference's own.  Until then the oracle is pinned to the reference's sources compiled against stand-in third-party headers
+(oracle/_ref, tests/test_ref_*.py); what only this dump can pin is the real Ceres loop / FLANN / Eigen arithmetic."""
 import os
 import re
 
@@ -53,7 +54,7 @@ REF_ODO 1 0.5 0.0 0.0 0.0 0.0 0.0 1.0
 
 def test_oracle_against_reference_dump():
     if not os.path.exists(DUMP):
-        pytest.skip("parity unpinned: no dump of the real reference (build oracle/ref_harness where PCL + Ceres exist, "
+        pytest.skip("third-party numerics unpinned: no dump of the reference built against the real PCL + Ceres (build oracle/ref_harness where PCL + Ceres exist, "
                     "run it on tests/golden/vlp16_golden.npz and commit tests/golden/ref_dump_vlp16.txt)")
     g = np.load(GOLDEN)
     d = parse_dump(open(DUMP).read())
