@@ -119,3 +119,17 @@ def extract_features(xyzi, ring, T_ext=None, min_range=0.3):
     out = {k: bufs[k][:cnt[k].value] for k in names}
     out["ring"] = full_ring[:cnt["full"].value]
     return out
+
+
+def scan2map_batch(map_corner, map_surf, scan_corner, corner_off, scan_surf, surf_off, poses, n_threads=1, fixed_attempts=0):
+    """B MatchScan2Map calls (LiDAR-only) on n_threads host threads; fixed_attempts > 0 = bench.py's fixed schedule.
+    Returns poses (B, 7)."""
+    mc, ms, sc, ss = (_f32(a, 4) for a in (map_corner, map_surf, scan_corner, scan_surf))
+    co = np.ascontiguousarray(corner_off, dtype=np.int32)
+    so = np.ascontiguousarray(surf_off, dtype=np.int32)
+    B = co.shape[0] - 1
+    x = np.ascontiguousarray(poses, dtype=np.float64).reshape(B, 7).copy()
+    ref_lib().msflref_scan2map_batch(_ptr(mc, C.c_float), C.c_int(mc.shape[0]), _ptr(ms, C.c_float), C.c_int(ms.shape[0]),
+                                     C.c_int(B), _ptr(sc, C.c_float), _ptr(co, C.c_int), _ptr(ss, C.c_float), _ptr(so, C.c_int),
+                                     _ptr(x, C.c_double), C.c_int(n_threads), C.c_int(fixed_attempts))
+    return x

@@ -22,7 +22,9 @@
 // the C ABI -- against these functions.
 #include <pcl/kdtree/kdtree_flann.h>
 
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 #include "msfl_oracle.h"
 #include "slam/imu_fusion/imu_factor.h"
@@ -100,8 +102,9 @@ IntegrationBase::IntegrationBase(const Eigen::Vector3d &acc0, const Eigen::Vecto
 bool IMUFactor::Evaluate(double const *const *, double *, double **) const { return false; }  // never evaluated: see Solve
 
 namespace msfl_ref {
+// per thread: the batch driver below runs independent scans on several host threads
 KnnLog &knn_log() {
-  static KnnLog log;
+  static thread_local KnnLog log;
   return log;
 }
 struct SolveRecord {
@@ -109,9 +112,13 @@ struct SolveRecord {
   msflo_lm_log log;
 };
 static std::vector<SolveRecord> &solve_log() {
-  static std::vector<SolveRecord> v;
+  static thread_local std::vector<SolveRecord> v;
   return v;
 }
+static bool g_keep_solve_log = true;  // off inside the timed batch driver
+// benchmark schedule: the reference asks Ceres for max_num_iterations = 6 with its termination tests on; bench.py's
+// workload is "2 x 5 attempts, fixed"  for both arms, which the stand-in solver can be told to follow
+static int g_fixed_attempts = 0;  // > 0: early exit off, this many attempts per solve
 }  // namespace msfl_ref
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -209,20 +216,24 @@ void Solve(const Solver::Options &options, Problem *problem, Solver::Summary *su
   if (!sizes_ok || !pose || pose->size != 7 || !pose->parameterization || pose->parameterization->LocalSize() != 6) {
     // e.g. the IMU-only predict (four blocks, two of them free): IMU side-car, out of scope -- parameters untouched
     summary->message = "stand-in ceres::Solve: problem shape not supported, parameters left unchanged";
-    msfl_ref::solve_log().push_back(rec);
+    if (msfl_ref::g_keep_solve_log) msfl_ref::solve_log().push_back(rec);
     return;
   }
   rec.supported = 1;
   msflo_params P;
   msflo_default_params(&P);  // Ceres' Solver::Options defaults (trust region, LM, Jacobi scaling, tolerances)
   P.max_num_iterations = options.max_num_iterations;
+  if (msfl_ref::g_fixed_attempts > 0) {
+    P.max_num_iterations = msfl_ref::g_fixed_attempts;
+    P.early_exit = 0;
+  }
   EvalCtx ctx{problem, pose->values, pose->parameterization};
   double x[7];
   std::memcpy(x, pose->values, sizeof x);
   msflo_lm_solve_cb(&P, eval_problem, &ctx, (int)problem->residual_blocks().size(), x, &rec.log);
   std::memcpy(pose->values, x, sizeof x);
   summary->message = "stand-in ceres::Solve: oracle trust-region loop over the reference's cost functions";
-  msfl_ref::solve_log().push_back(rec);
+  if (msfl_ref::g_keep_solve_log) msfl_ref::solve_log().push_back(rec);
 }
 }  // namespace ceres
 
@@ -303,6 +314,47 @@ int msflref_scan2map(const float *map_corner, int n_map_corner, const float *map
   const double sum_dt[2] = {-1e6, 1e6}, dq[8] = {0, 0, 0, 1, 0, 0, 0, 1}, dp[6] = {0, 0, 0, 0, 0, 0}, zero[3] = {0, 0, 0};
   return run_scan2map(map_corner, n_map_corner, map_surf, n_map_surf, scan_corner, n_scan_corner, scan_surf, n_scan_surf, false,
                       preintegration_from(sum_dt, dq, dp, 2), zero, zero, pose, nullptr);
+}
+
+// B independent MatchScan2Map calls (LiDAR-only branch) against one submap on n_threads host threads -- the CPU arm of
+// bench.py (--impl reference).  Every call is the reference's: it builds its two kd-trees from the map clouds like the
+// reference does every frame (mapping_scan_matcher.cc:66-72).  fixed_attempts > 0 = the benchmark schedule (see above).
+int msflref_scan2map_batch(const float *map_corner, int n_map_corner, const float *map_surf, int n_map_surf, int B,
+                           const float *scan_corner, const int *corner_off, const float *scan_surf, const int *surf_off,
+                           double *poses, int n_threads, int fixed_attempts) {
+  TimestampedPointCloud<PointType> cloud_map;
+  cloud_map.cloud_corner_less_sharp = cloud_from(map_corner, n_map_corner);
+  cloud_map.cloud_surf_less_flat = cloud_from(map_surf, n_map_surf);
+  const double sum_dt[2] = {-1e6, 1e6}, dq[8] = {0, 0, 0, 1, 0, 0, 0, 1}, dp[6] = {0, 0, 0, 0, 0, 0};
+  const std::shared_ptr<IntegrationBase> pre = preintegration_from(sum_dt, dq, dp, 2);
+  msfl_ref::g_fixed_attempts = fixed_attempts;
+  msfl_ref::g_keep_solve_log = false;
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (int b = next.fetch_add(1); b < B; b = next.fetch_add(1)) {
+      TimestampedPointCloud<PointType> scan_curr;
+      scan_curr.cloud_corner_less_sharp = cloud_from(scan_corner + 4 * (size_t)corner_off[b], corner_off[b + 1] - corner_off[b]);
+      scan_curr.cloud_surf_less_flat = cloud_from(scan_surf + 4 * (size_t)surf_off[b], surf_off[b + 1] - surf_off[b]);
+      double *pose = poses + 7 * (size_t)b;
+      RobotState prev;
+      prev.p = Eigen::Vector3d(pose[0], pose[1], pose[2]);
+      prev.q = Eigen::Quaterniond(pose[6], pose[3], pose[4], pose[5]);
+      prev.v = Eigen::Vector3d(0, 0, 0);
+      prev.imu_preintegration = pre;
+      Rigid3d T = rigid_from(pose);
+      Vector3d velocity(0, 0, 0);
+      MappingScanMatcher matcher;
+      matcher.MatchScan2Map(cloud_map, scan_curr, false, pre, Vector3d(0, 0, 0), prev, &T, &velocity);
+      rigid_to(T, pose);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+  work();
+  for (std::thread &t : pool) t.join();
+  msfl_ref::g_fixed_attempts = 0;
+  msfl_ref::g_keep_solve_log = true;
+  return B;
 }
 
 // the Deskew branch (is_initialized == true); pose = the pose after the IMU-only predict, V = bias_j.head<3>()
