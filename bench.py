@@ -496,6 +496,64 @@ def single_scan_latency(cx, workload="vlp16"):
     return out
 
 
+def deskew_batch(cx, workload="vlp16", B=512, steps=5):
+    """SURVEY.md 8f row 3 at batch scale: B scans of a replayed log through the IMU-initialised branch of MatchScan2Map
+    (Deskew factors, per-point GetDeltaQP) in ONE msfl_scan2map_deskew_batch call; every scan has its own preintegration
+    buffers (400 Hz over the scan period), velocity and gravity.  Host buffers -> host poses; pose check vs the oracle."""
+    import torch
+    from msf_loam_b200 import Engine, default_params
+    traj, scans = cx.raw[workload]
+    eng = Engine(default_params(**OVER), device=cx.local_rank)
+    mc, ms, queries, _ = build_case(lambda x, r: eng.extract_features(x, r, None), eng.voxel_grid, workload, traj, scans)
+    eng.set_submap(mc, ms)
+    D = len(queries)
+    rng = np.random.default_rng(3000 + cx.rank)
+    t = np.arange(0.0, 0.105 + 1e-9, 1.0 / 400.0)
+    tabs = []
+    for b in range(B):
+        omega, acc, v0 = rng.normal(scale=0.05, size=3), rng.normal(scale=0.3, size=3), rng.normal(scale=0.05, size=3)
+        dq = np.stack([S.rotvec_to_quat(omega * ti) for ti in t])
+        dp = np.stack([v0 * ti + 0.5 * acc * ti * ti for ti in t])
+        tabs.append((t, dq, dp, tuple(rng.normal(scale=0.2, size=3)), (0.0, 0.0, 9.81)))
+    corners, surfs = [queries[b % D][0] for b in range(B)], [queries[b % D][1] for b in range(B)]
+    inits = np.stack([S.perturb_pose(queries[b % D][2], rng) for b in range(B)])
+    batch = eng.prepare_deskew_batch(corners, surfs, tabs)
+    poses = inits.copy()
+    eng.scan2map_deskew_prepared(batch, poses)
+    x = inits.copy()
+    eng.scan2map_deskew_prepared(batch, x)
+    torch.cuda.synchronize(cx.dev)
+    eng.set_profiling(True)
+    eng.get_profile()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x[:] = inits
+        eng.scan2map_deskew_prepared(batch, x)
+    dt = time.perf_counter() - t0
+    gpu_ms, _ = eng.get_profile()
+    eng.set_profiling(False)
+    t1 = time.perf_counter()
+    for b in range(8):
+        eng.scan2map_deskew(corners[b], surfs[b], *tabs[b], inits[b], want_stats=False)
+    dt1 = (time.perf_counter() - t1) / 8
+    eng.close()
+    rec = {"value": round(B * steps / dt, 1), "unit": "scans/s", "ms_per_step": round(dt / steps * 1e3, 3), "scans_per_step": B,
+           "one_scan_per_call_us": round(dt1 * 1e6, 1), "preintegration_samples_per_scan": int(t.shape[0]),
+           "gpu_ms_per_step": {"association": round(gpu_ms[0] / steps, 3), "lm_solve": round(gpu_ms[1] / steps, 3)},
+           "api": "msfl_scan2map_deskew_batch (mapping_scan_matcher.cc with is_initialized == true, LiDAR part): host clouds "
+                  "(one array per cloud, pageable) + preintegration tables -> host poses, one synchronous call per step"}
+    if not cx.args.no_cpu and cx.rank == 0:
+        import oracle as O
+        P = O.default_params(**OVER)
+        errs = []
+        for b in range(min(4, B)):
+            _, x, _, _, _ = O.scan2map_deskew(P, mc, ms, corners[b], surfs[b], *tabs[b], inits[b])
+            errs.append(S.pose_error(poses[b], x))
+        rec["pose_err_vs_oracle"] = {"max_trans_m": float(max(e[0] for e in errs)), "max_rot_rad": float(max(e[1] for e in errs)),
+                                     "scans_checked": len(errs), "tolerance": "1e-4 m / 1e-4 rad"}
+    return rec
+
+
 def chain_raw_to_pose(cx, workload="vlp16", B=256, steps=5):
     """Whole chain through ONE C-ABI call per batch (msfl_register_and_match_batch): B raw scans in the reference's
     PointXYZIRT layout (32 B points, pageable host memory) -> scan registration -> VoxelGrid 0.2 / 0.4 -> scan-to-map,
@@ -625,6 +683,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             ch["value"] = round(float(t[0]), 1)
         workloads["chain_raw_to_pose_vlp16"] = ch
+        # the IMU-initialised (Deskew) branch at batch scale, rank-local like the chain
+        dk = deskew_batch(cx)
+        if world > 1:
+            t = torch.tensor([dk["value"]], dtype=torch.float64, device=cx.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dk["value"] = round(float(t[0]), 1)
+        workloads["deskew_branch_batch_vlp16"] = dk
     single = single_scan_latency(cx) if (rank == 0 and not args.only_device) else None
     if world > 1:
         dist.barrier()

@@ -201,10 +201,9 @@ class Engine:
                                                        C.byref(st) if st is not None else None))
         return rc, x, (st.as_dict() if st is not None else None)
 
-    def scan2map_deskew_batch(self, scan_corners, scan_surfs, tables, poses, want_stats=True):
-        """msfl_scan2map_deskew_batch: B scans of a replayed log through the IMU-initialised branch in one call.
-        tables[b] = (sum_dt, delta_q, delta_p, velocity, gravity) of scan b; poses (B, 7) = the poses after each scan's
-        IMU-only predict.  Returns (rc, poses (B, 7), list of stats dicts or None)."""
+    def prepare_deskew_batch(self, scan_corners, scan_surfs, tables):
+        """Builds the msfl_cloud / msfl_deskew tables of a Deskew-branch batch once (tables[b] = (sum_dt, delta_q,
+        delta_p, velocity, gravity) of scan b), so a timed loop only pays the C call."""
         B = len(scan_corners)
         vcs, vss = [_View(a) for a in scan_corners], [_View(a) for a in scan_surfs]
         keep, dks = [], (Deskew * B)()
@@ -216,11 +215,24 @@ class Engine:
             dks[b] = Deskew(t.ctypes.data_as(C.POINTER(C.c_double)), q.ctypes.data_as(C.POINTER(C.c_double)),
                             p.ctypes.data_as(C.POINTER(C.c_double)), t.shape[0], 0,
                             (C.c_double * 3)(*velocity), (C.c_double * 3)(*gravity))
-        x = np.ascontiguousarray(poses, dtype=np.float64).reshape(B, 7).copy()
-        st = (Stats * B)() if want_stats else None
-        rc = self._check(self.lib.msfl_scan2map_deskew_batch(
-            self.h, C.c_int(B), (Cloud * B)(*[v.cloud for v in vcs]), (Cloud * B)(*[v.cloud for v in vss]), dks,
-            x.ctypes.data_as(C.POINTER(C.c_double)), st))
+        return {"B": B, "views": (vcs, vss), "tables": keep, "carr": (Cloud * B)(*[v.cloud for v in vcs]),
+                "sarr": (Cloud * B)(*[v.cloud for v in vss]), "dks": dks}
+
+    def scan2map_deskew_prepared(self, batch, poses_inout: np.ndarray, stats=None):
+        """msfl_scan2map_deskew_batch on a prepared batch; poses_inout (B, 7) float64 is updated in place."""
+        assert poses_inout.dtype == np.float64 and poses_inout.flags.c_contiguous
+        return self._check(self.lib.msfl_scan2map_deskew_batch(
+            self.h, C.c_int(batch["B"]), batch["carr"], batch["sarr"], batch["dks"],
+            poses_inout.ctypes.data_as(C.POINTER(C.c_double)), stats))
+
+    def scan2map_deskew_batch(self, scan_corners, scan_surfs, tables, poses, want_stats=True):
+        """msfl_scan2map_deskew_batch: B scans of a replayed log through the IMU-initialised branch in one call.
+        tables[b] = (sum_dt, delta_q, delta_p, velocity, gravity) of scan b; poses (B, 7) = the poses after each scan's
+        IMU-only predict.  Returns (rc, poses (B, 7), list of stats dicts or None)."""
+        batch = self.prepare_deskew_batch(scan_corners, scan_surfs, tables)
+        x = np.ascontiguousarray(poses, dtype=np.float64).reshape(batch["B"], 7).copy()
+        st = (Stats * batch["B"])() if want_stats else None
+        rc = self.scan2map_deskew_prepared(batch, x, st)
         return rc, x, ([s.as_dict() for s in st] if st is not None else None)
 
     def prepare_batch(self, scan_corners, scan_surfs):
