@@ -82,6 +82,7 @@ def build_ref(force: bool = False):
     srcs += [os.path.join(REFERENCE_ROOT, "src/slam/imu_fusion", f) for f in
              ("pose_local_parameterization.cc", "scan_undistortion.cc")]
     srcs.append(os.path.join(REFERENCE_ROOT, "src/msf_loam_node.cc"))
+    srcs.append(os.path.join(REFERENCE_ROOT, "src/slam/map/hybrid_grid.cc"))
     if not all(os.path.exists(f) for f in srcs):
         return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
     cmd = ["make", "-C", _HERE, "REF=" + REFERENCE_ROOT, "ref"] + (["-B"] if force else [])

@@ -8,11 +8,11 @@
  * never links, imports or calls anything in this directory.
  *
  * PINNED TO THE REFERENCE'S OWN CODE: msf_loam_node.cc (scan registration), odometry_scan_matcher.cc,
- * mapping_scan_matcher.cc, scan_matcher.cc, lidar_factor.cc, pose_local_parameterization.cc and scan_undistortion.cc are
- * compiled UNMODIFIED into oracle/_ref/libmsfl_ref.so (Makefile target `ref`; ref_shim.cc / ref_extract_shim.cc) and this
+ * mapping_scan_matcher.cc, scan_matcher.cc, lidar_factor.cc, pose_local_parameterization.cc, scan_undistortion.cc and
+ * hybrid_grid.cc are compiled UNMODIFIED into oracle/_ref/libmsfl_ref.so (Makefile target `ref`; ref_*_shim.cc) and this
  * restatement is bit-equal to them: factors, Plus, TransformPoint, GetDeltaQP, the registered clouds and feature lists, the
- * poses / correspondence counts / iteration traces of MatchScan2Map (both branches) and MatchScan2Scan
- * (tests/test_ref_factors.py, test_ref_matchers.py, test_ref_extract.py, test_golden.py).
+ * poses / correspondence counts / iteration traces of MatchScan2Map (both branches) and MatchScan2Scan, the HybridGrid
+ * surround clouds (tests/test_ref_factors.py, test_ref_matchers.py, test_ref_extract.py, test_golden.py, test_stgm.py).
  * RESTATED, NOT PINNED: the third-party numerics underneath, which those sources get from stand-in headers
  * (oracle/ref_stubs/) because the libraries (PCL 1.10 / FLANN 1.9, Ceres <= 2.1,
  * Eigen 3.3, ROS) are un-vendored and absent from the image (no network); the reference's own tests hold

@@ -133,3 +133,31 @@ def scan2map_batch(map_corner, map_surf, scan_corner, corner_off, scan_surf, sur
                                      C.c_int(B), _ptr(sc, C.c_float), _ptr(co, C.c_int), _ptr(ss, C.c_float), _ptr(so, C.c_int),
                                      _ptr(x, C.c_double), C.c_int(n_threads), C.c_int(fixed_attempts))
     return x
+
+
+class Map:
+    """The reference's HybridGrid (slam/map/hybrid_grid.cc) with the caller's pcl::VoxelGrid of the given leaf size."""
+
+    def __init__(self, resolution=3.0, leaf=0.2):
+        L = ref_lib()
+        L.msflref_map_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.msflref_map_create(C.c_float(resolution), C.c_float(leaf)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref_lib().msflref_map_free(self.h)
+            self.h = None
+
+    def insert(self, scan_world_xyzi):
+        pts = _f32(scan_world_xyzi, 4)
+        ref_lib().msflref_map_insert(self.h, _ptr(pts, C.c_float), C.c_int(pts.shape[0]))
+
+    def surround(self, scan_xyzi, pose, cap=2_000_000):
+        """GetSurroundedCloud: (n, 4) float array, cells in the reference's (heap-address) order."""
+        pts = _f32(scan_xyzi, 4)
+        out = np.zeros((cap, 4), np.float32)
+        x = _pose(pose)
+        n = ref_lib().msflref_map_surround(self.h, _ptr(pts, C.c_float), C.c_int(pts.shape[0]), _ptr(x, C.c_double),
+                                           _ptr(out, C.c_float), C.c_int(cap))
+        assert n <= cap
+        return out[:n].copy()

@@ -26,7 +26,13 @@ struct FatalStream {
 #define CHECK_GT(a, b) CHECK((a) > (b))
 #define CHECK_LT(a, b) CHECK((a) < (b))
 #define CHECK_EQ(a, b) CHECK((a) == (b))
+#define CHECK_LE(a, b) CHECK((a) <= (b))
 #define LOG_IF(severity, condition) ::msfl_glog::NullStream()
+// debug checks: compiled, never evaluated (NDEBUG behaviour of glog)
+#define DCHECK(c) \
+  while (false) ::msfl_glog::NullStream()
+#define DCHECK_LT(a, b) DCHECK((a) < (b))
+#define DCHECK_GE(a, b) DCHECK((a) >= (b))
 // the gflags slice msf_loam_node.cc uses (glog pulls gflags in upstream)
 #include <string>
 #define DEFINE_bool(name, value, help) bool FLAGS_##name = value

@@ -93,6 +93,8 @@ template <typename D>
 struct ColwiseOp;
 template <typename M>
 struct ColPivQRStandin;
+template <typename S, int N>
+class Array;
 
 template <typename D>
 class MatrixBase {
@@ -194,6 +196,19 @@ class MatrixBase {
   auto col(int j) const { return this->template block<Rows, 1>(0, j); }
   Block<D, 1, Cols> row(int i) { return Block<D, 1, Cols>(derived(), i, 0); }
   auto row(int i) const { return this->template block<1, Cols>(i, 0); }
+  auto array() const {
+    static_assert(Cols == 1, "array(): column vectors only in this stand-in");
+    Array<Scalar, Rows> a;
+    for (int i = 0; i < Rows; ++i) a(i) = derived().coeff(i, 0);
+    return a;
+  }
+  template <typename O>
+  D &operator+=(const MatrixBase<O> &o) {
+    static_assert(Rows == O::Rows && Cols == O::Cols, "+=: size mismatch");
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) += o.derived().coeff(i, j);
+    return derived();
+  }
   RowwiseOp<D> rowwise() const { return RowwiseOp<D>{derived()}; }
   ColwiseOp<D> colwise() const { return ColwiseOp<D>{derived()}; }
   ColPivQRStandin<D> colPivHouseholderQr() const { return ColPivQRStandin<D>{derived()}; }
@@ -477,6 +492,98 @@ struct ColPivQRStandin {
     msflo_lstsq_5x3(A, bb, x);
     return Matrix<double, 3, 1>(x[0], x[1], x[2]);
   }
+};
+
+// ---- coefficient-wise arrays (slam/map/hybrid_grid.cc: cell indices) ----
+template <typename S, int N>
+class Array;
+template <int N>
+struct BoolArray {
+  bool v[N];
+  bool all() const {
+    for (int i = 0; i < N; ++i)
+      if (!v[i]) return false;
+    return true;
+  }
+  bool any() const {
+    for (int i = 0; i < N; ++i)
+      if (v[i]) return true;
+    return false;
+  }
+};
+template <typename S, int N>
+class Array {
+ public:
+  typedef S Scalar;
+  Array() {
+    for (int i = 0; i < N; ++i) d_[i] = 0;
+  }
+  Array(S x, S y, S z) : d_{x, y, z} { static_assert(N == 3, "3-array constructor"); }
+  template <typename D>
+  Array(const MatrixBase<D> &m) {  // Eigen converts between the matrix and array worlds on assignment / construction
+    static_assert(D::Rows * D::Cols == N, "Array(matrix): size mismatch");
+    for (int i = 0; i < N; ++i) d_[i] = m(i);
+  }
+  S x() const { return d_[0]; }
+  S y() const { return d_[1]; }
+  S z() const { return d_[2]; }
+  S operator()(int i) const { return d_[i]; }
+  S &operator()(int i) { return d_[i]; }
+  Matrix<S, N, 1> matrix() const {
+    Matrix<S, N, 1> m;
+    for (int i = 0; i < N; ++i) m.coeffRef(i, 0) = d_[i];
+    return m;
+  }
+  operator Matrix<S, N, 1>() const { return matrix(); }
+  template <typename T>
+  Array<T, N> cast() const {
+    Array<T, N> r;
+    for (int i = 0; i < N; ++i) r(i) = (T)d_[i];
+    return r;
+  }
+
+ private:
+  S d_[N];
+};
+#define MSFL_STANDIN_ARRAY_OP(OP)                                                  \
+  template <typename S, int N>                                                     \
+  Array<S, N> operator OP(const Array<S, N> &a, const Array<S, N> &b) {            \
+    Array<S, N> r;                                                                 \
+    for (int i = 0; i < N; ++i) r(i) = a(i) OP b(i);                               \
+    return r;                                                                      \
+  }                                                                                \
+  template <typename S, int N, typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type> \
+  Array<S, N> operator OP(const Array<S, N> &a, T s) {                             \
+    Array<S, N> r;                                                                 \
+    for (int i = 0; i < N; ++i) r(i) = a(i) OP(S) s;                               \
+    return r;                                                                      \
+  }
+MSFL_STANDIN_ARRAY_OP(+)
+MSFL_STANDIN_ARRAY_OP(-)
+MSFL_STANDIN_ARRAY_OP(*)
+MSFL_STANDIN_ARRAY_OP(/)
+#undef MSFL_STANDIN_ARRAY_OP
+#define MSFL_STANDIN_ARRAY_CMP(OP)                                                 \
+  template <typename S, int N, typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type> \
+  BoolArray<N> operator OP(const Array<S, N> &a, T s) {                            \
+    BoolArray<N> r;                                                                \
+    for (int i = 0; i < N; ++i) r.v[i] = a(i) OP(S) s;                             \
+    return r;                                                                      \
+  }
+MSFL_STANDIN_ARRAY_CMP(>=)
+MSFL_STANDIN_ARRAY_CMP(<)
+#undef MSFL_STANDIN_ARRAY_CMP
+typedef Array<int, 3> Array3i;
+typedef Array<float, 3> Array3f;
+// read-only array view of three floats (pcl point getArray3fMap()); converts to a vector where one is expected
+template <>
+class Map<const Array<float, 3>> {
+ public:
+  explicit Map(const float *p) : p_(p) {}
+  operator Matrix<float, 3, 1>() const { return Matrix<float, 3, 1>(p_[0], p_[1], p_[2]); }
+
+ private:
+  const float *p_;
 };
 
 // ---- quaternions: coefficients stored x, y, z, w (Eigen's layout; Map<Quaterniond>(x + 3) relies on it) ----

@@ -8,15 +8,16 @@
 #include <vector>
 
 #include "../common/copy_point.h"
+#include "filter.h"
 extern "C" int msflo_voxel_grid(const float *xyzi, int n, float leaf, float *out_xyzi);
 namespace pcl {
 typedef std::shared_ptr<std::vector<int>> IndicesPtr;
 template <typename PointT>
-class VoxelGrid {
+class VoxelGrid : public Filter<PointT> {
  public:
-  void setInputCloud(const std::shared_ptr<const PointCloud<PointT>> &cloud) { input_ = cloud; }
+  void setInputCloud(const std::shared_ptr<const PointCloud<PointT>> &cloud) override { input_ = cloud; }
   void setLeafSize(float lx, float, float) { leaf_ = lx; }
-  void filter(PointCloud<PointT> &out) {
+  void filter(PointCloud<PointT> &out) override {  // safe in place: the input is read completely first
     const int n = (int)input_->points.size();
     indices_.reset(new std::vector<int>(n));
     for (int i = 0; i < n; ++i) (*indices_)[i] = i;

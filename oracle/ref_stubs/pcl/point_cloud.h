@@ -32,6 +32,7 @@ class PointCloud {
   size_t size() const { return points.size(); }
   bool empty() const { return points.empty(); }
   void clear() { points.clear(); }
+  void reserve(size_t n) { points.reserve(n); }
   void push_back(const PointT &p) {
     points.push_back(p);
     width = (std::uint32_t)points.size();

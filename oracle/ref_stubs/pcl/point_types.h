@@ -14,7 +14,8 @@
     };                                                                                               \
   };                                                                                                 \
   inline Eigen::Map<Eigen::Vector3f> getVector3fMap() { return Eigen::Map<Eigen::Vector3f>(data); } \
-  inline Eigen::Map<const Eigen::Vector3f> getVector3fMap() const { return Eigen::Map<const Eigen::Vector3f>(data); }
+  inline Eigen::Map<const Eigen::Vector3f> getVector3fMap() const { return Eigen::Map<const Eigen::Vector3f>(data); } \
+  inline Eigen::Map<const Eigen::Array3f> getArray3fMap() const { return Eigen::Map<const Eigen::Array3f>(data); }
 #define PCL_ADD_INTENSITY float intensity
 #define POINT_CLOUD_REGISTER_POINT_STRUCT(name, fields)
 

@@ -128,6 +128,37 @@ def test_oracle_deskew_branch_equals_the_reference_matcher(vlp16_case):
             _same_trace(s["lm"], lg)
 
 
+def test_oracle_scan2map_equals_the_reference_matcher_hdl64_and_degenerate_inputs(vlp16_case):
+    """The 64-ring case (12.6 k queries, 43 k-point submap) and the inputs the reference handles without a solve: a scan
+    with no corner features, and an initial guess so far off that no query passes the d5^2 < 1 gate (no residual blocks:
+    the pose comes back untouched)."""
+    from conftest import make_map_case
+    P = O.default_params()
+    c = make_map_case("hdl64", "room80", 5, 200)
+    q = c["queries"][0]
+    R.reset_logs()
+    ok, x_ref = R.scan2map(c["map_corner"], c["map_surf"], q["corner"], q["surf"], q["init"])
+    solves = R.solves()
+    x, logs, counts = O.scan2map(P, c["map_corner"], c["map_surf"], q["corner"], q["surf"], q["init"])
+    assert ok and np.array_equal(x, x_ref)
+    assert [(s["n_edge"], s["n_plane"]) for s in solves] == [tuple(r) for r in counts] and counts[0, 1] > 5000
+    for s, lg in zip(solves, logs):
+        _same_trace(s["lm"], lg)
+    c, q = vlp16_case, vlp16_case["queries"][0]
+    none = np.zeros((0, 4), np.float32)
+    R.reset_logs()
+    ok, x_ref = R.scan2map(c["map_corner"], c["map_surf"], none, q["surf"], q["init"])
+    x, _, counts = O.scan2map(P, c["map_corner"], c["map_surf"], none, q["surf"], q["init"])
+    assert ok and np.array_equal(x, x_ref) and [s["n_edge"] for s in R.solves()] == [0, 0] and list(counts[:, 0]) == [0, 0]
+    far = q["init"].copy()
+    far[:3] += 500.0
+    R.reset_logs()
+    ok, x_ref = R.scan2map(c["map_corner"], c["map_surf"], q["corner"], q["surf"], far)
+    x, _, counts = O.scan2map(P, c["map_corner"], c["map_surf"], q["corner"], q["surf"], far)
+    assert ok and np.array_equal(x_ref, far) and np.array_equal(x, far) and not counts.any()
+    assert all(s["n_edge"] + s["n_plane"] == 0 for s in R.solves())
+
+
 # ------------------------------------------------------------------------------------------------ GPU vs the reference
 @pytest.mark.gpu
 def test_cuda_scan2map_equals_the_reference_matcher(vlp16_case):
@@ -153,6 +184,35 @@ def test_cuda_scan2map_equals_the_reference_matcher(vlp16_case):
             gate = d2.reshape(-1, 5)[:nq, 4] < 1.0
             assert np.array_equal(gate, knn[:, 0] >= 0)
             assert np.array_equal(idx.reshape(-1, 5)[:nq][gate], knn[gate])
+    finally:
+        e.close()
+
+
+@pytest.mark.gpu
+def test_cuda_scan2map_equals_the_reference_matcher_hdl64_and_degenerate_inputs(vlp16_case):
+    from conftest import make_map_case
+    from msf_loam_b200 import Engine
+    c = make_map_case("hdl64", "room80", 5, 200)
+    e = Engine()
+    try:
+        e.set_submap(c["map_corner"], c["map_surf"])
+        for q in c["queries"][:2]:
+            ok, x_ref = R.scan2map(c["map_corner"], c["map_surf"], q["corner"], q["surf"], q["init"])
+            rc, x, st = e.scan2map(q["corner"], q["surf"], q["init"])
+            dt, dr = S.pose_error(x, x_ref)
+            assert ok and rc == 0 and dt < 1e-8 and dr < 1e-8, (dt, dr)
+        c, q = vlp16_case, vlp16_case["queries"][0]
+        e.set_submap(c["map_corner"], c["map_surf"])
+        none = np.zeros((0, 4), np.float32)
+        ok, x_ref = R.scan2map(c["map_corner"], c["map_surf"], none, q["surf"], q["init"])
+        rc, x, st = e.scan2map(none, q["surf"], q["init"])
+        dt, dr = S.pose_error(x, x_ref)
+        assert rc == 0 and dt < 1e-8 and dr < 1e-8 and st["n_edge"] == [0, 0]
+        far = q["init"].copy()
+        far[:3] += 500.0
+        ok, x_ref = R.scan2map(c["map_corner"], c["map_surf"], q["corner"], q["surf"], far)
+        rc, x, st = e.scan2map(q["corner"], q["surf"], far)
+        assert rc == 0 and np.array_equal(x, x_ref) and np.array_equal(x, far)
     finally:
         e.close()
 

@@ -1,4 +1,7 @@
-"""SURVEY.md 8f row 1 -- GPU-resident STGM submap producer (HybridGrid) against the CPU oracle."""
+"""SURVEY.md 8f row 1 -- GPU-resident STGM submap producer (HybridGrid) against the CPU oracle, and both against the
+reference's own slam/map/hybrid_grid.cc compiled unmodified (oracle/_ref, oracle/ref_map_shim.cc).  The reference
+concatenates the cells of a surround query in hash order of their shared pointers (heap addresses), so its clouds are
+compared as multisets of points."""
 import numpy as np
 import pytest
 
@@ -42,6 +45,62 @@ def test_oracle_stgm_properties():
     assert 0.9 * len(allpts) <= len(sur) <= len(allpts)
     far = np.array([500.0, 0, 0, 0, 0, 0, 1.0])
     assert len(m.surround(scans[2][1], far)) == 0
+
+
+def _rows_sorted(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def _ref_available():
+    from oracle import ref as R
+    return R.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="no reference checkout and no prebuilt oracle/_ref library")
+def test_oracle_stgm_equals_the_reference_hybrid_grid():
+    """Insert four scans (two feature classes, their leaf sizes), query after every insert: the oracle's surround cloud
+    is the reference's, point for point (as a multiset); a far-away query returns nothing; points beyond 60 m are
+    ignored by the query (hybrid_grid.cc:474)."""
+    from oracle import ref as R
+    scans = _scans(4)
+    for cls, leaf in ((0, 0.2), (1, 0.4)):
+        r, o = R.Map(3.0, leaf), O.Stgm(3.0, leaf)
+        for k, sc in enumerate(scans):
+            w = S.transform_cloud(sc[2], sc[cls])
+            r.insert(w)
+            o.insert(w)
+            nxt = scans[(k + 1) % len(scans)]
+            guess = S.perturb_pose(nxt[2], np.random.default_rng(k))
+            a, b = r.surround(nxt[cls], guess), o.surround(nxt[cls], guess)
+            assert a.shape == b.shape and a.shape[0] > 100
+            assert np.array_equal(_rows_sorted(a), _rows_sorted(b))
+        far = np.array([500.0, 0, 0, 0, 0, 0, 1.0])
+        assert len(r.surround(scans[0][cls], far)) == 0
+        beyond = scans[0][cls].copy()
+        beyond[:, 0] += 100.0  # every point farther than kDist = 60 m from the sensor
+        assert len(r.surround(beyond, scans[0][2])) == 0 and len(o.surround(beyond, scans[0][2])) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _ref_available(), reason="no reference checkout and no prebuilt oracle/_ref library")
+def test_cuda_stgm_equals_the_reference_hybrid_grid():
+    from msf_loam_b200 import Engine, HybridGrid
+    from oracle import ref as R
+    scans = _scans(4)
+    e = Engine()
+    try:
+        for cls, leaf in ((0, 0.2), (1, 0.4)):
+            r, g = R.Map(3.0, leaf), HybridGrid(e, 3.0, leaf)
+            for k, sc in enumerate(scans):
+                r.insert(S.transform_cloud(sc[2], sc[cls]))
+                g.InsertScan(sc[cls], sc[2])
+                nxt = scans[(k + 1) % len(scans)]
+                guess = S.perturb_pose(nxt[2], np.random.default_rng(k))
+                assert np.array_equal(_rows_sorted(r.surround(nxt[cls], guess)), _rows_sorted(g.GetSurroundedCloud(nxt[cls], guess)))
+            g.close()
+    finally:
+        e.close()
 
 
 @pytest.mark.gpu
