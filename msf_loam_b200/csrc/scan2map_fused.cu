@@ -106,9 +106,19 @@ k_scan2map_fused(GridView gc, GridView gs, KParams kp, const float4 *__restrict_
 
   double acc[kAcc];
   int cnt_e, cnt_p;
+#ifdef MSFL_FUSED_TIMING  // development (-DMSFL_FUSED_TIMING): cycles per phase of this thread, printed by CTA 0 at exit
+  long long t_assoc = 0, t_sweep = 0, t_red = 0, t_comb = 0, t_step = 0;
+  int n_attempts = 0;
+#define MSFL_FTICK(v) const long long v = clock64()
+#define MSFL_FADD(acc_, a, b) acc_ += (b) - (a)
+#else
+#define MSFL_FTICK(v)
+#define MSFL_FADD(acc_, a, b)
+#endif
   for (int outer = 0; outer < num_outer; ++outer) {  // mapping_scan_matcher.cc:75
     msfl_lm_log *log = st ? &st->lm[outer] : nullptr;
     // ---- data association at the current pose (:109-246) into shared memory
+    MSFL_FTICK(f0);
     {
       double pose[7];
 #pragma unroll
@@ -152,8 +162,12 @@ k_scan2map_fused(GridView gc, GridView gs, KParams kp, const float4 *__restrict_
       }
     }
     __syncthreads();
+    MSFL_FTICK(f1);
+    MSFL_FADD(t_assoc, f0, f1);
     // ---- ceres::Solve (:250-272): evaluation at x, then the trust-region loop
     sweep_smem(acc, pe, ce, n_e, pp, cp, n_p, sh.x, hub, cnt_e, cnt_p);
+    MSFL_FTICK(f2);
+    MSFL_FADD(t_sweep, f1, f2);
     for (int o = 16; o > 0; o >>= 1) {
       cnt_e += __shfl_down_sync(0xffffffffu, cnt_e, o);
       cnt_p += __shfl_down_sync(0xffffffffu, cnt_p, o);
@@ -167,7 +181,11 @@ k_scan2map_fused(GridView gc, GridView gs, KParams kp, const float4 *__restrict_
       part_cnt[1] = np;
     }
     __syncthreads();
+    MSFL_FTICK(f3);
+    MSFL_FADD(t_red, f2, f3);
     combine(true);
+    MSFL_FTICK(f4);
+    MSFL_FADD(t_comb, f3, f4);
     if (tid == 0) {  // every CTA runs the same control code on the same sums
       const int ne = sh.n_edge, np = sh.n_plane;
       if (st) {
@@ -199,15 +217,24 @@ k_scan2map_fused(GridView gc, GridView gs, KParams kp, const float4 *__restrict_
       }
     }
     __syncthreads();
+    MSFL_FTICK(f5);
+    MSFL_FADD(t_step, f4, f5);
     while (!sh.done) {
+      MSFL_FTICK(g0);
       sweep_smem(acc, pe, ce, n_e, pp, cp, n_p, sh.xc, hub, cnt_e, cnt_p);
+      MSFL_FTICK(g1);
       block_reduce(acc, sh);
+      MSFL_FTICK(g2);
       combine(false);
+      MSFL_FTICK(g3);
       if (tid == 0) {
         lm_finish_step(sh, kp, log);
         if (!sh.done) lm_prepare_step(sh, kp, log);
       }
       __syncthreads();
+#ifdef MSFL_FUSED_TIMING
+      t_sweep += g1 - g0; t_red += g2 - g1; t_comb += g3 - g2; t_step += clock64() - g3; ++n_attempts;
+#endif
     }
     if (tid == 0 && log && sh.n_edge + sh.n_plane > 0) {
       log->termination = sh.termination;
@@ -215,6 +242,13 @@ k_scan2map_fused(GridView gc, GridView gs, KParams kp, const float4 *__restrict_
     }
     __syncthreads();  // sh.x is final for this outer iteration in every CTA
   }
+#ifdef MSFL_FUSED_TIMING
+  if (rank == 0 && (tid == 0 || tid == 33))
+    printf("fused timing rank 0 tid %d: assoc %lld sweep %lld reduce %lld combine %lld step %lld cycles, %d attempts (n_e %u n_p %u)\n",
+           (int)tid, t_assoc, t_sweep, t_red, t_comb, t_step, n_attempts, n_e, n_p);
+#endif
+#undef MSFL_FTICK
+#undef MSFL_FADD
   if (rank == 0) {
     if (tid < 7) pose_io[tid] = sh.x[tid];
     if (tid == 7 && status) status[0] = MSFL_OK;
