@@ -1,5 +1,6 @@
-"""ctypes bindings over oracle/_ref/libmsfl_ref.so -- the REFERENCE's own scan-matching sources compiled unmodified
-(oracle/ref_shim.cc says what is the reference's and what is stood in).  TEST INFRASTRUCTURE ONLY, like the rest of
+"""ctypes bindings over oracle/_ref/libmsfl_ref.so -- the REFERENCE's own hot-path sources (scan registration, both
+scan matchers, factors, parameterisation, GetDeltaQP, HybridGrid) compiled unmodified (oracle/ref_shim.cc,
+ref_extract_shim.cc and ref_map_shim.cc say what is the reference's and what is stood in).  TEST INFRASTRUCTURE ONLY, like the rest of
 oracle/: only tests/ may import it.  `available()` is False when there is neither a reference checkout to compile nor a
 prebuilt library (the GPU box gets the prebuilt file with the repo snapshot)."""
 from __future__ import annotations

@@ -1,6 +1,6 @@
 """The REFERENCE's own factor code as the checker (rows a-8 / a-9 Plus / f-3 factors of SURVEY.md section 8).
 
-oracle/_ref/libmsfl_ref_factors.so is lidar_factor.cc (:7-100) and pose_local_parameterization.cc (:6-27, through
+oracle/_ref/libmsfl_ref.so contains lidar_factor.cc (:7-100) and pose_local_parameterization.cc (:6-27, through
 Utility::deltaQ utility.h:8-31) compiled UNMODIFIED from the reference checkout (oracle/Makefile target `ref`; Eigen and
 Ceres are absent from the image, so the sources see the stand-in headers of oracle/ref_stubs/ -- msfl_eigen_standin.h
 says what that pins).  These tests check
@@ -84,7 +84,7 @@ def test_oracle_factors_equal_the_reference_factors():
             rr, Jr = ref_factor(kind, pose, p, c, n)
             scale = 1.0 + np.abs(Jr).max()
             worst = max(worst, np.abs(r - rr).max() / scale, np.abs(J - Jr).max() / scale)
-    assert worst <= 1e-14, worst  # same expression, different association of the products: a few ulp
+    assert worst <= 1e-14, worst  # measured: bit-equal
 
 
 def test_oracle_deskew_factors_equal_the_reference_factors():
