@@ -493,6 +493,32 @@ def single_scan_latency(cx, workload="vlp16"):
             e1.scan2map(c0, s0, init, want_stats=False)
         out[f"lm_cluster_{G}_us_per_scan_with_submap_build"] = round((time.perf_counter() - t0) / 20 * 1e6, 1)
         e1.close()
+    # the caller's whole frame (LaserMapping::MatchScan2Map + InsertScan2Map, laser_mapping.cc:258-340) as ONE call:
+    # VoxelGrid of the scan's feature clouds, GetSurroundedCloud of both GPU-resident maps, the gate, MatchScan2Map,
+    # InsertScan at the refined pose -- the un-down-sampled less-sharp / less-flat clouds in, the pose out
+    from msf_loam_b200 import HybridGrid, mapping_frame
+    e2 = Engine(default_params(lm_cluster=16), device=cx.local_rank)  # the reference's own schedule (Ceres termination tests on)
+    n_map = WORKLOADS[workload]["map_scans"]
+    frames = []
+    for k in range(min(len(scans), n_map + 12)):
+        f = e2.extract_features(scans[k][0], scans[k][1], None)
+        frames.append((f["full"][f["idx_less_sharp"]], f["full"][f["idx_less_flat"]], traj[k]))
+    gc, gs = HybridGrid(e2, 3.0, 0.2), HybridGrid(e2, 3.0, 0.4)
+    rng, ts, errs = np.random.default_rng(3), [], []
+    for k, (corner, surf, gt) in enumerate(frames):
+        guess = gt if k == 0 else S.perturb_pose(gt, rng)
+        t0 = time.perf_counter()
+        matched, pose, _ = mapping_frame(e2, gc, gs, corner, surf, guess, want_stats=False)
+        ts.append(time.perf_counter() - t0)
+        if matched:
+            errs.append(S.pose_error(pose, gt))
+    warm = ts[len(ts) // 2:]
+    out["mapping_frame_us"] = round(float(np.mean(warm)) * 1e6, 1)
+    out["mapping_frame"] = {"frames": len(frames), "timed": len(warm), "corner_points": int(frames[-1][0].shape[0]),
+                            "surf_points": int(frames[-1][1].shape[0]), "map_points": [gc.size()[0], gs.size()[0]],
+                            "max_err_vs_ground_truth_m": float(max(e[0] for e in errs)),
+                            "api": "msfl_mapping_frame: one call per frame, every intermediate on the device"}
+    gc.close(); gs.close(); e2.close()
     return out
 
 

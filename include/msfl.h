@@ -340,6 +340,16 @@ int msfl_map_size(const msfl_map *m, size_t *n_points, size_t *n_cells);
 int msfl_map_download(msfl_map *m, int which, float *out_xyzi, size_t capacity, size_t *n_out);
 /* cloud_map.cloud_corner_less_sharp / cloud_surf_less_flat := the two last surround results. */
 int msfl_set_submap_from_maps(msfl_engine *e, msfl_map *corner, msfl_map *surf);
+/* One frame of the caller, LaserMapping::MatchScan2Map + InsertScan2Map (laser_mapping.cc:258-340), in one call with every
+ * intermediate on the device: VoxelGrid of the scan's two feature clouds with the maps' leaf sizes (:264-270),
+ * GetSurroundedCloud of both maps at the incoming pose (:273-278), the "> 10 corner and > 50 surf map points" gate
+ * (:284-285), MappingScanMatcher::MatchScan2Map (LiDAR-only branch) against the two surround clouds (:304-311), then
+ * InsertScan of the un-down-sampled clouds at the refined pose (:330-338) -- which happens whether or not the gate passed.
+ * pose_tq in-out = pose_map_scan2world_; *matched = 1 when the gate passed (may be NULL); stats may be NULL.  The maps
+ * must belong to the engine.  Results are those of the separate calls (msfl_voxel_grid, msfl_map_surround,
+ * msfl_set_submap_from_maps, msfl_scan2map, msfl_map_insert). */
+int msfl_mapping_frame(msfl_engine *e, msfl_map *map_corner, msfl_map *map_surf, const msfl_cloud *corner_less_sharp,
+                       const msfl_cloud *surf_less_flat, double pose_tq[7], int32_t *matched, msfl_stats *stats);
 
 /* ---- wire format: view a sensor_msgs/PointCloud2 data buffer as an msfl_cloud
  *      (what pcl::fromROSMsg does at msf_loam_node.cc:166-167 with the field list of common.h:53-62).

@@ -5,9 +5,9 @@ as CUDA kernels behind the C ABI in ``include/msfl.h`` (``libmsfl.so``, built in
 ``msf_loam_b200.build``).  ``engine`` mirrors the reference's matcher interface on top of it;
 ``synth`` generates seeded synthetic LiDAR scenes.  There is no CPU fallback.
 """
-from .engine import (Engine, HybridGrid, set_submap_from_maps, MappingScanMatcher, OdometryScanMatcher, ScanRegistration,
+from .engine import (Engine, HybridGrid, set_submap_from_maps, mapping_frame, MappingScanMatcher, OdometryScanMatcher, ScanRegistration,
                      TimestampedPointCloud, default_params, to_pcl)
 from ._lib import MsflError, Params, load_library
 
-__all__ = ["Engine", "HybridGrid", "set_submap_from_maps", "MappingScanMatcher", "OdometryScanMatcher", "ScanRegistration",
+__all__ = ["Engine", "HybridGrid", "set_submap_from_maps", "mapping_frame", "MappingScanMatcher", "OdometryScanMatcher", "ScanRegistration",
            "TimestampedPointCloud", "default_params", "to_pcl", "MsflError", "Params", "load_library"]

@@ -28,7 +28,7 @@ EXPORTS = [
     "msfl_set_submap_device", "msfl_get_submap_device", "msfl_scan2map", "msfl_scan2map_batch",
     "msfl_scan2map_batch_device", "msfl_scan2map_batch_submit", "msfl_scan2map_batch_wait", "msfl_scan2map_deskew", "msfl_scan2map_deskew_batch", "msfl_associate_map", "msfl_scan2scan", "msfl_scan2scan_batch", "msfl_replay_batch", "msfl_associate_scan",
     "msfl_extract_features", "msfl_extract_features_batch", "msfl_register_and_match_batch", "msfl_voxel_grid", "msfl_accumulate", "msfl_map_create", "msfl_map_destroy",
-    "msfl_cloud_from_pointcloud2", "msfl_map_insert", "msfl_map_surround", "msfl_map_size", "msfl_map_download", "msfl_set_submap_from_maps",
+    "msfl_cloud_from_pointcloud2", "msfl_map_insert", "msfl_map_surround", "msfl_map_size", "msfl_map_download", "msfl_set_submap_from_maps", "msfl_mapping_frame",
 ]
 
 

@@ -399,7 +399,7 @@ void msfl_destroy(msfl_engine *e) {
                    &e->c_in, &e->c_off, &e->c_q, &e->ob_in, &e->ob_bounds, &e->ob_hdr, &e->ob_sorted, &e->ob_ring_sorted, &e->ob_cells,
                    &e->ob_keys, &e->ob_rank, &e->ob_tmp,
                    &e->a_xq, &e->a_keys, &e->a_keys_alt, &e->a_vals, &e->a_vals_alt, &e->a_tmp, &e->a_hist,
-                   &e->k_table, &e->k_dsk, &e->k_pprime, &e->a_fb};
+                   &e->k_table, &e->k_dsk, &e->k_pprime, &e->k_o4, &e->a_fb, &e->fr_qc, &e->fr_qs, &e->fr_misc};
   for (DevBuf *b : dbs) b->release();
   for (auto &sl : e->slots) {
     sl.d_in.release(); sl.d_in3.release(); sl.d_stats.release(); sl.h_stage.release(); sl.h_out.release(); sl.h_stats.release();

@@ -126,6 +126,7 @@ struct msfl_engine {
   msfl::DevBuf a_xq, a_keys, a_keys_alt, a_vals, a_vals_alt, a_tmp, a_hist;
   bool fuse_fit = true;  // batch path: plane fit inside the search kernel (MSFL_FUSE_FIT=0: separate k_fit launch)
   msfl::DevBuf a_fb;  // plane queries handed to the Householder fallback kernel: [count | slots]
+  msfl::DevBuf fr_qc, fr_qs, fr_misc;  // msfl_mapping_frame: VoxelGrid-ed scan clouds, offsets + pose + stats
   msfl::DevBuf k_table, k_dsk, k_pprime, k_o4;  // deskew branch: preintegration tables, per-query (dq, dp, dt), p', offset o
   const uint32_t *a_perm = nullptr;  // cell-order permutation of the batch being associated
 

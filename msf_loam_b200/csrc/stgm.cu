@@ -426,6 +426,39 @@ static int map_insert_device(msfl_map *m, uint32_t n, int do_transform, const do
   return MSFL_OK;
 }
 
+// HybridGrid::GetSurroundedCloud with the scan already in m->in (n packed points)
+static int map_surround_device(msfl_map *m, uint32_t n, const double pose_tq[7], size_t *n_out) {
+  msfl_engine *e = m->e;
+  cudaStream_t st = e->stream;
+  m->sur_n = 0;
+  if (n_out) *n_out = 0;
+  if (m->n_cells == 0 || n == 0) return MSFL_OK;
+  int rc;
+  const int nc = (int)m->n_cells, tb = 256;
+  if ((rc = m->flag.reserve((size_t)nc * 4))) return rc;
+  if ((rc = m->selcnt.reserve((size_t)(nc + 1) * 4))) return rc;
+  if ((rc = m->seloff.reserve((size_t)(nc + 1) * 4))) return rc;
+  MSFL_CUDA_OK(cudaMemsetAsync(m->flag.p, 0, (size_t)nc * 4, st));
+  MSFL_CUDA_OK(cudaMemsetAsync(m->selcnt.p, 0, (size_t)(nc + 1) * 4, st));
+  Pose7d T;
+  for (int i = 0; i < 7; ++i) T.v[i] = pose_tq[i];
+  k_stgm_mark<<<(n + tb - 1) / tb, tb, 0, st>>>(m->in.as<float4>(), n, T, m->resolution, m->cell_keys.as<unsigned long long>(), nc,
+                                               m->flag.as<uint32_t>());
+  k_stgm_selcnt<<<(nc + tb - 1) / tb, tb, 0, st>>>(m->flag.as<uint32_t>(), m->cell_off.as<uint32_t>(), nc, m->selcnt.as<uint32_t>());
+  if ((rc = scan_u32(m, m->selcnt.as<uint32_t>(), m->seloff.as<uint32_t>(), nc + 1))) return rc;
+  uint32_t total = 0;
+  MSFL_CUDA_OK(cudaMemcpyAsync(&total, m->seloff.as<uint32_t>() + nc, 4, cudaMemcpyDeviceToHost, st));
+  MSFL_CUDA_OK(cudaStreamSynchronize(st));
+  if ((rc = m->sur.reserve((size_t)total * 16 + 16))) return rc;
+  k_stgm_gather<<<(nc * 32 + tb - 1) / tb, tb, 0, st>>>(m->flag.as<uint32_t>(), m->cell_off.as<uint32_t>(), m->seloff.as<uint32_t>(),
+                                                       nc, m->pts.as<float4>(), m->sur.as<float4>());
+  e->launches += 3 + 2;
+  MSFL_CUDA_OK(cudaGetLastError());
+  m->sur_n = total;
+  if (n_out) *n_out = total;
+  return MSFL_OK;
+}
+
 extern "C" {
 
 int msfl_map_create(msfl_engine *e, float resolution, float leaf, msfl_map **out) {
@@ -467,37 +500,13 @@ int msfl_map_surround(msfl_map *m, const msfl_cloud *scan, const double pose_tq[
   if (!m || !scan || !pose_tq) { set_error("msfl_map_surround: bad argument"); return MSFL_ERR_ARG; }
   msfl_engine *e = m->e;
   MSFL_CUDA_OK(cudaSetDevice(e->device));
-  cudaStream_t st = e->stream;
   m->sur_n = 0;
   if (n_out) *n_out = 0;
   if (m->n_cells == 0 || scan->n == 0) return MSFL_OK;
   int rc;
   if ((rc = check_cloud(scan, false, "msfl_map_surround"))) return rc;
   if ((rc = upload_packed(e, scan, m->in))) return rc;
-  const int nc = (int)m->n_cells, tb = 256;
-  const uint32_t n = (uint32_t)scan->n;
-  if ((rc = m->flag.reserve((size_t)nc * 4))) return rc;
-  if ((rc = m->selcnt.reserve((size_t)(nc + 1) * 4))) return rc;
-  if ((rc = m->seloff.reserve((size_t)(nc + 1) * 4))) return rc;
-  MSFL_CUDA_OK(cudaMemsetAsync(m->flag.p, 0, (size_t)nc * 4, st));
-  MSFL_CUDA_OK(cudaMemsetAsync(m->selcnt.p, 0, (size_t)(nc + 1) * 4, st));
-  Pose7d T;
-  for (int i = 0; i < 7; ++i) T.v[i] = pose_tq[i];
-  k_stgm_mark<<<(n + tb - 1) / tb, tb, 0, st>>>(m->in.as<float4>(), n, T, m->resolution, m->cell_keys.as<unsigned long long>(), nc,
-                                               m->flag.as<uint32_t>());
-  k_stgm_selcnt<<<(nc + tb - 1) / tb, tb, 0, st>>>(m->flag.as<uint32_t>(), m->cell_off.as<uint32_t>(), nc, m->selcnt.as<uint32_t>());
-  if ((rc = scan_u32(m, m->selcnt.as<uint32_t>(), m->seloff.as<uint32_t>(), nc + 1))) return rc;
-  uint32_t total = 0;
-  MSFL_CUDA_OK(cudaMemcpyAsync(&total, m->seloff.as<uint32_t>() + nc, 4, cudaMemcpyDeviceToHost, st));
-  MSFL_CUDA_OK(cudaStreamSynchronize(st));
-  if ((rc = m->sur.reserve((size_t)total * 16 + 16))) return rc;
-  k_stgm_gather<<<(nc * 32 + tb - 1) / tb, tb, 0, st>>>(m->flag.as<uint32_t>(), m->cell_off.as<uint32_t>(), m->seloff.as<uint32_t>(),
-                                                       nc, m->pts.as<float4>(), m->sur.as<float4>());
-  e->launches += 3 + 2;
-  MSFL_CUDA_OK(cudaGetLastError());
-  m->sur_n = total;
-  if (n_out) *n_out = total;
-  return MSFL_OK;
+  return map_surround_device(m, (uint32_t)scan->n, pose_tq, n_out);
 }
 
 int msfl_map_download(msfl_map *m, int which, float *out_xyzi, size_t capacity, size_t *n_out) {
@@ -509,6 +518,88 @@ int msfl_map_download(msfl_map *m, int which, float *out_xyzi, size_t capacity, 
   if (n > capacity) { set_error("msfl_map_download: capacity %zu < %zu points", capacity, n); return MSFL_ERR_ARG; }
   if (n) MSFL_CUDA_OK(cudaMemcpyAsync(out_xyzi, src, n * 16, cudaMemcpyDeviceToHost, m->e->stream));
   MSFL_CUDA_OK(cudaStreamSynchronize(m->e->stream));
+  return MSFL_OK;
+}
+
+// One frame of LaserMapping (laser_mapping.cc:258-340) with every intermediate on the device: the two feature clouds are
+// uploaded once and serve as surround queries, VoxelGrid inputs and inserted scans.
+int msfl_mapping_frame(msfl_engine *e, msfl_map *map_corner, msfl_map *map_surf, const msfl_cloud *corner_less_sharp,
+                       const msfl_cloud *surf_less_flat, double pose_tq[7], int32_t *matched, msfl_stats *stats) {
+  if (!e || !map_corner || !map_surf || !corner_less_sharp || !surf_less_flat || !pose_tq) { set_error("msfl_mapping_frame: bad argument"); return MSFL_ERR_ARG; }
+  if (map_corner->e != e || map_surf->e != e) { set_error("msfl_mapping_frame: the maps belong to another engine"); return MSFL_ERR_ARG; }
+  if (matched) *matched = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  int rc;
+  if ((rc = check_cloud(corner_less_sharp, false, "msfl_mapping_frame corner_less_sharp"))) return rc;
+  if ((rc = check_cloud(surf_less_flat, false, "msfl_mapping_frame surf_less_flat"))) return rc;
+  MSFL_CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  const size_t nc = corner_less_sharp->n, ns = surf_less_flat->n;
+  // 1. both clouds to the device, once (one staging buffer: the two copies are in flight together)
+  if ((rc = e->h_stage.reserve((nc + ns) * 16 + 16))) return rc;
+  {
+    const msfl_cloud *cl[2] = {corner_less_sharp, surf_less_flat};
+    msfl_map *mp[2] = {map_corner, map_surf};
+    float *h = e->h_stage.as<float>();
+    for (int c = 0; c < 2; ++c) {
+      const size_t n = cl[c]->n;
+      if ((rc = mp[c]->in.reserve(n * 16 + 16))) return rc;
+      const char *base = (const char *)cl[c]->data;
+      const bool has_i = cl[c]->off_intensity != MSFL_NO_FIELD;
+      for (size_t i = 0; i < n; ++i) {
+        const char *pt = base + i * cl[c]->stride;
+        memcpy(h + 4 * i, pt + cl[c]->off_xyz, 12);
+        float w = 0.f;
+        if (has_i) memcpy(&w, pt + cl[c]->off_intensity, 4);
+        h[4 * i + 3] = w;
+      }
+      if (n) MSFL_CUDA_OK(cudaMemcpyAsync(mp[c]->in.p, h, n * 16, cudaMemcpyHostToDevice, st));
+      h += 4 * n;
+    }
+  }
+  // 2. GetSurroundedCloud of both maps at the incoming pose (:273-278)
+  size_t m_c = 0, m_s = 0;
+  if ((rc = map_surround_device(map_corner, (uint32_t)nc, pose_tq, &m_c))) return rc;
+  if ((rc = map_surround_device(map_surf, (uint32_t)ns, pose_tq, &m_s))) return rc;
+  // 3. the gate (:284-285), the scan's VoxelGrid (:264-270, the maps' own leaf sizes: one filter object serves both uses
+  //    upstream) and MatchScan2Map (:304-311) on the device-resident clouds
+  if (m_c > 10 && m_s > 50) {
+    if ((rc = e->fr_qc.reserve(nc * 16 + 16))) return rc;
+    if ((rc = e->fr_qs.reserve(ns * 16 + 16))) return rc;
+    size_t nqc = 0, nqs = 0;
+    if (nc && (rc = run_voxel_grid(e, map_corner->in.as<float4>(), nc, map_corner->leaf, e->fr_qc.as<float4>(), &nqc))) return rc;
+    if (ns && (rc = run_voxel_grid(e, map_surf->in.as<float4>(), ns, map_surf->leaf, e->fr_qs.as<float4>(), &nqs))) return rc;
+    if ((rc = msfl_set_submap_device(e, map_corner->sur.as<float>(), m_c, map_surf->sur.as<float>(), m_s))) return rc;
+    if (nqc + nqs > 0) {
+      // offsets (2 x 2 int32) + pose (7 doubles) + stats in one small device block
+      if ((rc = e->fr_misc.reserve(16 + 56 + sizeof(msfl_stats) + 16))) return rc;
+      if ((rc = e->h_misc.reserve(16 + 56 + sizeof(msfl_stats) + 16))) return rc;
+      char *hm = e->h_misc.as<char>();
+      int32_t *hoff = (int32_t *)hm;
+      hoff[0] = 0; hoff[1] = (int32_t)nqc; hoff[2] = 0; hoff[3] = (int32_t)nqs;
+      memcpy(hm + 16, pose_tq, 56);
+      MSFL_CUDA_OK(cudaMemcpyAsync(e->fr_misc.p, hm, 16 + 56, cudaMemcpyHostToDevice, st));
+      char *dm = e->fr_misc.as<char>();
+      double *d_pose = (double *)(dm + 16);
+      msfl_stats *d_stats = nullptr;
+      if (stats) {
+        d_stats = (msfl_stats *)(dm + 16 + 56 + 8);
+        MSFL_CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(msfl_stats), st));
+      }
+      if ((rc = scan2map_enqueue(e, 1, e->fr_qc.as<float4>(), (const int32_t *)dm, (uint32_t)nqc, e->fr_qs.as<float4>(),
+                                 (const int32_t *)dm + 2, (uint32_t)nqs, d_pose, d_stats)))
+        return rc;
+      MSFL_CUDA_OK(cudaMemcpyAsync(hm + 16, d_pose, 56, cudaMemcpyDeviceToHost, st));
+      if (stats) MSFL_CUDA_OK(cudaMemcpyAsync(hm + 16 + 56 + 8, d_stats, sizeof(msfl_stats), cudaMemcpyDeviceToHost, st));
+      MSFL_CUDA_OK(cudaStreamSynchronize(st));
+      memcpy(pose_tq, hm + 16, 56);
+      if (stats) memcpy(stats, hm + 16 + 56 + 8, sizeof(msfl_stats));
+    }
+    if (matched) *matched = 1;
+  }
+  // 4. InsertScan2Map (:330-338): the un-down-sampled clouds at the refined pose, whether or not the gate passed
+  if (nc && (rc = map_insert_device(map_corner, (uint32_t)nc, 1, pose_tq))) return rc;
+  if (ns && (rc = map_insert_device(map_surf, (uint32_t)ns, 1, pose_tq))) return rc;
   return MSFL_OK;
 }
 

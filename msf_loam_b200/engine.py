@@ -491,6 +491,21 @@ def set_submap_from_maps(engine: Engine, corner: "HybridGrid", surf: "HybridGrid
     engine._check(engine.lib.msfl_set_submap_from_maps(engine.h, corner.h, surf.h))
 
 
+def mapping_frame(engine: Engine, corner: "HybridGrid", surf: "HybridGrid", cloud_corner_less_sharp, cloud_surf_less_flat, pose,
+                  want_stats=True):
+    """msfl_mapping_frame: one frame of LaserMapping (laser_mapping.cc:258-340) -- VoxelGrid of the scan's feature clouds,
+    GetSurroundedCloud of both maps, the size gate, MatchScan2Map, InsertScan at the refined pose -- in one call.
+    Returns (matched, pose, stats dict or None)."""
+    vc, vs = _View(cloud_corner_less_sharp), _View(cloud_surf_less_flat)
+    x = _pose(pose)
+    st = Stats() if want_stats else None
+    matched = C.c_int32(0)
+    engine._check(engine.lib.msfl_mapping_frame(engine.h, corner.h, surf.h, C.byref(vc.cloud), C.byref(vs.cloud),
+                                                x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(matched),
+                                                C.byref(st) if st is not None else None))
+    return bool(matched.value), x, (st.as_dict() if st is not None else None)
+
+
 class TimestampedPointCloud:
     """The five clouds of the reference's TimestampedPointCloud (timestamped_pointcloud.h:11-48);
     each member is an (n,4) float32 array (plus ``*_ring`` uint16 for PointXYZIRT clouds)."""

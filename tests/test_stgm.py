@@ -143,3 +143,62 @@ def test_cuda_stgm_matches_oracle_bitwise_and_feeds_scan2map():
     for g in (gc, gs, empty):
         g.close()
     e.close()
+
+
+@pytest.mark.gpu
+def test_mapping_frame_equals_the_separate_calls_and_the_reference_loop():
+    """msfl_mapping_frame = one frame of LaserMapping (laser_mapping.cc:258-340).  Six frames along a trajectory, each
+    starting from a perturbed pose: the frame call against (a) the same steps issued as separate C-ABI calls on a second
+    pair of maps -- bitwise: poses, gate decisions, both maps -- and (b) the reference's own loop body assembled from its
+    compiled HybridGrid and MatchScan2Map (oracle/_ref) with the oracle's VoxelGrid."""
+    import time
+    from msf_loam_b200 import Engine, HybridGrid, mapping_frame, set_submap_from_maps
+    from oracle import ref as R
+    scans = _scans(6)
+    e = Engine()
+    try:
+        fc, fs = HybridGrid(e, 3.0, 0.2), HybridGrid(e, 3.0, 0.4)   # driven by the frame call
+        sc, ss = HybridGrid(e, 3.0, 0.2), HybridGrid(e, 3.0, 0.4)   # driven by separate calls
+        have_ref = R.available()
+        rc_, rs_ = (R.Map(3.0, 0.2), R.Map(3.0, 0.4)) if have_ref else (None, None)
+        t_frame = t_sep = 0.0
+        for k, (corner, surf, gt) in enumerate(scans):
+            guess = gt if k == 0 else S.perturb_pose(gt, np.random.default_rng(40 + k))
+            t0 = time.perf_counter()
+            matched, pose, st = mapping_frame(e, fc, fs, corner, surf, guess)
+            t_frame += time.perf_counter() - t0
+            # (a) the same frame as separate calls
+            t0 = time.perf_counter()
+            n_c, n_s = sc.GetSurroundedCloud(corner, guess, download=False), ss.GetSurroundedCloud(surf, guess, download=False)
+            pose_sep, gate = guess.copy(), n_c > 10 and n_s > 50
+            if gate:
+                set_submap_from_maps(e, sc, ss)
+                _, pose_sep, st_sep = e.scan2map(e.voxel_grid(corner, 0.2), e.voxel_grid(surf, 0.4), guess)
+            sc.InsertScan(corner, pose_sep)
+            ss.InsertScan(surf, pose_sep)
+            t_sep += time.perf_counter() - t0
+            assert matched == gate == (k > 0)  # the first frame only fills the empty maps
+            assert np.array_equal(pose, pose_sep)
+            if gate:
+                assert st["n_edge"] == st_sep["n_edge"] and st["n_plane"] == st_sep["n_plane"] and st["n_plane"][0] > 1000
+                dt, dr = S.pose_error(pose, gt)
+                assert dt < 0.05 and dr < 0.01
+            assert fc.size() == sc.size() and fs.size() == ss.size()
+            assert np.array_equal(fc.dump(), sc.dump()) and np.array_equal(fs.dump(), ss.dump())
+            # (b) the reference's loop body
+            if have_ref:
+                m_c, m_s = rc_.surround(corner, guess), rs_.surround(surf, guess)
+                pose_ref = guess.copy()
+                if len(m_c) > 10 and len(m_s) > 50:
+                    ok, pose_ref = R.scan2map(m_c, m_s, O.voxel_grid(corner, 0.2), O.voxel_grid(surf, 0.4), guess)
+                assert (len(m_c) > 10 and len(m_s) > 50) == matched
+                dt, dr = S.pose_error(pose, pose_ref)
+                assert dt < 1e-8 and dr < 1e-8, (k, dt, dr)
+                # keep the reference maps on the same trajectory as ours (poses agree to ~1e-12, the maps to float rounding)
+                rc_.insert(S.transform_cloud(pose, corner))
+                rs_.insert(S.transform_cloud(pose, surf))
+        print(f"mapping frame: {t_frame / len(scans) * 1e3:.2f} ms per frame in one call, {t_sep / len(scans) * 1e3:.2f} ms as separate calls")
+        for g in (fc, fs, sc, ss):
+            g.close()
+    finally:
+        e.close()
