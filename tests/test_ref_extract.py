@@ -63,6 +63,16 @@ def test_oracle_extraction_equals_the_reference_registration():
         _compare(f, r, 0.0)
 
 
+def test_oracle_extraction_equals_the_reference_registration_other_min_range():
+    """minimum_range is a node parameter (msf_loam_node.cc:434): 8 m removes the nearest floor rings and walls."""
+    xyzi, ring = S.raycast_scan(S.make_scene(), "vlp16", S.trajectory(2)[1], seed=11)
+    P = O.default_params(min_range=8.0)
+    r = R.extract_features(xyzi, ring, T_EXT, min_range=8.0)
+    f = O.extract_features(P, xyzi, ring, T_EXT)
+    assert r["full"].shape[0] < xyzi.shape[0] - 100
+    _compare(f, r, 0.0)
+
+
 def test_reference_less_flat_cloud_is_not_downsampled():
     """Quirk Q1: VoxelGridWrapper copies the filter's INPUT indices (msf_loam_node.cc:122-125), so the less-flat cloud is
     every FLAT / UNKNOWN point of the used sectors, far more than a 0.2 m voxel grid would leave."""

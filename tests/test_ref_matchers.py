@@ -108,6 +108,26 @@ def test_oracle_scan2scan_equals_the_reference_matcher():
     assert np.array_equal(x_ref, init) and np.array_equal(x, init)
 
 
+def test_oracle_scan2scan_equals_the_reference_matcher_hdl64():
+    """64 rings: the +-2.5-ring windows of the odometry association (odometry_scan_matcher.cc:96-141, :171-230) see many
+    more neighbouring rings than on a VLP-16."""
+    P = O.default_params()
+    sc = S.make_scene("room80")
+    traj = S.trajectory(3)
+    f = [O.extract_features(P, *S.raycast_scan(sc, "hdl64", traj[k], seed=70 + k), None) for k in range(2)]
+    lc, lcr = f[0]["full"][f[0]["idx_less_sharp"]], f[0]["ring"][f[0]["idx_less_sharp"]]
+    ls, lsr = f[0]["full"][f[0]["idx_less_flat"]], f[0]["ring"][f[0]["idx_less_flat"]]
+    cs, cf = f[1]["full"][f[1]["idx_sharp"]], f[1]["full"][f[1]["idx_flat"]]
+    R.reset_logs()
+    ok, x_ref = R.scan2scan(lc, lcr, ls, lsr, cs, cf, S.pose_identity())
+    solves = R.solves()
+    rc, x, logs, counts, _ = O.scan2scan(P, lc, lcr, ls, lsr, cs, cf, S.pose_identity())
+    assert ok and rc == 0 and np.array_equal(x, x_ref)
+    assert [(s["n_edge"], s["n_plane"]) for s in solves] == [tuple(r) for r in counts] and counts[0, 1] > 1000
+    dt, dr = S.pose_error(x, S.pose_mul(S.pose_inv(traj[0]), traj[1]))
+    assert dt < 0.05 and dr < 0.01
+
+
 def test_oracle_deskew_branch_equals_the_reference_matcher(vlp16_case):
     P = O.default_params()
     c = vlp16_case
