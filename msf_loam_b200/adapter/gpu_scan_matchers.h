@@ -6,6 +6,7 @@
 //
 //   OdometryScanMatcher::MatchScan2Scan   odometry_scan_matcher.h:10-12   -> msfl_scan2scan
 //   MappingScanMatcher::MatchScan2Map     mapping_scan_matcher.h:14-21    -> msfl_set_submap + msfl_scan2map
+//   LaserMapping's frame (MatchScan2Map + InsertScan2Map, laser_mapping.cc:258-340) -> msfl_mapping_frame (GpuMappingFrame)
 #pragma once
 
 #include <cstddef>
@@ -156,4 +157,40 @@ class GpuMappingScanMatcher : public MappingScanMatcher {
   }
 
   msfl_adapter::Engine engine_;
+};
+
+// Replaces the two HybridGrid members of LaserMapping (laser_mapping.h: hybrid_grid_map_corner_ / hybrid_grid_map_surf_,
+// resolution 3 m, leaf = the two down-size filters' 0.2 / 0.4) AND the matcher for the LiDAR-only branch: one call per
+// frame does LaserMapping::MatchScan2Map + InsertScan2Map (laser_mapping.cc:258-340) with every intermediate on the GPU.
+class GpuMappingFrame {
+ public:
+  explicit GpuMappingFrame(float resolution = 3.0f, float leaf_corner = 0.2f, float leaf_surf = 0.4f) {
+    if (msfl_map_create(engine_.get(), resolution, leaf_corner, &corner_) != MSFL_OK ||
+        msfl_map_create(engine_.get(), resolution, leaf_surf, &surf_) != MSFL_OK)
+      throw std::runtime_error(std::string("msfl_map_create: ") + msfl_last_error());
+  }
+  ~GpuMappingFrame() {
+    msfl_map_destroy(corner_);
+    msfl_map_destroy(surf_);
+  }
+  GpuMappingFrame(const GpuMappingFrame &) = delete;
+  GpuMappingFrame &operator=(const GpuMappingFrame &) = delete;
+
+  // odom_result.cloud_corner_less_sharp / cloud_surf_less_flat (un-down-sampled) in, pose_map_scan2world_ in-out;
+  // returns false when the surround clouds were too small to match (:284-285, :313) -- the scan is inserted either way
+  template <typename PointT>
+  bool MatchAndInsert(const pcl::PointCloud<PointT> &corner_less_sharp, const pcl::PointCloud<PointT> &surf_less_flat,
+                      Rigid3d *pose_map_scan2world) {
+    const msfl_cloud c = msfl_adapter::View(corner_less_sharp, false), s = msfl_adapter::View(surf_less_flat, false);
+    double pose[7];
+    msfl_adapter::ToArray(*pose_map_scan2world, pose);
+    int32_t matched = 0;
+    CHECK_EQ(msfl_mapping_frame(engine_.get(), corner_, surf_, &c, &s, pose, &matched, nullptr), MSFL_OK) << msfl_last_error();
+    *pose_map_scan2world = msfl_adapter::FromArray(pose);
+    return matched != 0;
+  }
+
+ private:
+  msfl_adapter::Engine engine_;
+  msfl_map *corner_ = nullptr, *surf_ = nullptr;
 };

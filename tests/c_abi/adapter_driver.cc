@@ -102,5 +102,15 @@ int main(int argc, char **argv) {
   const bool ok_dsk = mbase->MatchScan2Map(map, scan, true, pre, Vector3d(0, 0, 0), prev, &pose2, &vel2);
   msfl_adapter::ToArray(pose2, out);
   std::printf("DSK %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)ok_dsk, out[0], out[1], out[2], out[3], out[4], out[5], out[6]);
+
+  // ---- LaserMapping's whole frame (MatchScan2Map + InsertScan2Map, laser_mapping.cc:258-340) on GPU-resident maps:
+  // frame 0 inserts the map clouds (world frame = identity pose; nothing to match against yet), frame 1 matches the scan
+  GpuMappingFrame frame;
+  Rigid3d world = msfl_adapter::FromArray(init_odo);  // identity
+  const bool m0 = frame.MatchAndInsert(*map.cloud_corner_less_sharp, *map.cloud_surf_less_flat, &world);
+  Rigid3d pose3 = msfl_adapter::FromArray(init_map);
+  const bool m1 = frame.MatchAndInsert(*scan.cloud_corner_less_sharp, *scan.cloud_surf_less_flat, &pose3);
+  msfl_adapter::ToArray(pose3, out);
+  std::printf("FRM %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)(!m0 && m1), out[0], out[1], out[2], out[3], out[4], out[5], out[6]);
   return 0;
 }

@@ -60,7 +60,7 @@ def test_adapter_poses_equal_the_python_binding(tmp_path, vlp16_case):
         f.write(S.pose_identity().astype(np.float64).tobytes())
     r = subprocess.run([exe, path], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stdout + r.stderr
-    got = {l.split()[0]: np.array(l.split()[1:], dtype=np.float64) for l in r.stdout.splitlines() if l[:3] in ("MAP", "ODO", "DSK")}
+    got = {l.split()[0]: np.array(l.split()[1:], dtype=np.float64) for l in r.stdout.splitlines() if l[:3] in ("MAP", "ODO", "DSK", "FRM")}
     eng = Engine(default_params(lm_cluster=16))  # the adapter's engine configuration
     eng.set_submap(case["map_corner"], case["map_surf"])
     _, pose_map, _ = eng.scan2map(to_pcl(q["corner"]), to_pcl(q["surf"]), q["init"])
@@ -76,4 +76,11 @@ def test_adapter_poses_equal_the_python_binding(tmp_path, vlp16_case):
     ref, _, _ = O.scan2map(O.default_params(), case["map_corner"], case["map_surf"], q["corner"], q["surf"], q["init"])
     dt, dr = S.pose_error(got["MAP"][1:], ref)
     assert dt <= 1e-7 and dr <= 1e-7
+    # GpuMappingFrame: the first frame only fills the maps, the second matches against them.  The scan's feature clouds go
+    # through the maps' VoxelGrid (0.2 / 0.4) inside the call and the map clouds are re-filtered per 3 m cell on insert, so
+    # the pose is close to -- not bitwise -- the MatchScan2Map one above
+    dt, dr = S.pose_error(got["FRM"][1:], q["gt"])
+    assert got["FRM"][0] == 1 and dt < 0.05 and dr < 0.01
+    dt, dr = S.pose_error(got["FRM"][1:], pose_map)
+    assert dt < 0.02 and dr < 0.005
     eng.close()
