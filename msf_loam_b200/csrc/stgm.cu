@@ -280,17 +280,9 @@ static int upload_packed(msfl_engine *e, const msfl_cloud *c, DevBuf &dst) {
   int rc;
   if ((rc = e->h_stage.reserve(n * 16 + 16))) return rc;
   if ((rc = dst.reserve(n * 16 + 16))) return rc;
-  float *h = e->h_stage.as<float>();
-  const char *base = (const char *)c->data;
-  const bool has_i = c->off_intensity != MSFL_NO_FIELD;
-  for (size_t i = 0; i < n; ++i) {
-    const char *pt = base + i * c->stride;
-    memcpy(h + 4 * i, pt + c->off_xyz, 12);
-    float w = 0.f;
-    if (has_i) memcpy(&w, pt + c->off_intensity, 4);
-    h[4 * i + 3] = w;
-  }
-  MSFL_CUDA_OK(cudaMemcpyAsync(dst.p, h, n * 16, cudaMemcpyHostToDevice, e->stream));
+  const uint32_t off0 = 0;
+  pack_clouds_parallel(e, 1, c, e->h_stage.as<float>(), nullptr, &off0);
+  MSFL_CUDA_OK(cudaMemcpyAsync(dst.p, e->h_stage.p, n * 16, cudaMemcpyHostToDevice, e->stream));
   return MSFL_OK;
 }
 
@@ -538,24 +530,14 @@ int msfl_mapping_frame(msfl_engine *e, msfl_map *map_corner, msfl_map *map_surf,
   // 1. both clouds to the device, once (one staging buffer: the two copies are in flight together)
   if ((rc = e->h_stage.reserve((nc + ns) * 16 + 16))) return rc;
   {
-    const msfl_cloud *cl[2] = {corner_less_sharp, surf_less_flat};
-    msfl_map *mp[2] = {map_corner, map_surf};
+    const msfl_cloud cl[2] = {*corner_less_sharp, *surf_less_flat};
+    const uint32_t off[2] = {0u, (uint32_t)nc};
     float *h = e->h_stage.as<float>();
-    for (int c = 0; c < 2; ++c) {
-      const size_t n = cl[c]->n;
-      if ((rc = mp[c]->in.reserve(n * 16 + 16))) return rc;
-      const char *base = (const char *)cl[c]->data;
-      const bool has_i = cl[c]->off_intensity != MSFL_NO_FIELD;
-      for (size_t i = 0; i < n; ++i) {
-        const char *pt = base + i * cl[c]->stride;
-        memcpy(h + 4 * i, pt + cl[c]->off_xyz, 12);
-        float w = 0.f;
-        if (has_i) memcpy(&w, pt + cl[c]->off_intensity, 4);
-        h[4 * i + 3] = w;
-      }
-      if (n) MSFL_CUDA_OK(cudaMemcpyAsync(mp[c]->in.p, h, n * 16, cudaMemcpyHostToDevice, st));
-      h += 4 * n;
-    }
+    pack_clouds_parallel(e, 2, cl, h, nullptr, off);
+    if ((rc = map_corner->in.reserve(nc * 16 + 16))) return rc;
+    if ((rc = map_surf->in.reserve(ns * 16 + 16))) return rc;
+    if (nc) MSFL_CUDA_OK(cudaMemcpyAsync(map_corner->in.p, h, nc * 16, cudaMemcpyHostToDevice, st));
+    if (ns) MSFL_CUDA_OK(cudaMemcpyAsync(map_surf->in.p, h + 4 * nc, ns * 16, cudaMemcpyHostToDevice, st));
   }
   // 2. GetSurroundedCloud of both maps at the incoming pose (:273-278)
   size_t m_c = 0, m_s = 0;
