@@ -18,11 +18,35 @@
 
 namespace msfl {
 
+// Per-query streams of a batch (queries, transformed queries, keys, ranks, factor constants: 0.3-0.7 GB per launch) are
+// read or written exactly once per kernel, while the submap, its cell index and the counting-sort bin table (a few MB)
+// are hit by every query: the streams carry the evict-first hint (ld.global.cs / st.global.cs) so that they do not push
+// the hot tables out of L1 / L2.  -DMSFL_STREAM_HINTS=0 builds the plain loads / stores for A/B runs.
+#ifndef MSFL_STREAM_HINTS
+#define MSFL_STREAM_HINTS 1
+#endif
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T *p) {
+#if MSFL_STREAM_HINTS
+  return __ldcs(p);
+#else
+  return __ldg(p);
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, const T &v) {
+#if MSFL_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
 __device__ __forceinline__ void store_corr(double *corr, size_t q, const double a[3], const double n[3]) {
   double2 *o = reinterpret_cast<double2 *>(corr + q * 6);
-  o[0] = make_double2(a[0], a[1]);
-  o[1] = make_double2(a[2], n[0]);
-  o[2] = make_double2(n[1], n[2]);
+  st_stream(o, make_double2(a[0], a[1]));
+  st_stream(o + 1, make_double2(a[2], n[0]));
+  st_stream(o + 2, make_double2(n[1], n[2]));
 }
 
 // scan id of flat query k: largest b with off[b] <= k (off has B+1 ascending entries)
@@ -78,7 +102,7 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
   double pose[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) pose[i] = __ldg(poses + (size_t)scan * 7 + i);
-  const float4 p = __ldg((is_corner ? qc : qs) + kk);
+  const float4 p = ld_stream((is_corner ? qc : qs) + kk);
   const float3 x = transform_point_f(pose, p.x, p.y, p.z);
   const uint32_t ncell_c = (uint32_t)(gc.nx * gc.ny * gc.nz), ncell_s = (uint32_t)(gs.nx * gs.ny * gs.nz);
   const int c = cell_of(is_corner ? gc : gs, x.x, x.y, x.z);
@@ -96,9 +120,9 @@ k_transform_keys(GridView gc, GridView gs, int B, const float4 *__restrict__ qc,
               sz = min(ns - 1, max(0, (int)((uz - floorf(uz)) * fs)));
     key = (key << (3 * sub_log2)) | (uint32_t)((((sz << sub_log2) + sy) << sub_log2) + sx);
   }
-  xq[k] = make_float4(x.x, x.y, x.z, 0.f);
-  keys[k] = key;
-  vals[k] = COUNT ? atomicAdd(hist + key, 1u) : k;
+  st_stream(xq + k, make_float4(x.x, x.y, x.z, 0.f));
+  st_stream(keys + k, key);
+  st_stream(vals + k, COUNT ? atomicAdd(hist + key, 1u) : k);
 }
 
 // counting sort, last pass: slot = first slot of the query's bin + its rank inside the bin
@@ -107,7 +131,7 @@ k_scatter_perm(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ r
                uint32_t n, uint32_t *__restrict__ perm) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  perm[__ldg(bin_start + __ldg(keys + k)) + __ldg(rank + k)] = k;
+  perm[__ldg(bin_start + ld_stream(keys + k)) + ld_stream(rank + k)] = k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -502,9 +526,9 @@ k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32
            uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_total) return;
-  const uint32_t k = __ldg(perm + slot);
+  const uint32_t k = ld_stream(perm + slot);
   const bool is_corner = slot < n_corner_total;
-  const float4 xs = __ldg(xq + k);
+  const float4 xs = ld_stream(xq + k);
   const GridView &g = is_corner ? gc : gs;
   Top5 t;
   const bool gate = knn5_grid(g, xs.x, xs.y, xs.z, kp.knn_max_sq_f, t);
@@ -538,8 +562,8 @@ k_knn5_fit(GridView gc, GridView gs, KParams kp, uint32_t n_corner_total, uint32
   }
   double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(corr + (size_t)n_corner_total * 6) +
                                            (size_t)(k - n_corner_total) * 32);
-  o[0] = make_double2(n[0], n[1]);
-  o[1] = make_double2(n[2], __fma_rn(n[2], c[2], __fma_rn(n[1], c[1], __dmul_rn(n[0], c[0]))));
+  st_stream(o, make_double2(n[0], n[1]));
+  st_stream(o + 1, make_double2(n[2], __fma_rn(n[2], c[2], __fma_rn(n[1], c[1], __dmul_rn(n[0], c[0])))));
 }
 
 // One thread per query.  Kept apart from the search kernel so that the search runs at 40 registers / 75 %

@@ -1,13 +1,11 @@
-python -m pytest tests/test_c_abi_program.py -m gpu -x -q -s 2>&1 | grep -E "async|passed|failed|pose t" | head -5
-run() { echo "== $*"; env "$@" python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(d['value'], 'e2e', d['e2e']['value'], 'sync', d['e2e']['synchronous_call_value'])
-    else: print(l.rstrip())
-"; }
-run MSFL_X=geo4
-run MSFL_CHUNK_SCHED=eq4
-run MSFL_CHUNK_SCHED=3
-run MSFL_CHUNK_SCHED=2
-run MSFL_CHUNK_SCHED=b
+# dev A/B: the bench's device-timed leg with the tree's library and with a variant built earlier
+# (MSFL_NVCC_EXTRA=... python -m msf_loam_b200.build --force; cp msf_loam_b200/libmsfl.so msf_loam_b200/libmsfl_<name>.so)
+mkdir -p gpurun_out
+for v in "$@" ""; do
+  lib=msf_loam_b200/libmsfl${v:+_$v}.so
+  for rep in 1 2; do
+    MSFL_LIB_PATH=$PWD/$lib python bench.py --no-cpu --no-workloads --only-device --steps 30 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('$lib', d['value'], d['ms_per_step'], [round(v,4) for v in r['stage_ms_per_step'].values()])"
+  done
+done
