@@ -19,7 +19,9 @@
 //                     and IMUFactor::Evaluate; the IMU-only predict problem (mapping_scan_matcher.cc:35-60) is declined by
 //                     the stand-in solver, so the Deskew entry takes the pose AFTER that predict, like msfl_scan2map_deskew.
 // tests/test_ref_factors.py and tests/test_ref_matchers.py check the oracle -- and, on the GPU box, the CUDA path through
-// the C ABI -- against these functions.
+// the C ABI -- against these functions.  The same library also holds the reference's scan registration
+// (ref_extract_shim.cc: src/msf_loam_node.cc, rows a-1 .. a-4) and its sub-map store (ref_map_shim.cc:
+// src/slam/map/hybrid_grid.cc, row f-1).
 #include <pcl/kdtree/kdtree_flann.h>
 
 #include <atomic>
