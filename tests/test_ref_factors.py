@@ -171,3 +171,45 @@ def test_cuda_normal_equations_equal_the_reference_sums(vlp16_case):
             assert np.abs(g_g - g_r).max() <= 1e-11 * np.abs(g_r).max()
     finally:
         eng.close()
+
+
+def test_stand_in_algebra_agrees_with_scipy():
+    """The stand-in Eigen primitives under the compiled reference code (oracle/ref_stubs/msfl_eigen_standin.h) against an
+    independent implementation: quaternion * vector and toRotationMatrix (through the factors' residuals / Jacobians),
+    quaternion product + normalisation (through Plus), slerp (through GetDeltaQP) -- scipy.spatial.transform."""
+    from scipy.spatial.transform import Rotation, Slerp
+    from oracle import ref as RR
+    rng = np.random.default_rng(8)
+    for _ in range(200):
+        pose = _random_pose(rng)
+        Rm = Rotation.from_quat(pose[3:]).as_matrix()
+        p, c = rng.normal(scale=10, size=3), rng.normal(scale=10, size=3)
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        r, J = ref_factor(1, pose, p, c, n)
+        assert abs(r[0] - n @ (Rm @ p + pose[:3] - c)) < 1e-12
+        skew = np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+        assert np.abs(J[0, :3] - n).max() < 1e-15 and np.abs(J[0, 3:6] + n @ (Rm @ skew)).max() < 1e-12 and J[0, 6] == 0
+        r3, J3 = ref_factor(0, pose, p, c, n)
+        assert np.abs(r3 - np.cross(n, Rm @ p + pose[:3] - c)).max() < 1e-12
+        # Plus: q <- (q * exp(dtheta / 2)) normalised, p <- p + dp
+        d = np.concatenate([rng.normal(size=3), rng.normal(scale=0.3, size=3)])
+        y = ref_pose_plus(pose, d)
+        q_expect = (Rotation.from_quat(pose[3:]) * Rotation.from_rotvec(d[3:])).as_quat()
+        q_expect *= np.sign(q_expect @ y[3:])
+        assert np.abs(y[:3] - pose[:3] - d[:3]).max() < 1e-15 and np.abs(y[3:] - q_expect).max() < 1e-14
+        # TransformPoint: float -> double -> R p + t -> float
+        x = rng.normal(scale=30, size=(1, 3)).astype(np.float32)
+        got = RR.transform_point(pose, x)[0]
+        want = (Rm @ x[0].astype(np.float64) + pose[:3])
+        assert np.abs(got - want).max() <= 4e-6  # one float ulp at 60 m
+    # slerp + lerp of GetDeltaQP
+    t = np.linspace(0.0, 0.1, 11)
+    rots = Rotation.from_rotvec(np.outer(t, [0.3, -0.2, 1.1]))
+    dq, dp = rots.as_quat(), np.outer(t, [0.5, 0.1, -0.2])
+    sl = Slerp(t, rots)
+    for dt in rng.uniform(0.0, 0.0999, size=100):
+        q, pp = RR.get_delta_qp(t, dq, dp, float(dt))
+        qe = sl([dt]).as_quat()[0]
+        qe *= np.sign(qe @ q)
+        assert np.abs(q - qe).max() < 1e-14 and np.abs(pp - np.array([0.5, 0.1, -0.2]) * dt).max() < 1e-15
